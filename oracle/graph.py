@@ -1,0 +1,242 @@
+"""Oracle (numpy): mesh -> graph, kd decomposition with halo, subdomain build, stitch.
+
+TEST INFRASTRUCTURE -- see oracle/__init__.py.  Integer outputs of these functions are
+what the CUDA assembly / stitch kernels must reproduce bit for bit.
+
+Reference anchors (all under /root/reference):
+  * edges + edge_attr ...... dataset/GraphDataset.py:838-869  (AnsysDataset.vtk_to_pyg)
+  * per-subdomain contents . dataset/GraphDataset.py:1245-1284 (x, y, pos, edge_index,
+                             edge_attr, global_node_ids written per partition)
+  * decomposition .......... dataset/GraphDataset.py:1183-1230 (vtkRedistributeDataSetFilter,
+                             AssignToAllIntersectingRegions at :1219; Duct uses
+                             AssignToOneRegion at :565)
+  * stitch ................. dataset/GraphDataset.py:1370-1400 (mean over coincident points)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MODE_ONE_REGION = 0          # reference Duct path, GraphDataset.py:565
+MODE_ALL_INTERSECTING = 1    # reference Ansys path, GraphDataset.py:1219
+
+
+# --------------------------------------------------------------------------------------
+# a1: edges of a tetrahedral (or any simplex/cell) mesh
+# --------------------------------------------------------------------------------------
+def build_edges(cells: np.ndarray, pos: np.ndarray):
+    """All ordered point pairs of every cell, both directions, de-duplicated.
+
+    Follows GraphDataset.py:850-864 (the reference inserts (j,k) and (k,j) for every
+    j<k of every cell into a Python set).  The set's iteration order is arbitrary, so the
+    contract is the edge SET; we return it in the canonical order (dst, src) ascending --
+    the CSR-by-destination order every kernel uses.
+
+    edge_attr follows GraphDataset.py:866-867: fp32 ``np.linalg.norm(pos[src]-pos[dst])``.
+    Returns (src[E] int64, dst[E] int64, edge_attr[E] float32).
+    """
+    cells = np.asarray(cells, dtype=np.int64)
+    n = int(pos.shape[0])
+    k = cells.shape[1]
+    keys = []
+    for a in range(k):
+        for b in range(k):
+            if a != b:
+                keys.append(cells[:, b] * n + cells[:, a])      # key = dst * n + src
+    if not keys or cells.shape[0] == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return z, z.copy(), np.zeros(0, dtype=np.float32)
+    key = np.unique(np.concatenate(keys))
+    dst = key // n
+    src = key % n
+    keep = src != dst            # degenerate cells with a repeated vertex: the reference
+    src, dst = src[keep], dst[keep]  # would add a self loop; our meshes never have them
+    pos = np.asarray(pos, dtype=np.float32)
+    attr = np.linalg.norm(pos[src] - pos[dst], axis=1).astype(np.float32)
+    return src, dst, attr
+
+
+def csr_by_destination(src: np.ndarray, dst: np.ndarray, n: int):
+    """rowptr[n+1], perm[E]: edges sorted by (dst, src, original position)."""
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    perm = np.lexsort((np.arange(src.size), src, dst))
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(rowptr, dst + 1, 1)
+    rowptr = np.cumsum(rowptr)
+    return rowptr, perm
+
+
+# --------------------------------------------------------------------------------------
+# a2: kd decomposition
+# --------------------------------------------------------------------------------------
+def cell_centroids(pos: np.ndarray, cells: np.ndarray) -> np.ndarray:
+    """fp32 centroid with a fixed association: ((p0+p1)+(p2+p3))*0.25."""
+    p = np.asarray(pos, dtype=np.float32)[np.asarray(cells, dtype=np.int64)]
+    return ((p[:, 0] + p[:, 1]) + (p[:, 2] + p[:, 3])) * np.float32(0.25)
+
+
+def cell_aabb(pos: np.ndarray, cells: np.ndarray):
+    p = np.asarray(pos, dtype=np.float32)[np.asarray(cells, dtype=np.int64)]
+    return p.min(axis=1), p.max(axis=1)
+
+
+def kd_build(pos: np.ndarray, cells: np.ndarray, levels: int):
+    """Exact-median kd bisection of the cell centroids into 2**levels leaves.
+
+    Stands in for vtkRedistributeDataSetFilter's cut generation (GraphDataset.py:1208-1230;
+    VTK C++ is not available, so this definition IS the oracle -- parity unpinned).
+    Per tree node (heap order, children 2i+1 / 2i+2):
+      axis  = longest extent of the region's centroid bounding box (first max),
+      order = cells sorted by (centroid[axis], cell id),
+      left  = first m//2 cells, right = the rest, split = centroid[axis] of right[0].
+    An empty region has axis 0 and split +inf.
+    Returns (home_leaf[C] int32, tree_axis[2^k-1] int32, tree_split[2^k-1] float32).
+    """
+    C = int(cells.shape[0])
+    cent = cell_centroids(pos, cells)
+    region = np.zeros(C, dtype=np.int64)
+    n_internal = (1 << levels) - 1
+    tree_axis = np.zeros(n_internal, dtype=np.int32)
+    tree_split = np.full(n_internal, np.inf, dtype=np.float32)
+    for d in range(levels):
+        order_all = np.argsort(region, kind="stable")
+        counts = np.bincount(region, minlength=1 << d)
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        new_region = np.empty_like(region)
+        for r in range(1 << d):
+            ids = order_all[starts[r]:starts[r + 1]]          # ascending cell id
+            node = (1 << d) - 1 + r
+            m = ids.size
+            if m == 0:
+                continue
+            c = cent[ids]
+            ext = c.max(axis=0) - c.min(axis=0)
+            axis = 0 if (ext[0] >= ext[1] and ext[0] >= ext[2]) else (1 if ext[1] >= ext[2] else 2)
+            o = np.argsort(c[:, axis], kind="stable")
+            half = m // 2
+            tree_axis[node] = axis
+            tree_split[node] = c[o[half], axis]
+            new_region[ids[o[:half]]] = 2 * r
+            new_region[ids[o[half:]]] = 2 * r + 1
+        region = new_region
+    return region.astype(np.int32), tree_axis, tree_split
+
+
+def kd_assign(pos, cells, levels, mode, home_leaf, tree_axis, tree_split):
+    """(leaf_ptr[S+1], leaf_cells[sum]) -- cells of every leaf, ascending cell id.
+
+    ONE_REGION: the leaf of the centroid (home leaf).
+    ALL_INTERSECTING: every leaf whose half-space box the cell's AABB touches; at a tree
+    node the cell descends left if aabb_min[axis] < split, right if aabb_max[axis] >= split,
+    and always along its own home path.
+    """
+    S = 1 << levels
+    C = int(cells.shape[0])
+    if mode == MODE_ONE_REGION or levels == 0:
+        order = np.argsort(home_leaf, kind="stable").astype(np.int64)
+        counts = np.bincount(home_leaf, minlength=S)
+        return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), order
+    lo, hi = cell_aabb(pos, cells)
+    cur_cell = np.arange(C, dtype=np.int64)
+    cur_node = np.zeros(C, dtype=np.int64)     # within-level index
+    for d in range(levels):
+        heap = (1 << d) - 1 + cur_node
+        ax = tree_axis[heap]
+        sp = tree_split[heap]
+        home_here = (home_leaf[cur_cell].astype(np.int64) >> (levels - d)) == cur_node
+        home_right = ((home_leaf[cur_cell].astype(np.int64) >> (levels - d - 1)) & 1) == 1
+        go_left = (lo[cur_cell, ax] < sp) | (home_here & ~home_right)
+        go_right = (hi[cur_cell, ax] >= sp) | (home_here & home_right)
+        cur_cell = np.concatenate([cur_cell[go_left], cur_cell[go_right]])
+        cur_node = np.concatenate([2 * cur_node[go_left], 2 * cur_node[go_right] + 1])
+    order = np.lexsort((cur_cell, cur_node))
+    leaf_cells = cur_cell[order]
+    counts = np.bincount(cur_node, minlength=S)
+    leaf_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return leaf_ptr, leaf_cells
+
+
+def kd_partition(pos, cells, levels, mode=MODE_ALL_INTERSECTING):
+    home, ax, sp = kd_build(pos, cells, levels)
+    leaf_ptr, leaf_cells = kd_assign(pos, cells, levels, mode, home, ax, sp)
+    return {"home_leaf": home, "tree_axis": ax, "tree_split": sp,
+            "leaf_ptr": leaf_ptr, "leaf_cells": leaf_cells}
+
+
+# --------------------------------------------------------------------------------------
+# a2/a3: per-subdomain graphs, flattened as one block-diagonal batch
+# --------------------------------------------------------------------------------------
+def build_subdomains(pos, cells, leaf_ptr, leaf_cells):
+    """Per-subdomain node compaction + edge build, concatenated block-diagonally.
+
+    For subdomain s (GraphDataset.py:1245-1284): nodes = unique vertices of its cells in
+    ascending global id (-> ``global_ids``), local id = rank; edges = build_edges on the
+    subdomain's cells in local ids, canonical (dst, src) order; edge_attr fp32 length.
+    Batch-level indices (local + node_ptr[s]) are what PyG's Batch would produce
+    (reference models/scheduler_gnn.py:127,376).
+
+    Returns dict: node_ptr[S+1], global_ids[sum n], edge_ptr[S+1], edge_src[sum E],
+    edge_dst[sum E] (batch-level, int64), edge_attr[sum E] f32, rowptr[sum n + 1].
+    """
+    S = leaf_ptr.size - 1
+    N = int(pos.shape[0])
+    cells = np.asarray(cells, dtype=np.int64)
+    node_ptr = np.zeros(S + 1, dtype=np.int64)
+    edge_ptr = np.zeros(S + 1, dtype=np.int64)
+    gids, srcs, dsts, attrs = [], [], [], []
+    lut = np.full(N, -1, dtype=np.int64)
+    for s in range(S):
+        cs = cells[leaf_cells[leaf_ptr[s]:leaf_ptr[s + 1]]]
+        g = np.unique(cs)
+        lut[g] = np.arange(g.size)
+        lc = lut[cs]
+        src, dst, attr = build_edges(lc, pos[g])
+        gids.append(g)
+        srcs.append(src + node_ptr[s])
+        dsts.append(dst + node_ptr[s])
+        attrs.append(attr)
+        node_ptr[s + 1] = node_ptr[s] + g.size
+        edge_ptr[s + 1] = edge_ptr[s] + src.size
+    cat = lambda xs, dt: (np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt))
+    edge_dst = cat(dsts, np.int64)
+    n_tot = int(node_ptr[-1])
+    rowptr = np.zeros(n_tot + 1, dtype=np.int64)
+    np.add.at(rowptr, edge_dst + 1, 1)
+    return {"node_ptr": node_ptr, "global_ids": cat(gids, np.int64), "edge_ptr": edge_ptr,
+            "edge_src": cat(srcs, np.int64), "edge_dst": edge_dst,
+            "edge_attr": cat(attrs, np.float32), "rowptr": np.cumsum(rowptr)}
+
+
+# --------------------------------------------------------------------------------------
+# a10: overlap stitch
+# --------------------------------------------------------------------------------------
+def occurrence_csr(global_ids: np.ndarray, N: int):
+    """occ_ptr[N+1], occ_idx[sum n]: positions in the concatenated batch of every global
+    node, ascending (so ascending (subdomain, local) order)."""
+    global_ids = np.asarray(global_ids, dtype=np.int64)
+    occ_idx = np.argsort(global_ids, kind="stable").astype(np.int64)
+    occ_ptr = np.concatenate([[0], np.cumsum(np.bincount(global_ids, minlength=N))]).astype(np.int64)
+    return occ_ptr, occ_idx
+
+
+def stitch_mean(values: np.ndarray, global_ids: np.ndarray, N: int):
+    """Mean over all subdomain copies of each global node (GraphDataset.py:1383-1400:
+    ``np.mean(sub_vals, axis=0)`` over the coincident points, written back to every copy).
+
+    fp32, summed sequentially in ascending concatenation order, divided by the count
+    (numpy's mean on a float32 [m,4] array for m < 8 is exactly that).
+    Returns (field[N,C] f32, count[N] int32, merged[sum n, C] f32).
+    """
+    values = np.asarray(values, dtype=np.float32)
+    occ_ptr, occ_idx = occurrence_csr(global_ids, N)
+    count = np.diff(occ_ptr).astype(np.int32)
+    field = np.zeros((N, values.shape[1]), dtype=np.float32)
+    maxc = int(count.max()) if N else 0
+    acc = np.zeros_like(field)
+    for j in range(maxc):
+        sel = np.nonzero(count > j)[0]
+        acc[sel] = acc[sel] + values[occ_idx[occ_ptr[sel] + j]]
+    nz = count > 0
+    field[nz] = acc[nz] / count[nz, None].astype(np.float32)
+    merged = field[np.asarray(global_ids, dtype=np.int64)]
+    return field, count, merged

@@ -1,0 +1,72 @@
+"""CPU: the oracle restatement vs vectors produced by the reference's own code."""
+import numpy as np
+import torch
+
+from conftest import rel_l2, state_dict_from
+from oracle import graph as og
+from oracle import models as om
+from oracle import routing as orr
+
+
+def _edges(golden):
+    return torch.from_numpy(golden["ref_edge_index"]), torch.from_numpy(golden["ref_edge_attr"])
+
+
+def test_edge_set_and_attr_match_reference_vtk_to_pyg(golden):
+    src, dst, attr = og.build_edges(golden["cells"], golden["pos"])
+    n = golden["pos"].shape[0]
+    ref = golden["ref_edge_index"]
+    ref_key = ref[1] * n + ref[0]
+    order = np.argsort(ref_key)
+    assert np.array_equal(ref_key[order], dst * n + src)            # same SET, canonical order
+    assert np.array_equal(golden["ref_edge_attr"][order, 0].view(np.uint32), attr.view(np.uint32))  # bit-exact fp32
+
+
+def test_small_width_models_match_reference(golden):
+    ei, ea = _edges(golden)
+    x = torch.from_numpy(golden["x"])
+    for name, kind, w, L in (("kernelnn_w16", "neuralop", 16, 3), ("teecnet_w12", "teecnet", 12, 2),
+                             ("kernelnn_w48", "neuralop", 48, 2)):
+        m = om.make_model(kind, width=w, num_layers=L)
+        m.load_state_dict(state_dict_from(golden, name))
+        with torch.no_grad():
+            y = m(x, ei, ea).numpy()
+        assert rel_l2(y, golden[name + "_y"]) < 1e-6, name
+
+
+def test_train_step_matches_reference(golden):
+    ei, ea = _edges(golden)
+    x = torch.from_numpy(golden["x"])
+    y = torch.from_numpy(golden["y"])
+    for name, kind, w, L in (("kernelnn_w16", "neuralop", 16, 3), ("teecnet_w12", "teecnet", 12, 2)):
+        m = om.make_model(kind, width=w, num_layers=L)
+        m.load_state_dict(state_dict_from(golden, name))
+        opt = torch.optim.Adam(m.parameters(), lr=0.0005)
+        loss = om.train_step(m, opt, x, ei, ea, y)
+        assert abs(float(loss) - float(golden[name + "_loss"])) <= 1e-6 * abs(float(golden[name + "_loss"]))
+        for k, p in m.named_parameters():
+            assert rel_l2(p.grad.numpy(), golden[f"{name}_grad::{k}"]) < 1e-4, (name, k)
+            assert rel_l2(p.detach().numpy(), golden[f"{name}_sd_after::{k}"]) < 1e-5, (name, k)
+
+
+def test_node_weight_and_gradient_loss(golden):
+    ei, ea = _edges(golden)
+    y = torch.from_numpy(golden["y"])
+    pred = torch.from_numpy(golden["kernelnn_w43_y"])
+    nw = om.compute_node_weight(pred, y, ei, ea, y.shape[0]).numpy()
+    assert rel_l2(nw, golden["node_weight"]) < 1e-5
+    assert abs(float(om.gradient_loss(pred, y, ei, ea)) - float(golden["gradient_loss"])) < 1e-5 * abs(float(golden["gradient_loss"])) + 1e-9
+    assert abs(float(om.gradient_loss(pred, y, ei, ea, 4.0)) - float(golden["gradient_loss_mw4"])) < 1e-5 * abs(float(golden["gradient_loss_mw4"])) + 1e-9
+
+
+def test_routing_matches_reference_sklearn(golden):
+    from fesr_b200.dataset.synthetic import make_duct_mesh
+    mesh = make_duct_mesh(int(golden["route_mesh_n"]))
+    part = og.kd_partition(mesh.pos, mesh.cells, int(golden["route_levels"]))
+    sub = og.build_subdomains(mesh.pos, mesh.cells, part["leaf_ptr"], part["leaf_cells"])
+    xs = [mesh.x[sub["global_ids"][sub["node_ptr"][s]:sub["node_ptr"][s + 1]]] for s in range(sub["node_ptr"].size - 1)]
+    feat = orr.routing_features(xs)
+    labels, latent = orr.route(feat, golden["route_pca_mean"], golden["route_pca_components"],
+                               golden["route_scaler_mean"], golden["route_scaler_scale"], golden["route_centroids"])
+    assert rel_l2(latent, golden["route_latent"]) < 1e-5
+    assert np.array_equal(labels, golden["route_labels"])
