@@ -1,0 +1,105 @@
+"""ctypes binding of libfesr.so (the C ABI declared in include/fesr.h).
+
+There is no fallback: if the shared library is missing or the device is not sm_100 every
+entry point raises.  ``python -m fesr_b200.build`` (or ``__graft_entry__.build()``) builds it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libfesr.so")
+
+KERNELNN, TEECNET = 0, 1
+PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 2
+ONE_REGION, ALL_INTERSECTING = 0, 1
+REDUCE_WS_BYTES = 8192
+PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "tf32x3": PREC_TF32X3}
+
+
+class FesrError(RuntimeError):
+    pass
+
+
+class ModelDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("kind", "w", "wp", "in_ch", "out_ch", "layers", "n_hidden")] + \
+               [("hidden", C.c_int32 * 4)] + \
+               [(n, C.c_int32) for n in ("k1", "kt", "ktp", "passes", "kp", "k1p", "zk_main", "zk", "leaky")]
+
+
+_FP = C.c_void_p
+
+
+class Params(C.Structure):
+    _fields_ = [("fc1_w", _FP), ("fc1_b", _FP), ("mlp_w", _FP * 4), ("mlp_b", _FP * 4),
+                ("lin_w", _FP), ("lin_b", _FP), ("root", _FP), ("bias", _FP), ("fc2_w", _FP), ("fc2_b", _FP)]
+
+
+class ParamGrads(Params):
+    pass
+
+
+_i64, _i32, _sz, _vp, _f = C.c_int64, C.c_int32, C.c_size_t, C.c_void_p, C.c_float
+
+# name -> (restype, argtypes); the CPU test checks this table against include/fesr.h
+SIGNATURES = {
+    "fesr_version": (C.c_int, []),
+    "fesr_last_error": (C.c_char_p, []),
+    "fesr_device_check": (C.c_int, []),
+    "fesr_model_dims_init": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ModelDims)]),
+    "fesr_csr_workspace_bytes": (_sz, [_i64, _i64]),
+    "fesr_csr_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fesr_forward_workspace_bytes": (_sz, [C.POINTER(ModelDims), _i64, _i64, C.c_int]),
+    "fesr_nnconv_forward": (C.c_int, [C.POINTER(ModelDims), C.POINTER(Params), _vp, _vp, _vp, _vp, _vp, _i64, _i64,
+                                      C.c_int, C.c_int, _vp, _vp, _sz, _vp]),
+    "fesr_backward_workspace_bytes": (_sz, [C.POINTER(ModelDims), _i64, _i64]),
+    "fesr_nnconv_backward": (C.c_int, [C.POINTER(ModelDims), C.POINTER(Params), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _i64, _i64, C.c_int, _vp, _vp, C.POINTER(ParamGrads), _vp, _vp, _sz, _vp]),
+    "fesr_mse_loss": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "fesr_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i64, _vp]),
+    "fesr_node_weight": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
+    "fesr_occurrence_workspace_bytes": (_sz, [_i64, _i64]),
+    "fesr_occurrence_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "fesr_stitch_mean": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "fesr_partition_workspace_bytes": (_sz, [_i64, _i32]),
+    "fesr_partition_cells": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fesr_assign_count": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp]),
+    "fesr_assign_fill": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fesr_subdomain_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "fesr_subdomain_count": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp]),
+    "fesr_subdomain_fill": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fesr_route": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads libfesr.so and types every entry point.  Raises FesrError if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FesrError(
+            f"{LIB_PATH} not found: the CUDA library is not built. Run `python -m fesr_b200.build` "
+            "(nvcc, sm_100a). fesr_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().fesr_last_error().decode(errors="replace")
+        raise FesrError(f"{what or 'libfesr call'} failed ({rc}): {msg}")
+
+
+def model_dims(kind: int, w: int, in_ch: int, out_ch: int, layers: int) -> ModelDims:
+    d = ModelDims()
+    check(load().fesr_model_dims_init(kind, w, in_ch, out_ch, layers, C.byref(d)), "fesr_model_dims_init")
+    return d

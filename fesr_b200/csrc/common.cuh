@@ -1,0 +1,65 @@
+// Shared helpers for libfesr.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/fesr.h"
+
+namespace fesr {
+
+void set_error(const char* fmt, ...);
+
+#define FESR_CHECK_ARG(cond, ...)                                  \
+  do {                                                             \
+    if (!(cond)) {                                                 \
+      ::fesr::set_error(__VA_ARGS__);                              \
+      return FESR_EINVAL;                                          \
+    }                                                              \
+  } while (0)
+
+#define FESR_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t err__ = (call);                                                           \
+    if (err__ != cudaSuccess) {                                                           \
+      ::fesr::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+      return FESR_ECUDA;                                                                  \
+    }                                                                                     \
+  } while (0)
+
+#define FESR_LAUNCH_CHECK() FESR_CUDA(cudaGetLastError())
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Carves aligned sub-buffers out of a caller-provided workspace.
+struct Carver {
+  char* base;
+  size_t off;
+  explicit Carver(void* p) : base(static_cast<char*>(p)), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return p;
+  }
+  size_t used() const { return align_up(off, 256); }
+};
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int num_sms();
+
+// ---- prepared (padded / permuted) weights living at the head of the forward workspace ----
+struct Prepared {
+  float* tprime;     // [zk, wp]  row-major: T'[(k,a), b], root rows appended
+  float* tprime_t;   // [wp, zk]  K-major copy for the tensor-core path (tf32-rounded hi part)
+  float* tprime_t_lo;// [wp, zk]  lo part for TF32X3
+  float* bias_p;     // [wp]
+  float* fc1_wp;     // [in_ch, wp] transposed + padded
+  float* fc1_bp;     // [wp] (TEECNet: constant-1 column set here)
+};
+
+}  // namespace fesr

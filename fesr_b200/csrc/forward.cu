@@ -1,0 +1,72 @@
+// fesr_nnconv_forward: one block-diagonal batch of subdomains through KernelNN / TEECNet.
+#include "kernels.cuh"
+#include "workspace.cuh"
+
+using namespace fesr;
+
+namespace fesr {
+
+ForwardWs carve_forward(void* base, const fesr_model_dims& d, int64_t n, int64_t E, int keep) {
+  Carver c(base);
+  ForwardWs ws;
+  ws.prep = carve_prepared(c, d);
+  ws.g = c.take<float>((size_t)(E > 0 ? E : 1) * d.kp);
+  const int nh = keep ? d.layers + 1 : 2;
+  const int nz = keep ? d.layers : 1;
+  ws.n_h = nh;
+  ws.n_z = nz;
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  for (int i = 0; i < nh; ++i) ws.h[i] = c.take<float>(nn * d.wp);
+  for (int i = 0; i < nz; ++i) ws.Z[i] = c.take<float>(nn * d.zk);
+  ws.bytes = c.used();
+  return ws;
+}
+
+}  // namespace fesr
+
+extern "C" {
+
+size_t fesr_forward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E, int keep_for_backward) {
+  if (!dims || n < 0 || E < 0 || dims->layers > FESR_MAX_LAYERS) return 0;
+  return carve_forward(nullptr, *dims, n, E, keep_for_backward).bytes;
+}
+
+int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, const float* x,
+                        const int32_t* rowptr, const int32_t* src_sorted, const int32_t* perm,
+                        const float* edge_attr, int64_t n, int64_t E, int precision, int keep_for_backward,
+                        float* y, void* workspace, size_t workspace_bytes, void* stream_) {
+  FESR_CHECK_ARG(dims && params, "dims/params NULL");
+  FESR_CHECK_ARG(n >= 0 && E >= 0 && n < (1ll << 31) && E < (1ll << 31), "n/E out of range");
+  FESR_CHECK_ARG(dims->layers <= FESR_MAX_LAYERS, "too many layers");
+  FESR_CHECK_ARG(precision == FESR_PREC_FP32 || precision == FESR_PREC_TF32 || precision == FESR_PREC_TF32X3,
+                 "unknown precision %d", precision);
+  if (n == 0) return FESR_OK;
+  FESR_CHECK_ARG(x && y && rowptr && (E == 0 || (src_sorted && edge_attr)), "NULL pointer");
+  const fesr_model_dims& d = *dims;
+  ForwardWs ws = carve_forward(workspace, d, n, E, keep_for_backward);
+  if (!workspace || workspace_bytes < ws.bytes) {
+    set_error("forward workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
+    return FESR_EWORKSPACE;
+  }
+  cudaStream_t s = as_stream(stream_);
+  int rc;
+  if ((rc = launch_prepare_weights(d, *params, ws.prep, s))) return rc;
+  if ((rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s))) return rc;
+  if ((rc = launch_fc_in(d, ws.prep, x, n, ws.h[0], s))) return rc;
+  const float* h_last = ws.h[0];
+  for (int l = 0; l < d.layers; ++l) {
+    const float* h_in = keep_for_backward ? ws.h[l] : ws.h[l & 1];
+    float* h_out = keep_for_backward ? ws.h[l + 1] : ws.h[(l + 1) & 1];
+    float* Z = keep_for_backward ? ws.Z[l] : ws.Z[0];
+    if ((rc = launch_zbuild(d, rowptr, src_sorted, ws.g, h_in, n, Z, s))) return rc;
+    if (precision == FESR_PREC_FP32)
+      rc = launch_node_gemm_fp32(d, ws.prep, Z, n, h_out, nullptr, s);
+    else
+      rc = launch_node_gemm_tf32(d, ws.prep, Z, n, h_out, nullptr, precision == FESR_PREC_TF32X3, s);
+    if (rc) return rc;
+    h_last = h_out;
+  }
+  return launch_fc_out(d, *params, h_last, n, y, s);
+}
+
+}  // extern "C"

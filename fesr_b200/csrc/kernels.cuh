@@ -1,0 +1,31 @@
+// Internal launch wrappers shared between the translation units of libfesr.so.
+#pragma once
+#include "common.cuh"
+
+namespace fesr {
+
+// mlp.cu ------------------------------------------------------------------------------
+size_t prepared_bytes(const fesr_model_dims& d);
+Prepared carve_prepared(Carver& c, const fesr_model_dims& d);
+int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const Prepared& w, cudaStream_t s);
+// g[E, kp]: hidden activations of the edge MLP in CSR edge order, channel-permuted layout
+int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
+                       const int32_t* perm, int64_t E, float* g, cudaStream_t s);
+int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s);
+int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const float* h, int64_t n, float* y, cudaStream_t s);
+
+// zbuild.cu ---------------------------------------------------------------------------
+// Z[i, :] = (1/max(deg,1)) * sum_{e -> i} g_e (x) h[src_e]   ++  h[i]  (root block)
+int launch_zbuild(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted,
+                  const float* g, const float* h, int64_t n, float* Z, cudaStream_t s);
+
+// gemm_simt.cu ------------------------------------------------------------------------
+// h_out[n, wp] = epilogue(Z[n, zk] x tprime[zk, wp] + bias)
+int launch_node_gemm_fp32(const fesr_model_dims& d, const Prepared& w, const float* Z, int64_t n,
+                          float* h_out, float* pre_out, cudaStream_t s);
+
+// gemm_tc.cu --------------------------------------------------------------------------
+int launch_node_gemm_tf32(const fesr_model_dims& d, const Prepared& w, const float* Z, int64_t n,
+                          float* h_out, float* pre_out, int x3, cudaStream_t s);
+
+}  // namespace fesr

@@ -1,0 +1,316 @@
+// Weight preparation, edge-MLP hidden layers, input lift and output projection.
+//
+// The reference evaluates the whole edge MLP per edge per layer and materialises a [w,w]
+// matrix per edge (models/model.py:428,528).  Here only the HIDDEN layers run per edge, once
+// per forward (their input d_e and weights are layer invariant); the last Linear layer is
+// folded into the node-level contraction Z x T' (see DESIGN.md section 2).
+#include "kernels.cuh"
+
+namespace fesr {
+
+// ----------------------------------------------------------------------------- prepare
+size_t prepared_bytes(const fesr_model_dims& d) {
+  Carver c(nullptr);
+  (void)carve_prepared(c, d);
+  return c.used();
+}
+
+Prepared carve_prepared(Carver& c, const fesr_model_dims& d) {
+  Prepared w;
+  w.tprime = c.take<float>((size_t)d.zk * d.wp);
+  w.tprime_t = c.take<float>((size_t)d.zk * d.wp);
+  w.tprime_t_lo = c.take<float>((size_t)d.zk * d.wp);
+  w.bias_p = c.take<float>(d.wp);
+  w.fc1_wp = c.take<float>((size_t)d.in_ch * d.wp);
+  w.fc1_bp = c.take<float>(d.wp);
+  return w;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// T'[(k*wp + a), b]; one thread per element of the [zk, wp] matrix.
+__global__ void prepare_tprime_kernel(fesr_model_dims d, const float* __restrict__ w_last,
+                                      const float* __restrict__ b_last, const float* __restrict__ lin_w,
+                                      const float* __restrict__ lin_b, const float* __restrict__ root,
+                                      float* __restrict__ tprime, float* __restrict__ tprime_t,
+                                      float* __restrict__ tprime_t_lo) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)d.zk * d.wp;
+  if (idx >= total) return;
+  const int r = (int)(idx / d.wp), b = (int)(idx % d.wp);
+  const int w = d.w, K = d.k1 - 1;
+  float v = 0.f;
+  if (b < w) {
+    if (r < d.zk_main) {
+      const int k = r / d.wp, a = r % d.wp;
+      if (k < d.k1) {
+        if (d.kind == FESR_KERNELNN) {
+          if (a < w) v = (k < K) ? w_last[(size_t)(a * w + b) * K + k] : b_last[a * w + b];
+        } else if (a <= w) {
+          // fold kernel.linear (models/model.py:431): T''[k,a,b] = sum_a' Laug[a',a] T0[k,a',b]
+          float acc = 0.f;
+          for (int ap = 0; ap < w; ++ap) {
+            const float l = (a < w) ? lin_w[ap * w + a] : lin_b[ap];
+            const float t = (k < K) ? w_last[(size_t)(ap * w + b) * K + k] : b_last[ap * w + b];
+            acc = fmaf(l, t, acc);
+          }
+          v = acc;
+        }
+      }
+    } else if (r < d.zk_main + d.wp) {
+      const int a = r - d.zk_main;
+      if (a < w) v = root[a * w + b];
+    }
+  }
+  tprime[idx] = v;
+  const float hi = tf32_rna(v);
+  tprime_t[(size_t)b * d.zk + r] = hi;
+  tprime_t_lo[(size_t)b * d.zk + r] = tf32_rna(v - hi);
+}
+
+__global__ void prepare_small_kernel(fesr_model_dims d, const float* __restrict__ fc1_w,
+                                     const float* __restrict__ fc1_b, const float* __restrict__ bias,
+                                     float* __restrict__ bias_p, float* __restrict__ fc1_wp,
+                                     float* __restrict__ fc1_bp) {
+  const int t = threadIdx.x;
+  for (int b = t; b < d.wp; b += blockDim.x) {
+    bias_p[b] = (b < d.w) ? bias[b] : 0.f;
+    fc1_bp[b] = (b < d.w) ? fc1_b[b] : ((d.kind == FESR_TEECNET && b == d.w) ? 1.f : 0.f);
+    for (int c = 0; c < d.in_ch; ++c) fc1_wp[c * d.wp + b] = (b < d.w) ? fc1_w[b * d.in_ch + c] : 0.f;
+  }
+}
+
+int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const Prepared& w, cudaStream_t s) {
+  const int last = d.n_hidden;
+  FESR_CHECK_ARG(p.mlp_w[last] && p.mlp_b[last] && p.root && p.bias && p.fc1_w && p.fc1_b, "NULL parameter");
+  FESR_CHECK_ARG(d.kind != FESR_TEECNET || (p.lin_w && p.lin_b), "TEECNet needs kernel.linear");
+  const int64_t total = (int64_t)d.zk * d.wp;
+  prepare_tprime_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(d, p.mlp_w[last], p.mlp_b[last], p.lin_w,
+                                                                      p.lin_b, p.root, w.tprime, w.tprime_t,
+                                                                      w.tprime_t_lo);
+  FESR_LAUNCH_CHECK();
+  prepare_small_kernel<<<1, 64, 0, s>>>(d, p.fc1_w, p.fc1_b, p.bias, w.bias_p, w.fc1_wp, w.fc1_bp);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
+// ----------------------------------------------------------------------------- edge hidden
+constexpr int EH_TE = 64;        // edges per tile
+constexpr int EH_THREADS = 256;
+constexpr int EH_MAXD = 128;
+
+struct EdgeHiddenArgs {
+  const float* w[4];
+  const float* b[4];
+  int dims[4];
+  int n_hidden;
+  int leaky;
+  int kt, ktp, kp, k1;
+};
+
+__device__ __forceinline__ float act_fn(float v, int leaky) {
+  return leaky ? (v > 0.f ? v : 0.01f * v) : fmaxf(v, 0.f);
+}
+
+// Persistent CTAs; all hidden-layer weights stay in shared memory (transposed [in][outP]).
+__global__ void __launch_bounds__(EH_THREADS, 2)
+edge_hidden_kernel(EdgeHiddenArgs a, const float* __restrict__ edge_attr, const int32_t* __restrict__ perm,
+                   int64_t E, float* __restrict__ g) {
+  extern __shared__ __align__(16) float smem[];
+  // layout: w0[D0] b0[D0] | for l>=1: WT_l[Din][DoutP], b_l[DoutP] | bufA[MAXD][TE] bufB[MAXD][TE] | chan_of[kp]
+  float* w0 = smem;
+  float* b0 = w0 + EH_MAXD;
+  float* wt[4];
+  float* bb[4];
+  float* cur = b0 + EH_MAXD;
+  for (int l = 1; l < a.n_hidden; ++l) {
+    const int din = a.dims[l - 1], doutp = (a.dims[l] + 3) & ~3;
+    wt[l] = cur;
+    cur += din * doutp;
+    bb[l] = cur;
+    cur += doutp;
+  }
+  float* bufA = cur;
+  float* bufB = bufA + EH_MAXD * EH_TE;
+  int* chan_of = reinterpret_cast<int*>(bufB + EH_MAXD * EH_TE);
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < a.dims[0]; i += EH_THREADS) {
+    w0[i] = a.w[0][i];
+    b0[i] = a.b[0][i];
+  }
+  for (int l = 1; l < a.n_hidden; ++l) {
+    const int din = a.dims[l - 1], dout = a.dims[l], doutp = (dout + 3) & ~3;
+    for (int i = tid; i < din * doutp; i += EH_THREADS) {
+      const int ii = i / doutp, o = i % doutp;
+      wt[l][i] = (o < dout) ? a.w[l][o * din + ii] : 0.f;
+    }
+    for (int o = tid; o < doutp; o += EH_THREADS) bb[l][o] = (o < dout) ? a.b[l][o] : 0.f;
+  }
+  // g row offset -> source channel (k1-1 = constant one, -1 = padding)
+  for (int off = tid; off < a.kp; off += EH_THREADS) {
+    const int grp = off / a.ktp, kt = off % a.ktp;
+    const int k = grp * a.kt + kt;
+    chan_of[off] = (kt < a.kt && k < a.k1) ? k : -1;
+  }
+  __syncthreads();
+
+  const int64_t n_tiles = (E + EH_TE - 1) / EH_TE;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t e0 = tile * EH_TE;
+    // layer 0: Linear(1, D0) + act      (models/model.py:311-315 first two modules)
+    for (int i = tid; i < a.dims[0] * EH_TE; i += EH_THREADS) {
+      const int o = i / EH_TE, e = i % EH_TE;
+      const int64_t ge = e0 + e;
+      float d = 0.f;
+      if (ge < E) d = edge_attr[perm ? perm[ge] : ge];
+      bufA[o * EH_TE + e] = act_fn(fmaf(d, w0[o], b0[o]), a.leaky);
+    }
+    __syncthreads();
+    float* in = bufA;
+    float* out = bufB;
+    for (int l = 1; l < a.n_hidden; ++l) {
+      const int din = a.dims[l - 1], dout = a.dims[l], doutp = (dout + 3) & ~3;
+      const int tiles = (EH_TE / 4) * (doutp / 4);
+      for (int t = tid; t < tiles; t += EH_THREADS) {
+        const int e4 = (t % (EH_TE / 4)) * 4, o4 = (t / (EH_TE / 4)) * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+          for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
+        for (int i = 0; i < din; ++i) {
+          const float4 av = *reinterpret_cast<const float4*>(in + i * EH_TE + e4);
+          const float4 wv = *reinterpret_cast<const float4*>(wt[l] + i * doutp + o4);
+          const float ae[4] = {av.x, av.y, av.z, av.w};
+          const float wo[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(ae[x], wo[y], acc[x][y]);
+        }
+#pragma unroll
+        for (int y = 0; y < 4; ++y) {
+          const float bv = bb[l][o4 + y];
+          float4 o;
+          o.x = act_fn(acc[0][y] + bv, a.leaky);
+          o.y = act_fn(acc[1][y] + bv, a.leaky);
+          o.z = act_fn(acc[2][y] + bv, a.leaky);
+          o.w = act_fn(acc[3][y] + bv, a.leaky);
+          *reinterpret_cast<float4*>(out + (o4 + y) * EH_TE + e4) = o;
+        }
+      }
+      __syncthreads();
+      float* tmp = in;
+      in = out;
+      out = tmp;
+    }
+    // write g rows (coalesced over [edge][kp])
+    const int K = a.k1 - 1;
+    for (int i = tid; i < EH_TE * a.kp; i += EH_THREADS) {
+      const int e = i / a.kp, off = i % a.kp;
+      const int64_t ge = e0 + e;
+      if (ge >= E) break;
+      const int k = chan_of[off];
+      const float v = (k < 0) ? 0.f : (k == K ? 1.f : in[k * EH_TE + e]);
+      g[ge * a.kp + off] = v;
+    }
+    __syncthreads();
+  }
+}
+
+int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
+                       const int32_t* perm, int64_t E, float* g, cudaStream_t s) {
+  if (E == 0) return FESR_OK;
+  EdgeHiddenArgs a;
+  memset(&a, 0, sizeof(a));
+  size_t fl = 2 * EH_MAXD;
+  for (int l = 0; l < d.n_hidden; ++l) {
+    FESR_CHECK_ARG(p.mlp_w[l] && p.mlp_b[l], "NULL edge-MLP parameter %d", l);
+    FESR_CHECK_ARG(d.hidden[l] <= EH_MAXD, "edge MLP hidden size %d > %d", d.hidden[l], EH_MAXD);
+    a.w[l] = p.mlp_w[l];
+    a.b[l] = p.mlp_b[l];
+    a.dims[l] = d.hidden[l];
+    if (l >= 1) {
+      const int doutp = (d.hidden[l] + 3) & ~3;
+      fl += (size_t)d.hidden[l - 1] * doutp + doutp;
+    }
+  }
+  a.n_hidden = d.n_hidden;
+  a.leaky = d.leaky;
+  a.kt = d.kt;
+  a.ktp = d.ktp;
+  a.kp = d.kp;
+  a.k1 = d.k1;
+  fl = (fl + 3) & ~(size_t)3;
+  const size_t smem = (fl + 2 * (size_t)EH_MAXD * EH_TE + d.kp) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FESR_CUDA(cudaFuncSetAttribute(edge_hidden_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  FESR_CHECK_ARG(smem <= 200 * 1024, "edge MLP too large for shared memory");
+  const int64_t n_tiles = ceil_div(E, EH_TE);
+  const int grid = (int)(n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms());
+  edge_hidden_kernel<<<grid, EH_THREADS, smem, s>>>(a, edge_attr, perm, E, g);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
+// ----------------------------------------------------------------------------- fc1 / fc2
+// h0[i, :] = x[i, :] W1^T + b1 (models/model.py:557 / :279), padded columns 0 (TEECNet: h[w] = 1)
+__global__ void fc_in_kernel(const float* __restrict__ x, const float* __restrict__ wp_, const float* __restrict__ bp,
+                             int in_ch, int wp, int64_t n, float* __restrict__ h) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one float4 of h per thread
+  const int q = wp / 4;
+  if (idx >= n * q) return;
+  const int64_t i = idx / q;
+  const int b4 = (int)(idx % q) * 4;
+  float4 acc = *reinterpret_cast<const float4*>(bp + b4);
+  for (int c = 0; c < in_ch; ++c) {
+    const float xv = x[i * in_ch + c];
+    const float4 wv = *reinterpret_cast<const float4*>(wp_ + c * wp + b4);
+    acc.x = fmaf(xv, wv.x, acc.x);
+    acc.y = fmaf(xv, wv.y, acc.y);
+    acc.z = fmaf(xv, wv.z, acc.z);
+    acc.w = fmaf(xv, wv.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(h + i * wp + b4) = acc;
+}
+
+int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s) {
+  if (n == 0) return FESR_OK;
+  const int64_t total = n * (d.wp / 4);
+  fc_in_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.in_ch, d.wp, n, h);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
+// y[i, c] = h[i, :w] . W2[c, :] + b2[c]   (models/model.py:561 / :284); one warp per 8 nodes
+__global__ void fc_out_kernel(const float* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2,
+                              int w, int wp, int out_ch, int64_t n, float* __restrict__ y) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * out_ch) return;
+  const int64_t i = idx / out_ch;
+  const int c = (int)(idx % out_ch);
+  const float* hr = h + i * wp;
+  const float* wr = w2 + c * w;
+  float acc = b2[c];
+  for (int b = 0; b < w; ++b) acc = fmaf(hr[b], wr[b], acc);
+  y[idx] = acc;
+}
+
+int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const float* h, int64_t n, float* y, cudaStream_t s) {
+  if (n == 0) return FESR_OK;
+  FESR_CHECK_ARG(p.fc2_w && p.fc2_b, "NULL fc2 parameter");
+  const int64_t total = n * d.out_ch;
+  fc_out_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(h, p.fc2_w, p.fc2_b, d.w, d.wp, d.out_ch, n, y);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
+}  // namespace fesr

@@ -1,0 +1,244 @@
+// Overlap stitch (segmented mean keyed by global node id), node weight, MSE loss, Adam.
+// All HBM-bound streaming / gather kernels; every reduction has a fixed order.
+#include "common.cuh"
+
+namespace fesr {
+
+// ------------------------------------------------------------------------------ stitch
+// One thread per global node; copies are visited in ascending batch position, summed in
+// fp32 and divided by the count -- exactly numpy's mean over the coincident points
+// (reference dataset/GraphDataset.py:1396-1397).
+template <int C>
+__global__ void stitch_mean_kernel(const float* __restrict__ values, const int32_t* __restrict__ occ_ptr,
+                                   const int32_t* __restrict__ occ_idx, int64_t N, float* __restrict__ field,
+                                   int32_t* __restrict__ count) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int b = occ_ptr[i], e = occ_ptr[i + 1];
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  for (int j = b; j < e; ++j) {
+    const int64_t p = occ_idx[j];
+    if constexpr (C == 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(values) + p);
+      acc[0] = __fadd_rn(acc[0], v.x);
+      acc[1] = __fadd_rn(acc[1], v.y);
+      acc[2] = __fadd_rn(acc[2], v.z);
+      acc[3] = __fadd_rn(acc[3], v.w);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = __fadd_rn(acc[c], __ldg(values + p * C + c));
+    }
+  }
+  const int cnt = e - b;
+  if (cnt > 0) {
+    const float fc = (float)cnt;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = __fdiv_rn(acc[c], fc);
+  }
+  if constexpr (C == 4) {
+    reinterpret_cast<float4*>(field)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) field[i * C + c] = acc[c];
+  }
+  if (count) count[i] = cnt;
+}
+
+template <int C>
+__global__ void stitch_scatter_back_kernel(const float* __restrict__ field, const int64_t* __restrict__ gids,
+                                           int64_t n_tot, float* __restrict__ merged) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n_tot) return;
+  const int64_t gnode = gids[p];
+  if constexpr (C == 4) {
+    reinterpret_cast<float4*>(merged)[p] = __ldg(reinterpret_cast<const float4*>(field) + gnode);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) merged[p * C + c] = field[gnode * C + c];
+  }
+}
+
+// ------------------------------------------------------------------------------ node weight
+// per destination node: sum over its incoming edges (fixed CSR order) of
+//   max_c [ (p[src]-p[dst])/d - (y[src]-y[dst])/d ]       scheduler_gnn.py:507-510
+// (the reference scatters by source and then sums everything, :511-514 -- the scatter
+//  target is irrelevant for the total, so any fixed grouping gives the same number)
+template <int C>
+__global__ void node_weight_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
+                                           const int32_t* __restrict__ perm, const float* __restrict__ edge_attr,
+                                           int64_t n, float* __restrict__ partial) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float pd[C], yd[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    pd[c] = pred[i * C + c];
+    yd[c] = target[i * C + c];
+  }
+  float acc = 0.f;
+  for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+    const int64_t s = src_sorted[e];
+    const float d = edge_attr[perm ? perm[e] : e];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float gp = __fdiv_rn(__fsub_rn(pred[s * C + c], pd[c]), d);
+      const float gd = __fdiv_rn(__fsub_rn(target[s * C + c], yd[c]), d);
+      m = fmaxf(m, __fsub_rn(gp, gd));
+    }
+    acc = __fadd_rn(acc, m);
+  }
+  partial[i] = acc;
+}
+
+// one block per subdomain, fixed-shape tree reduction
+__global__ void segment_sum_kernel(const float* __restrict__ partial, const int32_t* __restrict__ node_ptr,
+                                   int64_t n, float* __restrict__ out) {
+  __shared__ float red[256];
+  const int s = blockIdx.x;
+  const int64_t b = node_ptr ? node_ptr[s] : 0, e = node_ptr ? node_ptr[s + 1] : n;
+  float acc = 0.f;
+  for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) acc += partial[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[s] = red[0];
+}
+
+// ------------------------------------------------------------------------------ MSE
+constexpr int MSE_BLOCKS = 1024;
+__global__ void mse_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t count,
+                                   float scale, float* __restrict__ grad, float* __restrict__ partial) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float d = pred[i] - target[i];
+    acc = fmaf(d, d, acc);
+    if (grad) grad[i] = scale * d;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void mse_final_kernel(const float* __restrict__ partial, int nblocks, float inv_count, float* __restrict__ loss) {
+  __shared__ float red[256];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) acc += partial[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = red[0] * inv_count;
+}
+
+// ------------------------------------------------------------------------------ Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t count, float beta1, float beta2, float eps,
+                            float step_size, float inv_sqrt_bc2) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float gi = g[i];
+  const float mi = m[i] + (1.f - beta1) * (gi - m[i]);            // exp_avg.lerp_(grad, 1-beta1)
+  const float vi = fmaf(1.f - beta2, gi * gi, beta2 * v[i]);      // mul_(beta2).addcmul_(g, g, 1-beta2)
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+  p[i] = p[i] - step_size * (mi / denom);
+}
+
+}  // namespace fesr
+
+using namespace fesr;
+
+extern "C" {
+
+int fesr_stitch_mean(const float* values, int32_t channels, const int32_t* occ_ptr, const int32_t* occ_idx,
+                     const int64_t* global_ids, int64_t n_tot, int64_t N, float* field, int32_t* count,
+                     float* merged, void* stream_) {
+  FESR_CHECK_ARG(channels == 4 || channels == 1 || channels == 3, "channels must be 1, 3 or 4");
+  FESR_CHECK_ARG(N >= 0 && n_tot >= 0, "negative size");
+  FESR_CHECK_ARG(N == 0 || (occ_ptr && field && (n_tot == 0 || (values && occ_idx))), "NULL pointer");
+  FESR_CHECK_ARG(!merged || global_ids, "merged needs global_ids");
+  cudaStream_t s = as_stream(stream_);
+  const int T = 256;
+  if (N > 0) {
+    const unsigned grid = (unsigned)ceil_div(N, T);
+    if (channels == 4) stitch_mean_kernel<4><<<grid, T, 0, s>>>(values, occ_ptr, occ_idx, N, field, count);
+    else if (channels == 3) stitch_mean_kernel<3><<<grid, T, 0, s>>>(values, occ_ptr, occ_idx, N, field, count);
+    else stitch_mean_kernel<1><<<grid, T, 0, s>>>(values, occ_ptr, occ_idx, N, field, count);
+    FESR_LAUNCH_CHECK();
+  }
+  if (merged && n_tot > 0) {
+    const unsigned grid = (unsigned)ceil_div(n_tot, T);
+    if (channels == 4) stitch_scatter_back_kernel<4><<<grid, T, 0, s>>>(field, global_ids, n_tot, merged);
+    else if (channels == 3) stitch_scatter_back_kernel<3><<<grid, T, 0, s>>>(field, global_ids, n_tot, merged);
+    else stitch_scatter_back_kernel<1><<<grid, T, 0, s>>>(field, global_ids, n_tot, merged);
+    FESR_LAUNCH_CHECK();
+  }
+  return FESR_OK;
+}
+
+int fesr_node_weight(const float* pred, const float* target, int32_t channels, const int32_t* rowptr,
+                     const int32_t* src_sorted, const int32_t* perm, const float* edge_attr,
+                     const int32_t* node_ptr, int32_t n_sub, int64_t n, int64_t E, float* out,
+                     float* node_scratch, void* stream_) {
+  FESR_CHECK_ARG(channels == 4, "node weight is built for 4 channels (vx, vy, vz, p)");
+  FESR_CHECK_ARG(n_sub >= 1 && n >= 0 && E >= 0, "bad sizes");
+  FESR_CHECK_ARG(out && (n == 0 || (pred && target && rowptr && node_scratch)), "NULL pointer");
+  FESR_CHECK_ARG(E == 0 || (src_sorted && edge_attr), "NULL edge arrays");
+  FESR_CHECK_ARG(node_ptr || n_sub == 1, "node_ptr is required for n_sub > 1");
+  cudaStream_t s = as_stream(stream_);
+  if (n > 0) {
+    node_weight_partial_kernel<4><<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(pred, target, rowptr, src_sorted, perm,
+                                                                            edge_attr, n, node_scratch);
+    FESR_LAUNCH_CHECK();
+  }
+  segment_sum_kernel<<<n_sub, 256, 0, s>>>(node_scratch, node_ptr, n, out);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
+int fesr_mse_loss(const float* pred, const float* target, int64_t count, float* loss, float* grad, void* workspace,
+                  void* stream_) {
+  FESR_CHECK_ARG(count > 0 && pred && target && loss && workspace, "bad arguments");
+  cudaStream_t s = as_stream(stream_);
+  float* partial = static_cast<float*>(workspace);
+  int blocks = (int)ceil_div(count, 256);
+  if (blocks > MSE_BLOCKS) blocks = MSE_BLOCKS;
+  mse_partial_kernel<<<blocks, 256, 0, s>>>(pred, target, count, 2.0f / (float)count, grad, partial);
+  FESR_LAUNCH_CHECK();
+  mse_final_kernel<<<1, 256, 0, s>>>(partial, blocks, 1.0f / (float)count, loss);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
+int fesr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, float lr,
+                   float beta1, float beta2, float eps, int64_t step, void* stream_) {
+  FESR_CHECK_ARG(count >= 0 && step >= 1, "bad count/step");
+  if (count == 0) return FESR_OK;
+  FESR_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "NULL pointer");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  adam_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, as_stream(stream_)>>>(param, grad, exp_avg, exp_avg_sq, count,
+                                                                             beta1, beta2, eps, step_size,
+                                                                             inv_sqrt_bc2);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,222 @@
+"""Torch-tensor wrappers over the C ABI.  PyTorch is plumbing here: device memory, streams.
+
+Every function requires CUDA tensors on an sm_100 device and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import FesrError, ModelDims, ParamGrads, Params, check
+
+_device_ok = {}
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise FesrError("fesr_b200 runs on a B200 (sm_100a) only: got a CPU tensor and there is no CPU fallback")
+    dev = next(t.device for t in tensors if t is not None)
+    if dev.index not in _device_ok:
+        with torch.cuda.device(dev):
+            check(_lib.load().fesr_device_check(), "fesr_device_check")
+        _device_ok[dev.index] = True
+    return dev
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.to(torch.float32).contiguous()
+    return t
+
+
+class _Workspace:
+    """Grow-only byte buffers per (device, tag): the caller-owned workspace the C ABI asks for."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, dev, tag, nbytes):
+        key = (dev.index, tag)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            self.bufs.pop(key, None)
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
+            self.bufs[key] = buf
+        return buf
+
+    def clear(self):
+        self.bufs.clear()
+
+
+workspace = _Workspace()
+
+
+# ---------------------------------------------------------------------------------- graph
+@dataclass
+class Csr:
+    """Destination-sorted CSR of a (block-diagonal) graph."""
+    rowptr: torch.Tensor       # [n+1] int32
+    src: torch.Tensor          # [E] int32, CSR order
+    perm: torch.Tensor | None  # [E] int32 original edge id per CSR slot (None: identity)
+    n: int
+    E: int
+
+
+def csr_build(edge_index: torch.Tensor, n: int) -> Csr:
+    """edge_index [2,E] int64 (any order) -> CSR by destination (fesr_csr_build)."""
+    dev = _require_cuda(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise FesrError("edge_index must be an int64 tensor of shape [2, E]")
+    edge_index = edge_index.contiguous()
+    E = int(edge_index.shape[1])
+    lib = _lib.load()
+    rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    src = torch.empty(E, dtype=torch.int32, device=dev)
+    perm = torch.empty(E, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.fesr_csr_workspace_bytes(n, E)
+        ws = workspace.get(dev, "sort", nbytes)
+        check(lib.fesr_csr_build(_ptr(edge_index), E, n, _ptr(rowptr), _ptr(src), _ptr(perm), _ptr(ws), ws.numel(),
+                                 _stream(dev)), "fesr_csr_build")
+    return Csr(rowptr, src, perm, n, E)
+
+
+# ---------------------------------------------------------------------------------- model
+def make_params(struct_cls, tensors: dict):
+    """tensors: fc1_w, fc1_b, mlp_w (list), mlp_b (list), lin_w, lin_b, root, bias, fc2_w, fc2_b."""
+    p = struct_cls()
+    keep = []
+    for name in ("fc1_w", "fc1_b", "lin_w", "lin_b", "root", "bias", "fc2_w", "fc2_b"):
+        t = tensors.get(name)
+        if t is not None:
+            if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                raise FesrError(f"parameter {name} must be a contiguous fp32 CUDA tensor")
+            keep.append(t)
+            setattr(p, name, t.data_ptr())
+    for name in ("mlp_w", "mlp_b"):
+        arr = getattr(p, name)
+        for i, t in enumerate(tensors[name]):
+            if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                raise FesrError(f"parameter {name}[{i}] must be a contiguous fp32 CUDA tensor")
+            keep.append(t)
+            arr[i] = t.data_ptr()
+    return p, keep
+
+
+def nnconv_forward(dims: ModelDims, tensors: dict, x: torch.Tensor, csr: Csr, edge_attr: torch.Tensor,
+                   precision: int = _lib.PREC_FP32, keep_for_backward: bool = False, ws_tag: str = "fwd"):
+    """Runs fesr_nnconv_forward.  Returns y [n, out_ch] (and the workspace tensor when kept)."""
+    dev = _require_cuda(x, edge_attr, csr.rowptr)
+    x = _f32c(x)
+    edge_attr = _f32c(edge_attr.reshape(-1))
+    n, E = csr.n, csr.E
+    if x.shape[0] != n or x.shape[1] != dims.in_ch:
+        raise FesrError(f"x must be [{n}, {dims.in_ch}], got {tuple(x.shape)}")
+    if edge_attr.numel() != E:
+        raise FesrError(f"edge_attr must have {E} entries, got {edge_attr.numel()}")
+    lib = _lib.load()
+    p, keep = make_params(Params, tensors)
+    y = torch.empty(n, dims.out_ch, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.fesr_forward_workspace_bytes(C.byref(dims), n, E, int(keep_for_backward))
+        if keep_for_backward:
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        else:
+            ws = workspace.get(dev, ws_tag, nbytes)
+        check(lib.fesr_nnconv_forward(C.byref(dims), C.byref(p), _ptr(x), _ptr(csr.rowptr), _ptr(csr.src),
+                                      _ptr(csr.perm), _ptr(edge_attr), n, E, precision, int(keep_for_backward),
+                                      _ptr(y), _ptr(ws), ws.numel(), _stream(dev)), "fesr_nnconv_forward")
+    del keep
+    return (y, ws) if keep_for_backward else y
+
+
+# ---------------------------------------------------------------------------------- node weight
+def node_weight(pred, target, csr: Csr, edge_attr, node_ptr=None):
+    """Per-subdomain scalar of GradientbasedLoss.compute_node_weight -> [S] fp32."""
+    dev = _require_cuda(pred, target, edge_attr)
+    pred, target = _f32c(pred), _f32c(target)
+    edge_attr = _f32c(edge_attr.reshape(-1))
+    n_sub = 1 if node_ptr is None else int(node_ptr.numel() - 1)
+    out = torch.empty(n_sub, dtype=torch.float32, device=dev)
+    scratch = torch.empty(max(csr.n, 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().fesr_node_weight(_ptr(pred), _ptr(target), pred.shape[1], _ptr(csr.rowptr), _ptr(csr.src),
+                                           _ptr(csr.perm), _ptr(edge_attr), _ptr(node_ptr), n_sub, csr.n, csr.E,
+                                           _ptr(out), _ptr(scratch), _stream(dev)), "fesr_node_weight")
+    return out
+
+
+# ---------------------------------------------------------------------------------- stitch
+@dataclass
+class Occurrence:
+    occ_ptr: torch.Tensor   # [N+1] int32
+    occ_idx: torch.Tensor   # [n_tot] int32
+    N: int
+    n_tot: int
+
+
+def occurrence_build(global_ids: torch.Tensor, N: int) -> Occurrence:
+    dev = _require_cuda(global_ids)
+    if global_ids.dtype != torch.int64:
+        raise FesrError("global_ids must be int64")
+    global_ids = global_ids.contiguous()
+    n_tot = int(global_ids.numel())
+    lib = _lib.load()
+    occ_ptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    occ_idx = torch.empty(n_tot, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = lib.fesr_occurrence_workspace_bytes(n_tot, N)
+        ws = workspace.get(dev, "sort", nbytes)
+        check(lib.fesr_occurrence_build(_ptr(global_ids), n_tot, N, _ptr(occ_ptr), _ptr(occ_idx), _ptr(ws),
+                                        ws.numel(), _stream(dev)), "fesr_occurrence_build")
+    return Occurrence(occ_ptr, occ_idx, N, n_tot)
+
+
+def stitch_mean(values: torch.Tensor, occ: Occurrence, global_ids: torch.Tensor | None = None,
+                want_merged: bool = False, want_count: bool = True):
+    """values [n_tot, c] -> (field [N, c], count [N] | None, merged [n_tot, c] | None)."""
+    dev = _require_cuda(values, occ.occ_ptr)
+    values = _f32c(values)
+    c = int(values.shape[1])
+    field = torch.empty(occ.N, c, dtype=torch.float32, device=dev)
+    count = torch.empty(occ.N, dtype=torch.int32, device=dev) if want_count else None
+    merged = torch.empty(occ.n_tot, c, dtype=torch.float32, device=dev) if want_merged else None
+    if want_merged and global_ids is None:
+        raise FesrError("merged output needs global_ids")
+    with torch.cuda.device(dev):
+        check(_lib.load().fesr_stitch_mean(_ptr(values), c, _ptr(occ.occ_ptr), _ptr(occ.occ_idx), _ptr(global_ids),
+                                           occ.n_tot, occ.N, _ptr(field), _ptr(count), _ptr(merged), _stream(dev)),
+              "fesr_stitch_mean")
+    return field, count, merged
+
+
+# ---------------------------------------------------------------------------------- train helpers
+def mse_loss(pred, target, want_grad=True):
+    dev = _require_cuda(pred, target)
+    pred, target = _f32c(pred), _f32c(target)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    grad = torch.empty_like(pred) if want_grad else None
+    ws = workspace.get(dev, "reduce", _lib.REDUCE_WS_BYTES)
+    with torch.cuda.device(dev):
+        check(_lib.load().fesr_mse_loss(_ptr(pred), _ptr(target), pred.numel(), _ptr(loss), _ptr(grad), _ptr(ws),
+                                        _stream(dev)), "fesr_mse_loss")
+    return loss, grad
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    dev = _require_cuda(param, grad, exp_avg, exp_avg_sq)
+    with torch.cuda.device(dev):
+        check(_lib.load().fesr_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
+                                         lr, beta1, beta2, eps, step, _stream(dev)), "fesr_adam_step")

@@ -30,3 +30,17 @@ def rel_l2(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+SHIPPED = os.path.join(ROOT, "tests", "golden", "shipped_w43_weights.npz")
+
+
+@pytest.fixture(scope="session")
+def shipped():
+    return dict(np.load(SHIPPED))
+
+
+def shipped_state_dict(shipped, tag):
+    import torch
+    pre = tag + "::"
+    return {k[len(pre):]: torch.from_numpy(v.copy()) for k, v in shipped.items() if k.startswith(pre)}

@@ -18,8 +18,9 @@ What is executed from /root/reference, unmodified, and how:
   * models/encoder.py PCAEncoder and models/classifier.py KMeansClassifier -- imported for
     real (sklearn is installed).
 Shipped checkpoints logs/models/collection_duct_{neuralop,teecnet}/partition_0.pth provide
-the w=43 weights; their tensors are NOT copied into the fixtures (tests that need them on the
-GPU box use the seeded small-width state_dicts saved here).
+the w=43 weights; they are re-saved as ``shipped_w43_weights.npz`` (arrays keyed
+``neuralop::<state_dict key>`` / ``teecnet::<key>``) so that the GPU box, which has no
+/root/reference, can run the w=43 parity tests and the benchmark on realistic weights.
 """
 from __future__ import annotations
 
@@ -241,6 +242,12 @@ def main():
                route_scaler_mean=clf.scaler.mean_, route_scaler_scale=clf.scaler.scale_,
                route_centroids=clf.model.cluster_centers_, route_latent=latent,
                route_labels=np.asarray(labels, dtype=np.int64))
+
+    weights = {}
+    for tag, m in (("neuralop", knn), ("teecnet", tee)):
+        for k, v in m.state_dict().items():
+            weights[f"{tag}::{k}"] = v.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "shipped_w43_weights.npz"), **weights)
 
     path = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(path, **out)
