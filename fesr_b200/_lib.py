@@ -65,10 +65,11 @@ SIGNATURES = {
     "fesr_partition_workspace_bytes": (_sz, [_i64, _i32]),
     "fesr_partition_cells": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fesr_assign_count": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp]),
-    "fesr_assign_fill": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fesr_assign_workspace_bytes": (_sz, [_i64, _i32, _i64]),
+    "fesr_assign_fill": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "fesr_subdomain_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "fesr_subdomain_count": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp]),
-    "fesr_subdomain_fill": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fesr_subdomain_fill": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fesr_route": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
 }
 

@@ -80,6 +80,16 @@ int launch_ptr_from_sorted(const uint64_t* keys, int64_t m, int shift, int64_t n
   return FESR_OK;
 }
 
+__global__ void scan_total_kernel(const int32_t* __restrict__ flags, int32_t* __restrict__ scan, int64_t m) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) scan[m] = (m > 0) ? scan[m - 1] + flags[m - 1] : 0;
+}
+
+int launch_scan_total(const int32_t* flags, int32_t* scan, int64_t m, cudaStream_t stream) {
+  scan_total_kernel<<<1, 32, 0, stream>>>(flags, scan, m);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
 size_t scan_temp_bytes(int64_t m) {
   size_t bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr, m > 0 ? m : 1);

@@ -28,6 +28,8 @@ int sort_keys_u64(const uint64_t* in, uint64_t* out, int64_t m, int begin_bit, i
 size_t scan_temp_bytes(int64_t m);
 int exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t m, void* temp, size_t temp_bytes, cudaStream_t stream);
 
+// scan[m] = scan[m-1] + flags[m-1]  (closes an exclusive scan of m flags)
+int launch_scan_total(const int32_t* flags, int32_t* scan, int64_t m, cudaStream_t stream);
 // out[j] = 1 if keys[j] != keys[j-1] (j = 0 -> 1)
 int launch_head_flags(const uint64_t* keys, int64_t m, int32_t* flags, cudaStream_t stream);
 // ptr[i] = first position j with (keys[j] >> shift) >= i, for i in [0, nseg]; ptr[nseg] = m

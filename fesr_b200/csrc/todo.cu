@@ -19,28 +19,6 @@ int fesr_nnconv_backward(const fesr_model_dims*, const fesr_params*, const float
   NOT_BUILT("fesr_nnconv_backward");
 }
 
-size_t fesr_partition_workspace_bytes(int64_t, int32_t) { return 0; }
-int fesr_partition_cells(const float*, const int32_t*, int64_t, int64_t, int32_t, int32_t*, int32_t*, float*, void*,
-                         size_t, void*) {
-  NOT_BUILT("fesr_partition_cells");
-}
-int fesr_assign_count(const float*, const int32_t*, int64_t, int32_t, int32_t, const int32_t*, const int32_t*,
-                      const float*, int32_t*, int64_t*, void*, size_t, void*) {
-  NOT_BUILT("fesr_assign_count");
-}
-int fesr_assign_fill(const float*, const int32_t*, int64_t, int32_t, int32_t, const int32_t*, const int32_t*,
-                     const float*, const int32_t*, int32_t*, void*, size_t, void*) {
-  NOT_BUILT("fesr_assign_fill");
-}
-size_t fesr_subdomain_workspace_bytes(int64_t, int64_t, int32_t) { return 0; }
-int fesr_subdomain_count(const int32_t*, const int32_t*, const int32_t*, int32_t, int64_t, int64_t, int32_t*,
-                         int32_t*, int64_t*, void*, size_t, void*) {
-  NOT_BUILT("fesr_subdomain_count");
-}
-int fesr_subdomain_fill(const float*, const int32_t*, const int32_t*, int32_t, int64_t, int64_t, int64_t*, int32_t*,
-                        int32_t*, float*, int32_t*, void*, size_t, void*) {
-  NOT_BUILT("fesr_subdomain_fill");
-}
 int fesr_route(const float*, int32_t, const int32_t*, int32_t, int32_t, const double*, const double*, int32_t,
                const double*, const double*, const double*, int32_t, int32_t*, double*, void*) {
   NOT_BUILT("fesr_route");

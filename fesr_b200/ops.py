@@ -220,3 +220,100 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
     with torch.cuda.device(dev):
         check(_lib.load().fesr_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
                                          lr, beta1, beta2, eps, step, _stream(dev)), "fesr_adam_step")
+
+
+# ---------------------------------------------------------------------------------- assembly
+@dataclass
+class Partition:
+    home_leaf: torch.Tensor   # [C] int32
+    tree_axis: torch.Tensor   # [2^k - 1] int32
+    tree_split: torch.Tensor  # [2^k - 1] fp32
+    leaf_ptr: torch.Tensor    # [S+1] int32
+    leaf_cells: torch.Tensor  # [pairs] int32
+    levels: int
+    mode: int
+
+
+@dataclass
+class SubdomainBatch:
+    """All subdomains of one mesh as one block-diagonal graph (device tensors)."""
+    node_ptr: torch.Tensor    # [S+1] int32
+    edge_ptr: torch.Tensor    # [S+1] int32
+    global_ids: torch.Tensor  # [n_tot] int64, ascending inside each subdomain
+    edge_src: torch.Tensor    # [e_tot] int32 batch-level
+    edge_dst: torch.Tensor    # [e_tot] int32 batch-level, (subdomain, dst, src) order
+    edge_attr: torch.Tensor   # [e_tot] fp32
+    rowptr: torch.Tensor      # [n_tot + 1] int32
+    n_sub: int
+    n_tot: int
+    e_tot: int
+
+    @property
+    def csr(self) -> Csr:
+        return Csr(self.rowptr, self.edge_src, None, self.n_tot, self.e_tot)
+
+
+def partition_cells(pos: torch.Tensor, cells: torch.Tensor, levels: int, mode: int = _lib.ALL_INTERSECTING) -> Partition:
+    """kd decomposition of the cells into 2**levels leaves (+ halo assignment)."""
+    dev = _require_cuda(pos, cells)
+    if pos.dtype != torch.float32 or cells.dtype != torch.int32:
+        raise FesrError("pos must be fp32 [N,3] and cells int32 [C,4]")
+    pos, cells = pos.contiguous(), cells.contiguous()
+    N, Cn = int(pos.shape[0]), int(cells.shape[0])
+    S = 1 << levels
+    lib = _lib.load()
+    home = torch.empty(max(Cn, 1), dtype=torch.int32, device=dev)[:Cn]
+    tree_axis = torch.zeros(max(S - 1, 1), dtype=torch.int32, device=dev)[:S - 1]
+    tree_split = torch.zeros(max(S - 1, 1), dtype=torch.float32, device=dev)[:S - 1]
+    leaf_ptr = torch.empty(S + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        ws = workspace.get(dev, "asm", lib.fesr_partition_workspace_bytes(Cn, levels))
+        check(lib.fesr_partition_cells(_ptr(pos), _ptr(cells), N, Cn, levels, _ptr(home), _ptr(tree_axis),
+                                       _ptr(tree_split), _ptr(ws), ws.numel(), st), "fesr_partition_cells")
+        total = C.c_int64(0)
+        ws = workspace.get(dev, "asm", lib.fesr_assign_workspace_bytes(Cn, levels, 0))
+        check(lib.fesr_assign_count(_ptr(pos), _ptr(cells), Cn, levels, mode, _ptr(home), _ptr(tree_axis),
+                                    _ptr(tree_split), _ptr(leaf_ptr), C.byref(total), _ptr(ws), ws.numel(), st),
+              "fesr_assign_count")
+        P = int(total.value)
+        leaf_cells = torch.empty(max(P, 1), dtype=torch.int32, device=dev)[:P]
+        ws = workspace.get(dev, "asm", lib.fesr_assign_workspace_bytes(Cn, levels, P))
+        check(lib.fesr_assign_fill(_ptr(pos), _ptr(cells), Cn, levels, mode, _ptr(home), _ptr(tree_axis),
+                                   _ptr(tree_split), _ptr(leaf_ptr), P, _ptr(leaf_cells), _ptr(ws), ws.numel(), st),
+              "fesr_assign_fill")
+    return Partition(home, tree_axis, tree_split, leaf_ptr, leaf_cells, levels, mode)
+
+
+def build_subdomains(pos: torch.Tensor, cells: torch.Tensor, leaf_ptr: torch.Tensor, leaf_cells: torch.Tensor) -> SubdomainBatch:
+    """Node compaction + edge build + CSR for every subdomain (one block-diagonal batch)."""
+    dev = _require_cuda(pos, cells, leaf_ptr)
+    pos, cells = pos.contiguous(), cells.contiguous()
+    N = int(pos.shape[0])
+    S = int(leaf_ptr.numel() - 1)
+    P = int(leaf_cells.numel())
+    lib = _lib.load()
+    node_ptr = torch.empty(S + 1, dtype=torch.int32, device=dev)
+    edge_ptr = torch.empty(S + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        ws = workspace.get(dev, "asm", lib.fesr_subdomain_workspace_bytes(P, N, S))
+        totals = (C.c_int64 * 2)(0, 0)
+        check(lib.fesr_subdomain_count(_ptr(cells), _ptr(leaf_ptr), _ptr(leaf_cells), S, P, N, _ptr(node_ptr),
+                                       _ptr(edge_ptr), totals, _ptr(ws), ws.numel(), st), "fesr_subdomain_count")
+        n_tot, e_tot = int(totals[0]), int(totals[1])
+        gids = torch.empty(max(n_tot, 1), dtype=torch.int64, device=dev)[:n_tot]
+        esrc = torch.empty(max(e_tot, 1), dtype=torch.int32, device=dev)[:e_tot]
+        edst = torch.empty(max(e_tot, 1), dtype=torch.int32, device=dev)[:e_tot]
+        eattr = torch.empty(max(e_tot, 1), dtype=torch.float32, device=dev)[:e_tot]
+        rowptr = torch.empty(n_tot + 1, dtype=torch.int32, device=dev)
+        check(lib.fesr_subdomain_fill(_ptr(pos), _ptr(node_ptr), _ptr(edge_ptr), S, P, n_tot, e_tot, _ptr(gids),
+                                      _ptr(esrc), _ptr(edst), _ptr(eattr), _ptr(rowptr), _ptr(ws), ws.numel(), st),
+              "fesr_subdomain_fill")
+    return SubdomainBatch(node_ptr, edge_ptr, gids, esrc, edst, eattr, rowptr, S, n_tot, e_tot)
+
+
+def assemble(pos, cells, levels: int, mode: int = _lib.ALL_INTERSECTING):
+    """partition_cells + build_subdomains: the GPU replacement of get_partition_domain."""
+    part = partition_cells(pos, cells, levels, mode)
+    return part, build_subdomains(pos, cells, part.leaf_ptr, part.leaf_cells)

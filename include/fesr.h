@@ -202,6 +202,7 @@ int fesr_stitch_mean(const float* values, int32_t channels, const int32_t* occ_p
  * host_totals (it synchronises the stream), the caller allocates, *_fill writes the arrays.
  * ---------------------------------------------------------------------------------- */
 size_t fesr_partition_workspace_bytes(int64_t C, int32_t levels);
+size_t fesr_assign_workspace_bytes(int64_t C, int32_t levels, int64_t total_pairs /* 0 for _count */);
 /* home_leaf[C] int32, tree_axis[2^levels-1] int32, tree_split[2^levels-1] fp32 */
 int fesr_partition_cells(const float* pos, const int32_t* cells, int64_t N, int64_t C,
                          int32_t levels, int32_t* home_leaf, int32_t* tree_axis, float* tree_split,
@@ -214,8 +215,8 @@ int fesr_assign_count(const float* pos, const int32_t* cells, int64_t C, int32_t
 /* leaf_cells[total] int32: cells of every leaf, ascending cell id */
 int fesr_assign_fill(const float* pos, const int32_t* cells, int64_t C, int32_t levels, int32_t mode,
                      const int32_t* home_leaf, const int32_t* tree_axis, const float* tree_split,
-                     const int32_t* leaf_ptr, int32_t* leaf_cells, void* workspace, size_t workspace_bytes,
-                     void* stream);
+                     const int32_t* leaf_ptr, int64_t total_pairs, int32_t* leaf_cells,
+                     void* workspace, size_t workspace_bytes, void* stream);
 
 size_t fesr_subdomain_workspace_bytes(int64_t total_pairs, int64_t N, int32_t n_sub);
 /* node_ptr[S+1], edge_ptr[S+1] int32 written; host_totals[0] = sum n_s, [1] = sum E_s.
@@ -228,7 +229,7 @@ int fesr_subdomain_count(const int32_t* cells, const int32_t* leaf_ptr, const in
  * indices in (subdomain, dst, src) order; edge_attr[sum E] fp32 = |pos[src]-pos[dst]|;
  * rowptr[sum n + 1] int32. */
 int fesr_subdomain_fill(const float* pos, const int32_t* node_ptr, const int32_t* edge_ptr,
-                        int32_t n_sub, int64_t n_tot, int64_t e_tot,
+                        int32_t n_sub, int64_t total_pairs, int64_t n_tot, int64_t e_tot,
                         int64_t* global_ids, int32_t* edge_src, int32_t* edge_dst, float* edge_attr,
                         int32_t* rowptr, void* workspace, size_t workspace_bytes, void* stream);
 
