@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- super-resolved mesh cells/s of the predict hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference ...                     the reference's algorithm on host cores
+
+Workload (config.workload): BASELINE config 2 -- run_DS_3D.py --mode=predict --model=neuralop
+on the synthetic 526 848-cell duct (n = 28), shipped w=43 checkpoint, 5 layers, 2^7 kd
+subdomains with a one-cell halo (AssignToAllIntersectingRegions).  One step = one predict pass:
+model forward over every subdomain of the rank's shard (one block-diagonal batch) + node weight
++ [N>1: one NCCL all-gather of the predictions] + overlap stitch onto the fine mesh.
+Weak scaling: at N GPUs the duct is N times longer (N x 526 848 cells), each rank owns a
+contiguous 1/N of the subdomains.  Subdomain assembly is one-time preprocessing in the
+reference (GraphDataset.get_partition_domain) and is timed separately (config.assembly_ms).
+
+value : cells/s with inputs resident in HBM; timed with CUDA events, max over ranks.
+e2e   : same pass through the public API with HOST (pinned) inputs: H2D of x and y copies,
+        predict, stitch, D2H of the stitched field and the node weights.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASE_N = 28                      # 24 * 28^3 = 526 848 cells
+BASE_LEVELS = 7
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fesr", choices=["fesr", "reference"])
+    ap.add_argument("--model", default="neuralop", choices=["neuralop", "teecnet"])
+    ap.add_argument("--precision", default=os.environ.get("FESR_PRECISION", "fp32"))
+    ap.add_argument("--mesh-n", type=int, default=BASE_N)
+    ap.add_argument("--levels", type=int, default=-1)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- shared setup
+def make_mesh(n, length_factor):
+    """n x n x (4 n length_factor) duct: cells = length_factor * 24 n^3."""
+    from fesr_b200.dataset import synthetic as syn
+    if length_factor == 1:
+        return syn.make_duct_mesh(n)
+    return syn.make_duct_mesh_long(n, length_factor)
+
+
+def load_weights(kind):
+    import torch
+    path = os.path.join(ROOT, "tests", "golden", "shipped_w43_weights.npz")
+    z = np.load(path)
+    pre = kind + "::"
+    return {k[len(pre):]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith(pre)}
+
+
+def levels_for(args, world):
+    if args.levels >= 0:
+        return args.levels
+    lv = BASE_LEVELS
+    w = world
+    while w > 1:
+        lv += 1
+        w //= 2
+    return lv
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def oracle_subdomain_pass(model, sub, mesh, s_list, home_cells):
+    """The reference's per-subdomain predict loop (models/scheduler_gnn.py:217-226) + stitch sample."""
+    import torch
+    from oracle import graph as og
+    from oracle import models as om
+    preds, gids = [], []
+    cells = 0
+    t0 = time.perf_counter()
+    for s in s_list:
+        nl, nh = sub["node_ptr"][s], sub["node_ptr"][s + 1]
+        el, eh = sub["edge_ptr"][s], sub["edge_ptr"][s + 1]
+        g = sub["global_ids"][nl:nh]
+        x = torch.from_numpy(mesh.x[g])
+        y = torch.from_numpy(mesh.y[g])
+        ei = torch.from_numpy(np.stack([sub["edge_src"][el:eh] - nl, sub["edge_dst"][el:eh] - nl]))
+        ea = torch.from_numpy(sub["edge_attr"][el:eh]).unsqueeze(1)
+        with torch.no_grad():
+            p = model(x, ei, ea)
+            om.compute_node_weight(p, y, ei, ea, x.shape[0])
+        preds.append(p.numpy())
+        gids.append(g)
+        cells += int(home_cells[s])
+    og.stitch_mean(np.concatenate(preds), np.concatenate(gids), mesh.num_nodes)
+    return time.perf_counter() - t0, cells
+
+
+def cpu_setup(args, length_factor, levels):
+    import torch
+    from oracle import graph as og
+    from oracle import models as om
+    torch.set_num_threads(os.cpu_count() or 1)
+    mesh = make_mesh(args.mesh_n, length_factor)
+    part = og.kd_partition(mesh.pos, mesh.cells, levels)
+    sub = og.build_subdomains(mesh.pos, mesh.cells, part["leaf_ptr"], part["leaf_cells"])
+    home_cells = np.bincount(part["home_leaf"], minlength=1 << levels)
+    model = om.make_model(args.model, 43, 5)
+    model.load_state_dict(load_weights(args.model))
+    model.eval()
+    return mesh, sub, home_cells, model
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    world = args.gpus
+    levels = levels_for(args, world)
+    mesh, sub, home_cells, model = cpu_setup(args, world, levels)
+    S = 1 << levels
+    # size the per-step sample so that one step is ~1/3 of the budget
+    t1, c1 = oracle_subdomain_pass(model, sub, mesh, [0], home_cells)
+    per_step = max(1, min(S, int(max(args.cpu_seconds / 3.0, 1.0) / max(t1, 1e-3))))
+    s_list = list(range(per_step))
+    for _ in range(min(args.warmup, 1)):
+        oracle_subdomain_pass(model, sub, mesh, s_list[:max(1, per_step // 4)], home_cells)
+    steps = max(1, min(args.steps, 3))
+    times, cells = [], 0
+    for _ in range(steps):
+        t, c = oracle_subdomain_pass(model, sub, mesh, s_list, home_cells)
+        times.append(t)
+        cells = c
+    best = min(times)
+    value = cells / best
+    sample = f"{per_step} of {S} subdomains ({cells} cells) per step, best of {steps}, torch CPU + numpy stitch"
+    line = {"impl": "reference", "metric": "super-resolved mesh cells/s (predict pass: forward + node weight + stitch)",
+            "value": value, "unit": "cells/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": best * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world, levels, mesh.num_cells, sub, per_step),
+            "cpu_baseline": {"value": value, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world, levels, cells, sub_or_batch, sample=None):
+    cfg = {"workload": f"run_DS_3D.py --mode=predict --model={args.model}, synthetic duct n={args.mesh_n} x{world} "
+                       f"({cells} cells), w=43, 5 layers, 2^{levels} kd subdomains + 1-cell halo",
+           "cells": int(cells), "subdomains": 1 << levels, "model": args.model, "width": 43, "layers": 5,
+           "parallelism": f"subdomain-sharded x{world}",
+           "l2": "inputs + per-layer intermediates exceed the 126 MB L2 (g, Z are 0.3-1.2 GB per layer)"}
+    if sample is not None:
+        cfg["cpu_sample_subdomains"] = sample
+    return cfg
+
+
+# ----------------------------------------------------------------------------- fesr arm
+def run_fesr(args):
+    import torch
+    import torch.distributed as dist
+    from fesr_b200 import _lib, ops
+    from fesr_b200.models.model import KernelNN, TEECNet
+    from fesr_b200.pipeline import MeshPredictor
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    levels = levels_for(args, world)
+    mesh = make_mesh(args.mesh_n, world)
+    pos = torch.from_numpy(mesh.pos).to(dev)
+    cells = torch.from_numpy(mesh.cells).to(dev)
+    if args.model == "neuralop":
+        model = KernelNN(43, 43, 5, in_width=4, out_width=4)
+    else:
+        model = TEECNet(4, 43, 4, num_layers=5, retrieve_weight=False)
+    model.load_state_dict(load_weights(args.model))
+    model = model.to(dev).eval()
+    model.precision = args.precision
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    a0, a1 = ev(), ev()
+    torch.cuda.synchronize()
+    a0.record()
+    pred = MeshPredictor(model, pos, cells, levels, rank=rank, world=world)
+    a1.record()
+    torch.cuda.synchronize()
+    assembly_ms = a0.elapsed_time(a1)
+
+    sh = pred.shard
+    gid_host = sh.global_ids.cpu().numpy()
+    x_host = torch.from_numpy(mesh.x[gid_host]).pin_memory()
+    y_host = torch.from_numpy(mesh.y[gid_host]).pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    field_host = torch.empty(mesh.num_nodes, 4, dtype=torch.float32).pin_memory()
+    w_host = torch.empty(sh.s1 - sh.s0, dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(steps):
+            fn()
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_resident():
+        pred.step(x_dev, y_dev)
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        yd = y_host.to(dev, non_blocking=True)
+        field, w, _ = pred.step(xd, yd)
+        field_host.copy_(field, non_blocking=True)
+        w_host.copy_(w, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    _lib.profile_enable(True)
+    ms = timed(step_resident, args.steps, max(args.warmup, 3))
+    prof = _lib.profile_collect()          # includes the warm-up launches; shares and per-launch means are what we use
+    _lib.profile_enable(False)
+    launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + max(args.warmup, 3))
+    ms_e2e = timed(step_e2e, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_cells = mesh.num_cells
+    value = total_cells / (ms / args.steps / 1e3)
+    e2e_value = total_cells / (ms_e2e / args.steps / 1e3)
+
+    # ---- roofline of the dominant kernel class (algorithmic bytes / flops per launch)
+    d = model.dims
+    n_s, E_s = sh.csr.n, sh.csr.E
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks = {"hbm_gbs": mp["hbm_gbs"], "bf16_tflops": mp["bf16_tflops"], "src": "measured"}
+    except (OSError, KeyError, ValueError):
+        pass
+    w = d.w
+    alg = {
+        # gather + segmented mean: src index, g row, gathered h row per edge; h row read + Z row written per node
+        "zbuild": ("hbm", E_s * (4 + 4 * d.k1 + 4 * w) + n_s * (4 * w + 4 * (d.k1 * w + w)) + 4 * (n_s + 1)),
+        # node contraction: Z row read, h row written; flops 2*n*zk*wp
+        "node_gemm": ("hbm" if args.precision != "fp32" else "fp32", n_s * (4 * (d.k1 * w + w) + 4 * w)),
+        "edge_hidden": ("hbm", E_s * (4 + 4 * d.k1)),
+        "stitch": ("hbm", pred.batch.n_tot * 20 + pred.N * 20),
+        "node_weight": ("hbm", E_s * (4 + 4 + 32) + n_s * 36),
+    }
+    kernels = {}
+    tot_prof = sum(v[0] for v in prof.values()) or 1.0
+    for k, (t_ms, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        per = t_ms / cnt
+        ent = {"ms_per_launch": per, "launches": int(cnt), "share": t_ms / tot_prof}
+        if k in alg:
+            ent["bound"] = alg[k][0]
+            ent["alg_bytes"] = int(alg[k][1])
+            ent["gbs"] = alg[k][1] / (per * 1e-3) / 1e9
+        if k == "node_gemm":
+            ent["tflops"] = 2.0 * n_s * d.zk * d.wp / (per * 1e-3) / 1e12
+        kernels[k] = ent
+    top = max(kernels, key=lambda k: kernels[k]["share"])
+    if top == "node_gemm" and args.precision != "fp32":
+        peak_tf = peaks["bf16_tflops"] / 2.0     # TF32 = half the measured bf16 rate (derived)
+        roof = {"kernel": top, "bound": "tensor", "achieved": kernels[top]["tflops"], "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": kernels[top]["tflops"] / peak_tf, "traffic": None,
+                "peak_source": peaks["src"] + " bf16/2 (derived TF32)"}
+    else:
+        k = top if "gbs" in kernels[top] else "zbuild"
+        roof = {"kernel": k, "bound": "hbm", "achieved": kernels[k]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": kernels[k]["gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = run_cpu_baseline(args, levels)
+
+    if rank == 0:
+        cfg = workload_config(args, world, levels, total_cells, pred.batch)
+        cfg.update({"assembly_ms": assembly_ms, "batch_nodes": pred.batch.n_tot, "batch_edges": pred.batch.e_tot,
+                    "precision": args.precision})
+        line = {"metric": "super-resolved mesh cells/s (predict pass: forward + node weight + stitch)",
+                "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+                "data": "synthetic", "config": cfg, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(x_host.numel() * 4 + y_host.numel() * 4),
+                        "d2h_bytes_per_step": int(field_host.numel() * 4 + w_host.numel() * 4)},
+                "gpu_launches": int(launches), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_cpu_baseline(args, levels):
+    mesh, sub, home_cells, model = cpu_setup(args, 1, levels)
+    S = 1 << levels
+    t1, _ = oracle_subdomain_pass(model, sub, mesh, [0], home_cells)
+    m = max(1, min(S, int(args.cpu_seconds / max(t1, 1e-3))))
+    t, c = oracle_subdomain_pass(model, sub, mesh, list(range(m)), home_cells)
+    return {"value": c / t, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{m} of {S} subdomains ({c} cells) in {t:.1f} s, torch CPU per-subdomain loop + numpy stitch"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    sys.exit(run_reference(a) if a.impl == "reference" else run_fesr(a))

@@ -47,6 +47,9 @@ SIGNATURES = {
     "fesr_version": (C.c_int, []),
     "fesr_last_error": (C.c_char_p, []),
     "fesr_device_check": (C.c_int, []),
+    "fesr_launch_count": (C.c_longlong, []),
+    "fesr_profile_enable": (C.c_int, [C.c_int]),
+    "fesr_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "fesr_model_dims_init": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(ModelDims)]),
     "fesr_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "fesr_csr_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -98,6 +101,26 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         msg = load().fesr_last_error().decode(errors="replace")
         raise FesrError(f"{what or 'libfesr call'} failed ({rc}): {msg}")
+
+
+PROF_KINDS = ("prepare", "edge_hidden", "fc_in", "zbuild", "node_gemm", "fc_out", "node_weight", "stitch", "graph",
+              "backward")
+
+
+def profile_enable(on: bool):
+    check(load().fesr_profile_enable(int(on)), "fesr_profile_enable")
+
+
+def profile_collect():
+    n = len(PROF_KINDS)
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(load().fesr_profile_collect(ms, cnt, n), "fesr_profile_collect")
+    return {k: (ms[i], cnt[i]) for i, k in enumerate(PROF_KINDS)}
+
+
+def launch_count() -> int:
+    return int(load().fesr_launch_count())
 
 
 def model_dims(kind: int, w: int, in_ch: int, out_ch: int, layers: int) -> ModelDims:

@@ -14,6 +14,29 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
+// ---- profiling: pairs of events per kernel class, recorded on the launching stream
+static bool g_prof_on = false;
+struct ProfPair { cudaEvent_t a, b; int kind; };
+static ProfPair g_pairs[8192];
+static int g_npairs = 0, g_nalloc = 0;
+
+ProfScope::ProfScope(int kind, cudaStream_t s) : slot(-1), stream(s) {
+  if (!g_prof_on || g_npairs >= 8192) return;
+  if (g_npairs >= g_nalloc) {
+    if (cudaEventCreate(&g_pairs[g_nalloc].a) != cudaSuccess || cudaEventCreate(&g_pairs[g_nalloc].b) != cudaSuccess) return;
+    ++g_nalloc;
+  }
+  slot = g_npairs++;
+  g_pairs[slot].kind = kind;
+  cudaEventRecord(g_pairs[slot].a, stream);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_pairs[slot].b, stream);
+}
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -42,6 +65,31 @@ int fesr_device_check(void) {
     fesr::set_error("libfesr.so is built for sm_100a only; device %d has compute capability %d.x", dev, major);
     return FESR_EDEVICE;
   }
+  return FESR_OK;
+}
+
+long long fesr_launch_count(void) { return fesr::g_launches; }
+
+int fesr_profile_enable(int on) {
+  fesr::g_prof_on = on != 0;
+  fesr::g_npairs = 0;
+  return FESR_OK;
+}
+
+int fesr_profile_collect(double* ms_by_kind, long long* launches_by_kind, int nkinds) {
+  FESR_CHECK_ARG(ms_by_kind && launches_by_kind && nkinds >= fesr::PROF_NKINDS, "need %d kinds", (int)fesr::PROF_NKINDS);
+  for (int k = 0; k < nkinds; ++k) {
+    ms_by_kind[k] = 0.0;
+    launches_by_kind[k] = 0;
+  }
+  for (int i = 0; i < fesr::g_npairs; ++i) {
+    FESR_CUDA(cudaEventSynchronize(fesr::g_pairs[i].b));
+    float ms = 0.f;
+    FESR_CUDA(cudaEventElapsedTime(&ms, fesr::g_pairs[i].a, fesr::g_pairs[i].b));
+    ms_by_kind[fesr::g_pairs[i].kind] += ms;
+    launches_by_kind[fesr::g_pairs[i].kind] += 1;
+  }
+  fesr::g_npairs = 0;
   return FESR_OK;
 }
 

@@ -28,7 +28,24 @@ void set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
-#define FESR_LAUNCH_CHECK() FESR_CUDA(cudaGetLastError())
+void count_launch();
+#define FESR_LAUNCH_CHECK()          \
+  do {                               \
+    ::fesr::count_launch();          \
+    FESR_CUDA(cudaGetLastError());   \
+  } while (0)
+
+// Optional per-kernel-class CUDA-event timing (bench.py's roofline numbers); off by default.
+enum ProfKind {
+  PROF_PREPARE = 0, PROF_EDGE_HIDDEN, PROF_FC_IN, PROF_ZBUILD, PROF_NODE_GEMM, PROF_FC_OUT,
+  PROF_NODE_WEIGHT, PROF_STITCH, PROF_GRAPH, PROF_BACKWARD, PROF_NKINDS
+};
+struct ProfScope {
+  int slot;
+  cudaStream_t stream;
+  ProfScope(int kind, cudaStream_t s);
+  ~ProfScope();
+};
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

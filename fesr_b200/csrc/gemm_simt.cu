@@ -89,6 +89,7 @@ int launch_node_gemm_fp32(const fesr_model_dims& d, const Prepared& w, const flo
   if (n == 0) return FESR_OK;
   const unsigned grid = (unsigned)ceil_div(n, SG_BM);
   const int tee = d.kind == FESR_TEECNET;
+  ProfScope prof(PROF_NODE_GEMM, s);
   switch (d.wp) {
     case 16: node_gemm_fp32_kernel<16><<<grid, SG_THREADS, 0, s>>>(Z, w.tprime, w.bias_p, n, d.zk, d.w, tee, h_out); break;
     case 32: node_gemm_fp32_kernel<32><<<grid, SG_THREADS, 0, s>>>(Z, w.tprime, w.bias_p, n, d.zk, d.w, tee, h_out); break;

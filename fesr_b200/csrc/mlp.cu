@@ -89,6 +89,7 @@ int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const
   FESR_CHECK_ARG(p.mlp_w[last] && p.mlp_b[last] && p.root && p.bias && p.fc1_w && p.fc1_b, "NULL parameter");
   FESR_CHECK_ARG(d.kind != FESR_TEECNET || (p.lin_w && p.lin_b), "TEECNet needs kernel.linear");
   const int64_t total = (int64_t)d.zk * d.wp;
+  ProfScope prof(PROF_PREPARE, s);
   prepare_tprime_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(d, p.mlp_w[last], p.mlp_b[last], p.lin_w,
                                                                       p.lin_b, p.root, w.tprime, w.tprime_t,
                                                                       w.tprime_t_lo);
@@ -256,6 +257,7 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
   FESR_CHECK_ARG(smem <= 200 * 1024, "edge MLP too large for shared memory");
   const int64_t n_tiles = ceil_div(E, EH_TE);
   const int grid = (int)(n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms());
+  ProfScope prof(PROF_EDGE_HIDDEN, s);
   edge_hidden_kernel<<<grid, EH_THREADS, smem, s>>>(a, edge_attr, perm, E, g);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
@@ -285,6 +287,7 @@ __global__ void fc_in_kernel(const float* __restrict__ x, const float* __restric
 int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s) {
   if (n == 0) return FESR_OK;
   const int64_t total = n * (d.wp / 4);
+  ProfScope prof(PROF_FC_IN, s);
   fc_in_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.in_ch, d.wp, n, h);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
@@ -308,6 +311,7 @@ int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const float* h
   if (n == 0) return FESR_OK;
   FESR_CHECK_ARG(p.fc2_w && p.fc2_b, "NULL fc2 parameter");
   const int64_t total = n * d.out_ch;
+  ProfScope prof(PROF_FC_OUT, s);
   fc_out_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(h, p.fc2_w, p.fc2_b, d.w, d.wp, d.out_ch, n, y);
   FESR_LAUNCH_CHECK();
   return FESR_OK;

@@ -174,6 +174,7 @@ int fesr_stitch_mean(const float* values, int32_t channels, const int32_t* occ_p
   FESR_CHECK_ARG(!merged || global_ids, "merged needs global_ids");
   cudaStream_t s = as_stream(stream_);
   const int T = 256;
+  ProfScope prof(PROF_STITCH, s);
   if (N > 0) {
     const unsigned grid = (unsigned)ceil_div(N, T);
     if (channels == 4) stitch_mean_kernel<4><<<grid, T, 0, s>>>(values, occ_ptr, occ_idx, N, field, count);
@@ -201,6 +202,7 @@ int fesr_node_weight(const float* pred, const float* target, int32_t channels, c
   FESR_CHECK_ARG(E == 0 || (src_sorted && edge_attr), "NULL edge arrays");
   FESR_CHECK_ARG(node_ptr || n_sub == 1, "node_ptr is required for n_sub > 1");
   cudaStream_t s = as_stream(stream_);
+  ProfScope prof(PROF_NODE_WEIGHT, s);
   if (n > 0) {
     node_weight_partial_kernel<4><<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(pred, target, rowptr, src_sorted, perm,
                                                                             edge_attr, n, node_scratch);

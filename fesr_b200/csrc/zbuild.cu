@@ -132,6 +132,7 @@ static int launch_zb(const fesr_model_dims& d, const int32_t* rowptr, const int3
   const int64_t blocks_needed = ceil_div(n, ZB_WARPS);
   const int64_t cap = (int64_t)num_sms() * 2 * 8;      // a few waves of persistent-ish CTAs
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  ProfScope prof(PROF_ZBUILD, s);
   zbuild_kernel<KT, WP><<<grid, ZB_WARPS * 32, smem, s>>>(rowptr, src_sorted, g, h, n, d.passes, d.kp, d.zk_main,
                                                          d.zk, Z);
   FESR_LAUNCH_CHECK();

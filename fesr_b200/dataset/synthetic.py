@@ -47,9 +47,9 @@ def _node_id(ix, iy, iz, n):
     return (iz * (n + 1) + iy) * (n + 1) + ix
 
 
-def make_cells(n: int) -> np.ndarray:
-    """[24 n^3, 4] int32 Kuhn tets; cell id = hex id * 6 + tet id."""
-    nz = 4 * n
+def make_cells(n: int, nz: int | None = None) -> np.ndarray:
+    """[6 n^2 nz, 4] int32 Kuhn tets (nz = 4n by default); cell id = hex id * 6 + tet id."""
+    nz = 4 * n if nz is None else nz
     ix, iy, iz = np.meshgrid(np.arange(n), np.arange(n), np.arange(nz), indexing="ij")
     # hex id order: z slowest, then y, then x (matches node numbering)
     order = np.argsort(_node_id(ix, iy, iz, n).ravel(), kind="stable")
@@ -65,8 +65,8 @@ def make_cells(n: int) -> np.ndarray:
     return cells.reshape(-1, 4).astype(np.int32)
 
 
-def make_positions(n: int, seed: int = 0) -> np.ndarray:
-    nz = 4 * n
+def make_positions(n: int, seed: int = 0, nz: int | None = None) -> np.ndarray:
+    nz = 4 * n if nz is None else nz
     rng = np.random.default_rng(seed)
     gz, gy, gx = np.meshgrid(np.arange(nz + 1), np.arange(n + 1), np.arange(n + 1), indexing="ij")
     lattice = np.stack([gx.ravel(), gy.ravel(), gz.ravel()], axis=1).astype(np.float64)
@@ -74,13 +74,14 @@ def make_positions(n: int, seed: int = 0) -> np.ndarray:
     return ((lattice + jitter) * MESH_SCALE).astype(np.float32)
 
 
-def make_field(n: int, pos: np.ndarray, seed: int) -> np.ndarray:
+def make_field(n: int, pos: np.ndarray, seed: int, nz: int | None = None) -> np.ndarray:
     """Smooth duct profile + noise, normalised as the reference does."""
     rng = np.random.default_rng(seed)
+    nz = 4 * n if nz is None else nz
     L = n * MESH_SCALE
     xi = 2.0 * pos[:, 0].astype(np.float64) / L - 1.0
     eta = 2.0 * pos[:, 1].astype(np.float64) / L - 1.0
-    zeta = pos[:, 2].astype(np.float64) / (4.0 * L)
+    zeta = pos[:, 2].astype(np.float64) / (nz * MESH_SCALE)
     prof = np.clip(1.0 - xi * xi, 0.0, None) * np.clip(1.0 - eta * eta, 0.0, None)
     vz = prof * (1.0 + 0.1 * np.sin(2 * np.pi * zeta))
     vx = 0.05 * prof * np.sin(np.pi * eta) * np.cos(2 * np.pi * zeta)
@@ -105,6 +106,15 @@ def make_duct_mesh(n: int | str, seed: int = 0) -> DuctMesh:
     x = make_field(n, pos, seed + 1)
     y = make_field(n, pos, seed + 2)
     return DuctMesh(pos=pos, cells=cells, x=x, y=y, n=n)
+
+
+def make_duct_mesh_long(n: int, length_factor: int, seed: int = 0) -> DuctMesh:
+    """Weak-scaling variant: same n x n cross-section, length_factor times longer duct
+    (cells = length_factor * 24 n^3)."""
+    nz = 4 * n * int(length_factor)
+    pos = make_positions(n, seed, nz)
+    cells = make_cells(n, nz)
+    return DuctMesh(pos=pos, cells=cells, x=make_field(n, pos, seed + 1, nz), y=make_field(n, pos, seed + 2, nz), n=n)
 
 
 def default_kd_levels(num_nodes: int, target_nodes: int = 1000) -> int:

@@ -51,6 +51,16 @@ const char* fesr_last_error(void);
 /* 0 if the current device is sm_100; FESR_EDEVICE otherwise. */
 int fesr_device_check(void);
 
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long fesr_launch_count(void);
+/* Optional CUDA-event timing per kernel class, recorded on the launching stream (bench.py's
+ * roofline figures).  Classes: 0 prepare, 1 edge_hidden, 2 fc_in, 3 zbuild, 4 node_gemm,
+ * 5 fc_out, 6 node_weight, 7 stitch, 8 graph, 9 backward.  _collect synchronises the recorded
+ * events, sums milliseconds / scopes per class and clears the record. */
+#define FESR_PROF_NKINDS 10
+int fesr_profile_enable(int on);
+int fesr_profile_collect(double* ms_by_kind, long long* launches_by_kind, int nkinds);
+
 /* ------------------------------------------------------------------------------------
  * Model geometry.  Filled by fesr_model_dims_init from (kind, width, channels, layers).
  * Replaces nothing in the reference; it fixes the padded HBM layouts every kernel uses.
