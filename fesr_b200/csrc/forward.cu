@@ -58,7 +58,7 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
     const float* h_in = keep_for_backward ? ws.h[l] : ws.h[l & 1];
     float* h_out = keep_for_backward ? ws.h[l + 1] : ws.h[(l + 1) & 1];
     float* Z = keep_for_backward ? ws.Z[l] : ws.Z[0];
-    if ((rc = launch_zbuild(d, rowptr, src_sorted, ws.g, h_in, n, Z, s))) return rc;
+    if ((rc = launch_zbuild(d, rowptr, src_sorted, ws.g, h_in, n, Z, precision != FESR_PREC_FP32, s))) return rc;
     if (precision == FESR_PREC_FP32)
       rc = launch_node_gemm_fp32(d, ws.prep, Z, n, h_out, nullptr, s);
     else

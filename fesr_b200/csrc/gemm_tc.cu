@@ -1,12 +1,305 @@
-// Tensor-core (tcgen05, TF32) node contraction -- placeholder until the TMA/TMEM kernel lands.
+// Tensor-core node contraction  h' = act(Z x T' + bias)  on tcgen05 (kind::tf32), sm_100a.
+//
+// This is the last Linear layer of the reference's edge MLP ([E,K] x [K,w*w], models/model.py:
+// 428/528) plus the root weight (:445/:533), moved from "per edge per layer" to "per node per
+// layer" by the reordering described in zbuild.cu -- a dense [n, zk] x [zk, wp] GEMM:
+//   A = Z       [n,  zk]  fp32 (tf32-rounded by the producer), K-major, TMA-loaded 128x32 boxes
+//   B = T'^T    [wp, zk]  tf32-rounded, K-major, TMA-loaded wp x 32 boxes (L2 resident)
+//   D           [128, wp] fp32 accumulators in TMEM (two stages, so the epilogue of tile t
+//                         overlaps the main loop of tile t+1)
+// Persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer
+// (one elected lane), warps 2..5 = epilogue (tcgen05.ld -> +bias -> activation -> global).
+// The kernel is HBM-bound on streaming Z (AI = 2*wp/4 = 24 flop/B), so the 8-deep TMA ring
+// (176 KB in flight per SM) is what matters, not MMA issue rate.
+#include <cuda.h>
+
 #include "kernels.cuh"
 
 namespace fesr {
 
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;           // fp32 elements = 128 bytes = one SWIZZLE_128B row
+constexpr int TC_STAGES = 8;
+constexpr int TC_THREADS = 192;     // 6 warps
+constexpr int TC_ACC_COLS = 64;     // TMEM columns per accumulator stage (>= wp)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version = 1):
+// rows are 128 B apart, 8-row groups 1024 B apart (SBO), LBO unused for swizzled K-major.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)1 << 16;                 // LBO (ignored)
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+}
+
+template <int WP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const float* __restrict__ bias_p, int64_t n, int zk, int w, int teecnet,
+                      float* __restrict__ h_out) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+  constexpr uint32_t B_BYTES = WP * TC_BK * 4;      // wp * 128 B
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + TC_STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tmem_full = empty_bar + TC_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_tiles = (n + TC_BM - 1) / TC_BM;
+  const int n_kb = zk / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {   // TMEM allocation: 2 accumulator stages
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(2 * TC_ACC_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int row0 = (int)(tile * TC_BM);
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], kb * TC_BK, row0);
+          tma_load_2d(smem_b + stage * B_BYTES, &tmB, &full_bar[stage], kb * TC_BK, 0);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = WP, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(WP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[as], aphase ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tmem_d = tmem_base + as * TC_ACC_COLS;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + stage * A_BYTES));
+          const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + stage * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)   // 8 tf32 = 32 bytes per MMA: advance the start address by 2 (x16 B)
+            umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
+          if (kb == n_kb - 1) umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
+        if (++stage == TC_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    const int quad = warp & 3;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t row = tile * TC_BM + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * TC_ACC_COLS;
+#pragma unroll
+      for (int c0 = 0; c0 < WP; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < n) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float v[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int c = c0 + j + t;
+              float x = __uint_as_float(r[j + t]) + bias_p[c];
+              if (teecnet) {
+                if (c == w) x = 1.f;
+              } else {
+                x = fmaxf(x, 0.f);
+              }
+              v[t] = x;
+            }
+            *reinterpret_cast<float4*>(h_out + row * WP + c0 + j) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_ACC_COLS));
+  }
+}
+
+static int encode_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                      uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    const char* msg = nullptr;
+    cuGetErrorString(r, &msg);
+    set_error("cuTensorMapEncodeTiled failed: %s", msg ? msg : "?");
+    return FESR_ECUDA;
+  }
+  return FESR_OK;
+}
+
+template <int WP>
+static int launch_tc(const fesr_model_dims& d, const Prepared& w, const float* Z, int64_t n, float* h_out, cudaStream_t s) {
+  constexpr size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 4 + WP * TC_BK * 4) + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FESR_CUDA(cudaFuncSetAttribute(node_gemm_tf32_kernel<WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = encode_map(&tmA, Z, (uint64_t)d.zk, (uint64_t)n, TC_BK, TC_BM))) return rc;
+  if ((rc = encode_map(&tmB, w.tprime_t, (uint64_t)d.zk, (uint64_t)d.wp, TC_BK, WP))) return rc;
+  const int64_t n_tiles = ceil_div(n, TC_BM);
+  const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
+  ProfScope prof(PROF_NODE_GEMM, s);
+  node_gemm_tf32_kernel<WP><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, w.bias_p, n, d.zk, d.w, d.kind == FESR_TEECNET,
+                                                          h_out);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
 int launch_node_gemm_tf32(const fesr_model_dims& d, const Prepared& w, const float* Z, int64_t n, float* h_out,
                           float* pre_out, int x3, cudaStream_t s) {
-  (void)d; (void)w; (void)Z; (void)n; (void)h_out; (void)pre_out; (void)x3; (void)s;
-  set_error("FESR_PREC_TF32 is not built yet");
+  (void)pre_out;
+  if (x3) {
+    set_error("FESR_PREC_TF32X3 is not built yet");
+    return FESR_EINVAL;
+  }
+  if (n == 0) return FESR_OK;
+  switch (d.wp) {
+    case 16: return launch_tc<16>(d, w, Z, n, h_out, s);
+    case 32: return launch_tc<32>(d, w, Z, n, h_out, s);
+    case 48: return launch_tc<48>(d, w, Z, n, h_out, s);
+    case 64: return launch_tc<64>(d, w, Z, n, h_out, s);
+  }
+  set_error("unsupported padded width %d", d.wp);
   return FESR_EINVAL;
 }
 

@@ -17,7 +17,7 @@ int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const float* h
 // zbuild.cu ---------------------------------------------------------------------------
 // Z[i, :] = (1/max(deg,1)) * sum_{e -> i} g_e (x) h[src_e]   ++  h[i]  (root block)
 int launch_zbuild(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted,
-                  const float* g, const float* h, int64_t n, float* Z, cudaStream_t s);
+                  const float* g, const float* h, int64_t n, float* Z, int round_tf32, cudaStream_t s);
 
 // gemm_simt.cu ------------------------------------------------------------------------
 // h_out[n, wp] = epilogue(Z[n, zk] x tprime[zk, wp] + bias)

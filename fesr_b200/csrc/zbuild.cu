@@ -9,17 +9,26 @@
 // bilinear in (g_e, h_src) the sum over a node's incoming edges commutes with W3, so the
 // per-edge work is one outer product and W3 is applied once per NODE by the Z x T' GEMM.
 //
-// One warp owns one destination node.  The node's g rows are contiguous in CSR order
-// (streamed, 128-bit loads); the h[src] rows are gathered with 128-bit loads into a per-warp
-// shared-memory slab; each lane then accumulates a KT x AT register tile of the outer product
-// (lane = 8*q + ag: channel group q of 4, column group ag of 8) in a fixed edge order, so the
-// fp32 result is reproducible run to run.
+// One warp owns one destination node at a time (tasks of ZB_TASK consecutive nodes per warp,
+// persistent CTAs).  The node's g rows are contiguous in CSR order (streamed with 128-bit
+// cp.async.cg); the h[src] rows are gathered with 128-bit cp.async.ca into a per-warp shared
+// memory slab.  Slabs are double buffered: the copies of the next chunk are in flight while the
+// current one is consumed, and the source indices are fetched two chunks ahead.  Each lane
+// accumulates a KT x AT register tile of the outer product (lane = 8*q + ag: channel group q of
+// 4, column group ag of 8) in a fixed edge order, so the fp32 result is reproducible run to run.
 #include "kernels.cuh"
 
 namespace fesr {
 
 constexpr int ZB_WARPS = 8;
 constexpr int ZB_DEGC = 16;   // edges staged per chunk
+constexpr int ZB_TASK = 8;    // consecutive destination nodes per warp task
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 
 template <int AT>
 __device__ __forceinline__ void load_cols(const float* p, float (&v)[AT]) {
@@ -50,116 +59,195 @@ __device__ __forceinline__ void store_cols(float* p, const float (&v)[AT]) {
   }
 }
 
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool l1) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  if (l1)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// A work item = one chunk of <= ZB_DEGC incoming edges of (node k of the warp's task, pass p).
+struct ZbItem {
+  int k, p, c0, eb, ee;
+};
+
 template <int KT, int WP>
 __global__ void __launch_bounds__(ZB_WARPS * 32, 2)
 zbuild_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
               const float* __restrict__ g, const float* __restrict__ h, int64_t n, int passes, int kp,
-              int zk_main, int zk, float* __restrict__ Z) {
+              int zk_main, int zk, int round_tf32, float* __restrict__ Z) {
   constexpr int KTP = (KT + 3) / 4 * 4;
   constexpr int AT = WP / 8;
   constexpr int GROW = 4 * KTP;              // floats of g staged per edge per pass
-  constexpr int SLAB = ZB_DEGC * (GROW + WP);
+  constexpr int BUF = ZB_DEGC * (GROW + WP);
+  constexpr int LPR = WP / 4;                // lanes (float4) per gathered h row
+  constexpr int RPI = 32 / LPR;              // h rows gathered per warp iteration
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* sg = smem + warp * SLAB;            // [DEGC][GROW]
-  float* sh = sg + ZB_DEGC * GROW;           // [DEGC][WP]
+  float* slab = smem + warp * (2 * BUF);     // two buffers: [DEGC][GROW] g rows + [DEGC][WP] h rows
   const int q = lane >> 3, ag = lane & 7;
+  const int hj = lane / LPR, hc = lane % LPR;
+  const bool h_lane = lane < RPI * LPR;
+  const unsigned FULL = 0xffffffffu;
 
+  const int64_t n_tasks = (n + ZB_TASK - 1) / ZB_TASK;
   const int64_t warp_global = (int64_t)blockIdx.x * ZB_WARPS + warp;
   const int64_t warp_stride = (int64_t)gridDim.x * ZB_WARPS;
-  for (int64_t i = warp_global; i < n; i += warp_stride) {
-    const int e_begin = rowptr[i], e_end = rowptr[i + 1];
-    const int deg = e_end - e_begin;
-    const float inv = 1.0f / (float)(deg > 0 ? deg : 1);
-    float* zrow = Z + i * (int64_t)zk;
-    for (int p = 0; p < passes; ++p) {
-      float acc[KT][AT];
-#pragma unroll
-      for (int k = 0; k < KT; ++k)
-#pragma unroll
-        for (int t = 0; t < AT; ++t) acc[k][t] = 0.f;
-      for (int c0 = e_begin; c0 < e_end; c0 += ZB_DEGC) {
-        const int m = min(ZB_DEGC, e_end - c0);
-        // stage g rows (contiguous in CSR order) and gathered h rows, 128-bit
+
+  for (int64_t task = warp_global; task < n_tasks; task += warp_stride) {
+    const int64_t i0 = task * ZB_TASK;
+    const int nn = (int)min((int64_t)ZB_TASK, n - i0);
+    const int rp = (lane <= nn) ? __ldg(rowptr + i0 + lane) : 0;
+
+    auto node_item = [&](int k) {
+      ZbItem it;
+      it.k = k;
+      it.p = 0;
+      it.eb = __shfl_sync(FULL, rp, min(k, ZB_TASK));
+      it.ee = __shfl_sync(FULL, rp, min(k + 1, ZB_TASK));
+      it.c0 = it.eb;
+      return it;
+    };
+    auto advance = [&](ZbItem it) {
+      if (it.k >= nn) return it;
+      it.c0 += ZB_DEGC;
+      if (it.c0 >= it.ee) {
+        it.c0 = it.eb;
+        if (++it.p == passes) return node_item(it.k + 1);
+      }
+      return it;
+    };
+    auto load_src = [&](const ZbItem& it) {
+      const int e = it.c0 + lane;
+      return (it.k < nn && lane < ZB_DEGC && e < it.ee) ? __ldg(src_sorted + e) : 0;
+    };
+    auto issue = [&](const ZbItem& it, int buf, int src_reg) {
+      float* sg = slab + buf * BUF;
+      float* sh = sg + ZB_DEGC * GROW;
+      const int m = min(ZB_DEGC, it.ee - it.c0);
+      if (passes == 1) {                      // rows of the chunk are one contiguous block
+        const float* gsrc = g + (int64_t)it.c0 * GROW;
+        for (int t = lane; t < m * (GROW / 4); t += 32) cp_async16(sg + 4 * t, gsrc + 4 * t, false);
+      } else {
         for (int t = lane; t < m * (GROW / 4); t += 32) {
           const int j = t / (GROW / 4), c = t % (GROW / 4);
-          const float4 v = __ldg(reinterpret_cast<const float4*>(g + (int64_t)(c0 + j) * kp + p * GROW) + c);
-          *reinterpret_cast<float4*>(sg + j * GROW + 4 * c) = v;
+          cp_async16(sg + j * GROW + 4 * c, g + (int64_t)(it.c0 + j) * kp + it.p * GROW + 4 * c, false);
         }
-        for (int t = lane; t < m * (WP / 4); t += 32) {
-          const int j = t / (WP / 4), c = t % (WP / 4);
-          const int s = __ldg(src_sorted + c0 + j);
-          const float4 v = __ldg(reinterpret_cast<const float4*>(h + (int64_t)s * WP) + c);
-          *reinterpret_cast<float4*>(sh + j * WP + 4 * c) = v;
-        }
-        __syncwarp();
-        for (int j = 0; j < m; ++j) {
-          float gq[KTP];
-          load_cols<KTP>(sg + j * GROW + q * KTP, gq);
-          float ha[AT];
-          load_cols<AT>(sh + j * WP + ag * AT, ha);
-#pragma unroll
-          for (int k = 0; k < KT; ++k)
-#pragma unroll
-            for (int t = 0; t < AT; ++t) acc[k][t] = fmaf(gq[k], ha[t], acc[k][t]);
-        }
-        __syncwarp();
       }
-      // channel k = (p*4 + q)*KT + kt  ->  columns [k*WP + ag*AT, +AT)
-#pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        float o[AT];
-#pragma unroll
-        for (int t = 0; t < AT; ++t) o[t] = acc[k][t] * inv;
-        store_cols<AT>(zrow + ((p * 4 + q) * KT + k) * WP + ag * AT, o);
+      for (int j0 = 0; j0 < m; j0 += RPI) {
+        const int j = j0 + hj;
+        const int s = __shfl_sync(FULL, src_reg, j & 31);
+        if (h_lane && j < m) cp_async16(sh + j * WP + 4 * hc, h + (int64_t)s * WP + 4 * hc, true);
       }
+      cp_async_commit();
+    };
+
+    ZbItem cur = node_item(0);
+    int buf = 0;
+    issue(cur, 0, load_src(cur));
+    ZbItem nxt = advance(cur);
+    int src_nxt = load_src(nxt);
+    float acc[KT][AT];
+    while (cur.k < nn) {
+      const bool has_next = nxt.k < nn;
+      if (has_next) issue(nxt, buf ^ 1, src_nxt);
+      const ZbItem nn2 = advance(nxt);
+      const int src_nn2 = load_src(nn2);     // in flight while this item is computed
+      if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncwarp();
+      if (cur.c0 == cur.eb) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+#pragma unroll
+          for (int t = 0; t < AT; ++t) acc[k][t] = 0.f;
+      }
+      const float* sg = slab + buf * BUF;
+      const float* sh = sg + ZB_DEGC * GROW;
+      const int m = min(ZB_DEGC, cur.ee - cur.c0);
+      for (int j = 0; j < m; ++j) {
+        float gq[KTP];
+        load_cols<KTP>(sg + j * GROW + q * KTP, gq);
+        float ha[AT];
+        load_cols<AT>(sh + j * WP + ag * AT, ha);
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+#pragma unroll
+          for (int t = 0; t < AT; ++t) acc[k][t] = fmaf(gq[k], ha[t], acc[k][t]);
+      }
+      if (cur.c0 + ZB_DEGC >= cur.ee) {      // last chunk of (node, pass): scale by 1/deg and store
+        const int deg = cur.ee - cur.eb;
+        const float inv = 1.0f / (float)(deg > 0 ? deg : 1);
+        const int64_t i = i0 + cur.k;
+        float* zrow = Z + i * (int64_t)zk;
+        // channel k = (p*4 + q)*KT + kt  ->  columns [k*WP + ag*AT, +AT)
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          float o[AT];
+#pragma unroll
+          for (int t = 0; t < AT; ++t) o[t] = round_tf32 ? tf32_rna(acc[k][t] * inv) : acc[k][t] * inv;
+          store_cols<AT>(zrow + ((cur.p * 4 + q) * KT + k) * WP + ag * AT, o);
+        }
+        if (cur.p == passes - 1) {           // root block + zero tail
+          for (int c = lane; c < zk - zk_main; c += 32) {
+            const float hv = (c < WP) ? h[i * WP + c] : 0.f;
+            zrow[zk_main + c] = round_tf32 ? tf32_rna(hv) : hv;
+          }
+        }
+      }
+      __syncwarp();
+      cur = nxt;
+      nxt = nn2;
+      src_nxt = src_nn2;
+      buf ^= 1;
     }
-    // root block + zero tail
-    for (int c = lane; c < zk - zk_main; c += 32) zrow[zk_main + c] = (c < WP) ? h[i * WP + c] : 0.f;
   }
 }
 
 template <int KT, int WP>
 static int launch_zb(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
-                     const float* h, int64_t n, float* Z, cudaStream_t s) {
+                     const float* h, int64_t n, float* Z, int rnd, cudaStream_t s) {
   constexpr int KTP = (KT + 3) / 4 * 4;
-  constexpr size_t smem = (size_t)ZB_WARPS * ZB_DEGC * (4 * KTP + WP) * sizeof(float);
+  constexpr size_t smem = (size_t)ZB_WARPS * 2 * ZB_DEGC * (4 * KTP + WP) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     FESR_CUDA(cudaFuncSetAttribute(zbuild_kernel<KT, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int64_t blocks_needed = ceil_div(n, ZB_WARPS);
-  const int64_t cap = (int64_t)num_sms() * 2 * 8;      // a few waves of persistent-ish CTAs
+  const int64_t blocks_needed = ceil_div(ceil_div(n, ZB_TASK), ZB_WARPS);
+  const int64_t cap = (int64_t)num_sms() * 2;          // persistent: 2 resident CTAs per SM
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   ProfScope prof(PROF_ZBUILD, s);
   zbuild_kernel<KT, WP><<<grid, ZB_WARPS * 32, smem, s>>>(rowptr, src_sorted, g, h, n, d.passes, d.kp, d.zk_main,
-                                                         d.zk, Z);
+                                                         d.zk, rnd, Z);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
 
 template <int KT>
 static int dispatch_wp(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
-                       const float* h, int64_t n, float* Z, cudaStream_t s) {
+                       const float* h, int64_t n, float* Z, int rnd, cudaStream_t s) {
   switch (d.wp) {
-    case 16: return launch_zb<KT, 16>(d, rowptr, src_sorted, g, h, n, Z, s);
-    case 32: return launch_zb<KT, 32>(d, rowptr, src_sorted, g, h, n, Z, s);
-    case 48: return launch_zb<KT, 48>(d, rowptr, src_sorted, g, h, n, Z, s);
-    case 64: return launch_zb<KT, 64>(d, rowptr, src_sorted, g, h, n, Z, s);
+    case 16: return launch_zb<KT, 16>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
+    case 32: return launch_zb<KT, 32>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
+    case 48: return launch_zb<KT, 48>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
+    case 64: return launch_zb<KT, 64>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
   }
   set_error("unsupported padded width %d", d.wp);
   return FESR_EINVAL;
 }
 
 int launch_zbuild(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
-                  const float* h, int64_t n, float* Z, cudaStream_t s) {
+                  const float* h, int64_t n, float* Z, int rnd, cudaStream_t s) {
   if (n == 0) return FESR_OK;
   switch (d.kt) {
-    case 4: return dispatch_wp<4>(d, rowptr, src_sorted, g, h, n, Z, s);
-    case 8: return dispatch_wp<8>(d, rowptr, src_sorted, g, h, n, Z, s);
-    case 11: return dispatch_wp<11>(d, rowptr, src_sorted, g, h, n, Z, s);
-    case 13: return dispatch_wp<13>(d, rowptr, src_sorted, g, h, n, Z, s);
+    case 4: return dispatch_wp<4>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
+    case 8: return dispatch_wp<8>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
+    case 11: return dispatch_wp<11>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
+    case 13: return dispatch_wp<13>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
   }
   set_error("unsupported kt %d", d.kt);
   return FESR_EINVAL;

@@ -122,3 +122,35 @@ def test_forward_is_deterministic(golden, shipped):
     a = _run(m, golden["x"], golden["ref_edge_index"], golden["ref_edge_attr"])
     b = _run(m, golden["x"], golden["ref_edge_index"], golden["ref_edge_attr"])
     assert np.array_equal(a, b)
+
+
+# ----------------------------------------------------------------------------- tensor-core path
+@pytest.mark.parametrize("kind", ["neuralop", "teecnet"])
+def test_tf32_tcgen05_path_50k(shipped, kind):
+    """Z x T' on tcgen05 kind::tf32: rel-L2 <= 1e-3 vs the fp32 CPU oracle (north_star tolerance)."""
+    from fesr_b200.dataset.synthetic import make_duct_mesh
+    mesh = make_duct_mesh("50k")
+    src, dst, ea = og.build_edges(mesh.cells, mesh.pos)
+    ei = np.stack([src, dst])
+    m, o = _models(kind, 43, 5)
+    sd = shipped_state_dict(shipped, kind)
+    m.load_state_dict(sd)
+    o.load_state_dict(sd)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        yo = o(torch.from_numpy(mesh.x), torch.from_numpy(ei), torch.from_numpy(ea)).numpy()
+    y = _run(m, mesh.x, ei, ea, precision="tf32")
+    err = rel_l2(y, yo)
+    print(f"tf32 {kind}: rel-L2 {err:.3e}")
+    assert err < TOL["tf32"]
+    y32 = _run(m, mesh.x, ei, ea, precision="fp32")
+    assert rel_l2(y32, yo) < TOL["fp32"]
+
+
+@pytest.mark.parametrize("name,kind,w,L", [("kernelnn_w16", "neuralop", 16, 3), ("teecnet_w12", "teecnet", 12, 2),
+                                           ("kernelnn_w48", "neuralop", 48, 2)])
+def test_tf32_small_widths(golden, name, kind, w, L):
+    m, _ = _models(kind, w, L)
+    m.load_state_dict(state_dict_from(golden, name))
+    y = _run(m, golden["x"], golden["ref_edge_index"], golden["ref_edge_attr"], precision="tf32")
+    assert rel_l2(y, golden[name + "_y"]) < TOL["tf32"]
