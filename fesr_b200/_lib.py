@@ -61,7 +61,7 @@ SIGNATURES = {
                                        _i64, _i64, C.c_int, _vp, _vp, C.POINTER(ParamGrads), _vp, _vp, _sz, _vp]),
     "fesr_mse_loss": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "fesr_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i64, _vp]),
-    "fesr_node_weight": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp]),
+    "fesr_node_weight": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _i64, _f, _vp, _vp, _vp]),
     "fesr_occurrence_workspace_bytes": (_sz, [_i64, _i64]),
     "fesr_occurrence_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "fesr_stitch_mean": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
@@ -73,6 +73,7 @@ SIGNATURES = {
     "fesr_subdomain_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "fesr_subdomain_count": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp]),
     "fesr_subdomain_fill": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "fesr_cluster": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "fesr_route": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
 }
 

@@ -60,8 +60,7 @@ def build(verbose: bool = False) -> str:
             if did:
                 print(f"[fesr build] compiled {os.path.basename(obj)}")
     if rebuilt or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB, *[r[0] for r in results], "-gencode", "arch=compute_100a,code=sm_100a",
-               "-lcuda"]
+        cmd = [NVCC, "-shared", "-o", LIB, *[r[0] for r in results], "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

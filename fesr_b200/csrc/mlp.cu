@@ -224,9 +224,97 @@ edge_hidden_kernel(EdgeHiddenArgs a, const float* __restrict__ edge_attr, const 
   }
 }
 
+// Two-hidden-layer variant (KernelNN: Linear(1,w) act Linear(w,w) act): one thread per edge,
+// activations in registers, W1^T in shared memory read as broadcast 128-bit loads.
+template <int WPAD>
+__global__ void __launch_bounds__(128)
+edge_hidden2_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
+                    const float* __restrict__ b1g, int w, int leaky, int kt, int ktp, int kp, int k1,
+                    const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int64_t E,
+                    float* __restrict__ g) {
+  __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1[WPAD];
+  __shared__ __align__(16) float w1t[WPAD][WPAD];     // [in][out]
+  __shared__ int off_of[WPAD + 1];                    // channel -> offset in the g row
+  extern __shared__ __align__(16) float stage[];      // [4 warps][32 edges][kp + 4]
+  const int sstride = kp + 4;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < WPAD; i += blockDim.x) {
+    w0[i] = i < w ? w0g[i] : 0.f;
+    b0[i] = i < w ? b0g[i] : 0.f;
+    b1[i] = i < w ? b1g[i] : 0.f;
+  }
+  for (int i = tid; i < WPAD * WPAD; i += blockDim.x) {
+    const int in = i / WPAD, out = i % WPAD;
+    w1t[in][out] = (in < w && out < w) ? w1g[out * w + in] : 0.f;
+  }
+  for (int k = tid; k <= WPAD; k += blockDim.x) off_of[k] = (k / kt) * ktp + (k % kt);
+  __syncthreads();
+  const int64_t E32 = (E + 31) / 32 * 32;            // whole warps iterate together
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + tid; e < E32; e += (int64_t)gridDim.x * blockDim.x) {
+    const float d = (e < E) ? edge_attr[perm ? perm[e] : e] : 0.f;
+    float acc[WPAD];
+#pragma unroll
+    for (int o = 0; o < WPAD; ++o) acc[o] = b1[o];
+#pragma unroll 4
+    for (int i = 0; i < WPAD; ++i) {
+      const float a = act_fn(fmaf(d, w0[i], b0[i]), leaky);
+#pragma unroll
+      for (int o4 = 0; o4 < WPAD; o4 += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(&w1t[i][o4]);
+        acc[o4 + 0] = fmaf(a, wv.x, acc[o4 + 0]);
+        acc[o4 + 1] = fmaf(a, wv.y, acc[o4 + 1]);
+        acc[o4 + 2] = fmaf(a, wv.z, acc[o4 + 2]);
+        acc[o4 + 3] = fmaf(a, wv.w, acc[o4 + 3]);
+      }
+    }
+    // stage the row in shared memory, then write the warp's 32 rows with coalesced 128-bit stores
+    float* srow = stage + (size_t)(tid >> 5) * 32 * sstride + (size_t)(tid & 31) * sstride;
+    for (int c = 0; c < kp; c += 4) *reinterpret_cast<float4*>(srow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int o = 0; o < WPAD; ++o)
+      if (o < w) srow[off_of[o]] = act_fn(acc[o], leaky);
+    srow[off_of[k1 - 1]] = 1.f;
+    __syncwarp();
+    const int64_t e_base = e - (tid & 31);
+    const float* wst = stage + (size_t)(tid >> 5) * 32 * sstride;
+    const int q4 = kp >> 2;
+    for (int t = tid & 31; t < 32 * q4; t += 32) {
+      const int r = t / q4, c4 = t - r * q4;
+      if (e_base + r < E)
+        *reinterpret_cast<float4*>(g + (e_base + r) * kp + 4 * c4) = *reinterpret_cast<const float4*>(wst + r * sstride + 4 * c4);
+    }
+    __syncwarp();
+  }
+}
+
 int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
                        const int32_t* perm, int64_t E, float* g, cudaStream_t s) {
   if (E == 0) return FESR_OK;
+  if (d.n_hidden == 2 && d.hidden[0] == d.w && d.hidden[1] == d.w) {
+    FESR_CHECK_ARG(p.mlp_w[0] && p.mlp_b[0] && p.mlp_w[1] && p.mlp_b[1], "NULL edge-MLP parameter");
+    const int64_t blocks = ceil_div(E, 128);
+    const int grid = (int)(blocks < 16 * (int64_t)num_sms() ? blocks : 16 * (int64_t)num_sms());
+    const size_t stage_bytes = (size_t)4 * 32 * (d.kp + 4) * sizeof(float);
+    static bool eh2_attr = false;
+    if (!eh2_attr) {
+      FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      eh2_attr = true;
+    }
+    ProfScope prof(PROF_EDGE_HIDDEN, s);
+#define FESR_EH2(WPAD)                                                                                             \
+  edge_hidden2_kernel<WPAD><<<grid, 128, stage_bytes, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.leaky, d.kt, \
+                                                 d.ktp, d.kp, d.k1, edge_attr, perm, E, g)
+    if (d.w <= 16) FESR_EH2(16);
+    else if (d.w <= 32) FESR_EH2(32);
+    else if (d.w <= 48) FESR_EH2(48);
+    else FESR_EH2(64);
+#undef FESR_EH2
+    FESR_LAUNCH_CHECK();
+    return FESR_OK;
+  }
   EdgeHiddenArgs a;
   memset(&a, 0, sizeof(a));
   size_t fl = 2 * EH_MAXD;

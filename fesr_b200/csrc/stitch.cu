@@ -69,7 +69,7 @@ template <int C>
 __global__ void node_weight_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                            const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
                                            const int32_t* __restrict__ perm, const float* __restrict__ edge_attr,
-                                           int64_t n, float* __restrict__ partial) {
+                                           int64_t n, float clamp_max, float* __restrict__ partial) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float pd[C], yd[C];
@@ -91,7 +91,7 @@ __global__ void node_weight_partial_kernel(const float* __restrict__ pred, const
     }
     acc = __fadd_rn(acc, m);
   }
-  partial[i] = acc;
+  partial[i] = fminf(acc, clamp_max);
 }
 
 // one block per subdomain, fixed-shape tree reduction
@@ -194,8 +194,8 @@ int fesr_stitch_mean(const float* values, int32_t channels, const int32_t* occ_p
 
 int fesr_node_weight(const float* pred, const float* target, int32_t channels, const int32_t* rowptr,
                      const int32_t* src_sorted, const int32_t* perm, const float* edge_attr,
-                     const int32_t* node_ptr, int32_t n_sub, int64_t n, int64_t E, float* out,
-                     float* node_scratch, void* stream_) {
+                     const int32_t* node_ptr, int32_t n_sub, int64_t n, int64_t E, float clamp_max,
+                     float* out, float* node_scratch, void* stream_) {
   FESR_CHECK_ARG(channels == 4, "node weight is built for 4 channels (vx, vy, vz, p)");
   FESR_CHECK_ARG(n_sub >= 1 && n >= 0 && E >= 0, "bad sizes");
   FESR_CHECK_ARG(out && (n == 0 || (pred && target && rowptr && node_scratch)), "NULL pointer");
@@ -205,7 +205,7 @@ int fesr_node_weight(const float* pred, const float* target, int32_t channels, c
   ProfScope prof(PROF_NODE_WEIGHT, s);
   if (n > 0) {
     node_weight_partial_kernel<4><<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(pred, target, rowptr, src_sorted, perm,
-                                                                            edge_attr, n, node_scratch);
+                                                                            edge_attr, n, clamp_max, node_scratch);
     FESR_LAUNCH_CHECK();
   }
   segment_sum_kernel<<<n_sub, 256, 0, s>>>(node_scratch, node_ptr, n, out);

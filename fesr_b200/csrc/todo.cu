@@ -19,9 +19,4 @@ int fesr_nnconv_backward(const fesr_model_dims*, const fesr_params*, const float
   NOT_BUILT("fesr_nnconv_backward");
 }
 
-int fesr_route(const float*, int32_t, const int32_t*, int32_t, int32_t, const double*, const double*, int32_t,
-               const double*, const double*, const double*, int32_t, int32_t*, double*, void*) {
-  NOT_BUILT("fesr_route");
-}
-
 }  // extern "C"

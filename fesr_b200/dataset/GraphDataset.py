@@ -1,0 +1,197 @@
+"""Dataset side of the hot path: subdomain assembly and overlap stitching on the GPU.
+
+Mirrors the interface of the reference's ``AnsysDataset`` (dataset/GraphDataset.py:751-1484) for
+the methods on the path -- ``len``/``get`` (:760-797), ``get_one_full_sample`` (:1464-1484),
+``reconstruct_from_partition`` (:1308-1409) -- on synthetic duct meshes, because the reference's
+ANSYS data is not shipped (README.md:26) and its ingest needs VTK.  The decomposition that the
+reference runs once through vtkRedistributeDataSetFilter and stores in HDF5 (:1183-1306) is a
+GPU pass here (fesr_partition_cells / fesr_build_subdomains), kept resident on the device.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from ..data import Data
+from . import synthetic
+
+
+class SubdomainSample(list):
+    """``list[Data]`` (CPU tensors, what the reference's loader returns) that also carries the
+    device-resident block-diagonal batch, so predict/stitch never go through per-subdomain copies."""
+
+    def __init__(self, datas, batch, x_dev, y_dev, mesh_idx, num_nodes):
+        super().__init__(datas)
+        self.batch = batch
+        self.x_dev = x_dev
+        self.y_dev = y_dev
+        self.mesh_idx = mesh_idx
+        self.num_nodes = num_nodes
+
+
+class StitchedMesh:
+    """Result of reconstruct_from_partition: the appended partitions with averaged point data
+    (what the reference returns as a vtkUnstructuredGrid) plus the field on the original mesh."""
+
+    def __init__(self, pos, cells, field, ref_field, merged, merged_ref, global_ids, count):
+        self.pos, self.cells = pos, cells            # original mesh (numpy)
+        self.field, self.ref_field = field, ref_field  # [N, 4] torch CPU
+        self.merged, self.merged_ref = merged, merged_ref  # [sum n_s, 4] torch CPU
+        self.global_ids = global_ids
+        self.count = count
+        self.point_data = {"velocity": merged[:, :3], "pressure": merged[:, 3],
+                           "ref_velocity": merged_ref[:, :3], "ref_pressure": merged_ref[:, 3]}
+
+    def GetNumberOfPoints(self):
+        return int(self.merged.shape[0])
+
+    def write_vtu(self, path):
+        """ASCII .vtu of the ORIGINAL mesh with the stitched point arrays (run_ALDS_3D.py:33-38)."""
+        pos, cells = np.asarray(self.pos), np.asarray(self.cells)
+        f, r = self.field.numpy(), self.ref_field.numpy()
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        with open(path, "w") as fh:
+            fh.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="0.1" byte_order="LittleEndian">\n')
+            fh.write(f'<UnstructuredGrid><Piece NumberOfPoints="{pos.shape[0]}" NumberOfCells="{cells.shape[0]}">\n')
+            fh.write('<PointData Vectors="velocity" Scalars="pressure">\n')
+            for name, arr, nc in (("velocity", f[:, :3], 3), ("pressure", f[:, 3:4], 1),
+                                  ("ref_velocity", r[:, :3], 3), ("ref_pressure", r[:, 3:4], 1)):
+                fh.write(f'<DataArray type="Float32" Name="{name}" NumberOfComponents="{nc}" format="ascii">\n')
+                np.savetxt(fh, arr, fmt="%.7g")
+                fh.write('</DataArray>\n')
+            fh.write('</PointData>\n<Points><DataArray type="Float32" NumberOfComponents="3" format="ascii">\n')
+            np.savetxt(fh, pos, fmt="%.7g")
+            fh.write('</DataArray></Points>\n<Cells>\n<DataArray type="Int32" Name="connectivity" format="ascii">\n')
+            np.savetxt(fh, cells, fmt="%d")
+            fh.write('</DataArray>\n<DataArray type="Int32" Name="offsets" format="ascii">\n')
+            np.savetxt(fh, np.arange(1, cells.shape[0] + 1) * cells.shape[1], fmt="%d")
+            fh.write('</DataArray>\n<DataArray type="UInt8" Name="types" format="ascii">\n')
+            np.savetxt(fh, np.full(cells.shape[0], 10), fmt="%d")
+            fh.write('</DataArray>\n</Cells>\n</Piece></UnstructuredGrid>\n</VTKFile>\n')
+
+
+class SyntheticDuctDataset:
+    """``num_meshes`` synthetic ducts, each decomposed into 2^levels overlapping subdomains on the GPU.
+
+    kwargs follow the reference's flat exp_config (configs/exp_config/*.yaml): ``partition``,
+    ``sub_size`` (requested number of subdomains; rounded up to a power of two exactly as
+    vtkRedistributeDataSetFilter does), plus ``mesh_n`` (duct cross-section in hexes) and
+    ``num_meshes``; unknown keys are ignored, as in the reference's constructors.
+    """
+
+    def __init__(self, root=None, transform=None, pre_transform=None, partition=True, sub_size=None, mesh_n=13,
+                 num_meshes=4, boundary_mode="all", device=None, **kwargs):
+        self.root = root
+        self.partition = partition
+        self.mesh_n = int(mesh_n)
+        self.num_meshes = int(num_meshes)
+        self.mode = _lib.ALL_INTERSECTING if boundary_mode == "all" else _lib.ONE_REGION
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        probe = synthetic.make_positions(self.mesh_n).shape[0]
+        if sub_size:
+            self.levels = max(0, math.ceil(math.log2(int(sub_size))))
+        else:
+            self.levels = synthetic.default_kd_levels(probe)
+        self.sub_size = 1 << self.levels
+        self._cache = {}
+
+    # -- assembly ---------------------------------------------------------------------------
+    def _mesh(self, idx):
+        if idx >= self.num_meshes or idx < 0:
+            raise IndexError(f"Mesh index {idx} out of range. Maximum index is {self.num_meshes - 1}.")
+        if idx not in self._cache:
+            mesh = synthetic.make_duct_mesh(self.mesh_n, seed=idx)
+            dev = self.device
+            pos = torch.from_numpy(mesh.pos).to(dev)
+            cells = torch.from_numpy(mesh.cells).to(dev)
+            part, batch = ops.assemble(pos, cells, self.levels, self.mode)
+            x_dev = torch.from_numpy(mesh.x).to(dev).index_select(0, batch.global_ids)
+            y_dev = torch.from_numpy(mesh.y).to(dev).index_select(0, batch.global_ids)
+            self._cache[idx] = {"mesh": mesh, "pos": pos, "part": part, "batch": batch, "x": x_dev, "y": y_dev,
+                                "occ": ops.occurrence_build(batch.global_ids, mesh.num_nodes)}
+        return self._cache[idx]
+
+    def len(self):
+        return self.num_meshes * self.sub_size
+
+    __len__ = len
+
+    def _datas(self, c):
+        b = c["batch"]
+        node_ptr = b.node_ptr.cpu().numpy()
+        edge_ptr = b.edge_ptr.cpu().numpy()
+        x, y = c["x"].cpu(), c["y"].cpu()
+        gids = b.global_ids.cpu()
+        pos = torch.from_numpy(c["mesh"].pos)[gids]
+        src, dst = b.edge_src.cpu().long(), b.edge_dst.cpu().long()
+        ea = b.edge_attr.cpu()
+        out = []
+        for s in range(b.n_sub):
+            nl, nh, el, eh = node_ptr[s], node_ptr[s + 1], edge_ptr[s], edge_ptr[s + 1]
+            out.append(Data(x=x[nl:nh], y=y[nl:nh], pos=pos[nl:nh],
+                            edge_index=torch.stack([src[el:eh] - nl, dst[el:eh] - nl]),
+                            edge_attr=ea[el:eh].unsqueeze(1), global_node_ids=gids[nl:nh]))
+        return out
+
+    def get(self, idx):
+        mesh_idx, sub_idx = divmod(int(idx), self.sub_size)
+        c = self._mesh(mesh_idx)
+        if "datas" not in c:
+            c["datas"] = self._datas(c)
+        return c["datas"][sub_idx]
+
+    __getitem__ = get
+
+    def get_one_full_sample(self, idx):
+        """All subdomains of mesh ``idx`` (reference :1464-1484), with the device batch attached."""
+        c = self._mesh(idx)
+        if "datas" not in c:
+            c["datas"] = self._datas(c)
+        return SubdomainSample(c["datas"], c["batch"], c["x"], c["y"], idx, c["mesh"].num_nodes)
+
+    # -- stitch -----------------------------------------------------------------------------
+    def reconstruct_from_partition(self, subdomain_data_list, subdomain_ref_list, subdomain_idx, model_idx=None,
+                                   weights_list=None):
+        """Mean over all subdomain copies of every mesh node (reference :1308-1409).  Accepts the
+        5-argument call of run_ALDS_3D.py:26 (model_idx / weights are carried but, as in the
+        reference, not used by the averaging)."""
+        c = self._mesh(subdomain_idx)
+        b = c["batch"]
+        dev = self.device
+
+        def to_dev(lst):
+            dev_t = getattr(lst, "dev", None)
+            if dev_t is not None:
+                return dev_t
+            t = torch.cat([torch.as_tensor(v, dtype=torch.float32) for v in lst], dim=0)
+            if t.shape[0] != b.n_tot:
+                raise ValueError(f"expected {b.n_tot} rows over all subdomains, got {t.shape[0]}")
+            return t.to(dev)
+
+        pred, ref = to_dev(subdomain_data_list), to_dev(subdomain_ref_list)
+        field, count, merged = ops.stitch_mean(pred, c["occ"], b.global_ids, want_merged=True)
+        rfield, _, rmerged = ops.stitch_mean(ref, c["occ"], b.global_ids, want_merged=True)
+        return StitchedMesh(c["mesh"].pos, c["mesh"].cells, field.cpu(), rfield.cpu(), merged.cpu(), rmerged.cpu(),
+                            b.global_ids.cpu(), count.cpu())
+
+
+class AnsysDataset(SyntheticDuctDataset):
+    """The reference's AnsysDataset reads proprietary Fluent data through VTK and HDF5; neither
+    the data nor those libraries exist here, so this name resolves to the synthetic duct with the
+    Ansys boundary mode (AssignToAllIntersectingRegions, reference :1219)."""
+
+    def __init__(self, root=None, **kwargs):
+        kwargs.setdefault("boundary_mode", "all")
+        super().__init__(root, **kwargs)
+
+
+class DuctAnalysisDataset(SyntheticDuctDataset):
+    """Synthetic duct with the Duct boundary mode (AssignToOneRegion, reference :565)."""
+
+    def __init__(self, root=None, **kwargs):
+        kwargs.setdefault("boundary_mode", "one")
+        super().__init__(root, **kwargs)

@@ -1,0 +1,239 @@
+"""GNNPartitionScheduler / GradientbasedLoss with the reference's interface
+(models/scheduler_gnn.py:23-514), executing on one B200 per process.
+
+What changes against the reference:
+  * predict() runs ALL subdomains of the rank's shard as one block-diagonal batch (the
+    reference loops subdomains one at a time with two PCIe copies each, :217-226, :328-340);
+  * multi-GPU is one process per GPU (torchrun): contiguous edge-balanced shards and ONE NCCL
+    all-gather of the predictions, instead of mp.Process + Manager().dict() pickling (:254-291);
+  * every cluster gets its own model copy (the reference appends the same module object for
+    every cluster, :42-51, so its clusters alias the last checkpoint);
+  * train() is the DDP branch of the reference (:349-469: MSELoss, Adam, StepLR stepped on
+    validation epochs) with the gradient all-reduce issued on one flat buffer.
+"""
+from __future__ import annotations
+
+import copy
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+from ..dataset.GraphDataset import SubdomainSample
+
+
+class TensorList(list):
+    """list of per-subdomain CPU tensors that remembers the device-resident concatenation."""
+    dev = None
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+class GradientbasedLoss(nn.Module):
+    """models/scheduler_gnn.py:472-514, on the device."""
+
+    def __init__(self, max_weight=1.0):
+        super().__init__()
+        self.max_weight = max_weight
+
+    @staticmethod
+    def _csr(edge_index, n):
+        return edge_index if isinstance(edge_index, ops.Csr) else ops.csr_build(edge_index, n)
+
+    def forward(self, pred, data, edge_index, edge_attr):
+        csr = self._csr(edge_index, pred.shape[0])
+        s = ops.node_weight(pred, data, csr, edge_attr, None, clamp_max=float(self.max_weight))
+        loss, _ = ops.mse_loss(pred, data, want_grad=False)
+        return (loss * s).squeeze(0)
+
+    def compute_node_weight(self, pred, data, edge_index, edge_attr, num_nodes):
+        csr = self._csr(edge_index, num_nodes)
+        s = ops.node_weight(pred, data, csr, edge_attr, None)
+        return s.expand(num_nodes).contiguous()
+
+
+def _as_batch(x, device):
+    """list[Data] -> (csr, edge_attr, node_ptr, x_dev, y_dev, sizes) as one block-diagonal graph."""
+    if isinstance(x, SubdomainSample):
+        b = x.batch
+        sizes = np.diff(b.node_ptr.cpu().numpy()).tolist()
+        return b.csr, b.edge_attr, b.node_ptr, x.x_dev, x.y_dev, sizes
+    sizes = [int(d.x.shape[0]) for d in x]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    xs = torch.cat([d.x for d in x]).to(device, dtype=torch.float32)
+    ys = torch.cat([d.y for d in x]).to(device, dtype=torch.float32)
+    ei = torch.cat([d.edge_index.to(torch.int64) + int(o) for d, o in zip(x, offs[:-1])], dim=1).to(device)
+    ea = torch.cat([d.edge_attr.reshape(-1) for d in x]).to(device, dtype=torch.float32)
+    csr = ops.csr_build(ei, int(offs[-1]))
+    node_ptr = torch.from_numpy(offs.astype(np.int32)).to(device)
+    return csr, ea, node_ptr, xs, ys, sizes
+
+
+def select_subdomains(csr, edge_attr, node_ptr, keep_sub):
+    """Block-diagonal sub-batch of the subdomains flagged in keep_sub [S] (device bool)."""
+    dev = node_ptr.device
+    S = node_ptr.numel() - 1
+    sizes = (node_ptr[1:] - node_ptr[:-1]).long()
+    sub_of_node = torch.repeat_interleave(torch.arange(S, device=dev), sizes)
+    node_keep = keep_sub[sub_of_node]
+    new_index = torch.cumsum(node_keep.to(torch.int64), 0) - 1
+    deg = (csr.rowptr[1:] - csr.rowptr[:-1]).long()
+    if csr.perm is not None:
+        edge_attr = edge_attr.reshape(-1)[csr.perm.long()]
+    dst = torch.repeat_interleave(torch.arange(csr.n, device=dev), deg)
+    edge_keep = node_keep[dst]
+    src_new = new_index[csr.src.long()[edge_keep]].to(torch.int32)
+    rowptr_new = torch.zeros(int(node_keep.sum()) + 1, dtype=torch.int32, device=dev)
+    rowptr_new[1:] = torch.cumsum(deg[node_keep], 0).to(torch.int32)
+    node_ptr_new = torch.zeros(int(keep_sub.sum()) + 1, dtype=torch.int32, device=dev)
+    node_ptr_new[1:] = torch.cumsum(sizes[keep_sub], 0).to(torch.int32)
+    sub = ops.Csr(rowptr_new, src_new.contiguous(), None, int(rowptr_new.numel() - 1), int(src_new.numel()))
+    return sub, edge_attr.reshape(-1)[edge_keep].contiguous(), node_ptr_new, node_keep
+
+
+class GNNPartitionScheduler():
+    def __init__(self, exp_name, num_partitons, dataset, model=None, train=True, encoder=None, classifier=None):
+        self.name = exp_name
+        self.num_partitions = num_partitons
+        if num_partitons != 1:
+            self.encoder = encoder
+            self.classifier = classifier
+        self.model = model
+        self.dataset = dataset
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.subsets = self._train_partitions(num_partitons, train)
+        if not train:
+            self.models = self._load_models()
+
+    def get_sub_dataset(self):
+        return self.subsets
+
+    def _model_dir(self):
+        return 'logs/models/collection_{}'.format(self.name)
+
+    def _initialize_model(self):
+        return copy.deepcopy(self.model)
+
+    def _load_models(self):
+        models = []
+        for i in range(self.num_partitions):
+            model = self._initialize_model()
+            path = os.path.join(self._model_dir(), 'partition_{}.pth'.format(i))
+            model.load_state_dict(torch.load(path, map_location=torch.device('cpu'), weights_only=True))
+            models.append(model.to(self.device).eval())
+        return models
+
+    def _train_partitions(self, num_partitions, train):
+        if num_partitions == 1:
+            return [self.dataset]
+        path = self._model_dir()
+        if train:
+            os.makedirs(path, exist_ok=True)
+            self.encoder.train(self.dataset, save_model=True, path=path)
+            latent_space = self.encoder.get_latent_space(self.dataset)
+            self.classifier.train(latent_space, save_model=True, path=path)
+            labels = self.classifier.cluster(latent_space)
+        else:
+            self.encoder.load_model(path)
+            self.classifier.load_model(path)
+            latent_space = self.encoder.get_latent_space(self.dataset)
+            labels = self.classifier.cluster(latent_space)
+        subsets = []
+        for i in range(num_partitions):
+            idx = np.where(np.asarray(labels) == i)[0]
+            print(f'Partition {i}: {len(idx)} samples')
+            subsets.append([self.dataset[int(j)] for j in idx])
+        return subsets
+
+    # ----------------------------------------------------------------------------- predict
+    def _route(self, x_dev, node_ptr):
+        if self.num_partitions == 1:
+            return torch.zeros(node_ptr.numel() - 1, dtype=torch.int32, device=x_dev.device)
+        pca = self.encoder.model
+        km, sc = self.classifier.model, self.classifier.scaler
+        labels, _ = ops.route(x_dev, node_ptr, pca.mean_, pca.components_, sc.mean_, sc.scale_, km.cluster_centers_,
+                              rows=self.encoder.min_length)
+        return labels
+
+    @torch.no_grad()
+    def predict(self, x):
+        """-> (pred_y_list, ref_y_list, model_idx, weights_list), as models/scheduler_gnn.py:228,311."""
+        if not hasattr(self, 'models'):
+            raise ValueError('Models are not trained yet')
+        dev = self.device
+        csr, edge_attr, node_ptr, x_dev, y_dev, sizes = _as_batch(x, dev)
+        S = len(sizes)
+        dist, rank, world = _dist()
+        labels = self._route(x_dev, node_ptr)
+
+        # this rank's contiguous, edge-balanced share of the subdomain list
+        if world > 1:
+            from ..pipeline import shard_bounds
+            node_ptr_h = node_ptr.cpu().numpy().astype(np.int64)
+            edge_cum = csr.rowptr[node_ptr.long()].cpu().numpy().astype(np.int64)
+            bounds = shard_bounds(edge_cum, world)
+            mine = torch.zeros(S, dtype=torch.bool, device=dev)
+            mine[bounds[rank]:bounds[rank + 1]] = True
+        else:
+            mine = torch.ones(S, dtype=torch.bool, device=dev)
+
+        pred = torch.zeros(csr.n, self.models[0].dims.out_ch, dtype=torch.float32, device=dev)
+        weight_s = torch.zeros(S, dtype=torch.float32, device=dev)
+        for i in range(self.num_partitions):
+            keep = (labels == i) & mine
+            if not bool(keep.any()):
+                continue
+            model = self.models[i]
+            if bool(keep.all()):
+                sub, ea, nptr, node_keep = csr, edge_attr, node_ptr, None
+                xi, yi = x_dev, y_dev
+            else:
+                sub, ea, nptr, node_keep = select_subdomains(csr, edge_attr, node_ptr, keep)
+                xi, yi = x_dev[node_keep], y_dev[node_keep]
+            pi = model(xi, sub, ea)
+            wi = ops.node_weight(pi, yi, sub, ea, nptr)
+            if node_keep is None:
+                pred, weight_s = pi, wi
+            else:
+                pred[node_keep] = pi
+                weight_s[keep] = wi
+        if world > 1:
+            # predictions of the other ranks: one all-gather(v) in rank = subdomain order
+            rows = [int(node_ptr_h[bounds[r + 1]] - node_ptr_h[bounds[r]]) for r in range(world)]
+            lo = int(node_ptr_h[bounds[rank]])
+            full = torch.empty_like(pred)
+            dist.all_gather(list(full.split(rows, dim=0)), pred[lo:lo + rows[rank]].contiguous())
+            pred = full
+            wfull = torch.empty_like(weight_s)
+            cnt = [bounds[r + 1] - bounds[r] for r in range(world)]
+            dist.all_gather(list(wfull.split(cnt)), weight_s[bounds[rank]:bounds[rank + 1]].contiguous())
+            weight_s = wfull
+
+        pred_cpu = pred.cpu()
+        pred_y_list = TensorList(torch.split(pred_cpu, sizes))
+        pred_y_list.dev = pred
+        if isinstance(x, SubdomainSample):
+            ref_y_list = TensorList([d.y for d in x])
+        else:
+            ref_y_list = TensorList([d.y for d in x])
+        ref_y_list.dev = y_dev
+        w_cpu = weight_s.cpu()
+        weights_list = [w_cpu[s].expand(sizes[s]) for s in range(S)]
+        model_idx = labels.cpu().numpy().astype(int)
+        return pred_y_list, ref_y_list, model_idx, weights_list
+
+    # ----------------------------------------------------------------------------- train
+    def train(self, train_config, subset_idx=None, start_from_pretrained=False):
+        from .training import train_subsets
+        subsets = self.subsets if subset_idx is None else [self.subsets[i] for i in subset_idx]
+        models = self._load_models() if start_from_pretrained else None
+        trained = train_subsets(self, subsets, train_config, models)
+        self.models = trained
+        return trained

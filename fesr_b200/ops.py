@@ -143,7 +143,7 @@ def nnconv_forward(dims: ModelDims, tensors: dict, x: torch.Tensor, csr: Csr, ed
 
 
 # ---------------------------------------------------------------------------------- node weight
-def node_weight(pred, target, csr: Csr, edge_attr, node_ptr=None):
+def node_weight(pred, target, csr: Csr, edge_attr, node_ptr=None, clamp_max=float('inf')):
     """Per-subdomain scalar of GradientbasedLoss.compute_node_weight -> [S] fp32."""
     dev = _require_cuda(pred, target, edge_attr)
     pred, target = _f32c(pred), _f32c(target)
@@ -154,7 +154,7 @@ def node_weight(pred, target, csr: Csr, edge_attr, node_ptr=None):
     with torch.cuda.device(dev):
         check(_lib.load().fesr_node_weight(_ptr(pred), _ptr(target), pred.shape[1], _ptr(csr.rowptr), _ptr(csr.src),
                                            _ptr(csr.perm), _ptr(edge_attr), _ptr(node_ptr), n_sub, csr.n, csr.E,
-                                           _ptr(out), _ptr(scratch), _stream(dev)), "fesr_node_weight")
+                                           clamp_max, _ptr(out), _ptr(scratch), _stream(dev)), "fesr_node_weight")
     return out
 
 
@@ -317,3 +317,46 @@ def assemble(pos, cells, levels: int, mode: int = _lib.ALL_INTERSECTING):
     """partition_cells + build_subdomains: the GPU replacement of get_partition_domain."""
     part = partition_cells(pos, cells, levels, mode)
     return part, build_subdomains(pos, cells, part.leaf_ptr, part.leaf_cells)
+
+
+# ---------------------------------------------------------------------------------- ALDS routing
+def _f64(a, dev):
+    return torch.as_tensor(a, dtype=torch.float64).contiguous().to(dev)
+
+
+def route(x, node_ptr, pca_mean, pca_components, scaler_mean=None, scaler_scale=None, centroids=None, rows=280):
+    """PCA latent of the first `rows` nodes of every subdomain (+ k-means label when a classifier
+    is given).  Returns (labels int32 [S] | None, latent fp64 [S, n_comp])."""
+    dev = _require_cuda(x, node_ptr)
+    x = _f32c(x)
+    S = int(node_ptr.numel() - 1)
+    comps = _f64(pca_components, dev)
+    n_comp = int(comps.shape[0])
+    mean = _f64(pca_mean, dev)
+    if mean.numel() != rows * x.shape[1] or comps.shape[1] != rows * x.shape[1]:
+        raise FesrError(f"PCA was fitted on {mean.numel()} features, expected rows*channels = {rows * x.shape[1]}")
+    latent = torch.empty(S, n_comp, dtype=torch.float64, device=dev)
+    labels = None
+    sm = ss = cc = None
+    k = 0
+    if centroids is not None:
+        sm, ss, cc = _f64(scaler_mean, dev), _f64(scaler_scale, dev), _f64(centroids, dev)
+        k = int(cc.shape[0])
+        labels = torch.empty(S, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().fesr_route(_ptr(x), int(x.shape[1]), _ptr(node_ptr), S, rows, _ptr(mean), _ptr(comps), n_comp,
+                                     _ptr(sm), _ptr(ss), _ptr(cc), k, _ptr(labels), _ptr(latent), _stream(dev)),
+              "fesr_route")
+    return labels, latent
+
+
+def cluster(latent, scaler_mean, scaler_scale, centroids):
+    dev = _require_cuda(latent)
+    latent = latent.to(torch.float64).contiguous()
+    S, n_comp = int(latent.shape[0]), int(latent.shape[1])
+    sm, ss, cc = _f64(scaler_mean, dev), _f64(scaler_scale, dev), _f64(centroids, dev)
+    labels = torch.empty(S, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().fesr_cluster(_ptr(latent), S, n_comp, _ptr(sm), _ptr(ss), _ptr(cc), int(cc.shape[0]),
+                                       _ptr(labels), _stream(dev)), "fesr_cluster")
+    return labels

@@ -179,11 +179,13 @@ int fesr_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
  *   node_ptr     : [S+1] int32 node range of every subdomain (NULL: one subdomain = all n nodes)
  *   out          : [S] fp32 (the reference broadcasts it to [n_s]; the host wrapper does that)
  *   node_scratch : [n] fp32 scratch (per-destination partial sums; reduced in a fixed order)
+ *   clamp_max    : per-node clamp applied before the sum (GradientbasedLoss.forward, :491-495,
+ *                  which scatters by destination); pass +INFINITY for compute_node_weight
  * ---------------------------------------------------------------------------------- */
 int fesr_node_weight(const float* pred, const float* target, int32_t channels,
                      const int32_t* rowptr, const int32_t* src_sorted, const int32_t* perm,
                      const float* edge_attr, const int32_t* node_ptr, int32_t n_sub,
-                     int64_t n, int64_t E, float* out, float* node_scratch, void* stream);
+                     int64_t n, int64_t E, float clamp_max, float* out, float* node_scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Overlap stitch.  Replaces AnsysDataset.reconstruct_from_partition's averaging loop
@@ -255,6 +257,11 @@ int fesr_route(const float* x, int32_t channels, const int32_t* node_ptr, int32_
                const double* scaler_mean, const double* scaler_scale,
                const double* centroids, int32_t n_clusters,
                int32_t* labels, double* latent, void* stream);
+
+/* KMeansClassifier.cluster alone (models/classifier.py:48-50) on a latent array [S, n_comp] fp64. */
+int fesr_cluster(const double* latent, int32_t n_sub, int32_t n_comp, const double* scaler_mean,
+                 const double* scaler_scale, const double* centroids, int32_t n_clusters,
+                 int32_t* labels, void* stream);
 
 #ifdef __cplusplus
 }

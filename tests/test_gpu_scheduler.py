@@ -1,0 +1,134 @@
+"""GPU: scheduler.predict + reconstruct_from_partition (the reference-facing API) vs the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2, shipped_state_dict
+from oracle import graph as og
+from oracle import models as om
+from oracle import routing as orr
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(tmp_path, n_clusters, shipped, monkeypatch):
+    from fesr_b200.dataset.GraphDataset import AnsysDataset
+    from fesr_b200.models.model import KernelNN
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("logs/models/collection_t", exist_ok=True)
+    sd = shipped_state_dict(shipped, "neuralop")
+    sds = []
+    for i in range(n_clusters):
+        s = {k: v.clone() for k, v in sd.items()}
+        s["fc2.bias"] = s["fc2.bias"] + 0.1 * i          # make the per-cluster models distinguishable
+        torch.save(s, f"logs/models/collection_t/partition_{i}.pth")
+        sds.append(s)
+    ds = AnsysDataset(mesh_n=12, num_meshes=2, sub_size=16)
+    model = KernelNN(43, 43, 5, in_width=4, out_width=4)
+    return ds, model, sds
+
+
+def _oracle_predict(ds, idx, sds, labels):
+    c = ds._mesh(idx)
+    mesh = c["mesh"]
+    part = og.kd_partition(mesh.pos, mesh.cells, ds.levels)
+    sub = og.build_subdomains(mesh.pos, mesh.cells, part["leaf_ptr"], part["leaf_cells"])
+    preds = []
+    models = []
+    for sd in sds:
+        o = om.make_model("neuralop", 43, 5)
+        o.load_state_dict(sd)
+        models.append(o)
+    ws = []
+    with torch.no_grad():
+        for s in range(sub["node_ptr"].size - 1):
+            nl, nh = sub["node_ptr"][s], sub["node_ptr"][s + 1]
+            el, eh = sub["edge_ptr"][s], sub["edge_ptr"][s + 1]
+            ei = torch.from_numpy(np.stack([sub["edge_src"][el:eh] - nl, sub["edge_dst"][el:eh] - nl]))
+            ea = torch.from_numpy(sub["edge_attr"][el:eh]).unsqueeze(1)
+            g = sub["global_ids"][nl:nh]
+            p = models[labels[s]](torch.from_numpy(mesh.x[g]), ei, ea)
+            ws.append(float(om.edge_weight(p.double(), torch.from_numpy(mesh.y[g]).double(), ei, ea.double()).sum()))
+            preds.append(p.numpy())
+    field, count, merged = og.stitch_mean(np.concatenate(preds), sub["global_ids"], mesh.num_nodes)
+    return sub, preds, field, merged, ws
+
+
+def test_predict_and_stitch_single_cluster(tmp_path, shipped, monkeypatch):
+    from fesr_b200.models.scheduler_gnn import GNNPartitionScheduler
+    ds, model, sds = _setup(tmp_path, 1, shipped, monkeypatch)
+    sched = GNNPartitionScheduler("t", 1, ds, model, train=False)
+    x = ds.get_one_full_sample(1)
+    pred_y_list, ref_y_list, model_idx, weights_list = sched.predict(x)
+    assert len(pred_y_list) == len(x) == 16 and model_idx.shape == (16,)
+    sub, preds, field, merged, ws = _oracle_predict(ds, 1, sds, np.zeros(16, dtype=int))
+    for s in range(16):
+        assert pred_y_list[s].shape == preds[s].shape
+        assert rel_l2(pred_y_list[s].numpy(), preds[s]) < 1e-5
+        assert weights_list[s].shape == (preds[s].shape[0],)
+        assert abs(float(weights_list[s][0]) - ws[s]) <= 1e-4 * max(1.0, abs(ws[s]))
+    out = ds.reconstruct_from_partition(pred_y_list, ref_y_list, 1, model_idx, weights_list)   # 5-arg call
+    assert rel_l2(out.field.numpy(), field) < 1e-5
+    assert rel_l2(out.merged.numpy(), merged) < 1e-5
+    assert rel_l2(out.ref_field.numpy(), ds._mesh(1)["mesh"].y) < 1e-6
+    # generic path: plain list of Data without the attached device batch gives the same numbers
+    p2, _, _, _ = sched.predict(list(x))
+    assert rel_l2(torch.cat(list(p2)).numpy(), torch.cat(list(pred_y_list)).numpy()) < 1e-6
+    out.write_vtu("logs/vtk/t/pred_1.vtu")
+    assert os.path.getsize("logs/vtk/t/pred_1.vtu") > 1000
+
+
+def test_alds_routing_and_per_cluster_models(tmp_path, shipped, monkeypatch):
+    from fesr_b200.models.classifier import KMeansClassifier
+    from fesr_b200.models.encoder import PCAEncoder
+    from fesr_b200.models.scheduler_gnn import GNNPartitionScheduler
+    ds, model, sds = _setup(tmp_path, 3, shipped, monkeypatch)
+    enc, clf = PCAEncoder(n_components=2), KMeansClassifier(n_clusters=3)
+    x = ds.get_one_full_sample(0)
+    enc.train(list(x), save_model=True, path="logs/models/collection_t")
+    latent = enc.get_latent_space(x)
+    clf.train(latent, save_model=True, path="logs/models/collection_t")
+    # oracle routing from the same fitted sklearn objects
+    feat = orr.routing_features([d.x.numpy() for d in x])
+    labels_ref, latent_ref = orr.route(feat, enc.model.mean_, enc.model.components_, clf.scaler.mean_,
+                                       clf.scaler.scale_, clf.model.cluster_centers_)
+    assert rel_l2(latent, latent_ref) < 1e-6
+    assert np.array_equal(clf.cluster(latent), labels_ref)
+    assert len(set(labels_ref.tolist())) == 3
+    sched = GNNPartitionScheduler("t", 3, ds, model, train=False, encoder=enc, classifier=clf)
+    pred_y_list, ref_y_list, model_idx, weights_list = sched.predict(x)
+    assert np.array_equal(model_idx, labels_ref)
+    sub, preds, field, merged, ws = _oracle_predict(ds, 0, sds, labels_ref)
+    for s in range(16):
+        assert rel_l2(pred_y_list[s].numpy(), preds[s]) < 1e-5
+    out = ds.reconstruct_from_partition(pred_y_list, ref_y_list, 0, model_idx, weights_list)
+    assert rel_l2(out.field.numpy(), field) < 1e-5
+
+
+def test_routing_vs_reference_sklearn_vectors(golden):
+    """fesr_route vs the latent / labels the reference's PCAEncoder + KMeansClassifier produced."""
+    from fesr_b200 import ops
+    from fesr_b200.dataset.synthetic import make_duct_mesh
+    mesh = make_duct_mesh(int(golden["route_mesh_n"]))
+    part, batch = ops.assemble(torch.from_numpy(mesh.pos).cuda(), torch.from_numpy(mesh.cells).cuda(),
+                               int(golden["route_levels"]))
+    x_dev = torch.from_numpy(mesh.x).cuda()[batch.global_ids]
+    labels, latent = ops.route(x_dev, batch.node_ptr, golden["route_pca_mean"], golden["route_pca_components"],
+                               golden["route_scaler_mean"], golden["route_scaler_scale"], golden["route_centroids"])
+    assert rel_l2(latent.cpu().numpy(), golden["route_latent"]) < 1e-5
+    assert np.array_equal(labels.cpu().numpy(), golden["route_labels"])
+
+
+def test_gradient_loss_forward(golden):
+    from fesr_b200.models.scheduler_gnn import GradientbasedLoss
+    pred = torch.from_numpy(golden["kernelnn_w43_y"]).cuda()
+    y = torch.from_numpy(golden["y"]).cuda()
+    ei = torch.from_numpy(golden["ref_edge_index"]).cuda()
+    ea = torch.from_numpy(golden["ref_edge_attr"]).cuda()
+    for mw, key in ((1.0, "gradient_loss"), (4.0, "gradient_loss_mw4")):
+        v = float(GradientbasedLoss(max_weight=mw)(pred, y, ei, ea))
+        assert abs(v - float(golden[key])) <= 2e-5 * abs(float(golden[key])) + 1e-9
+    nw = GradientbasedLoss().compute_node_weight(pred, y, ei, ea, y.shape[0])
+    assert nw.shape == (y.shape[0],)
