@@ -1,0 +1,350 @@
+// fesr_nnconv_backward: gradients of one block-diagonal batch through KernelNN / TEECNet.
+//
+// Mirrors the forward factorisation (zbuild.cu / gemm_*.cu).  Per layer l (last to first), with
+// dpre = dL/d(pre-activation of layer l):
+//   dT'    += Z_l^T dpre                         (reduction over nodes, split-K, fixed order)
+//   dZ      = dpre T'^T                          -> dg += edge_grad(dZ, h_l)     (forward CSR)
+//   Z~      = sum_{e: src=j} g_e (x) dpre[dst_e]/deg[dst_e]  ++ dpre[j]          (zbuild on the
+//             REVERSED CSR: the same gather/segmented-sum kernel as the forward)
+//   dh_l    = Z~ T~                              (the same node GEMM as the forward, fp32 or
+//             tcgen05 tf32, with every wp x wp block of T' transposed)
+// then the edge-MLP hidden layers, fc1 / fc2.  Replaces loss.backward() of the reference's train
+// step (models/scheduler_gnn.py:407) -- where autograd materialises the [E, w*w] edge matrices
+// and their gradients -- for the same parameters, named as in the state_dict.
+#include "backward.cuh"
+#include "workspace.cuh"
+
+namespace fesr {
+
+// ------------------------------------------------------------------------------- small kernels
+__global__ void inv_deg_kernel(const int32_t* __restrict__ rowptr, int64_t n, float* __restrict__ inv) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int deg = rowptr[i + 1] - rowptr[i];
+  inv[i] = 1.0f / (float)(deg > 0 ? deg : 1);
+}
+
+// dpre = dh * act'(h_next) on the first w columns, 0 on the padding (and on TEECNet's constant column)
+__global__ void mask_kernel(const float* __restrict__ dh, const float* __restrict__ h_next, int64_t n, int wp, int w,
+                            int relu, float* __restrict__ dpre) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n * wp) return;
+  const int c = (int)(idx % wp);
+  float v = 0.f;
+  if (c < w) {
+    v = dh[idx];
+    if (relu && !(h_next[idx] > 0.f)) v = 0.f;
+  }
+  dpre[idx] = v;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ index, int64_t rows,
+                                   int row_f4, float* __restrict__ dst) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= rows * row_f4) return;
+  const int64_t r = idx / row_f4;
+  const int c = (int)(idx % row_f4);
+  reinterpret_cast<float4*>(dst)[idx] = reinterpret_cast<const float4*>(src)[(int64_t)index[r] * row_f4 + c];
+}
+
+__global__ void gather_scalar_kernel(const float* __restrict__ src, const int32_t* __restrict__ index, int64_t m,
+                                     float* __restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < m) dst[i] = src[index ? index[i] : i];
+}
+
+__global__ void add_first_cols_kernel(const float* __restrict__ srcv, int w, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < w) dst[i] += srcv[i];
+}
+
+// dT' [zk, wp] -> gradients of the last edge-MLP layer, kernel.linear and root
+__global__ void scatter_tgrad_kernelnn(fesr_model_dims d, const float* __restrict__ dT, float* __restrict__ gw_last,
+                                       float* __restrict__ gb_last, float* __restrict__ groot) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int w = d.w, K = d.k1 - 1;
+  const int64_t total = (int64_t)(d.k1 + 1) * w * w;     // k in [0,k1): mlp ; k == k1: root
+  if (idx >= total) return;
+  const int k = (int)(idx / (w * w)), a = (int)((idx / w) % w), b = (int)(idx % w);
+  if (k < K) gw_last[(size_t)(a * w + b) * K + k] += dT[(size_t)(k * d.wp + a) * d.wp + b];
+  else if (k == K) gb_last[a * w + b] += dT[(size_t)(K * d.wp + a) * d.wp + b];
+  else groot[a * w + b] += dT[(size_t)(d.zk_main + a) * d.wp + b];
+}
+
+// TEECNet: T''[k,a,b] = sum_a' Laug[a',a] T0[k,a',b]  =>
+//   dT0[k,a',b] = sum_a Laug[a',a] dT''[k,a,b] ; dLaug[a',a] = sum_{k,b} T0[k,a',b] dT''[k,a,b]
+__global__ void scatter_tgrad_teecnet_t0(fesr_model_dims d, const float* __restrict__ dT, const float* __restrict__ lin_w,
+                                         const float* __restrict__ lin_b, float* __restrict__ gw_last,
+                                         float* __restrict__ gb_last, float* __restrict__ groot) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int w = d.w, K = d.k1 - 1;
+  const int64_t total = (int64_t)(d.k1 + 1) * w * w;
+  if (idx >= total) return;
+  const int k = (int)(idx / (w * w)), ap = (int)((idx / w) % w), b = (int)(idx % w);
+  if (k > K) {
+    groot[ap * w + b] += dT[(size_t)(d.zk_main + ap) * d.wp + b];
+    return;
+  }
+  float acc = 0.f;
+  for (int a = 0; a <= w; ++a) {
+    const float l = (a < w) ? lin_w[ap * w + a] : lin_b[ap];
+    acc = fmaf(l, dT[(size_t)(k * d.wp + a) * d.wp + b], acc);
+  }
+  if (k < K) gw_last[(size_t)(ap * w + b) * K + k] += acc;
+  else gb_last[ap * w + b] += acc;
+}
+
+__global__ void scatter_tgrad_teecnet_lin(fesr_model_dims d, const float* __restrict__ dT,
+                                          const float* __restrict__ w_last, const float* __restrict__ b_last,
+                                          float* __restrict__ glin_w, float* __restrict__ glin_b) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = d.w, K = d.k1 - 1;
+  if (idx >= w * (w + 1)) return;
+  const int ap = idx / (w + 1), a = idx % (w + 1);
+  float acc = 0.f;
+  for (int k = 0; k <= K; ++k)
+    for (int b = 0; b < w; ++b) {
+      const float t0 = (k < K) ? w_last[(size_t)(ap * w + b) * K + k] : b_last[ap * w + b];
+      acc = fmaf(t0, dT[(size_t)(k * d.wp + a) * d.wp + b], acc);
+    }
+  if (a < w) glin_w[ap * w + a] += acc;
+  else glin_b[ap] += acc;
+}
+
+// ---- edge MLP hidden layers (recomputed with stored activations for the backward)
+__device__ __forceinline__ float act_f(float v, int leaky) { return leaky ? (v > 0.f ? v : 0.01f * v) : fmaxf(v, 0.f); }
+__device__ __forceinline__ float act_grad(float a, int leaky) { return a > 0.f ? 1.f : (leaky ? 0.01f : 0.f); }
+
+__global__ void mlp_layer0_kernel(const float* __restrict__ dattr, const float* __restrict__ w0,
+                                  const float* __restrict__ b0, int64_t E, int D, int leaky, float* __restrict__ a0) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= E * D) return;
+  const int o = (int)(idx % D);
+  a0[idx] = act_f(fmaf(dattr[idx / D], w0[o], b0[o]), leaky);
+}
+
+__global__ void bias_act_kernel(float* __restrict__ a, const float* __restrict__ b, int64_t E, int D, int leaky) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= E * D) return;
+  a[idx] = act_f(a[idx] + b[idx % D], leaky);
+}
+
+// da_last[e, k] = dg[e, off(k)] * act'(a_last[e, k])   (un-permute the padded g layout)
+__global__ void dg_to_dpre_kernel(const float* __restrict__ dg, const float* __restrict__ a_last, int64_t E, int K,
+                                  int kt, int ktp, int kp, int leaky, float* __restrict__ dpre) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= E * K) return;
+  const int64_t e = idx / K;
+  const int k = (int)(idx % K);
+  const int off = (k / kt) * ktp + (k % kt);
+  dpre[idx] = dg[e * kp + off] * act_grad(a_last[idx], leaky);
+}
+
+__global__ void act_grad_kernel(float* __restrict__ da, const float* __restrict__ a, int64_t count, int leaky) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx < count) da[idx] *= act_grad(a[idx], leaky);
+}
+
+// ------------------------------------------------------------------------------- workspace
+struct BackwardWs {
+  float* dh[2];
+  float* dpre;
+  float* BZ;
+  float* g_rev;
+  float* dg;
+  float* dT;
+  float* inv_deg;
+  float* dbias;
+  float* dattr;
+  float* act[4];
+  float* da[2];
+  float* gemm_ws;
+  size_t gemm_ws_bytes;
+  float* colsum_ws;
+  size_t bytes;
+};
+
+static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n, int64_t E) {
+  Carver c(base);
+  BackwardWs w;
+  const size_t nn = (size_t)(n > 0 ? n : 1), ee = (size_t)(E > 0 ? E : 1);
+  w.dh[0] = c.take<float>(nn * d.wp);
+  w.dh[1] = c.take<float>(nn * d.wp);
+  w.dpre = c.take<float>(nn * d.wp);
+  w.BZ = c.take<float>(nn * d.zk);
+  w.g_rev = c.take<float>(ee * d.kp);
+  w.dg = c.take<float>(ee * d.kp);
+  w.dT = c.take<float>((size_t)d.zk * d.wp);
+  w.inv_deg = c.take<float>(nn);
+  w.dbias = c.take<float>(d.wp);
+  w.dattr = c.take<float>(ee);
+  int dmax = 1;
+  for (int l = 0; l < d.n_hidden; ++l) {
+    w.act[l] = c.take<float>(ee * d.hidden[l]);
+    if (d.hidden[l] > dmax) dmax = d.hidden[l];
+  }
+  w.da[0] = c.take<float>(ee * dmax);
+  w.da[1] = c.take<float>(ee * dmax);
+  size_t g = gemm_ws_bytes(d.zk, d.wp, n);
+  for (int l = 0; l < d.n_hidden; ++l) {
+    const size_t b = gemm_ws_bytes(d.hidden[l], l > 0 ? d.hidden[l - 1] : 1, E);
+    if (b > g) g = b;
+  }
+  size_t b2 = gemm_ws_bytes(d.out_ch, d.w, n);
+  if (b2 > g) g = b2;
+  b2 = gemm_ws_bytes(d.w, d.in_ch, n);
+  if (b2 > g) g = b2;
+  w.gemm_ws_bytes = g + 256;
+  w.gemm_ws = c.take<float>(w.gemm_ws_bytes / sizeof(float));
+  w.colsum_ws = c.take<float>(colsum_ws_bytes(256) / sizeof(float));
+  w.bytes = c.used();
+  return w;
+}
+
+}  // namespace fesr
+
+using namespace fesr;
+
+extern "C" {
+
+size_t fesr_backward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E) {
+  if (!dims || n < 0 || E < 0) return 0;
+  return carve_backward(nullptr, *dims, n, E).bytes;
+}
+
+int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params, const float* x,
+                         const int32_t* rowptr, const int32_t* src_sorted, const int32_t* perm,
+                         const int32_t* rowptr_t, const int32_t* src_t, const int32_t* rev_to_fwd,
+                         const float* edge_attr, int64_t n, int64_t E, int precision, const float* grad_y,
+                         const void* forward_workspace, fesr_param_grads* grads, float* grad_x, void* workspace,
+                         size_t workspace_bytes, void* stream_) {
+  FESR_CHECK_ARG(dims && params && grads, "dims/params/grads NULL");
+  FESR_CHECK_ARG(n >= 0 && E >= 0 && n < (1ll << 31) && E < (1ll << 31), "n/E out of range");
+  FESR_CHECK_ARG(precision == FESR_PREC_FP32 || precision == FESR_PREC_TF32, "unsupported precision %d", precision);
+  if (n == 0) return FESR_OK;
+  FESR_CHECK_ARG(x && grad_y && rowptr && forward_workspace, "NULL pointer");
+  FESR_CHECK_ARG(E == 0 || (src_sorted && rowptr_t && src_t && rev_to_fwd && edge_attr), "NULL edge arrays");
+  const fesr_model_dims& d = *dims;
+  const fesr_params& p = *params;
+  ForwardWs fw = carve_forward(const_cast<void*>(forward_workspace), d, n, E, 1);
+  BackwardWs w = carve_backward(workspace, d, n, E);
+  if (!workspace || workspace_bytes < w.bytes) {
+    set_error("backward workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);
+    return FESR_EWORKSPACE;
+  }
+  cudaStream_t s = as_stream(stream_);
+  ProfScope prof(PROF_BACKWARD, s);
+  const int T = 256;
+  const int L = d.layers;
+  const int relu = d.kind == FESR_KERNELNN;
+  const int rnd = precision != FESR_PREC_FP32;
+  int rc;
+#define GEMM(...)                                                     \
+  do {                                                                \
+    GemmArgs ga__ = {__VA_ARGS__};                                    \
+    if ((rc = launch_gemm(ga__, w.gemm_ws, w.gemm_ws_bytes, s))) return rc; \
+  } while (0)
+
+  inv_deg_kernel<<<(unsigned)ceil_div(n, T), T, 0, s>>>(rowptr, n, w.inv_deg);
+  FESR_LAUNCH_CHECK();
+  FESR_CUDA(cudaMemsetAsync(w.dT, 0, (size_t)d.zk * d.wp * sizeof(float), s));
+  FESR_CUDA(cudaMemsetAsync(w.dbias, 0, (size_t)d.wp * sizeof(float), s));
+  if (E > 0) {
+    FESR_CUDA(cudaMemsetAsync(w.dg, 0, (size_t)E * d.kp * sizeof(float), s));
+    gather_rows_kernel<<<(unsigned)ceil_div(E * (d.kp / 4), T), T, 0, s>>>(fw.g, rev_to_fwd, E, d.kp / 4, w.g_rev);
+    FESR_LAUNCH_CHECK();
+  }
+
+  // ---- fc2 / fc_out:  y = h_L W2^T + b2
+  const float* hL = fw.h[L];
+  GEMM(grad_y, 1, d.out_ch, hL, d.wp, 1, grads->fc2_w, d.w, 1, d.out_ch, d.w, n, 1);
+  if ((rc = launch_colsum(grad_y, n, d.out_ch, d.out_ch, 1, grads->fc2_b, w.colsum_ws, s))) return rc;
+  FESR_CUDA(cudaMemsetAsync(w.dh[0], 0, (size_t)n * d.wp * sizeof(float), s));
+  GEMM(grad_y, d.out_ch, 1, p.fc2_w, d.w, 1, w.dh[0], d.wp, 1, n, d.w, d.out_ch, 0);
+
+  int cur = 0;
+  for (int l = L - 1; l >= 0; --l) {
+    mask_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dh[cur], fw.h[l + 1], n, d.wp, d.w, relu, w.dpre);
+    FESR_LAUNCH_CHECK();
+    if ((rc = launch_colsum(w.dpre, n, d.wp, d.wp, 1, w.dbias, w.colsum_ws, s))) return rc;
+    // dT' += Z_l^T dpre
+    GEMM(fw.Z[l], 1, d.zk, w.dpre, d.wp, 1, w.dT, d.wp, 1, d.zk, d.wp, n, 1);
+    if (E > 0) {
+      // dZ = dpre T'^T ; dg += edge_grad(dZ, h_l)
+      GEMM(w.dpre, d.wp, 1, fw.prep.tprime, 1, d.wp, w.BZ, d.zk, 1, n, d.zk, d.wp, 0);
+      if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, 1, w.dg, s))) return rc;
+    }
+    // dh_l = [sum over out-edges of g (x) dpre[dst]/deg[dst]  ++  dpre] T~
+    if ((rc = launch_zbuild(d, rowptr_t, src_t, w.g_rev, w.dpre, n, w.BZ, rnd, s, /*mean=*/0, w.inv_deg))) return rc;
+    if (precision == FESR_PREC_FP32)
+      rc = launch_node_gemm_fp32(d, fw.prep.ttilde, nullptr, EPI_NONE, w.BZ, n, w.dh[cur ^ 1], s);
+    else
+      rc = launch_node_gemm_tf32(d, fw.prep.ttilde_t, nullptr, EPI_NONE, w.BZ, n, w.dh[cur ^ 1], s);
+    if (rc) return rc;
+    cur ^= 1;
+  }
+
+  // ---- conv bias / root / last edge-MLP layer / kernel.linear from dT'
+  add_first_cols_kernel<<<1, 64, 0, s>>>(w.dbias, d.w, grads->bias);
+  FESR_LAUNCH_CHECK();
+  {
+    const int last = d.n_hidden;
+    const int64_t total = (int64_t)(d.k1 + 1) * d.w * d.w;
+    if (d.kind == FESR_KERNELNN) {
+      scatter_tgrad_kernelnn<<<(unsigned)ceil_div(total, T), T, 0, s>>>(d, w.dT, grads->mlp_w[last],
+                                                                       grads->mlp_b[last], grads->root);
+      FESR_LAUNCH_CHECK();
+    } else {
+      scatter_tgrad_teecnet_t0<<<(unsigned)ceil_div(total, T), T, 0, s>>>(d, w.dT, p.lin_w, p.lin_b,
+                                                                         grads->mlp_w[last], grads->mlp_b[last],
+                                                                         grads->root);
+      FESR_LAUNCH_CHECK();
+      scatter_tgrad_teecnet_lin<<<(unsigned)ceil_div(d.w * (d.w + 1), 64), 64, 0, s>>>(
+          d, w.dT, p.mlp_w[last], p.mlp_b[last], grads->lin_w, grads->lin_b);
+      FESR_LAUNCH_CHECK();
+    }
+  }
+
+  // ---- fc1:  h_0 = x W1^T + b1
+  const float* dh0 = w.dh[cur];
+  GEMM(dh0, 1, d.wp, x, d.in_ch, 1, grads->fc1_w, d.in_ch, 1, d.w, d.in_ch, n, 1);
+  if ((rc = launch_colsum(dh0, n, d.w, d.wp, 1, grads->fc1_b, w.colsum_ws, s))) return rc;
+  if (grad_x) GEMM(dh0, d.wp, 1, p.fc1_w, d.in_ch, 1, grad_x, d.in_ch, 1, n, d.in_ch, d.w, 0);
+
+  // ---- edge MLP hidden layers
+  if (E > 0) {
+    const int nh = d.n_hidden, leaky = d.leaky;
+    gather_scalar_kernel<<<(unsigned)ceil_div(E, T), T, 0, s>>>(edge_attr, perm, E, w.dattr);
+    FESR_LAUNCH_CHECK();
+    mlp_layer0_kernel<<<(unsigned)ceil_div(E * d.hidden[0], T), T, 0, s>>>(w.dattr, p.mlp_w[0], p.mlp_b[0], E,
+                                                                         d.hidden[0], leaky, w.act[0]);
+    FESR_LAUNCH_CHECK();
+    for (int l = 1; l < nh; ++l) {
+      const int din = d.hidden[l - 1], dout = d.hidden[l];
+      GEMM(w.act[l - 1], din, 1, p.mlp_w[l], 1, din, w.act[l], dout, 1, E, dout, din, 0);
+      bias_act_kernel<<<(unsigned)ceil_div(E * dout, T), T, 0, s>>>(w.act[l], p.mlp_b[l], E, dout, leaky);
+      FESR_LAUNCH_CHECK();
+    }
+    const int K = d.hidden[nh - 1];
+    dg_to_dpre_kernel<<<(unsigned)ceil_div(E * K, T), T, 0, s>>>(w.dg, w.act[nh - 1], E, K, d.kt, d.ktp, d.kp, leaky,
+                                                                w.da[0]);
+    FESR_LAUNCH_CHECK();
+    int dc = 0;
+    for (int l = nh - 1; l >= 0; --l) {
+      const int dout = d.hidden[l], din = l > 0 ? d.hidden[l - 1] : 1;
+      const float* prev = l > 0 ? w.act[l - 1] : w.dattr;
+      GEMM(w.da[dc], 1, dout, prev, din, 1, grads->mlp_w[l], din, 1, dout, din, E, 1);
+      if ((rc = launch_colsum(w.da[dc], E, dout, dout, 1, grads->mlp_b[l], w.colsum_ws, s))) return rc;
+      if (l > 0) {
+        GEMM(w.da[dc], dout, 1, p.mlp_w[l], din, 1, w.da[dc ^ 1], din, 1, E, din, dout, 0);
+        act_grad_kernel<<<(unsigned)ceil_div(E * din, T), T, 0, s>>>(w.da[dc ^ 1], w.act[l - 1], E * (int64_t)din, leaky);
+        FESR_LAUNCH_CHECK();
+        dc ^= 1;
+      }
+    }
+  }
+#undef GEMM
+  return FESR_OK;
+}
+
+}  // extern "C"

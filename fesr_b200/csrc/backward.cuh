@@ -1,0 +1,30 @@
+// Helpers shared by the backward translation units.
+#pragma once
+#include "kernels.cuh"
+
+namespace fesr {
+
+struct GemmArgs {
+  const float* A;
+  int64_t sAm, sAk;
+  const float* B;
+  int64_t sBk, sBn;
+  float* C;
+  int64_t sCm, sCn;
+  int64_t M, N, K;
+  int accumulate;
+};
+
+size_t gemm_ws_bytes(int64_t M, int64_t N, int64_t K);
+int launch_gemm(const GemmArgs& a, float* ws, size_t ws_bytes, cudaStream_t s);
+
+constexpr int COLSUM_BLOCKS = 512;
+size_t colsum_ws_bytes(int cols);
+int launch_colsum(const float* X, int64_t rows, int cols, int64_t ld, int accumulate, float* out, float* ws,
+                  cudaStream_t s);
+
+// dg[e, :] (+)= inv_deg[dst_e] * sum_a h[src_e, a] * dZ[dst_e, k, a]      (forward CSR order)
+int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* dZ,
+                     const float* h, int64_t n, int accumulate, float* dg, cudaStream_t s);
+
+}  // namespace fesr

@@ -74,6 +74,8 @@ struct Prepared {
   float* tprime;     // [zk, wp]  row-major: T'[(k,a), b], root rows appended
   float* tprime_t;   // [wp, zk]  K-major copy for the tensor-core path (tf32-rounded hi part)
   float* tprime_t_lo;// [wp, zk]  lo part for TF32X3
+  float* ttilde;     // [zk, wp]  T~[(k,b), a] = T'[(k,a), b] (every wp x wp block transposed) -- backward
+  float* ttilde_t;   // [wp, zk]  K-major tf32 copy of T~
   float* bias_p;     // [wp]
   float* fc1_wp;     // [in_ch, wp] transposed + padded
   float* fc1_bp;     // [wp] (TEECNet: constant-1 column set here)

@@ -1,0 +1,150 @@
+// Generic strided fp32 GEMM with deterministic split-K, used by the backward pass for the
+// reductions over nodes / edges (weight gradients) and the thin input-gradient products.
+//   C[M,N] (+)= A[M,K] * B[K,N]       element (i,j) of X at X[i*sXrow + j*sXcol]
+#include "backward.cuh"
+
+namespace fesr {
+
+constexpr int GG_BM = 64, GG_BN = 64, GG_BK = 16, GG_THREADS = 256;
+
+__global__ void __launch_bounds__(GG_THREADS)
+gemm_generic_kernel(GemmArgs a, int64_t kchunk, float* __restrict__ partial) {
+  __shared__ __align__(16) float As[GG_BK][GG_BM + 4];
+  __shared__ __align__(16) float Bs[GG_BK][GG_BN + 4];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * GG_BM, n0 = (int64_t)blockIdx.y * GG_BN;
+  const int64_t kb = (int64_t)blockIdx.z * kchunk;
+  const int64_t ke = min(a.K, kb + kchunk);
+  const int tm = (tid >> 4) * 4, tn = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_m_fast = a.sAm == 1, b_n_fast = a.sBn == 1;
+  for (int64_t k0 = kb; k0 < ke; k0 += GG_BK) {
+#pragma unroll
+    for (int it = 0; it < (GG_BM * GG_BK) / GG_THREADS; ++it) {
+      const int idx = tid + it * GG_THREADS;
+      const int mm = a_m_fast ? (idx % GG_BM) : (idx / GG_BK);
+      const int kk = a_m_fast ? (idx / GG_BM) : (idx % GG_BK);
+      const int64_t gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < a.M && gk < ke) ? a.A[gm * a.sAm + gk * a.sAk] : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < (GG_BN * GG_BK) / GG_THREADS; ++it) {
+      const int idx = tid + it * GG_THREADS;
+      const int nn = b_n_fast ? (idx % GG_BN) : (idx / GG_BK);
+      const int kk = b_n_fast ? (idx / GG_BN) : (idx % GG_BK);
+      const int64_t gn = n0 + nn, gk = k0 + kk;
+      Bs[kk][nn] = (gn < a.N && gk < ke) ? a.B[gk * a.sBk + gn * a.sBn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GG_BK; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][tm]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tn]);
+      const float ar[4] = {av.x, av.y, av.z, av.w};
+      const float br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t gm = m0 + tm + i;
+    if (gm >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t gn = n0 + tn + j;
+      if (gn >= a.N) continue;
+      if (partial) {
+        partial[((int64_t)blockIdx.z * a.M + gm) * a.N + gn] = acc[i][j];
+      } else {
+        float* c = a.C + gm * a.sCm + gn * a.sCn;
+        *c = a.accumulate ? *c + acc[i][j] : acc[i][j];
+      }
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int ks, GemmArgs a) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= a.M * a.N) return;
+  float s = 0.f;
+  for (int z = 0; z < ks; ++z) s += partial[(int64_t)z * a.M * a.N + idx];   // fixed order
+  const int64_t m = idx / a.N, n = idx % a.N;
+  float* c = a.C + m * a.sCm + n * a.sCn;
+  *c = a.accumulate ? *c + s : s;
+}
+
+int gemm_pick_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = ceil_div(M, GG_BM) * ceil_div(N, GG_BN);
+  int64_t want = (4 * (int64_t)num_sms() + tiles - 1) / tiles;
+  const int64_t maxk = ceil_div(K, 8 * GG_BK);
+  if (want > maxk) want = maxk;
+  if (want > 256) want = 256;
+  return (int)(want < 1 ? 1 : want);
+}
+
+size_t gemm_ws_bytes(int64_t M, int64_t N, int64_t K) {
+  const int ks = gemm_pick_splits(M, N, K);
+  return ks > 1 ? (size_t)ks * M * N * sizeof(float) : 0;
+}
+
+int launch_gemm(const GemmArgs& a, float* ws, size_t ws_bytes, cudaStream_t s) {
+  if (a.M == 0 || a.N == 0) return FESR_OK;
+  int ks = gemm_pick_splits(a.M, a.N, a.K);
+  if (ks > 1 && (!ws || ws_bytes < (size_t)ks * a.M * a.N * sizeof(float))) ks = 1;
+  int64_t kchunk = ceil_div(ceil_div(a.K, ks), GG_BK) * GG_BK;
+  if (kchunk == 0) kchunk = GG_BK;
+  ks = (int)ceil_div(a.K > 0 ? a.K : 1, kchunk);
+  dim3 grid((unsigned)ceil_div(a.M, GG_BM), (unsigned)ceil_div(a.N, GG_BN), (unsigned)ks);
+  gemm_generic_kernel<<<grid, GG_THREADS, 0, s>>>(a, kchunk, ks > 1 ? ws : nullptr);
+  FESR_LAUNCH_CHECK();
+  if (ks > 1) {
+    splitk_reduce_kernel<<<(unsigned)ceil_div(a.M * a.N, 256), 256, 0, s>>>(ws, ks, a);
+    FESR_LAUNCH_CHECK();
+  }
+  return FESR_OK;
+}
+
+// out[j] (+)= sum_i X[i*ld + j], j < cols; deterministic two-stage (rows split over blocks)
+__global__ void colsum_partial_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld, int64_t rchunk,
+                                      float* __restrict__ partial) {
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  const int64_t r0 = (int64_t)blockIdx.x * rchunk, r1 = min(rows, r0 + rchunk);
+  float s = 0.f;
+  for (int64_t i = r0; i < r1; ++i) s += X[i * ld + j];
+  partial[(int64_t)blockIdx.x * cols + j] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, int cols, int accumulate,
+                                    float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += partial[(int64_t)b * cols + j];
+  out[j] = accumulate ? out[j] + s : s;
+}
+
+size_t colsum_ws_bytes(int cols) { return (size_t)COLSUM_BLOCKS * cols * sizeof(float); }
+
+int launch_colsum(const float* X, int64_t rows, int cols, int64_t ld, int accumulate, float* out, float* ws,
+                  cudaStream_t s) {
+  if (cols == 0) return FESR_OK;
+  int nb = (int)(rows < COLSUM_BLOCKS ? (rows > 0 ? rows : 1) : COLSUM_BLOCKS);
+  const int64_t rchunk = ceil_div(rows > 0 ? rows : 1, nb);
+  nb = (int)ceil_div(rows > 0 ? rows : 1, rchunk);
+  dim3 grid(nb, (unsigned)ceil_div(cols, 64));
+  colsum_partial_kernel<<<grid, 64, 0, s>>>(X, rows, cols, ld, rchunk, ws);
+  FESR_LAUNCH_CHECK();
+  colsum_final_kernel<<<(unsigned)ceil_div(cols, 64), 64, 0, s>>>(ws, nb, cols, accumulate, out);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
+}  // namespace fesr

@@ -13,7 +13,7 @@ constexpr int SG_THREADS = 256;
 template <int WP>
 __global__ void __launch_bounds__(SG_THREADS, 2)
 node_gemm_fp32_kernel(const float* __restrict__ Z, const float* __restrict__ tprime, const float* __restrict__ bias_p,
-                      int64_t n, int zk, int w, int teecnet, float* __restrict__ h_out) {
+                      int64_t n, int zk, int w, int epi, float* __restrict__ h_out) {
   constexpr int TN = WP / 8;
   __shared__ __align__(16) float As[SG_BK][SG_BM + 4];
   __shared__ __align__(16) float Bs[SG_BK][WP];
@@ -70,11 +70,15 @@ node_gemm_fp32_kernel(const float* __restrict__ Z, const float* __restrict__ tpr
 #pragma unroll
     for (int y = 0; y < TN; y += 2) {
       const int c = cg * TN + y;
-      float v0 = acc[x][y] + bias_p[c], v1 = acc[x][y + 1] + bias_p[c + 1];
-      if (teecnet) {               // no activation between layers (models/model.py:280-282); keep h[:, w] = 1
+      float v0 = acc[x][y], v1 = acc[x][y + 1];
+      if (epi != EPI_NONE) {
+        v0 += bias_p[c];
+        v1 += bias_p[c + 1];
+      }
+      if (epi == EPI_BIAS_CONST1) {  // no activation between layers (models/model.py:280-282); keep h[:, w] = 1
         if (c == w) v0 = 1.f;
         if (c + 1 == w) v1 = 1.f;
-      } else {                     // F.relu(conv1(...))   models/model.py:559
+      } else if (epi == EPI_BIAS_RELU) {  // F.relu(conv1(...))   models/model.py:559
         v0 = fmaxf(v0, 0.f);
         v1 = fmaxf(v1, 0.f);
       }
@@ -83,18 +87,16 @@ node_gemm_fp32_kernel(const float* __restrict__ Z, const float* __restrict__ tpr
   }
 }
 
-int launch_node_gemm_fp32(const fesr_model_dims& d, const Prepared& w, const float* Z, int64_t n, float* h_out,
-                          float* pre_out, cudaStream_t s) {
-  (void)pre_out;
+int launch_node_gemm_fp32(const fesr_model_dims& d, const float* B, const float* bias_p, int epi, const float* Z,
+                          int64_t n, float* h_out, cudaStream_t s) {
   if (n == 0) return FESR_OK;
   const unsigned grid = (unsigned)ceil_div(n, SG_BM);
-  const int tee = d.kind == FESR_TEECNET;
   ProfScope prof(PROF_NODE_GEMM, s);
   switch (d.wp) {
-    case 16: node_gemm_fp32_kernel<16><<<grid, SG_THREADS, 0, s>>>(Z, w.tprime, w.bias_p, n, d.zk, d.w, tee, h_out); break;
-    case 32: node_gemm_fp32_kernel<32><<<grid, SG_THREADS, 0, s>>>(Z, w.tprime, w.bias_p, n, d.zk, d.w, tee, h_out); break;
-    case 48: node_gemm_fp32_kernel<48><<<grid, SG_THREADS, 0, s>>>(Z, w.tprime, w.bias_p, n, d.zk, d.w, tee, h_out); break;
-    case 64: node_gemm_fp32_kernel<64><<<grid, SG_THREADS, 0, s>>>(Z, w.tprime, w.bias_p, n, d.zk, d.w, tee, h_out); break;
+    case 16: node_gemm_fp32_kernel<16><<<grid, SG_THREADS, 0, s>>>(Z, B, bias_p, n, d.zk, d.w, epi, h_out); break;
+    case 32: node_gemm_fp32_kernel<32><<<grid, SG_THREADS, 0, s>>>(Z, B, bias_p, n, d.zk, d.w, epi, h_out); break;
+    case 48: node_gemm_fp32_kernel<48><<<grid, SG_THREADS, 0, s>>>(Z, B, bias_p, n, d.zk, d.w, epi, h_out); break;
+    case 64: node_gemm_fp32_kernel<64><<<grid, SG_THREADS, 0, s>>>(Z, B, bias_p, n, d.zk, d.w, epi, h_out); break;
     default: set_error("unsupported padded width %d", d.wp); return FESR_EINVAL;
   }
   FESR_LAUNCH_CHECK();

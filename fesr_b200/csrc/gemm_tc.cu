@@ -103,7 +103,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
 template <int WP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const float* __restrict__ bias_p, int64_t n, int zk, int w, int teecnet,
+                      const float* __restrict__ bias_p, int64_t n, int zk, int w, int epi,
                       float* __restrict__ h_out) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
   constexpr uint32_t B_BYTES = WP * TC_BK * 4;      // wp * 128 B
@@ -221,10 +221,11 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const int c = c0 + j + t;
-              float x = __uint_as_float(r[j + t]) + bias_p[c];
-              if (teecnet) {
+              float x = __uint_as_float(r[j + t]);
+              if (epi != EPI_NONE) x += bias_p[c];
+              if (epi == EPI_BIAS_CONST1) {
                 if (c == w) x = 1.f;
-              } else {
+              } else if (epi == EPI_BIAS_RELU) {
                 x = fmaxf(x, 0.f);
               }
               v[t] = x;
@@ -279,7 +280,8 @@ static int encode_map(CUtensorMap* map, const float* base, uint64_t inner, uint6
 }
 
 template <int WP>
-static int launch_tc(const fesr_model_dims& d, const Prepared& w, const float* Z, int64_t n, float* h_out, cudaStream_t s) {
+static int launch_tc(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi, const float* Z,
+                     int64_t n, float* h_out, cudaStream_t s) {
   constexpr size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 4 + WP * TC_BK * 4) + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
@@ -289,29 +291,23 @@ static int launch_tc(const fesr_model_dims& d, const Prepared& w, const float* Z
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = encode_map(&tmA, Z, (uint64_t)d.zk, (uint64_t)n, TC_BK, TC_BM))) return rc;
-  if ((rc = encode_map(&tmB, w.tprime_t, (uint64_t)d.zk, (uint64_t)d.wp, TC_BK, WP))) return rc;
+  if ((rc = encode_map(&tmB, B_kmajor, (uint64_t)d.zk, (uint64_t)d.wp, TC_BK, WP))) return rc;
   const int64_t n_tiles = ceil_div(n, TC_BM);
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   ProfScope prof(PROF_NODE_GEMM, s);
-  node_gemm_tf32_kernel<WP><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, w.bias_p, n, d.zk, d.w, d.kind == FESR_TEECNET,
-                                                          h_out);
+  node_gemm_tf32_kernel<WP><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, bias_p, n, d.zk, d.w, epi, h_out);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
 
-int launch_node_gemm_tf32(const fesr_model_dims& d, const Prepared& w, const float* Z, int64_t n, float* h_out,
-                          float* pre_out, int x3, cudaStream_t s) {
-  (void)pre_out;
-  if (x3) {
-    set_error("FESR_PREC_TF32X3 is not built yet");
-    return FESR_EINVAL;
-  }
+int launch_node_gemm_tf32(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi, const float* Z,
+                          int64_t n, float* h_out, cudaStream_t s) {
   if (n == 0) return FESR_OK;
   switch (d.wp) {
-    case 16: return launch_tc<16>(d, w, Z, n, h_out, s);
-    case 32: return launch_tc<32>(d, w, Z, n, h_out, s);
-    case 48: return launch_tc<48>(d, w, Z, n, h_out, s);
-    case 64: return launch_tc<64>(d, w, Z, n, h_out, s);
+    case 16: return launch_tc<16>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
+    case 32: return launch_tc<32>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
+    case 48: return launch_tc<48>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
+    case 64: return launch_tc<64>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
   }
   set_error("unsupported padded width %d", d.wp);
   return FESR_EINVAL;

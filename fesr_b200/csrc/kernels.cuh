@@ -17,15 +17,20 @@ int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const float* h
 // zbuild.cu ---------------------------------------------------------------------------
 // Z[i, :] = (1/max(deg,1)) * sum_{e -> i} g_e (x) h[src_e]   ++  h[i]  (root block)
 int launch_zbuild(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted,
-                  const float* g, const float* h, int64_t n, float* Z, int round_tf32, cudaStream_t s);
+                  const float* g, const float* h, int64_t n, float* Z, int round_tf32, cudaStream_t s,
+                  int mean = 1, const float* gather_scale = nullptr);
 
 // gemm_simt.cu ------------------------------------------------------------------------
 // h_out[n, wp] = epilogue(Z[n, zk] x tprime[zk, wp] + bias)
-int launch_node_gemm_fp32(const fesr_model_dims& d, const Prepared& w, const float* Z, int64_t n,
-                          float* h_out, float* pre_out, cudaStream_t s);
+// epilogue modes
+enum { EPI_BIAS_RELU = 0, EPI_BIAS_CONST1 = 1, EPI_NONE = 2 };
+// B_rowmajor: [zk, wp]
+int launch_node_gemm_fp32(const fesr_model_dims& d, const float* B_rowmajor, const float* bias_p, int epi,
+                          const float* Z, int64_t n, float* h_out, cudaStream_t s);
 
 // gemm_tc.cu --------------------------------------------------------------------------
-int launch_node_gemm_tf32(const fesr_model_dims& d, const Prepared& w, const float* Z, int64_t n,
-                          float* h_out, float* pre_out, int x3, cudaStream_t s);
+// B_kmajor: [wp, zk] tf32-rounded
+int launch_node_gemm_tf32(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi,
+                          const float* Z, int64_t n, float* h_out, cudaStream_t s);
 
 }  // namespace fesr

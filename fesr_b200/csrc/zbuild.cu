@@ -79,11 +79,12 @@ template <int KT, int WP>
 __global__ void __launch_bounds__(ZB_WARPS * 32, 2)
 zbuild_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
               const float* __restrict__ g, const float* __restrict__ h, int64_t n, int passes, int kp,
-              int zk_main, int zk, int round_tf32, float* __restrict__ Z) {
+              int zk_main, int zk, int round_tf32, int mean, const float* __restrict__ gather_scale,
+              float* __restrict__ Z) {
   constexpr int KTP = (KT + 3) / 4 * 4;
   constexpr int AT = WP / 8;
   constexpr int GROW = 4 * KTP;              // floats of g staged per edge per pass
-  constexpr int BUF = ZB_DEGC * (GROW + WP);
+  constexpr int BUF = ZB_DEGC * (GROW + WP) + ZB_DEGC;   // + per-edge gather scale
   constexpr int LPR = WP / 4;                // lanes (float4) per gathered h row
   constexpr int RPI = 32 / LPR;              // h rows gathered per warp iteration
   extern __shared__ __align__(16) float smem[];
@@ -125,10 +126,14 @@ zbuild_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ sr
       const int e = it.c0 + lane;
       return (it.k < nn && lane < ZB_DEGC && e < it.ee) ? __ldg(src_sorted + e) : 0;
     };
-    auto issue = [&](const ZbItem& it, int buf, int src_reg) {
+    auto load_scale = [&](const ZbItem& it, int src_reg) {
+      return (gather_scale && it.k < nn && lane < ZB_DEGC && it.c0 + lane < it.ee) ? __ldg(gather_scale + src_reg) : 1.f;
+    };
+    auto issue = [&](const ZbItem& it, int buf, int src_reg, float sc_reg) {
       float* sg = slab + buf * BUF;
       float* sh = sg + ZB_DEGC * GROW;
       const int m = min(ZB_DEGC, it.ee - it.c0);
+      if (gather_scale && lane < ZB_DEGC) sh[ZB_DEGC * WP + lane] = sc_reg;
       if (passes == 1) {                      // rows of the chunk are one contiguous block
         const float* gsrc = g + (int64_t)it.c0 * GROW;
         for (int t = lane; t < m * (GROW / 4); t += 32) cp_async16(sg + 4 * t, gsrc + 4 * t, false);
@@ -148,13 +153,17 @@ zbuild_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ sr
 
     ZbItem cur = node_item(0);
     int buf = 0;
-    issue(cur, 0, load_src(cur));
+    {
+      const int s0 = load_src(cur);
+      issue(cur, 0, s0, load_scale(cur, s0));
+    }
     ZbItem nxt = advance(cur);
     int src_nxt = load_src(nxt);
+    float sc_nxt = load_scale(nxt, src_nxt);
     float acc[KT][AT];
     while (cur.k < nn) {
       const bool has_next = nxt.k < nn;
-      if (has_next) issue(nxt, buf ^ 1, src_nxt);
+      if (has_next) issue(nxt, buf ^ 1, src_nxt, sc_nxt);
       const ZbItem nn2 = advance(nxt);
       const int src_nn2 = load_src(nn2);     // in flight while this item is computed
       if (has_next) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -173,6 +182,11 @@ zbuild_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ sr
         load_cols<KTP>(sg + j * GROW + q * KTP, gq);
         float ha[AT];
         load_cols<AT>(sh + j * WP + ag * AT, ha);
+        if (gather_scale) {
+          const float sc = sh[ZB_DEGC * WP + j];
+#pragma unroll
+          for (int k = 0; k < KT; ++k) gq[k] *= sc;
+        }
 #pragma unroll
         for (int k = 0; k < KT; ++k)
 #pragma unroll
@@ -180,7 +194,7 @@ zbuild_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ sr
       }
       if (cur.c0 + ZB_DEGC >= cur.ee) {      // last chunk of (node, pass): scale by 1/deg and store
         const int deg = cur.ee - cur.eb;
-        const float inv = 1.0f / (float)(deg > 0 ? deg : 1);
+        const float inv = mean ? 1.0f / (float)(deg > 0 ? deg : 1) : 1.0f;
         const int64_t i = i0 + cur.k;
         float* zrow = Z + i * (int64_t)zk;
         // channel k = (p*4 + q)*KT + kt  ->  columns [k*WP + ag*AT, +AT)
@@ -202,6 +216,7 @@ zbuild_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ sr
       cur = nxt;
       nxt = nn2;
       src_nxt = src_nn2;
+      sc_nxt = load_scale(nxt, src_nxt);
       buf ^= 1;
     }
   }
@@ -209,9 +224,9 @@ zbuild_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ sr
 
 template <int KT, int WP>
 static int launch_zb(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
-                     const float* h, int64_t n, float* Z, int rnd, cudaStream_t s) {
+                     const float* h, int64_t n, float* Z, int rnd, cudaStream_t s, int mean, const float* gsc) {
   constexpr int KTP = (KT + 3) / 4 * 4;
-  constexpr size_t smem = (size_t)ZB_WARPS * 2 * ZB_DEGC * (4 * KTP + WP) * sizeof(float);
+  constexpr size_t smem = (size_t)ZB_WARPS * 2 * (ZB_DEGC * (4 * KTP + WP) + ZB_DEGC) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     FESR_CUDA(cudaFuncSetAttribute(zbuild_kernel<KT, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -222,32 +237,32 @@ static int launch_zb(const fesr_model_dims& d, const int32_t* rowptr, const int3
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   ProfScope prof(PROF_ZBUILD, s);
   zbuild_kernel<KT, WP><<<grid, ZB_WARPS * 32, smem, s>>>(rowptr, src_sorted, g, h, n, d.passes, d.kp, d.zk_main,
-                                                         d.zk, rnd, Z);
+                                                         d.zk, rnd, mean, gsc, Z);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
 
 template <int KT>
 static int dispatch_wp(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
-                       const float* h, int64_t n, float* Z, int rnd, cudaStream_t s) {
+                       const float* h, int64_t n, float* Z, int rnd, cudaStream_t s, int mean, const float* gsc) {
   switch (d.wp) {
-    case 16: return launch_zb<KT, 16>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
-    case 32: return launch_zb<KT, 32>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
-    case 48: return launch_zb<KT, 48>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
-    case 64: return launch_zb<KT, 64>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
+    case 16: return launch_zb<KT, 16>(d, rowptr, src_sorted, g, h, n, Z, rnd, s, mean, gsc);
+    case 32: return launch_zb<KT, 32>(d, rowptr, src_sorted, g, h, n, Z, rnd, s, mean, gsc);
+    case 48: return launch_zb<KT, 48>(d, rowptr, src_sorted, g, h, n, Z, rnd, s, mean, gsc);
+    case 64: return launch_zb<KT, 64>(d, rowptr, src_sorted, g, h, n, Z, rnd, s, mean, gsc);
   }
   set_error("unsupported padded width %d", d.wp);
   return FESR_EINVAL;
 }
 
 int launch_zbuild(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
-                  const float* h, int64_t n, float* Z, int rnd, cudaStream_t s) {
+                  const float* h, int64_t n, float* Z, int rnd, cudaStream_t s, int mean, const float* gsc) {
   if (n == 0) return FESR_OK;
   switch (d.kt) {
-    case 4: return dispatch_wp<4>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
-    case 8: return dispatch_wp<8>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
-    case 11: return dispatch_wp<11>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
-    case 13: return dispatch_wp<13>(d, rowptr, src_sorted, g, h, n, Z, rnd, s);
+    case 4: return dispatch_wp<4>(d, rowptr, src_sorted, g, h, n, Z, rnd, s, mean, gsc);
+    case 8: return dispatch_wp<8>(d, rowptr, src_sorted, g, h, n, Z, rnd, s, mean, gsc);
+    case 11: return dispatch_wp<11>(d, rowptr, src_sorted, g, h, n, Z, rnd, s, mean, gsc);
+    case 13: return dispatch_wp<13>(d, rowptr, src_sorted, g, h, n, Z, rnd, s, mean, gsc);
   }
   set_error("unsupported kt %d", d.kt);
   return FESR_EINVAL;

@@ -360,3 +360,44 @@ def cluster(latent, scaler_mean, scaler_scale, centroids):
         check(_lib.load().fesr_cluster(_ptr(latent), S, n_comp, _ptr(sm), _ptr(ss), _ptr(cc), int(cc.shape[0]),
                                        _ptr(labels), _stream(dev)), "fesr_cluster")
     return labels
+
+
+# ---------------------------------------------------------------------------------- backward
+def reverse_csr(csr: Csr) -> Csr:
+    """CSR of the reversed graph over the forward CSR slots: rowptr groups edges by SOURCE,
+    .src is the original destination, .perm maps reversed slot -> forward slot."""
+    cached = getattr(csr, "_rev", None)
+    if cached is not None:
+        return cached
+    dev = csr.rowptr.device
+    deg = (csr.rowptr[1:] - csr.rowptr[:-1]).long()
+    dst = torch.repeat_interleave(torch.arange(csr.n, device=dev, dtype=torch.int64), deg)
+    rev = csr_build(torch.stack([dst, csr.src.long()]).contiguous(), csr.n)
+    csr._rev = rev
+    return rev
+
+
+def nnconv_backward(dims: ModelDims, tensors: dict, x, csr: Csr, edge_attr, precision, grad_y, fwd_ws,
+                    need_grad_x: bool = False):
+    """Runs fesr_nnconv_backward. Returns (grads dict shaped like `tensors`, grad_x | None)."""
+    dev = _require_cuda(x, grad_y)
+    x = _f32c(x)
+    grad_y = _f32c(grad_y)
+    edge_attr = _f32c(edge_attr.reshape(-1))
+    rev = reverse_csr(csr)
+    lib = _lib.load()
+    p, keep = make_params(Params, tensors)
+    gt = {k: (None if v is None else torch.zeros_like(v) if torch.is_tensor(v) else [torch.zeros_like(t) for t in v])
+          for k, v in tensors.items()}
+    g, keep_g = make_params(ParamGrads, gt)
+    grad_x = torch.empty_like(x) if need_grad_x else None
+    n, E = csr.n, csr.E
+    with torch.cuda.device(dev):
+        nbytes = lib.fesr_backward_workspace_bytes(C.byref(dims), n, E)
+        ws = workspace.get(dev, "bwd", nbytes)
+        check(lib.fesr_nnconv_backward(C.byref(dims), C.byref(p), _ptr(x), _ptr(csr.rowptr), _ptr(csr.src),
+                                       _ptr(csr.perm), _ptr(rev.rowptr), _ptr(rev.src), _ptr(rev.perm),
+                                       _ptr(edge_attr), n, E, precision, _ptr(grad_y), _ptr(fwd_ws), C.byref(g),
+                                       _ptr(grad_x), _ptr(ws), ws.numel(), _stream(dev)), "fesr_nnconv_backward")
+    del keep, keep_g
+    return gt, grad_x

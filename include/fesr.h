@@ -147,15 +147,16 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params,
                         float* y, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the above for the train step (models/scheduler_gnn.py:398-408: MSELoss ->
- * loss.backward()).  Needs the workspace of a forward run with keep_for_backward = 1 and
- * the CSR of the REVERSED graph (fesr_csr_build on edge_index with rows swapped):
- *   rowptr_t / dst_sorted_t / perm_t : edges grouped by SOURCE node.
- * grad_y [n, out_ch] in; parameter gradients are ADDED into *grads; grad_x may be NULL. */
+ * loss.backward()).  Needs the workspace of a forward run with keep_for_backward = 1 and the CSR
+ * of the REVERSED graph built from the forward CSR slots (fesr_csr_build on the [2,E] array
+ * {dst of slot e ; src of slot e}): rowptr_t [n+1] groups the edges by SOURCE node, src_t [E] is
+ * the original destination of each reversed slot and rev_to_fwd [E] its forward CSR slot.
+ * grad_y [n, out_ch] in; parameter gradients are ADDED into *grads; grad_x [n, in_ch] may be NULL. */
 size_t fesr_backward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E);
 int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
                          const float* x, const int32_t* rowptr, const int32_t* src_sorted,
-                         const int32_t* perm, const int32_t* rowptr_t, const int32_t* dst_sorted_t,
-                         const int32_t* perm_t, const float* edge_attr,
+                         const int32_t* perm, const int32_t* rowptr_t, const int32_t* src_t,
+                         const int32_t* rev_to_fwd, const float* edge_attr,
                          int64_t n, int64_t E, int precision, const float* grad_y,
                          const void* forward_workspace, fesr_param_grads* grads, float* grad_x,
                          void* workspace, size_t workspace_bytes, void* stream);
