@@ -208,13 +208,10 @@ class GNNPartitionScheduler():
             # predictions of the other ranks: one all-gather(v) in rank = subdomain order
             rows = [int(node_ptr_h[bounds[r + 1]] - node_ptr_h[bounds[r]]) for r in range(world)]
             lo = int(node_ptr_h[bounds[rank]])
-            full = torch.empty_like(pred)
-            dist.all_gather(list(full.split(rows, dim=0)), pred[lo:lo + rows[rank]].contiguous())
-            pred = full
-            wfull = torch.empty_like(weight_s)
+            from ..pipeline import all_gather_rows
+            pred = all_gather_rows(pred[lo:lo + rows[rank]].contiguous(), rows)
             cnt = [bounds[r + 1] - bounds[r] for r in range(world)]
-            dist.all_gather(list(wfull.split(cnt)), weight_s[bounds[rank]:bounds[rank + 1]].contiguous())
-            weight_s = wfull
+            weight_s = all_gather_rows(weight_s[bounds[rank]:bounds[rank + 1]].contiguous(), cnt)
 
         pred_cpu = pred.cpu()
         pred_y_list = TensorList(torch.split(pred_cpu, sizes))

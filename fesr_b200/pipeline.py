@@ -43,6 +43,23 @@ def shard_bounds(edge_ptr_host: np.ndarray, world: int):
     return bounds
 
 
+def all_gather_rows(local: torch.Tensor, rows, group=None) -> torch.Tensor:
+    """All-gather of row blocks of different lengths (rank r contributes rows[r] rows): every rank
+    pads its block to max(rows), one equal-size all-gather, then the blocks are concatenated in
+    rank order.  Works on NCCL (GPU) and gloo (CPU tests)."""
+    import torch.distributed as dist
+    world = len(rows)
+    if world == 1:
+        return local
+    mx = max(rows)
+    tail = local.shape[1:]
+    pad = local.new_zeros((mx, *tail))
+    pad[:local.shape[0]] = local
+    parts = [local.new_empty((mx, *tail)) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([parts[r][:rows[r]] for r in range(world)], dim=0)
+
+
 def make_shard(batch: ops.SubdomainBatch, s0: int, s1: int) -> Shard:
     node_ptr_h = batch.node_ptr[[s0, s1]].cpu().numpy()
     edge_ptr_h = batch.edge_ptr[[s0, s1]].cpu().numpy()
@@ -88,13 +105,7 @@ class MeshPredictor:
 
     def all_gather(self, pred_shard: torch.Tensor) -> torch.Tensor:
         """One NCCL all-gather(v) of the per-subdomain predictions (rank order = subdomain order)."""
-        if self.world == 1:
-            return pred_shard
-        import torch.distributed as dist
-        out = torch.empty(self.batch.n_tot, pred_shard.shape[1], dtype=pred_shard.dtype, device=pred_shard.device)
-        chunks = list(out.split(self.shard_rows, dim=0))
-        dist.all_gather(chunks, pred_shard.contiguous(), group=self.group)
-        return out
+        return all_gather_rows(pred_shard.contiguous(), self.shard_rows, self.group)
 
     def stitch(self, pred_all: torch.Tensor, want_merged=False):
         return ops.stitch_mean(pred_all, self.occ, self.batch.global_ids, want_merged=want_merged, want_count=False)

@@ -1,0 +1,73 @@
+"""CPU, world_size 2, gloo: the host-side sharding / gather / gradient-averaging logic of the
+multi-GPU path (the kernels themselves need a B200 and are covered by the -m gpu tests)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fesr_b200.pipeline import all_gather_rows, shard_bounds
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, edge_ptr, node_ptr, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        bounds = shard_bounds(edge_ptr, world)
+        rows = [int(node_ptr[bounds[r + 1]] - node_ptr[bounds[r]]) for r in range(world)]
+        full = torch.arange(int(node_ptr[-1]) * 4, dtype=torch.float32).reshape(-1, 4)     # "predictions"
+        lo = int(node_ptr[bounds[rank]])
+        mine = full[lo:lo + rows[rank]].clone()
+        got = all_gather_rows(mine, rows)
+        ok_gather = bool(torch.equal(got, full))
+        # gradient averaging as FlatAdam.step does it (sum / world)
+        g = torch.full((10,), float(rank + 1))
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        g /= world
+        ok_grad = bool(torch.allclose(g, torch.full((10,), (1 + world) / 2.0)))
+        ret[rank] = (ok_gather, ok_grad, bounds)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds_balance_and_cover():
+    rng = np.random.default_rng(0)
+    edges = rng.integers(1000, 20000, size=128)
+    edge_ptr = np.concatenate([[0], np.cumsum(edges)])
+    for world in (1, 2, 4, 8):
+        b = shard_bounds(edge_ptr, world)
+        assert b[0] == 0 and b[-1] == 128 and all(b[i] <= b[i + 1] for i in range(world))
+        per = [edge_ptr[b[r + 1]] - edge_ptr[b[r]] for r in range(world)]
+        assert max(per) - min(per) <= 2 * edges.max()
+    # more ranks than subdomains: empty shards are allowed, nothing is lost
+    b = shard_bounds(np.array([0, 5, 9]), 4)
+    assert b[0] == 0 and b[-1] == 2 and len(b) == 5
+
+
+def test_two_rank_gather_and_grad_average():
+    world = 2
+    rng = np.random.default_rng(1)
+    sizes = rng.integers(300, 900, size=9)
+    node_ptr = np.concatenate([[0], np.cumsum(sizes)])
+    edge_ptr = np.concatenate([[0], np.cumsum(sizes * 12)])
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, edge_ptr, node_ptr, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        ok_gather, ok_grad, bounds = ret[r]
+        assert ok_gather and ok_grad
+    assert ret[0][2] == ret[1][2]

@@ -86,3 +86,68 @@ def test_backward_is_deterministic(golden):
     _, b = _grads(m, golden["x"], golden["ref_edge_index"], golden["ref_edge_attr"], golden["y"])
     for k in a:
         assert np.array_equal(a[k], b[k]), k
+
+
+# ----------------------------------------------------------------------------- train step / loop
+@pytest.mark.parametrize("name,kind,w,L", [("kernelnn_w16", "neuralop", 16, 3), ("teecnet_w12", "teecnet", 12, 2)])
+def test_train_step_vs_reference_vectors(golden, name, kind, w, L):
+    """zero_grad -> forward -> MSELoss -> backward -> Adam(lr=5e-4).step (scheduler_gnn.py:402-409)."""
+    from fesr_b200 import ops
+    from fesr_b200.models.training import FlatAdam, train_step
+    m = _model(kind, w, L).cuda().train()
+    sd = state_dict_from(golden, name)
+    m.load_state_dict(sd)
+    opt = FlatAdam(m, lr=0.0005)
+    ei = torch.from_numpy(golden["ref_edge_index"]).cuda()
+    csr = ops.csr_build(ei, golden["x"].shape[0])
+    loss = train_step(m, opt, torch.from_numpy(golden["x"]).cuda(), csr, torch.from_numpy(golden["ref_edge_attr"]).cuda(),
+                      torch.from_numpy(golden["y"]).cuda())
+    assert abs(float(loss) - float(golden[name + "_loss"])) <= 1e-5 * abs(float(golden[name + "_loss"]))
+    after = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    for k, v in after.items():
+        ref_after, before = golden[f"{name}_sd_after::{k}"], sd[k].numpy()
+        assert rel_l2(v, ref_after) < 1e-6, k
+        # the Adam update itself (first step: -lr * g / (|g| + eps)); entries with |g| ~ eps are ill-conditioned
+        d, dref = v - before, ref_after - before
+        assert np.abs(d - dref).max() <= 0.02 * 0.0005 + 1e-9, (k, np.abs(d - dref).max())
+
+
+def test_scheduler_train_loop_writes_checkpoint_and_learns(tmp_path, monkeypatch, shipped):
+    from fesr_b200.dataset.GraphDataset import AnsysDataset
+    from fesr_b200.models.model import KernelNN
+    from fesr_b200.models.scheduler_gnn import GNNPartitionScheduler
+    monkeypatch.chdir(tmp_path)
+    ds = AnsysDataset(mesh_n=6, num_meshes=1, sub_size=8)
+    torch.manual_seed(0)
+    model = KernelNN(16, 16, 3, in_width=4, out_width=4)
+    sched = GNNPartitionScheduler("tr", 1, ds, model, train=True)
+    cfg = {"epochs": 6, "batch_size": 2, "lr": 0.005, "step_size": 30, "gamma": 0.1, "log_interval": 1, "val_interval": 2}
+    import io, contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        sched.train(cfg)
+    losses = [float(l.split("Train loss:")[1]) for l in buf.getvalue().splitlines() if "Train loss" in l]
+    assert len(losses) == 6 and losses[-1] < losses[0]
+    sd = torch.load("logs/models/collection_tr/partition_0.pth", weights_only=True)
+    assert set(sd) == set(model.state_dict())
+    # the checkpoint loads back through the predict path
+    sched2 = GNNPartitionScheduler("tr", 1, ds, KernelNN(16, 16, 3, in_width=4, out_width=4), train=False)
+    p, r, mi, w = sched2.predict(ds.get_one_full_sample(0))
+    assert len(p) == 8 and all(torch.isfinite(t).all() for t in p)
+
+
+def test_run_script_end_to_end(tmp_path, shipped):
+    """python run_DS_3D.py --mode predict ... : flags, timers and the .vtu output of the entry script."""
+    import subprocess, sys, os
+    from conftest import ROOT
+    os.makedirs(tmp_path / "logs/models/collection_duct_neuralop", exist_ok=True)
+    torch.save(shipped_state_dict(shipped, "neuralop"), tmp_path / "logs/models/collection_duct_neuralop/partition_0.pth")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "run_DS_3D.py"), "--mode", "predict", "--model", "neuralop",
+                        "--dataset", "duct", "--exp_name", "duct_neuralop", "--exp_config",
+                        os.path.join(ROOT, "configs/exp_config/teecnet_duct.yaml"), "--train_config",
+                        os.path.join(ROOT, "configs/train_config/teecnet.yaml")], cwd=tmp_path, env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "Prediction time:" in r.stdout and "Reconstruction time:" in r.stdout and "Prediction done!" in r.stdout
+    assert os.path.getsize(tmp_path / "logs/vtk/duct_neuralop/pred_1.vtu") > 10000
