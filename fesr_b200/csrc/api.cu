@@ -137,7 +137,7 @@ int fesr_model_dims_init(int kind, int w, int in_ch, int out_ch, int layers, fes
   d->kp = d->passes * 4 * d->ktp;
   d->k1p = d->passes * 4 * d->kt;
   d->zk_main = d->k1p * d->wp;
-  d->zk = (d->zk_main + d->wp + 31) / 32 * 32;
+  d->zk = (d->zk_main + d->wp + 63) / 64 * 64;   // 64: one 128-byte TMA row of 16-bit elements
   return FESR_OK;
 }
 

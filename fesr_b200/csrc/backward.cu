@@ -220,7 +220,8 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
                          size_t workspace_bytes, void* stream_) {
   FESR_CHECK_ARG(dims && params && grads, "dims/params/grads NULL");
   FESR_CHECK_ARG(n >= 0 && E >= 0 && n < (1ll << 31) && E < (1ll << 31), "n/E out of range");
-  FESR_CHECK_ARG(precision == FESR_PREC_FP32 || precision == FESR_PREC_TF32, "unsupported precision %d", precision);
+  FESR_CHECK_ARG(precision == FESR_PREC_FP32 || precision == FESR_PREC_TF32,
+                 "backward supports fp32 | tf32 (f16 is a predict-only precision), got %d", precision);
   if (n == 0) return FESR_OK;
   FESR_CHECK_ARG(x && grad_y && rowptr && forward_workspace, "NULL pointer");
   FESR_CHECK_ARG(E == 0 || (src_sorted && rowptr_t && src_t && rev_to_fwd && edge_attr), "NULL edge arrays");
@@ -275,7 +276,11 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
       if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, 1, w.dg, s))) return rc;
     }
     // dh_l = [sum over out-edges of g (x) dpre[dst]/deg[dst]  ++  dpre] T~
-    if ((rc = launch_zbuild(d, rowptr_t, src_t, w.g_rev, w.dpre, n, w.BZ, rnd, s, /*mean=*/0, w.inv_deg))) return rc;
+    if (rnd)
+      rc = launch_zbuild_mma(d, rowptr_t, src_t, w.g_rev, w.dpre, n, w.BZ, 1, s, /*mean=*/0, w.inv_deg);
+    else
+      rc = launch_zbuild(d, rowptr_t, src_t, w.g_rev, w.dpre, n, w.BZ, 0, s, /*mean=*/0, w.inv_deg);
+    if (rc) return rc;
     if (precision == FESR_PREC_FP32)
       rc = launch_node_gemm_fp32(d, fw.prep.ttilde, nullptr, EPI_NONE, w.BZ, n, w.dh[cur ^ 1], s);
     else

@@ -76,6 +76,8 @@ struct Prepared {
   float* tprime_t_lo;// [wp, zk]  lo part for TF32X3
   float* ttilde;     // [zk, wp]  T~[(k,b), a] = T'[(k,a), b] (every wp x wp block transposed) -- backward
   float* ttilde_t;   // [wp, zk]  K-major tf32 copy of T~
+  void* tprime_t_h;  // [wp, zk]  K-major fp16 copy of T'   (FESR_PREC_F16)
+  void* ttilde_t_h;  // [wp, zk]  K-major fp16 copy of T~
   float* bias_p;     // [wp]
   float* fc1_wp;     // [in_ch, wp] transposed + padded
   float* fc1_bp;     // [wp] (TEECNet: constant-1 column set here)

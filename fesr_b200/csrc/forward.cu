@@ -1,4 +1,6 @@
 // fesr_nnconv_forward: one block-diagonal batch of subdomains through KernelNN / TEECNet.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 #include "workspace.cuh"
 
@@ -38,8 +40,8 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   FESR_CHECK_ARG(dims && params, "dims/params NULL");
   FESR_CHECK_ARG(n >= 0 && E >= 0 && n < (1ll << 31) && E < (1ll << 31), "n/E out of range");
   FESR_CHECK_ARG(dims->layers <= FESR_MAX_LAYERS, "too many layers");
-  FESR_CHECK_ARG(precision == FESR_PREC_FP32 || precision == FESR_PREC_TF32, "unsupported precision %d (fp32 | tf32)",
-                 precision);
+  FESR_CHECK_ARG(precision == FESR_PREC_FP32 || precision == FESR_PREC_TF32 || precision == FESR_PREC_F16,
+                 "unsupported precision %d (fp32 | tf32 | f16)", precision);
   if (n == 0) return FESR_OK;
   FESR_CHECK_ARG(x && y && rowptr && (E == 0 || (src_sorted && edge_attr)), "NULL pointer");
   const fesr_model_dims& d = *dims;
@@ -58,12 +60,20 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
     const float* h_in = keep_for_backward ? ws.h[l] : ws.h[l & 1];
     float* h_out = keep_for_backward ? ws.h[l + 1] : ws.h[(l + 1) & 1];
     float* Z = keep_for_backward ? ws.Z[l] : ws.Z[0];
-    if ((rc = launch_zbuild(d, rowptr, src_sorted, ws.g, h_in, n, Z, precision != FESR_PREC_FP32, s))) return rc;
+    const int zmode = precision == FESR_PREC_FP32 ? 0 : (precision == FESR_PREC_F16 ? 2 : 1);
+    static const bool ffma_only = getenv("FESR_ZBUILD_FFMA") != nullptr;   // A/B switch for profiling
+    if (zmode == 0 || ffma_only)
+      rc = launch_zbuild(d, rowptr, src_sorted, ws.g, h_in, n, Z, zmode, s);
+    else
+      rc = launch_zbuild_mma(d, rowptr, src_sorted, ws.g, h_in, n, Z, zmode, s);
+    if (rc) return rc;
     const int epi = d.kind == FESR_TEECNET ? EPI_BIAS_CONST1 : EPI_BIAS_RELU;
     if (precision == FESR_PREC_FP32)
       rc = launch_node_gemm_fp32(d, ws.prep.tprime, ws.prep.bias_p, epi, Z, n, h_out, s);
-    else
+    else if (precision == FESR_PREC_TF32)
       rc = launch_node_gemm_tf32(d, ws.prep.tprime_t, ws.prep.bias_p, epi, Z, n, h_out, s);
+    else
+      rc = launch_node_gemm_f16(d, ws.prep.tprime_t_h, ws.prep.bias_p, epi, Z, n, h_out, s);
     if (rc) return rc;
     h_last = h_out;
   }

@@ -87,6 +87,16 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -100,7 +110,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
       : "r"(addr));
 }
 
-template <int WP>
+template <int WP, bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const float* __restrict__ bias_p, int64_t n, int zk, int w, int epi,
@@ -120,7 +130,8 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_tiles = (n + TC_BM - 1) / TC_BM;
-  const int n_kb = zk / TC_BK;
+  constexpr int ELEMS_PER_KB = HALF ? 2 * TC_BK : TC_BK;   // one k-block is always 128 bytes per row
+  const int n_kb = zk / ELEMS_PER_KB;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -157,8 +168,8 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], kb * TC_BK, row0);
-          tma_load_2d(smem_b + stage * B_BYTES, &tmB, &full_bar[stage], kb * TC_BK, 0);
+          tma_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], kb * ELEMS_PER_KB, row0);
+          tma_load_2d(smem_b + stage * B_BYTES, &tmB, &full_bar[stage], kb * ELEMS_PER_KB, 0);
           if (++stage == TC_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -168,8 +179,9 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    // instruction descriptor: D = F32, A = B = TF32, both K-major, N = WP, M = 128
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(WP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    // instruction descriptor: D = F32, A = B = TF32 (2) or F16 (0), both K-major, N = WP, M = 128
+    constexpr uint32_t fmt = HALF ? 0u : 2u;
+    constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(WP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -186,8 +198,10 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + stage * A_BYTES));
           const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + stage * B_BYTES));
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)   // 8 tf32 = 32 bytes per MMA: advance the start address by 2 (x16 B)
-            umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < TC_BK / 8; ++k) {  // 32 bytes (8 tf32 / 16 f16) per MMA: advance the start address by 2 (x16 B)
+            if constexpr (HALF) umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
           umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
           if (kb == n_kb - 1) umma_commit(&tmem_full[as]);
         }
@@ -247,10 +261,10 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 }
 
-static int encode_map(CUtensorMap* map, const float* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
-                      uint32_t box_outer) {
+static int encode_map(CUtensorMap* map, const void* base, bool half, uint64_t inner, uint64_t outer,
+                      uint32_t box_inner, uint32_t box_outer) {
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * sizeof(float)};
+  cuuint64_t strides[1] = {inner * (half ? 2 : 4)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   // the driver entry point is resolved at run time so that libfesr.so has no link-time
@@ -269,7 +283,8 @@ static int encode_map(CUtensorMap* map, const float* base, uint64_t inner, uint6
     }
     encode = reinterpret_cast<encode_fn_t>(fn);
   }
-  CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+  CUresult r = encode(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                      const_cast<void*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -279,38 +294,52 @@ static int encode_map(CUtensorMap* map, const float* base, uint64_t inner, uint6
   return FESR_OK;
 }
 
-template <int WP>
-static int launch_tc(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi, const float* Z,
+template <int WP, bool HALF>
+static int launch_tc(const fesr_model_dims& d, const void* B_kmajor, const float* bias_p, int epi, const void* Z,
                      int64_t n, float* h_out, cudaStream_t s) {
   constexpr size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 4 + WP * TC_BK * 4) + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr uint32_t box_inner = HALF ? 2 * TC_BK : TC_BK;
   static bool attr_set = false;
   if (!attr_set) {
-    FESR_CUDA(cudaFuncSetAttribute(node_gemm_tf32_kernel<WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FESR_CUDA(cudaFuncSetAttribute(node_gemm_tf32_kernel<WP, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
     attr_set = true;
   }
+  FESR_CHECK_ARG(d.zk % (int)box_inner == 0, "zk must be a multiple of %u", box_inner);
   CUtensorMap tmA, tmB;
   int rc;
-  if ((rc = encode_map(&tmA, Z, (uint64_t)d.zk, (uint64_t)n, TC_BK, TC_BM))) return rc;
-  if ((rc = encode_map(&tmB, B_kmajor, (uint64_t)d.zk, (uint64_t)d.wp, TC_BK, WP))) return rc;
+  if ((rc = encode_map(&tmA, Z, HALF, (uint64_t)d.zk, (uint64_t)n, box_inner, TC_BM))) return rc;
+  if ((rc = encode_map(&tmB, B_kmajor, HALF, (uint64_t)d.zk, (uint64_t)d.wp, box_inner, WP))) return rc;
   const int64_t n_tiles = ceil_div(n, TC_BM);
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   ProfScope prof(PROF_NODE_GEMM, s);
-  node_gemm_tf32_kernel<WP><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, bias_p, n, d.zk, d.w, epi, h_out);
+  node_gemm_tf32_kernel<WP, HALF><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, bias_p, n, d.zk, d.w, epi, h_out);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
 
-int launch_node_gemm_tf32(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi, const float* Z,
-                          int64_t n, float* h_out, cudaStream_t s) {
+template <bool HALF>
+static int dispatch_tc(const fesr_model_dims& d, const void* B, const float* bias_p, int epi, const void* Z, int64_t n,
+                       float* h_out, cudaStream_t s) {
   if (n == 0) return FESR_OK;
   switch (d.wp) {
-    case 16: return launch_tc<16>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
-    case 32: return launch_tc<32>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
-    case 48: return launch_tc<48>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
-    case 64: return launch_tc<64>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
+    case 16: return launch_tc<16, HALF>(d, B, bias_p, epi, Z, n, h_out, s);
+    case 32: return launch_tc<32, HALF>(d, B, bias_p, epi, Z, n, h_out, s);
+    case 48: return launch_tc<48, HALF>(d, B, bias_p, epi, Z, n, h_out, s);
+    case 64: return launch_tc<64, HALF>(d, B, bias_p, epi, Z, n, h_out, s);
   }
   set_error("unsupported padded width %d", d.wp);
   return FESR_EINVAL;
+}
+
+int launch_node_gemm_tf32(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi, const float* Z,
+                          int64_t n, float* h_out, cudaStream_t s) {
+  return dispatch_tc<false>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
+}
+
+int launch_node_gemm_f16(const fesr_model_dims& d, const void* B_kmajor_h, const float* bias_p, int epi, const void* Z_h,
+                         int64_t n, float* h_out, cudaStream_t s) {
+  return dispatch_tc<true>(d, B_kmajor_h, bias_p, epi, Z_h, n, h_out, s);
 }
 
 }  // namespace fesr

@@ -20,6 +20,12 @@ int launch_zbuild(const fesr_model_dims& d, const int32_t* rowptr, const int32_t
                   const float* g, const float* h, int64_t n, float* Z, int round_tf32, cudaStream_t s,
                   int mean = 1, const float* gather_scale = nullptr);
 
+// zbuild_mma.cu: same contract, outer products on mma.sync tf32 (reduced-precision arms only);
+// zmode 1 = fp32 Z rounded to tf32, 2 = fp16 Z
+int launch_zbuild_mma(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted,
+                      const float* g, const float* h, int64_t n, void* Z, int zmode, cudaStream_t s,
+                      int mean = 1, const float* gather_scale = nullptr);
+
 // gemm_simt.cu ------------------------------------------------------------------------
 // h_out[n, wp] = epilogue(Z[n, zk] x tprime[zk, wp] + bias)
 // epilogue modes
@@ -29,6 +35,9 @@ int launch_node_gemm_fp32(const fesr_model_dims& d, const float* B_rowmajor, con
                           const float* Z, int64_t n, float* h_out, cudaStream_t s);
 
 // gemm_tc.cu --------------------------------------------------------------------------
+// fp16 variant: Z [n, zk] fp16, B_kmajor [wp, zk] fp16 (tcgen05 kind::f16, fp32 accumulate)
+int launch_node_gemm_f16(const fesr_model_dims& d, const void* B_kmajor_h, const float* bias_p, int epi,
+                         const void* Z_h, int64_t n, float* h_out, cudaStream_t s);
 // B_kmajor: [wp, zk] tf32-rounded
 int launch_node_gemm_tf32(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi,
                           const float* Z, int64_t n, float* h_out, cudaStream_t s);

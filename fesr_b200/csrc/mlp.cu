@@ -4,6 +4,8 @@
 // matrix per edge (models/model.py:428,528).  Here only the HIDDEN layers run per edge, once
 // per forward (their input d_e and weights are layer invariant); the last Linear layer is
 // folded into the node-level contraction Z x T' (see DESIGN.md section 2).
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace fesr {
@@ -22,6 +24,8 @@ Prepared carve_prepared(Carver& c, const fesr_model_dims& d) {
   w.tprime_t_lo = c.take<float>((size_t)d.zk * d.wp);
   w.ttilde = c.take<float>((size_t)d.zk * d.wp);
   w.ttilde_t = c.take<float>((size_t)d.zk * d.wp);
+  w.tprime_t_h = c.take<__half>((size_t)d.zk * d.wp);
+  w.ttilde_t_h = c.take<__half>((size_t)d.zk * d.wp);
   w.bias_p = c.take<float>(d.wp);
   w.fc1_wp = c.take<float>((size_t)d.in_ch * d.wp);
   w.fc1_bp = c.take<float>(d.wp);
@@ -40,7 +44,8 @@ __global__ void prepare_tprime_kernel(fesr_model_dims d, const float* __restrict
                                       const float* __restrict__ lin_b, const float* __restrict__ root,
                                       float* __restrict__ tprime, float* __restrict__ tprime_t,
                                       float* __restrict__ tprime_t_lo, float* __restrict__ ttilde,
-                                      float* __restrict__ ttilde_t) {
+                                      float* __restrict__ ttilde_t, __half* __restrict__ tprime_t_h,
+                                      __half* __restrict__ ttilde_t_h) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)d.zk * d.wp;
   if (idx >= total) return;
@@ -73,12 +78,14 @@ __global__ void prepare_tprime_kernel(fesr_model_dims d, const float* __restrict
   const float hi = tf32_rna(v);
   tprime_t[(size_t)b * d.zk + r] = hi;
   tprime_t_lo[(size_t)b * d.zk + r] = tf32_rna(v - hi);
+  tprime_t_h[(size_t)b * d.zk + r] = __float2half_rn(v);
   // transposed blocks for the backward: row (kk*wp + b), column a  <-  T'[kk*wp + a, b]
   const int kk = r / d.wp, a = r % d.wp;
   const int rt = kk * d.wp + b;
   if (rt < d.zk) {
     ttilde[(size_t)rt * d.wp + a] = v;
     ttilde_t[(size_t)a * d.zk + rt] = hi;
+    ttilde_t_h[(size_t)a * d.zk + rt] = __float2half_rn(v);
   }
 }
 
@@ -102,9 +109,12 @@ int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const
   ProfScope prof(PROF_PREPARE, s);
   FESR_CUDA(cudaMemsetAsync(w.ttilde, 0, (size_t)total * sizeof(float), s));      // partial tail block stays zero
   FESR_CUDA(cudaMemsetAsync(w.ttilde_t, 0, (size_t)total * sizeof(float), s));
+  FESR_CUDA(cudaMemsetAsync(w.ttilde_t_h, 0, (size_t)total * sizeof(__half), s));
   prepare_tprime_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(d, p.mlp_w[last], p.mlp_b[last], p.lin_w,
                                                                       p.lin_b, p.root, w.tprime, w.tprime_t,
-                                                                      w.tprime_t_lo, w.ttilde, w.ttilde_t);
+                                                                      w.tprime_t_lo, w.ttilde, w.ttilde_t,
+                                                                      static_cast<__half*>(w.tprime_t_h),
+                                                                      static_cast<__half*>(w.ttilde_t_h));
   FESR_LAUNCH_CHECK();
   prepare_small_kernel<<<1, 64, 0, s>>>(d, p.fc1_w, p.fc1_b, p.bias, w.bias_p, w.fc1_wp, w.fc1_bp);
   FESR_LAUNCH_CHECK();

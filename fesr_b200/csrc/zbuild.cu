@@ -16,6 +16,8 @@
 // current one is consumed, and the source indices are fetched two chunks ahead.  Each lane
 // accumulates a KT x AT register tile of the outer product (lane = 8*q + ag: channel group q of
 // 4, column group ag of 8) in a fixed edge order, so the fp32 result is reproducible run to run.
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace fesr {
@@ -28,6 +30,13 @@ __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+
+// two floats -> half2, round to nearest, clamped to +-65504 (no inf in the fp16 intermediate)
+__device__ __forceinline__ __half2 f2h2_sat(float a, float b) {
+  a = fminf(fmaxf(a, -65504.f), 65504.f);
+  b = fminf(fmaxf(b, -65504.f), 65504.f);
+  return __floats2half2_rn(a, b);
 }
 
 template <int AT>
@@ -198,17 +207,33 @@ zbuild_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ sr
         const int64_t i = i0 + cur.k;
         float* zrow = Z + i * (int64_t)zk;
         // channel k = (p*4 + q)*KT + kt  ->  columns [k*WP + ag*AT, +AT)
+        if (round_tf32 == 2) {               // fp16 row (FESR_PREC_F16), saturating
+          __half* zh = reinterpret_cast<__half*>(Z) + i * (int64_t)zk;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-          float o[AT];
+          for (int k = 0; k < KT; ++k) {
+            __half2* dst = reinterpret_cast<__half2*>(zh + ((cur.p * 4 + q) * KT + k) * WP + ag * AT);
 #pragma unroll
-          for (int t = 0; t < AT; ++t) o[t] = round_tf32 ? tf32_rna(acc[k][t] * inv) : acc[k][t] * inv;
-          store_cols<AT>(zrow + ((cur.p * 4 + q) * KT + k) * WP + ag * AT, o);
-        }
-        if (cur.p == passes - 1) {           // root block + zero tail
-          for (int c = lane; c < zk - zk_main; c += 32) {
-            const float hv = (c < WP) ? h[i * WP + c] : 0.f;
-            zrow[zk_main + c] = round_tf32 ? tf32_rna(hv) : hv;
+            for (int t = 0; t < AT; t += 2) dst[t / 2] = f2h2_sat(acc[k][t] * inv, acc[k][t + 1] * inv);
+          }
+          if (cur.p == passes - 1) {
+            for (int c = lane * 2; c < zk - zk_main; c += 64) {
+              const float h0 = (c < WP) ? h[i * WP + c] : 0.f, h1 = (c + 1 < WP) ? h[i * WP + c + 1] : 0.f;
+              *reinterpret_cast<__half2*>(zh + zk_main + c) = f2h2_sat(h0, h1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) {
+            float o[AT];
+#pragma unroll
+            for (int t = 0; t < AT; ++t) o[t] = round_tf32 ? tf32_rna(acc[k][t] * inv) : acc[k][t] * inv;
+            store_cols<AT>(zrow + ((cur.p * 4 + q) * KT + k) * WP + ag * AT, o);
+          }
+          if (cur.p == passes - 1) {           // root block + zero tail
+            for (int c = lane; c < zk - zk_main; c += 32) {
+              const float hv = (c < WP) ? h[i * WP + c] : 0.f;
+              zrow[zk_main + c] = round_tf32 ? tf32_rna(hv) : hv;
+            }
           }
         }
       }

@@ -42,8 +42,9 @@ enum { FESR_KERNELNN = 0, FESR_TEECNET = 1 };
 /* arithmetic of the node contraction Z x T' (everything else is fp32 CUDA-core):
  *   FP32   fp32 FFMA, rel-L2 <= 1e-5 vs the reference's fp32 CPU result
  *   TF32   tcgen05.mma kind::tf32, fp32 accumulate in TMEM, rel-L2 <= 1e-3
- *   TF32X3 three tcgen05 passes on hi/lo splits (fp32-class accuracy on tensor cores) */
-enum { FESR_PREC_FP32 = 0, FESR_PREC_TF32 = 1, FESR_PREC_TF32X3 = 2 };
+ *   F16    tcgen05.mma kind::f16 on fp16 Z / T' (11-bit mantissa like TF32, half the HBM bytes of
+ *          the [n, zk] intermediate; values saturate at +-65504), fp32 accumulate, rel-L2 <= 1e-3 */
+enum { FESR_PREC_FP32 = 0, FESR_PREC_TF32 = 1, FESR_PREC_TF32X3 = 2 /* reserved */, FESR_PREC_F16 = 3 };
 enum { FESR_ONE_REGION = 0, FESR_ALL_INTERSECTING = 1 };
 
 int fesr_version(void);
@@ -81,7 +82,7 @@ typedef struct fesr_model_dims {
   int32_t kp;          /* row stride of g (floats) = passes*4*ktp */
   int32_t k1p;         /* padded channel count = passes*4*kt */
   int32_t zk_main;     /* k1p*wp */
-  int32_t zk;          /* row stride of Z (floats): zk_main + wp rounded up to 32 */
+  int32_t zk;          /* row stride of Z (elements): zk_main + wp rounded up to 64 */
   int32_t leaky;       /* 0: ReLU edge MLP + ReLU between layers; 1: LeakyReLU(0.01), none between */
 } fesr_model_dims;
 

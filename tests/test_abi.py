@@ -38,7 +38,7 @@ def test_version_and_dims(lib):
     t = _lib.model_dims(_lib.TEECNET, 43, 4, 4, 5)
     assert (t.wp, t.k1, t.kt, t.passes, t.kp, t.k1p, t.zk) == (48, 129, 11, 3, 144, 132, 6400)
     d48 = _lib.model_dims(_lib.KERNELNN, 48, 4, 4, 5)
-    assert (d48.wp, d48.k1, d48.kt, d48.passes) == (48, 49, 13, 1)
+    assert (d48.wp, d48.k1, d48.kt, d48.passes, d48.zk) == (48, 49, 13, 1, 2560)
     t48 = _lib.model_dims(_lib.TEECNET, 48, 4, 4, 5)
     assert t48.wp == 64
 
