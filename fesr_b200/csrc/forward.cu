@@ -53,15 +53,18 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   cudaStream_t s = as_stream(stream_);
   int rc;
   if ((rc = launch_prepare_weights(d, *params, ws.prep, s))) return rc;
-  if ((rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s))) return rc;
-  if ((rc = launch_fc_in(d, ws.prep, x, n, ws.h[0], s))) return rc;
+  static const bool ffma_only = getenv("FESR_ZBUILD_FFMA") != nullptr;   // A/B switch for profiling
+  // reduced-precision arms: g and h are rounded to tf32 by their producers, so the gather kernel
+  // feeds them to the tensor cores without converting
+  const int rnd_in = precision != FESR_PREC_FP32;
+  if ((rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s, rnd_in))) return rc;
+  if ((rc = launch_fc_in(d, ws.prep, x, n, ws.h[0], s, rnd_in))) return rc;
   const float* h_last = ws.h[0];
   for (int l = 0; l < d.layers; ++l) {
     const float* h_in = keep_for_backward ? ws.h[l] : ws.h[l & 1];
     float* h_out = keep_for_backward ? ws.h[l + 1] : ws.h[(l + 1) & 1];
     float* Z = keep_for_backward ? ws.Z[l] : ws.Z[0];
     const int zmode = precision == FESR_PREC_FP32 ? 0 : (precision == FESR_PREC_F16 ? 2 : 1);
-    static const bool ffma_only = getenv("FESR_ZBUILD_FFMA") != nullptr;   // A/B switch for profiling
     if (zmode == 0 || ffma_only)
       rc = launch_zbuild(d, rowptr, src_sorted, ws.g, h_in, n, Z, zmode, s);
     else
@@ -71,9 +74,9 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
     if (precision == FESR_PREC_FP32)
       rc = launch_node_gemm_fp32(d, ws.prep.tprime, ws.prep.bias_p, epi, Z, n, h_out, s);
     else if (precision == FESR_PREC_TF32)
-      rc = launch_node_gemm_tf32(d, ws.prep.tprime_t, ws.prep.bias_p, epi, Z, n, h_out, s);
+      rc = launch_node_gemm_tf32(d, ws.prep.tprime_t, ws.prep.bias_p, epi, Z, n, h_out, s, 1);
     else
-      rc = launch_node_gemm_f16(d, ws.prep.tprime_t_h, ws.prep.bias_p, epi, Z, n, h_out, s);
+      rc = launch_node_gemm_f16(d, ws.prep.tprime_t_h, ws.prep.bias_p, epi, Z, n, h_out, s, 1);
     if (rc) return rc;
     h_last = h_out;
   }

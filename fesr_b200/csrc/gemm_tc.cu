@@ -113,7 +113,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
 template <int WP, bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const float* __restrict__ bias_p, int64_t n, int zk, int w, int epi,
+                      const float* __restrict__ bias_p, int64_t n, int zk, int w, int epi, int round_out,
                       float* __restrict__ h_out) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
   constexpr uint32_t B_BYTES = WP * TC_BK * 4;      // wp * 128 B
@@ -242,6 +242,11 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               } else if (epi == EPI_BIAS_RELU) {
                 x = fmaxf(x, 0.f);
               }
+              if (round_out) {
+                uint32_t u;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+                x = __uint_as_float(u);
+              }
               v[t] = x;
             }
             *reinterpret_cast<float4*>(h_out + row * WP + c0 + j) = make_float4(v[0], v[1], v[2], v[3]);
@@ -296,7 +301,7 @@ static int encode_map(CUtensorMap* map, const void* base, bool half, uint64_t in
 
 template <int WP, bool HALF>
 static int launch_tc(const fesr_model_dims& d, const void* B_kmajor, const float* bias_p, int epi, const void* Z,
-                     int64_t n, float* h_out, cudaStream_t s) {
+                     int64_t n, float* h_out, cudaStream_t s, int round_out) {
   constexpr size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 4 + WP * TC_BK * 4) + 1024 /*align*/ + 256 /*barriers*/;
   constexpr uint32_t box_inner = HALF ? 2 * TC_BK : TC_BK;
   static bool attr_set = false;
@@ -313,33 +318,33 @@ static int launch_tc(const fesr_model_dims& d, const void* B_kmajor, const float
   const int64_t n_tiles = ceil_div(n, TC_BM);
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   ProfScope prof(PROF_NODE_GEMM, s);
-  node_gemm_tf32_kernel<WP, HALF><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, bias_p, n, d.zk, d.w, epi, h_out);
+  node_gemm_tf32_kernel<WP, HALF><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, bias_p, n, d.zk, d.w, epi, round_out, h_out);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
 
 template <bool HALF>
 static int dispatch_tc(const fesr_model_dims& d, const void* B, const float* bias_p, int epi, const void* Z, int64_t n,
-                       float* h_out, cudaStream_t s) {
+                       float* h_out, cudaStream_t s, int round_out) {
   if (n == 0) return FESR_OK;
   switch (d.wp) {
-    case 16: return launch_tc<16, HALF>(d, B, bias_p, epi, Z, n, h_out, s);
-    case 32: return launch_tc<32, HALF>(d, B, bias_p, epi, Z, n, h_out, s);
-    case 48: return launch_tc<48, HALF>(d, B, bias_p, epi, Z, n, h_out, s);
-    case 64: return launch_tc<64, HALF>(d, B, bias_p, epi, Z, n, h_out, s);
+    case 16: return launch_tc<16, HALF>(d, B, bias_p, epi, Z, n, h_out, s, round_out);
+    case 32: return launch_tc<32, HALF>(d, B, bias_p, epi, Z, n, h_out, s, round_out);
+    case 48: return launch_tc<48, HALF>(d, B, bias_p, epi, Z, n, h_out, s, round_out);
+    case 64: return launch_tc<64, HALF>(d, B, bias_p, epi, Z, n, h_out, s, round_out);
   }
   set_error("unsupported padded width %d", d.wp);
   return FESR_EINVAL;
 }
 
 int launch_node_gemm_tf32(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi, const float* Z,
-                          int64_t n, float* h_out, cudaStream_t s) {
-  return dispatch_tc<false>(d, B_kmajor, bias_p, epi, Z, n, h_out, s);
+                          int64_t n, float* h_out, cudaStream_t s, int round_out) {
+  return dispatch_tc<false>(d, B_kmajor, bias_p, epi, Z, n, h_out, s, round_out);
 }
 
 int launch_node_gemm_f16(const fesr_model_dims& d, const void* B_kmajor_h, const float* bias_p, int epi, const void* Z_h,
-                         int64_t n, float* h_out, cudaStream_t s) {
-  return dispatch_tc<true>(d, B_kmajor_h, bias_p, epi, Z_h, n, h_out, s);
+                         int64_t n, float* h_out, cudaStream_t s, int round_out) {
+  return dispatch_tc<true>(d, B_kmajor_h, bias_p, epi, Z_h, n, h_out, s, round_out);
 }
 
 }  // namespace fesr

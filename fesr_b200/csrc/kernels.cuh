@@ -10,8 +10,9 @@ Prepared carve_prepared(Carver& c, const fesr_model_dims& d);
 int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const Prepared& w, cudaStream_t s);
 // g[E, kp]: hidden activations of the edge MLP in CSR edge order, channel-permuted layout
 int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
-                       const int32_t* perm, int64_t E, float* g, cudaStream_t s);
-int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s);
+                       const int32_t* perm, int64_t E, float* g, cudaStream_t s, int round_tf32 = 0);
+int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s,
+                 int round_tf32 = 0);
 int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const float* h, int64_t n, float* y, cudaStream_t s);
 
 // zbuild.cu ---------------------------------------------------------------------------
@@ -37,9 +38,9 @@ int launch_node_gemm_fp32(const fesr_model_dims& d, const float* B_rowmajor, con
 // gemm_tc.cu --------------------------------------------------------------------------
 // fp16 variant: Z [n, zk] fp16, B_kmajor [wp, zk] fp16 (tcgen05 kind::f16, fp32 accumulate)
 int launch_node_gemm_f16(const fesr_model_dims& d, const void* B_kmajor_h, const float* bias_p, int epi,
-                         const void* Z_h, int64_t n, float* h_out, cudaStream_t s);
+                         const void* Z_h, int64_t n, float* h_out, cudaStream_t s, int round_out = 0);
 // B_kmajor: [wp, zk] tf32-rounded
 int launch_node_gemm_tf32(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi,
-                          const float* Z, int64_t n, float* h_out, cudaStream_t s);
+                          const float* Z, int64_t n, float* h_out, cudaStream_t s, int round_out = 0);
 
 }  // namespace fesr

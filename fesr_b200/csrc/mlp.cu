@@ -142,7 +142,7 @@ __device__ __forceinline__ float act_fn(float v, int leaky) {
 // Persistent CTAs; all hidden-layer weights stay in shared memory (transposed [in][outP]).
 __global__ void __launch_bounds__(EH_THREADS, 2)
 edge_hidden_kernel(EdgeHiddenArgs a, const float* __restrict__ edge_attr, const int32_t* __restrict__ perm,
-                   int64_t E, float* __restrict__ g) {
+                   int64_t E, int round_tf32, float* __restrict__ g) {
   extern __shared__ __align__(16) float smem[];
   // layout: w0[D0] b0[D0] | for l>=1: WT_l[Din][DoutP], b_l[DoutP] | bufA[MAXD][TE] bufB[MAXD][TE] | chan_of[kp]
   float* w0 = smem;
@@ -240,7 +240,7 @@ edge_hidden_kernel(EdgeHiddenArgs a, const float* __restrict__ edge_attr, const 
       if (ge >= E) break;
       const int k = chan_of[off];
       const float v = (k < 0) ? 0.f : (k == K ? 1.f : in[k * EH_TE + e]);
-      g[ge * a.kp + off] = v;
+      g[ge * a.kp + off] = round_tf32 ? tf32_rna(v) : v;
     }
     __syncthreads();
   }
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(128)
 edge_hidden2_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
                     const float* __restrict__ b1g, int w, int leaky, int kt, int ktp, int kp, int k1,
                     const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int64_t E,
-                    float* __restrict__ g) {
+                    int round_tf32, float* __restrict__ g) {
   __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1[WPAD];
   __shared__ __align__(16) float w1t[WPAD][WPAD];     // [in][out]
   __shared__ int off_of[WPAD + 1];                    // channel -> offset in the g row
@@ -294,7 +294,7 @@ edge_hidden2_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g
     for (int c = 0; c < kp; c += 4) *reinterpret_cast<float4*>(srow + c) = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int o = 0; o < WPAD; ++o)
-      if (o < w) srow[off_of[o]] = act_fn(acc[o], leaky);
+      if (o < w) srow[off_of[o]] = round_tf32 ? tf32_rna(act_fn(acc[o], leaky)) : act_fn(acc[o], leaky);
     srow[off_of[k1 - 1]] = 1.f;
     __syncwarp();
     const int64_t e_base = e - (tid & 31);
@@ -310,7 +310,7 @@ edge_hidden2_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g
 }
 
 int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
-                       const int32_t* perm, int64_t E, float* g, cudaStream_t s) {
+                       const int32_t* perm, int64_t E, float* g, cudaStream_t s, int round_tf32) {
   if (E == 0) return FESR_OK;
   if (d.n_hidden == 2 && d.hidden[0] == d.w && d.hidden[1] == d.w) {
     FESR_CHECK_ARG(p.mlp_w[0] && p.mlp_b[0] && p.mlp_w[1] && p.mlp_b[1], "NULL edge-MLP parameter");
@@ -328,7 +328,7 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
     ProfScope prof(PROF_EDGE_HIDDEN, s);
 #define FESR_EH2(WPAD)                                                                                             \
   edge_hidden2_kernel<WPAD><<<grid, 128, stage_bytes, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.leaky, d.kt, \
-                                                 d.ktp, d.kp, d.k1, edge_attr, perm, E, g)
+                                                 d.ktp, d.kp, d.k1, edge_attr, perm, E, round_tf32, g)
     if (d.w <= 16) FESR_EH2(16);
     else if (d.w <= 32) FESR_EH2(32);
     else if (d.w <= 48) FESR_EH2(48);
@@ -368,7 +368,7 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
   const int64_t n_tiles = ceil_div(E, EH_TE);
   const int grid = (int)(n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms());
   ProfScope prof(PROF_EDGE_HIDDEN, s);
-  edge_hidden_kernel<<<grid, EH_THREADS, smem, s>>>(a, edge_attr, perm, E, g);
+  edge_hidden_kernel<<<grid, EH_THREADS, smem, s>>>(a, edge_attr, perm, E, round_tf32, g);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
@@ -376,7 +376,7 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
 // ----------------------------------------------------------------------------- fc1 / fc2
 // h0[i, :] = x[i, :] W1^T + b1 (models/model.py:557 / :279), padded columns 0 (TEECNet: h[w] = 1)
 __global__ void fc_in_kernel(const float* __restrict__ x, const float* __restrict__ wp_, const float* __restrict__ bp,
-                             int in_ch, int wp, int64_t n, float* __restrict__ h) {
+                             int in_ch, int wp, int64_t n, int round_tf32, float* __restrict__ h) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one float4 of h per thread
   const int q = wp / 4;
   if (idx >= n * q) return;
@@ -391,14 +391,21 @@ __global__ void fc_in_kernel(const float* __restrict__ x, const float* __restric
     acc.z = fmaf(xv, wv.z, acc.z);
     acc.w = fmaf(xv, wv.w, acc.w);
   }
+  if (round_tf32) {
+    acc.x = tf32_rna(acc.x);
+    acc.y = tf32_rna(acc.y);
+    acc.z = tf32_rna(acc.z);
+    acc.w = tf32_rna(acc.w);
+  }
   *reinterpret_cast<float4*>(h + i * wp + b4) = acc;
 }
 
-int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s) {
+int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s,
+                 int round_tf32) {
   if (n == 0) return FESR_OK;
   const int64_t total = n * (d.wp / 4);
   ProfScope prof(PROF_FC_IN, s);
-  fc_in_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.in_ch, d.wp, n, h);
+  fc_in_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.in_ch, d.wp, n, round_tf32, h);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }

@@ -4,14 +4,17 @@
 // reduced-precision arms (FESR_PREC_TF32 / FESR_PREC_F16) where Z is consumed as an 11-bit-mantissa
 // operand anyway.  Per destination node the sum of outer products is a tiny GEMM
 //     Z_i [GROW x WP] = G_i^T [GROW x deg] . H_i [deg x WP]          (deg ~ 12, GROW = WP = 48)
-// with a contraction length of one node's in-degree: far below tcgen05's M >= 64 / one-CTA-wide
-// issue granularity, so it is issued as mma.sync.m16n8k8 (tf32 in, fp32 accumulate) by the warp
-// that owns the node.  This cuts the instruction count of the kernel from ~135 to ~30 per edge
-// and leaves it bound by HBM (g read + Z write).  The fp32 arm keeps the FFMA kernel (zbuild.cu).
+// whose contraction length is one node's in-degree: far below tcgen05's M >= 64, CTA-wide issue
+// granularity, so it is issued as mma.sync.m16n8k8 (tf32 in, fp32 accumulate) by the warp that
+// owns the node.  Against the FFMA kernel this cuts the instruction count per edge ~2.5x and
+// leaves the kernel bound by HBM (g read + Z write).  The fp32 arm keeps the FFMA kernel.
 //
-// Staging is as in zbuild.cu: per-warp double-buffered slabs, g rows streamed with cp.async.cg,
-// h[src] rows gathered with cp.async.ca, source ids fetched two chunks ahead; slab rows are padded
-// by 8 floats so that the MMA fragment loads are bank-conflict free.
+// Staging: every edge row is ONE bulk asynchronous copy (cp.async.bulk global->shared, the
+// non-tensor TMA path) issued by one lane -- lane j copies the g row and the gathered h[src_j]
+// row of edge j -- completing on a per-warp mbarrier; slabs are double buffered and the source
+// ids are fetched two chunks ahead.  Slab rows are padded by 8 floats so that the MMA fragment
+// loads are bank-conflict free.  In the forward, g and h are already tf32-rounded by their
+// producers, so the fragments are loaded without any conversion.
 #include <cuda_fp16.h>
 
 #include "kernels.cuh"
@@ -22,17 +25,37 @@ constexpr int ZM_WARPS = 8;
 constexpr int ZM_DEGC = 16;   // edges per chunk = 2 MMA k-steps
 constexpr int ZM_TASK = 8;
 
-__device__ __forceinline__ void zm_cp_async16(float* dst_smem, const float* src, bool l1) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
-  if (l1)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-  else
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+__device__ __forceinline__ uint32_t zm_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void zm_bulk(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   zm_smem(dst_smem)),
+               "l"(src), "r"(bytes), "r"(zm_smem(bar))
+               : "memory");
+}
+__device__ __forceinline__ void zm_expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(zm_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void zm_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "ZM_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra ZM_DONE;\n\t"
+      "bra ZM_WAIT;\n\t"
+      "ZM_DONE:\n\t"
+      "}" ::"r"(zm_smem(bar)), "r"(parity)
+      : "memory");
 }
 __device__ __forceinline__ uint32_t zm_tf32(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return u;
+}
+__device__ __forceinline__ uint32_t zm_h2_sat(float lo, float hi) {   // {lo, hi} -> packed f16x2, saturating
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void zm_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -45,28 +68,33 @@ struct ZmItem {
   int k, p, c0, eb, ee;
 };
 
-// MT = (floats of g per edge per pass) / 16, NT = WP / 8
-template <int MT, int WP>
+// MT = (floats of g per edge per pass) / 16; ZMODE 1 = fp32 Z rounded to tf32, 2 = fp16 Z;
+// BWD: backward use (sum instead of mean, per-gathered-row scale, inputs not pre-rounded)
+template <int MT, int WP, int ZMODE, bool BWD>
 __global__ void __launch_bounds__(ZM_WARPS * 32, 2)
 zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
                   const float* __restrict__ g, const float* __restrict__ h, int64_t n, int passes, int kp, int kt,
-                  int ktp, int zk_main, int zk, int zmode, int mean, const float* __restrict__ gather_scale,
-                  void* __restrict__ Zv) {
+                  int ktp, int zk_main, int zk, const float* __restrict__ gather_scale, void* __restrict__ Zv) {
   constexpr int GROW = 16 * MT;
   constexpr int NT = WP / 8;
   constexpr int SG = GROW + 8, SH = WP + 8;                 // padded slab row strides (floats)
-  constexpr int BUF = ZM_DEGC * (SG + SH) + ZM_DEGC;        // + per-edge gather scale
-  constexpr int LPR = WP / 4, RPI = 32 / LPR;
+  constexpr int BUF = ZM_DEGC * (SG + SH);                  // the gather scale of edge j lives in the pad of g row j
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* slab = smem + warp * (2 * BUF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ZM_WARPS * 2 * BUF) + warp * 2;
   const int gq = lane >> 2, tq = lane & 3;                  // MMA fragment coordinates
-  const int hj = lane / LPR, hc = lane % LPR;
-  const bool h_lane = lane < RPI * LPR;
   const unsigned FULL = 0xffffffffu;
 
   for (int t = lane; t < 2 * BUF; t += 32) slab[t] = 0.f;   // stale slab contents must stay finite
+  if (lane == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(zm_smem(&bars[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(zm_smem(&bars[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
+  uint32_t phase0 = 0, phase1 = 0;
 
   // output rows owned by this lane: slot = mt*16 + gq (+8) -> channel (skipping the pad slots)
   int chan[MT][2];
@@ -111,29 +139,24 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
       return (it.k < nn && lane < ZM_DEGC && e < it.ee) ? __ldg(src_sorted + e) : 0;
     };
     auto load_scale = [&](const ZmItem& it, int src_reg) {
-      return (gather_scale && it.k < nn && lane < ZM_DEGC && it.c0 + lane < it.ee) ? __ldg(gather_scale + src_reg) : 1.f;
+      return (BWD && it.k < nn && lane < ZM_DEGC && it.c0 + lane < it.ee) ? __ldg(gather_scale + src_reg) : 1.f;
     };
+    // lane j (< m) copies edge row j: the g row (GROW floats of this pass) and the gathered h row
     auto issue = [&](const ZmItem& it, int buf, int src_reg, float sc_reg) {
       float* sg = slab + buf * BUF;
       float* sh = sg + ZM_DEGC * SG;
       const int m = min(ZM_DEGC, it.ee - it.c0);
-      if (gather_scale && lane < ZM_DEGC) sh[ZM_DEGC * SH + lane] = sc_reg;
-      for (int t = lane; t < m * (GROW / 4); t += 32) {
-        const int j = t / (GROW / 4), c = t % (GROW / 4);
-        zm_cp_async16(sg + j * SG + 4 * c, g + (int64_t)(it.c0 + j) * kp + it.p * GROW + 4 * c, false);
+      if (lane == 0) zm_expect(&bars[buf], (uint32_t)(m * (GROW + WP) * 4));
+      __syncwarp();
+      if (lane < m) {
+        zm_bulk(sg + lane * SG, g + (int64_t)(it.c0 + lane) * kp + it.p * GROW, GROW * 4, &bars[buf]);
+        zm_bulk(sh + lane * SH, h + (int64_t)src_reg * WP, WP * 4, &bars[buf]);
+      } else if (lane < ((m + 7) & ~7)) {
+        // unused edge slots of an issued k-step: g row = 0 (the stale h row is finite)
+#pragma unroll
+        for (int c = 0; c < GROW; c += 4) *reinterpret_cast<float4*>(sg + lane * SG + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      // zero the g rows of the unused edge slots of the k-steps that will be issued
-      const int mpad = (m + 7) & ~7;
-      for (int t = lane + m * (GROW / 4); t < mpad * (GROW / 4); t += 32) {
-        const int j = t / (GROW / 4), c = t % (GROW / 4);
-        *reinterpret_cast<float4*>(sg + j * SG + 4 * c) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      for (int j0 = 0; j0 < m; j0 += RPI) {
-        const int j = j0 + hj;
-        const int s = __shfl_sync(FULL, src_reg, j & 31);
-        if (h_lane && j < m) zm_cp_async16(sh + j * SH + 4 * hc, h + (int64_t)s * WP + 4 * hc, true);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (BWD && lane < ZM_DEGC) sg[lane * SG + GROW] = sc_reg;
     };
 
     ZmItem cur = node_item(0);
@@ -147,12 +170,16 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     float sc_nxt = load_scale(nxt, src_nxt);
     float acc[MT][NT][4];
     while (cur.k < nn) {
-      const bool has_next = nxt.k < nn;
-      if (has_next) issue(nxt, buf ^ 1, src_nxt, sc_nxt);
+      if (nxt.k < nn) issue(nxt, buf ^ 1, src_nxt, sc_nxt);
       const ZmItem nn2 = advance(nxt);
       const int src_nn2 = load_src(nn2);
-      if (has_next) asm volatile("cp.async.wait_group 1;" ::: "memory");
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (buf == 0) {
+        zm_wait(&bars[0], phase0);
+        phase0 ^= 1;
+      } else {
+        zm_wait(&bars[1], phase1);
+        phase1 ^= 1;
+      }
       __syncwarp();
       if (cur.c0 == cur.eb) {
 #pragma unroll
@@ -165,54 +192,65 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
       const float* sg = slab + buf * BUF;
       const float* sh = sg + ZM_DEGC * SG;
       const int m = min(ZM_DEGC, cur.ee - cur.c0);
-      for (int ks = 0; ks * 8 < m; ++ks) {
-        const int e0 = ks * 8 + tq, e1 = e0 + 4;            // this lane's two edge rows of the k-step
-        float s0 = 1.f, s1 = 1.f;
-        if (gather_scale) {
-          s0 = sh[ZM_DEGC * SH + e0];
-          s1 = sh[ZM_DEGC * SH + e1];
-        }
-        uint32_t a[MT][4];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          a[mt][0] = zm_tf32(sg[e0 * SG + mt * 16 + gq] * s0);
-          a[mt][1] = zm_tf32(sg[e0 * SG + mt * 16 + gq + 8] * s0);
-          a[mt][2] = zm_tf32(sg[e1 * SG + mt * 16 + gq] * s1);
-          a[mt][3] = zm_tf32(sg[e1 * SG + mt * 16 + gq + 8] * s1);
-        }
+      for (int ks = 0; ks < 2; ++ks) {
+        if (ks * 8 < m) {
+          const int e0 = ks * 8 + tq, e1 = e0 + 4;            // this lane's two edge rows of the k-step
+          uint32_t a[MT][4];
+          if constexpr (BWD) {
+            const float s0 = sg[e0 * SG + GROW], s1 = sg[e1 * SG + GROW];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          const uint32_t b0 = zm_tf32(sh[e0 * SH + nt * 8 + gq]);
-          const uint32_t b1 = zm_tf32(sh[e1 * SH + nt * 8 + gq]);
+            for (int mt = 0; mt < MT; ++mt) {
+              a[mt][0] = zm_tf32(sg[e0 * SG + mt * 16 + gq] * s0);
+              a[mt][1] = zm_tf32(sg[e0 * SG + mt * 16 + gq + 8] * s0);
+              a[mt][2] = zm_tf32(sg[e1 * SG + mt * 16 + gq] * s1);
+              a[mt][3] = zm_tf32(sg[e1 * SG + mt * 16 + gq + 8] * s1);
+            }
+          } else {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) zm_mma(acc[mt][nt], a[mt], b0, b1);
+            for (int mt = 0; mt < MT; ++mt) {
+              a[mt][0] = __float_as_uint(sg[e0 * SG + mt * 16 + gq]);
+              a[mt][1] = __float_as_uint(sg[e0 * SG + mt * 16 + gq + 8]);
+              a[mt][2] = __float_as_uint(sg[e1 * SG + mt * 16 + gq]);
+              a[mt][3] = __float_as_uint(sg[e1 * SG + mt * 16 + gq + 8]);
+            }
+          }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            uint32_t b0, b1;
+            if constexpr (BWD) {
+              b0 = zm_tf32(sh[e0 * SH + nt * 8 + gq]);
+              b1 = zm_tf32(sh[e1 * SH + nt * 8 + gq]);
+            } else {
+              b0 = __float_as_uint(sh[e0 * SH + nt * 8 + gq]);
+              b1 = __float_as_uint(sh[e1 * SH + nt * 8 + gq]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) zm_mma(acc[mt][nt], a[mt], b0, b1);
+          }
         }
       }
       if (cur.c0 + ZM_DEGC >= cur.ee) {
         const int deg = cur.ee - cur.eb;
-        const float inv = mean ? 1.0f / (float)(deg > 0 ? deg : 1) : 1.0f;
+        const float inv = BWD ? 1.0f : 1.0f / (float)(deg > 0 ? deg : 1);
         const int64_t i = i0 + cur.k;
         const int kbase = cur.p * 4 * kt;                  // first channel of this pass
-        if (zmode == 2) {
+        if constexpr (ZMODE == 2) {
           __half* zh = reinterpret_cast<__half*>(Zv) + i * (int64_t)zk;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
               if (chan[mt][hh] < 0) continue;
-              __half* row = zh + (kbase + chan[mt][hh]) * WP + 2 * tq;
+              uint32_t* row = reinterpret_cast<uint32_t*>(zh + (kbase + chan[mt][hh]) * WP + 2 * tq);
 #pragma unroll
-              for (int nt = 0; nt < NT; ++nt) {
-                const float v0 = fminf(fmaxf(acc[mt][nt][2 * hh] * inv, -65504.f), 65504.f);
-                const float v1 = fminf(fmaxf(acc[mt][nt][2 * hh + 1] * inv, -65504.f), 65504.f);
-                *reinterpret_cast<__half2*>(row + nt * 8) = __floats2half2_rn(v0, v1);
-              }
+              for (int nt = 0; nt < NT; ++nt)
+                row[nt * 4] = zm_h2_sat(acc[mt][nt][2 * hh] * inv, acc[mt][nt][2 * hh + 1] * inv);
             }
           if (cur.p == passes - 1) {
             for (int c = lane * 2; c < zk - zk_main; c += 64) {
               const float h0 = (c < WP) ? h[i * WP + c] : 0.f, h1 = (c + 1 < WP) ? h[i * WP + c + 1] : 0.f;
-              *reinterpret_cast<__half2*>(zh + zk_main + c) =
-                  __floats2half2_rn(fminf(fmaxf(h0, -65504.f), 65504.f), fminf(fmaxf(h1, -65504.f), 65504.f));
+              *reinterpret_cast<uint32_t*>(zh + zk_main + c) = zm_h2_sat(h0, h1);
             }
           }
         } else {
@@ -235,6 +273,8 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
           }
         }
       }
+      // the slab just consumed is overwritten by the async proxy two items from now
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       cur = nxt;
       nxt = nn2;
@@ -245,33 +285,50 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
   }
 }
 
-template <int MT, int WP>
+template <int MT, int WP, int ZMODE, bool BWD>
 static int launch_zm(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
-                     const float* h, int64_t n, void* Z, int zmode, cudaStream_t s, int mean, const float* gsc) {
-  constexpr size_t smem = (size_t)ZM_WARPS * 2 * (ZM_DEGC * (16 * MT + 8 + WP + 8) + ZM_DEGC) * sizeof(float);
+                     const float* h, int64_t n, void* Z, cudaStream_t s, const float* gsc) {
+  constexpr size_t smem =
+      (size_t)ZM_WARPS * 2 * (ZM_DEGC * (16 * MT + 8 + WP + 8)) * sizeof(float) + ZM_WARPS * 2 * sizeof(uint64_t);
   static bool attr_set = false;
   if (!attr_set) {
-    FESR_CUDA(cudaFuncSetAttribute(zbuild_mma_kernel<MT, WP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FESR_CUDA(cudaFuncSetAttribute(zbuild_mma_kernel<MT, WP, ZMODE, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
     attr_set = true;
   }
   const int64_t blocks_needed = ceil_div(ceil_div(n, ZM_TASK), ZM_WARPS);
   const int64_t cap = (int64_t)num_sms() * 2;
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   ProfScope prof(PROF_ZBUILD, s);
-  zbuild_mma_kernel<MT, WP><<<grid, ZM_WARPS * 32, smem, s>>>(rowptr, src_sorted, g, h, n, d.passes, d.kp, d.kt, d.ktp,
-                                                             d.zk_main, d.zk, zmode, mean, gsc, Z);
+  zbuild_mma_kernel<MT, WP, ZMODE, BWD><<<grid, ZM_WARPS * 32, smem, s>>>(rowptr, src_sorted, g, h, n, d.passes, d.kp, d.kt,
+                                                                         d.ktp, d.zk_main, d.zk, gsc, Z);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
+}
+
+template <int MT, int WP>
+static int zm_dispatch_mode(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
+                            const float* h, int64_t n, void* Z, int zmode, cudaStream_t s, int mean, const float* gsc) {
+  const bool bwd = (mean == 0);
+  if (bwd) {
+    if (!gsc || zmode != 1) {
+      set_error("backward zbuild needs a gather scale and the tf32 mode");
+      return FESR_EINVAL;
+    }
+    return launch_zm<MT, WP, 1, true>(d, rowptr, src_sorted, g, h, n, Z, s, gsc);
+  }
+  if (zmode == 2) return launch_zm<MT, WP, 2, false>(d, rowptr, src_sorted, g, h, n, Z, s, nullptr);
+  return launch_zm<MT, WP, 1, false>(d, rowptr, src_sorted, g, h, n, Z, s, nullptr);
 }
 
 template <int MT>
 static int zm_dispatch_wp(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
                           const float* h, int64_t n, void* Z, int zmode, cudaStream_t s, int mean, const float* gsc) {
   switch (d.wp) {
-    case 16: return launch_zm<MT, 16>(d, rowptr, src_sorted, g, h, n, Z, zmode, s, mean, gsc);
-    case 32: return launch_zm<MT, 32>(d, rowptr, src_sorted, g, h, n, Z, zmode, s, mean, gsc);
-    case 48: return launch_zm<MT, 48>(d, rowptr, src_sorted, g, h, n, Z, zmode, s, mean, gsc);
-    case 64: return launch_zm<MT, 64>(d, rowptr, src_sorted, g, h, n, Z, zmode, s, mean, gsc);
+    case 16: return zm_dispatch_mode<MT, 16>(d, rowptr, src_sorted, g, h, n, Z, zmode, s, mean, gsc);
+    case 32: return zm_dispatch_mode<MT, 32>(d, rowptr, src_sorted, g, h, n, Z, zmode, s, mean, gsc);
+    case 48: return zm_dispatch_mode<MT, 48>(d, rowptr, src_sorted, g, h, n, Z, zmode, s, mean, gsc);
+    case 64: return zm_dispatch_mode<MT, 64>(d, rowptr, src_sorted, g, h, n, Z, zmode, s, mean, gsc);
   }
   set_error("unsupported padded width %d", d.wp);
   return FESR_EINVAL;
