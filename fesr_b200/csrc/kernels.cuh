@@ -11,6 +11,9 @@ int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const
 // g[E, kp]: hidden activations of the edge MLP in CSR edge order, channel-permuted layout
 int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
                        const int32_t* perm, int64_t E, float* g, cudaStream_t s, int round_tf32 = 0);
+// edge_mlp_mma.cu: the two-hidden-layer (KernelNN) case on mma.sync 3xTF32 (fp32-class accuracy)
+int launch_edge_hidden2_mma(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
+                            const int32_t* perm, int64_t E, float* g, cudaStream_t s, int round_tf32);
 int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s,
                  int round_tf32 = 0);
 int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const float* h, int64_t n, float* y, cudaStream_t s);

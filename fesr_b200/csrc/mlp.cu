@@ -5,6 +5,7 @@
 // per forward (their input d_e and weights are layer invariant); the last Linear layer is
 // folded into the node-level contraction Z x T' (see DESIGN.md section 2).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -314,6 +315,8 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
   if (E == 0) return FESR_OK;
   if (d.n_hidden == 2 && d.hidden[0] == d.w && d.hidden[1] == d.w) {
     FESR_CHECK_ARG(p.mlp_w[0] && p.mlp_b[0] && p.mlp_w[1] && p.mlp_b[1], "NULL edge-MLP parameter");
+    static const bool ffma_only = getenv("FESR_EDGE_FFMA") != nullptr;    // A/B switch for profiling
+    if (!ffma_only) return launch_edge_hidden2_mma(d, p, edge_attr, perm, E, g, s, round_tf32);
     const int64_t blocks = ceil_div(E, 128);
     const int grid = (int)(blocks < 16 * (int64_t)num_sms() ? blocks : 16 * (int64_t)num_sms());
     const size_t stage_bytes = (size_t)4 * 32 * (d.kp + 4) * sizeof(float);
