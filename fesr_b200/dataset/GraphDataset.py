@@ -29,8 +29,17 @@ class SubdomainSample(list):
         self.batch = batch
         self.x_dev = x_dev
         self.y_dev = y_dev
+        self.x_host = None        # set by with_host_inputs(): predict() then copies x / y host -> device
+        self.y_host = None
         self.mesh_idx = mesh_idx
         self.num_nodes = num_nodes
+
+    def with_host_inputs(self, x_host, y_host):
+        """Same subdomains, but the per-subdomain input / reference fields come from (pinned) host
+        memory on every predict() call -- a new time step on a mesh whose decomposition is resident."""
+        out = SubdomainSample(list(self), self.batch, None, None, self.mesh_idx, self.num_nodes)
+        out.x_host, out.y_host = x_host, y_host
+        return out
 
 
 class StitchedMesh:
@@ -84,11 +93,12 @@ class SyntheticDuctDataset:
     """
 
     def __init__(self, root=None, transform=None, pre_transform=None, partition=True, sub_size=None, mesh_n=13,
-                 num_meshes=4, boundary_mode="all", device=None, **kwargs):
+                 num_meshes=4, boundary_mode="all", device=None, length_factor=1, **kwargs):
         self.root = root
         self.partition = partition
         self.mesh_n = int(mesh_n)
         self.num_meshes = int(num_meshes)
+        self.length_factor = int(length_factor)
         self.mode = _lib.ALL_INTERSECTING if boundary_mode == "all" else _lib.ONE_REGION
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         probe = synthetic.make_positions(self.mesh_n).shape[0]
@@ -104,7 +114,8 @@ class SyntheticDuctDataset:
         if idx >= self.num_meshes or idx < 0:
             raise IndexError(f"Mesh index {idx} out of range. Maximum index is {self.num_meshes - 1}.")
         if idx not in self._cache:
-            mesh = synthetic.make_duct_mesh(self.mesh_n, seed=idx)
+            mesh = (synthetic.make_duct_mesh(self.mesh_n, seed=idx) if self.length_factor == 1 else
+                    synthetic.make_duct_mesh_long(self.mesh_n, self.length_factor, seed=idx))
             dev = self.device
             pos = torch.from_numpy(mesh.pos).to(dev)
             cells = torch.from_numpy(mesh.cells).to(dev)
@@ -146,11 +157,12 @@ class SyntheticDuctDataset:
 
     __getitem__ = get
 
-    def get_one_full_sample(self, idx):
-        """All subdomains of mesh ``idx`` (reference :1464-1484), with the device batch attached."""
+    def get_one_full_sample(self, idx, materialize=True):
+        """All subdomains of mesh ``idx`` (reference :1464-1484), with the device batch attached.
+        materialize=False skips building the per-subdomain CPU ``Data`` list (large meshes)."""
         c = self._mesh(idx)
         if "datas" not in c:
-            c["datas"] = self._datas(c)
+            c["datas"] = self._datas(c) if materialize else []
         return SubdomainSample(c["datas"], c["batch"], c["x"], c["y"], idx, c["mesh"].num_nodes)
 
     # -- stitch -----------------------------------------------------------------------------
@@ -175,8 +187,22 @@ class SyntheticDuctDataset:
         pred, ref = to_dev(subdomain_data_list), to_dev(subdomain_ref_list)
         field, count, merged = ops.stitch_mean(pred, c["occ"], b.global_ids, want_merged=True)
         rfield, _, rmerged = ops.stitch_mean(ref, c["occ"], b.global_ids, want_merged=True)
-        return StitchedMesh(c["mesh"].pos, c["mesh"].cells, field.cpu(), rfield.cpu(), merged.cpu(), rmerged.cpu(),
-                            b.global_ids.cpu(), count.cpu())
+        if "gids_cpu" not in c:
+            c["gids_cpu"] = b.global_ids.cpu()
+        # one packed device->host copy of everything the caller gets back
+        n_tot, N = b.n_tot, c["mesh"].num_nodes
+        pack = torch.cat([field.reshape(-1), rfield.reshape(-1), merged.reshape(-1), rmerged.reshape(-1),
+                          count.to(torch.float32)])
+        host = torch.empty(pack.numel(), dtype=torch.float32, pin_memory=True)
+        host.copy_(pack, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        o = 0
+        parts = []
+        for rows, cols in ((N, 4), (N, 4), (n_tot, 4), (n_tot, 4), (N, 1)):
+            parts.append(host[o:o + rows * cols].view(rows, cols))
+            o += rows * cols
+        return StitchedMesh(c["mesh"].pos, c["mesh"].cells, parts[0], parts[1], parts[2], parts[3], c["gids_cpu"],
+                            parts[4].view(-1).to(torch.int32))
 
 
 class AnsysDataset(SyntheticDuctDataset):

@@ -63,8 +63,12 @@ def _as_batch(x, device):
     """list[Data] -> (csr, edge_attr, node_ptr, x_dev, y_dev, sizes) as one block-diagonal graph."""
     if isinstance(x, SubdomainSample):
         b = x.batch
-        sizes = np.diff(b.node_ptr.cpu().numpy()).tolist()
-        return b.csr, b.edge_attr, b.node_ptr, x.x_dev, x.y_dev, sizes
+        if getattr(b, "_sizes", None) is None:
+            b._sizes = np.diff(b.node_ptr.cpu().numpy()).tolist()
+        if x.x_host is not None:          # new input / reference fields arriving from the host
+            return (b.csr, b.edge_attr, b.node_ptr, x.x_host.to(device, non_blocking=True),
+                    x.y_host.to(device, non_blocking=True), b._sizes)
+        return b.csr, b.edge_attr, b.node_ptr, x.x_dev, x.y_dev, b._sizes
     sizes = [int(d.x.shape[0]) for d in x]
     offs = np.concatenate([[0], np.cumsum(sizes)])
     xs = torch.cat([d.x for d in x]).to(device, dtype=torch.float32)
@@ -213,15 +217,18 @@ class GNNPartitionScheduler():
             cnt = [bounds[r + 1] - bounds[r] for r in range(world)]
             weight_s = all_gather_rows(weight_s[bounds[rank]:bounds[rank + 1]].contiguous(), cnt)
 
-        pred_cpu = pred.cpu()
+        host = torch.empty(pred.numel() + S, dtype=torch.float32, pin_memory=True)    # one packed D2H copy
+        host.copy_(torch.cat([pred.reshape(-1), weight_s]), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        pred_cpu = host[:pred.numel()].view(pred.shape)
         pred_y_list = TensorList(torch.split(pred_cpu, sizes))
         pred_y_list.dev = pred
-        if isinstance(x, SubdomainSample):
-            ref_y_list = TensorList([d.y for d in x])
+        if isinstance(x, SubdomainSample) and x.y_host is not None:
+            ref_y_list = TensorList(torch.split(x.y_host, sizes))
         else:
             ref_y_list = TensorList([d.y for d in x])
         ref_y_list.dev = y_dev
-        w_cpu = weight_s.cpu()
+        w_cpu = host[pred.numel():]
         weights_list = [w_cpu[s].expand(sizes[s]) for s in range(S)]
         model_idx = labels.cpu().numpy().astype(int)
         return pred_y_list, ref_y_list, model_idx, weights_list
