@@ -46,17 +46,34 @@ class StitchedMesh:
     """Result of reconstruct_from_partition: the appended partitions with averaged point data
     (what the reference returns as a vtkUnstructuredGrid) plus the field on the original mesh."""
 
-    def __init__(self, pos, cells, field, ref_field, merged, merged_ref, global_ids, count):
+    def __init__(self, pos, cells, dev_arrays, global_ids):
         self.pos, self.cells = pos, cells            # original mesh (numpy)
-        self.field, self.ref_field = field, ref_field  # [N, 4] torch CPU
-        self.merged, self.merged_ref = merged, merged_ref  # [sum n_s, 4] torch CPU
+        self._dev = dev_arrays                       # name -> device tensor; copied to the host on first access
+        self._host = {}
         self.global_ids = global_ids
-        self.count = count
-        self.point_data = {"velocity": merged[:, :3], "pressure": merged[:, 3],
-                           "ref_velocity": merged_ref[:, :3], "ref_pressure": merged_ref[:, 3]}
+
+    def _get(self, name):
+        if name not in self._host:
+            t = self._dev[name]
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            host.copy_(t, non_blocking=True)
+            torch.cuda.current_stream(t.device).synchronize()
+            self._host[name] = host
+        return self._host[name]
+
+    field = property(lambda self: self._get("field"))            # [N, 4] prediction on the original mesh
+    ref_field = property(lambda self: self._get("ref_field"))
+    merged = property(lambda self: self._get("merged"))          # [sum n_s, 4] appended partitions, averaged
+    merged_ref = property(lambda self: self._get("merged_ref"))
+    count = property(lambda self: self._get("count"))
+
+    @property
+    def point_data(self):
+        m, r = self.merged, self.merged_ref
+        return {"velocity": m[:, :3], "pressure": m[:, 3], "ref_velocity": r[:, :3], "ref_pressure": r[:, 3]}
 
     def GetNumberOfPoints(self):
-        return int(self.merged.shape[0])
+        return int(self._dev["merged"].shape[0])
 
     def write_vtu(self, path):
         """ASCII .vtu of the ORIGINAL mesh with the stitched point arrays (run_ALDS_3D.py:33-38)."""
@@ -189,20 +206,9 @@ class SyntheticDuctDataset:
         rfield, _, rmerged = ops.stitch_mean(ref, c["occ"], b.global_ids, want_merged=True)
         if "gids_cpu" not in c:
             c["gids_cpu"] = b.global_ids.cpu()
-        # one packed device->host copy of everything the caller gets back
-        n_tot, N = b.n_tot, c["mesh"].num_nodes
-        pack = torch.cat([field.reshape(-1), rfield.reshape(-1), merged.reshape(-1), rmerged.reshape(-1),
-                          count.to(torch.float32)])
-        host = torch.empty(pack.numel(), dtype=torch.float32, pin_memory=True)
-        host.copy_(pack, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        o = 0
-        parts = []
-        for rows, cols in ((N, 4), (N, 4), (n_tot, 4), (n_tot, 4), (N, 1)):
-            parts.append(host[o:o + rows * cols].view(rows, cols))
-            o += rows * cols
-        return StitchedMesh(c["mesh"].pos, c["mesh"].cells, parts[0], parts[1], parts[2], parts[3], c["gids_cpu"],
-                            parts[4].view(-1).to(torch.int32))
+        return StitchedMesh(c["mesh"].pos, c["mesh"].cells,
+                            {"field": field, "ref_field": rfield, "merged": merged, "merged_ref": rmerged, "count": count},
+                            c["gids_cpu"])
 
 
 class AnsysDataset(SyntheticDuctDataset):
