@@ -64,6 +64,14 @@ __device__ __forceinline__ void zm_mma(float (&c)[4], const uint32_t (&a)[4], ui
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// same MMA with a zero C operand: starts an accumulator without a separate zeroing pass
+__device__ __forceinline__ void zm_mma0(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+
 struct ZmItem {
   int k, p, c0, eb, ee;
 };
@@ -77,13 +85,19 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                   int ktp, int zk_main, int zk, const float* __restrict__ gather_scale, void* __restrict__ Zv) {
   constexpr int GROW = 16 * MT;
   constexpr int NT = WP / 8;
-  constexpr int SG = GROW + 8, SH = WP + 8;                 // padded slab row strides (floats)
-  constexpr int BUF = ZM_DEGC * (SG + SH);                  // the gather scale of edge j lives in the pad of g row j
+  // slab row strides (floats): h rows padded by 8 (conflict-free B fragments); g rows unpadded so
+  // that a chunk is one contiguous bulk copy (A fragment loads are then 2-way conflicted)
+  constexpr int SG = GROW, SH = WP + 8;
+  constexpr int BUF = ZM_DEGC * (SG + SH) + ZM_DEGC;        // + per-edge gather scale (backward)
+  constexpr int LPR = WP / 4, RPI = 32 / LPR;
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* slab = smem + warp * (2 * BUF);
+  const uint32_t slab_u32 = zm_smem(slab);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ZM_WARPS * 2 * BUF) + warp * 2;
   const int gq = lane >> 2, tq = lane & 3;                  // MMA fragment coordinates
+  const int hj = lane / LPR, hc = lane % LPR;
+  const bool h_lane = lane < RPI * LPR;
   const unsigned FULL = 0xffffffffu;
 
   for (int t = lane; t < 2 * BUF; t += 32) slab[t] = 0.f;   // stale slab contents must stay finite
@@ -146,17 +160,34 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
       float* sg = slab + buf * BUF;
       float* sh = sg + ZM_DEGC * SG;
       const int m = min(ZM_DEGC, it.ee - it.c0);
-      if (lane == 0) zm_expect(&bars[buf], (uint32_t)(m * (GROW + WP) * 4));
+      // g: the chunk's rows are one contiguous block when a row is exactly one pass wide -> ONE bulk
+      // copy (unpadded rows, SG == GROW); otherwise one bulk copy per row.  h[src]: 16-byte cp.async,
+      // LPR lanes per gathered row.
+      if (lane == 0) zm_expect(&bars[buf], (uint32_t)(m * GROW * 4));
       __syncwarp();
-      if (lane < m) {
+      if (kp == GROW) {
+        if (lane == 0 && m > 0) zm_bulk(sg, g + (int64_t)it.c0 * GROW, (uint32_t)(m * GROW * 4), &bars[buf]);
+      } else if (lane < m) {
         zm_bulk(sg + lane * SG, g + (int64_t)(it.c0 + lane) * kp + it.p * GROW, GROW * 4, &bars[buf]);
-        zm_bulk(sh + lane * SH, h + (int64_t)src_reg * WP, WP * 4, &bars[buf]);
-      } else if (lane < ((m + 7) & ~7)) {
+      }
+      if (lane >= m && lane < ((m + 7) & ~7)) {
         // unused edge slots of an issued k-step: g row = 0 (the stale h row is finite)
 #pragma unroll
         for (int c = 0; c < GROW; c += 4) *reinterpret_cast<float4*>(sg + lane * SG + c) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (BWD && lane < ZM_DEGC) sg[lane * SG + GROW] = sc_reg;
+      const uint32_t sh_lane = slab_u32 + (uint32_t)(buf * BUF + ZM_DEGC * SG + hj * SH + 4 * hc) * 4u;
+      const float* h_lane_ptr = h + 4 * hc;
+#pragma unroll 2
+      for (int j0 = 0; j0 < m; j0 += RPI) {
+        const int j = j0 + hj;
+        const int s = __shfl_sync(FULL, src_reg, j & 31);
+        if (h_lane && j < m)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sh_lane + (uint32_t)(j0 * SH * 4)),
+                       "l"(h_lane_ptr + (int64_t)s * WP)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (BWD && lane < ZM_DEGC) sh[ZM_DEGC * SH + lane] = sc_reg;
     };
 
     ZmItem cur = node_item(0);
@@ -170,9 +201,12 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     float sc_nxt = load_scale(nxt, src_nxt);
     float acc[MT][NT][4];
     while (cur.k < nn) {
-      if (nxt.k < nn) issue(nxt, buf ^ 1, src_nxt, sc_nxt);
+      const bool has_next = nxt.k < nn;
+      if (has_next) issue(nxt, buf ^ 1, src_nxt, sc_nxt);
       const ZmItem nn2 = advance(nxt);
       const int src_nn2 = load_src(nn2);
+      if (has_next) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
       if (buf == 0) {
         zm_wait(&bars[0], phase0);
         phase0 ^= 1;
@@ -181,7 +215,8 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
         phase1 ^= 1;
       }
       __syncwarp();
-      if (cur.c0 == cur.eb) {
+      const bool fresh = cur.c0 == cur.eb;                 // first chunk of (node, pass)
+      if (fresh && cur.ee == cur.eb) {                      // zero in-degree: the row is all zeros
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -198,7 +233,7 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
           const int e0 = ks * 8 + tq, e1 = e0 + 4;            // this lane's two edge rows of the k-step
           uint32_t a[MT][4];
           if constexpr (BWD) {
-            const float s0 = sg[e0 * SG + GROW], s1 = sg[e1 * SG + GROW];
+            const float s0 = sh[ZM_DEGC * SH + e0], s1 = sh[ZM_DEGC * SH + e1];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
               a[mt][0] = zm_tf32(sg[e0 * SG + mt * 16 + gq] * s0);
@@ -225,8 +260,13 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
               b0 = __float_as_uint(sh[e0 * SH + nt * 8 + gq]);
               b1 = __float_as_uint(sh[e1 * SH + nt * 8 + gq]);
             }
+            if (ks == 0 && fresh) {
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) zm_mma(acc[mt][nt], a[mt], b0, b1);
+              for (int mt = 0; mt < MT; ++mt) zm_mma0(acc[mt][nt], a[mt], b0, b1);
+            } else {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) zm_mma(acc[mt][nt], a[mt], b0, b1);
+            }
           }
         }
       }
@@ -289,7 +329,7 @@ template <int MT, int WP, int ZMODE, bool BWD>
 static int launch_zm(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* g,
                      const float* h, int64_t n, void* Z, cudaStream_t s, const float* gsc) {
   constexpr size_t smem =
-      (size_t)ZM_WARPS * 2 * (ZM_DEGC * (16 * MT + 8 + WP + 8)) * sizeof(float) + ZM_WARPS * 2 * sizeof(uint64_t);
+      (size_t)ZM_WARPS * 2 * (ZM_DEGC * (16 * MT + WP + 8) + ZM_DEGC) * sizeof(float) + ZM_WARPS * 2 * sizeof(uint64_t);
   static bool attr_set = false;
   if (!attr_set) {
     FESR_CUDA(cudaFuncSetAttribute(zbuild_mma_kernel<MT, WP, ZMODE, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
