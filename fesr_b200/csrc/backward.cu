@@ -186,6 +186,7 @@ static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n
   w.da[0] = c.take<float>(ee * dmax);
   w.da[1] = c.take<float>(ee * dmax);
   size_t g = gemm_ws_bytes(d.zk, d.wp, n);
+  if (wgrad_mma_ws_bytes(d) > g) g = wgrad_mma_ws_bytes(d);
   for (int l = 0; l < d.n_hidden; ++l) {
     const size_t b = gemm_ws_bytes(d.hidden[l], l > 0 ? d.hidden[l - 1] : 1, E);
     if (b > g) g = b;
@@ -269,10 +270,18 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     FESR_LAUNCH_CHECK();
     if ((rc = launch_colsum(w.dpre, n, d.wp, d.wp, 1, w.dbias, w.colsum_ws, s))) return rc;
     // dT' += Z_l^T dpre
-    GEMM(fw.Z[l], 1, d.zk, w.dpre, d.wp, 1, w.dT, d.wp, 1, d.zk, d.wp, n, 1);
+    if (rnd) {
+      if ((rc = launch_wgrad_mma(d, fw.Z[l], w.dpre, n, w.dT, w.gemm_ws, s))) return rc;
+    } else {
+      GEMM(fw.Z[l], 1, d.zk, w.dpre, d.wp, 1, w.dT, d.wp, 1, d.zk, d.wp, n, 1);
+    }
     if (E > 0) {
       // dZ = dpre T'^T ; dg += edge_grad(dZ, h_l)
-      GEMM(w.dpre, d.wp, 1, fw.prep.tprime, 1, d.wp, w.BZ, d.zk, 1, n, d.zk, d.wp, 0);
+      if (rnd) {
+        if ((rc = launch_dz_mma(d, w.dpre, fw.prep.tprime, n, w.BZ, s))) return rc;
+      } else {
+        GEMM(w.dpre, d.wp, 1, fw.prep.tprime, 1, d.wp, w.BZ, d.zk, 1, n, d.zk, d.wp, 0);
+      }
       if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, 1, w.dg, s))) return rc;
     }
     // dh_l = [sum over out-edges of g (x) dpre[dst]/deg[dst]  ++  dpre] T~
