@@ -5,6 +5,8 @@
 // One warp owns 32 consecutive CSR edges: layer 0 is evaluated straight into MMA A-fragments
 // (no shared-memory round trip), W_hi/W_lo live in shared memory with a conflict-free row pad,
 // the g rows are staged in shared memory and written with coalesced 128-bit stores.
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace fesr {
@@ -111,17 +113,37 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
           const int row = mt * 16 + gq + 8 * (r >> 1);
           if (c < w) {
             float v = em_act(acc[mt][nt][r] + b1[c], leaky);
-            if (round_tf32) v = __uint_as_float(em_tf32(v));
+            if (round_tf32 == 1) v = __uint_as_float(em_tf32(v));
             wst[row * sstride + off_of[c]] = v;
           }
         }
     wst[lane * sstride + off_of[k1 - 1]] = 1.f;
     __syncwarp();
-    const int q4 = kp >> 2;
-    for (int t = lane; t < 32 * q4; t += 32) {
-      const int r = t / q4, c4 = t - r * q4;
-      if (e_base + r < E)
-        *reinterpret_cast<float4*>(g + (e_base + r) * kp + 4 * c4) = *reinterpret_cast<const float4*>(wst + r * sstride + 4 * c4);
+    if (round_tf32 == 2) {                       // fp16 rows (FESR_PREC_F16): 8 halfs = 16 bytes per store
+      __half* gh = reinterpret_cast<__half*>(g);
+      const int q8 = kp >> 3;
+      for (int t = lane; t < 32 * q8; t += 32) {
+        const int r = t / q8, c8 = t - r * q8;
+        if (e_base + r < E) {
+          const float4 lo = *reinterpret_cast<const float4*>(wst + r * sstride + 8 * c8);
+          const float4 hi = *reinterpret_cast<const float4*>(wst + r * sstride + 8 * c8 + 4);
+          __half2 p0 = __floats2half2_rn(lo.x, lo.y), p1 = __floats2half2_rn(lo.z, lo.w);
+          __half2 p2 = __floats2half2_rn(hi.x, hi.y), p3 = __floats2half2_rn(hi.z, hi.w);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&p0);
+          pk.y = *reinterpret_cast<uint32_t*>(&p1);
+          pk.z = *reinterpret_cast<uint32_t*>(&p2);
+          pk.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(gh + (e_base + r) * kp + 8 * c8) = pk;
+        }
+      }
+    } else {
+      const int q4 = kp >> 2;
+      for (int t = lane; t < 32 * q4; t += 32) {
+        const int r = t / q4, c4 = t - r * q4;
+        if (e_base + r < E)
+          *reinterpret_cast<float4*>(g + (e_base + r) * kp + 4 * c4) = *reinterpret_cast<const float4*>(wst + r * sstride + 4 * c4);
+      }
     }
     __syncwarp();
   }

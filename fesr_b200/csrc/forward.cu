@@ -56,7 +56,7 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   static const bool ffma_only = getenv("FESR_ZBUILD_FFMA") != nullptr;   // A/B switch for profiling
   // reduced-precision arms: g and h are rounded to tf32 by their producers, so the gather kernel
   // feeds them to the tensor cores without converting
-  const int rnd_in = precision != FESR_PREC_FP32;
+  const int rnd_in = precision == FESR_PREC_FP32 ? 0 : (precision == FESR_PREC_F16 ? 2 : 1);   // 2: fp16 g and h
   if ((rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s, rnd_in))) return rc;
   if ((rc = launch_fc_in(d, ws.prep, x, n, ws.h[0], s, rnd_in))) return rc;
   const float* h_last = ws.h[0];
@@ -65,7 +65,9 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
     float* h_out = keep_for_backward ? ws.h[l + 1] : ws.h[(l + 1) & 1];
     float* Z = keep_for_backward ? ws.Z[l] : ws.Z[0];
     const int zmode = precision == FESR_PREC_FP32 ? 0 : (precision == FESR_PREC_F16 ? 2 : 1);
-    if (zmode == 0 || ffma_only)
+    if (zmode == 2)
+      rc = launch_zbuild_f16(d, rowptr, src_sorted, ws.g, h_in, n, Z, s);
+    else if (zmode == 0 || ffma_only)
       rc = launch_zbuild(d, rowptr, src_sorted, ws.g, h_in, n, Z, zmode, s);
     else
       rc = launch_zbuild_mma(d, rowptr, src_sorted, ws.g, h_in, n, Z, zmode, s);
@@ -76,11 +78,11 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
     else if (precision == FESR_PREC_TF32)
       rc = launch_node_gemm_tf32(d, ws.prep.tprime_t, ws.prep.bias_p, epi, Z, n, h_out, s, 1);
     else
-      rc = launch_node_gemm_f16(d, ws.prep.tprime_t_h, ws.prep.bias_p, epi, Z, n, h_out, s, 1);
+      rc = launch_node_gemm_f16(d, ws.prep.tprime_t_h, ws.prep.bias_p, epi, Z, n, h_out, s, 2);
     if (rc) return rc;
     h_last = h_out;
   }
-  return launch_fc_out(d, *params, h_last, n, y, s);
+  return launch_fc_out(d, *params, h_last, n, y, s, precision == FESR_PREC_F16);
 }
 
 }  // extern "C"

@@ -12,6 +12,7 @@
 // The kernel is HBM-bound on streaming Z (AI = 2*wp/4 = 24 flop/B), so the 8-deep TMA ring
 // (176 KB in flight per SM) is what matters, not MMA issue rate.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "kernels.cuh"
 
@@ -228,7 +229,29 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < n) {
+        if (row < n && round_out == 2) {          // fp16 h (FESR_PREC_F16): 16 columns = 2 x 16-byte stores
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float x0 = __uint_as_float(r[j]), x1 = __uint_as_float(r[j + 1]);
+            const int c = c0 + j;
+            if (epi != EPI_NONE) {
+              x0 += bias_p[c];
+              x1 += bias_p[c + 1];
+            }
+            if (epi == EPI_BIAS_CONST1) {
+              if (c == w) x0 = 1.f;
+              if (c + 1 == w) x1 = 1.f;
+            } else if (epi == EPI_BIAS_RELU) {
+              x0 = fmaxf(x0, 0.f);
+              x1 = fmaxf(x1, 0.f);
+            }
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[j / 2]) : "f"(x1), "f"(x0));
+          }
+          __half* hh = reinterpret_cast<__half*>(h_out) + row * WP + c0;
+          *reinterpret_cast<uint4*>(hh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(hh + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        } else if (row < n) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float v[4];
@@ -242,7 +265,7 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               } else if (epi == EPI_BIAS_RELU) {
                 x = fmaxf(x, 0.f);
               }
-              if (round_out) {
+              if (round_out == 1) {
                 uint32_t u;
                 asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
                 x = __uint_as_float(u);

@@ -16,7 +16,8 @@ int launch_edge_hidden2_mma(const fesr_model_dims& d, const fesr_params& p, cons
                             const int32_t* perm, int64_t E, float* g, cudaStream_t s, int round_tf32);
 int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s,
                  int round_tf32 = 0);
-int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const float* h, int64_t n, float* y, cudaStream_t s);
+int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const void* h, int64_t n, float* y, cudaStream_t s,
+                  int h_half = 0);
 
 // zbuild.cu ---------------------------------------------------------------------------
 // Z[i, :] = (1/max(deg,1)) * sum_{e -> i} g_e (x) h[src_e]   ++  h[i]  (root block)
@@ -29,6 +30,10 @@ int launch_zbuild(const fesr_model_dims& d, const int32_t* rowptr, const int32_t
 int launch_zbuild_mma(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted,
                       const float* g, const float* h, int64_t n, void* Z, int zmode, cudaStream_t s,
                       int mean = 1, const float* gather_scale = nullptr);
+
+// zbuild_f16.cu: FESR_PREC_F16 arm -- g [E,kp], h [n,wp] and Z [n,zk] are all fp16
+int launch_zbuild_f16(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted,
+                      const void* g_half, const void* h_half, int64_t n, void* Z_half, cudaStream_t s);
 
 // gemm_simt.cu ------------------------------------------------------------------------
 // h_out[n, wp] = epilogue(Z[n, zk] x tprime[zk, wp] + bias)

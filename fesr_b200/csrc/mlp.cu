@@ -241,7 +241,8 @@ edge_hidden_kernel(EdgeHiddenArgs a, const float* __restrict__ edge_attr, const 
       if (ge >= E) break;
       const int k = chan_of[off];
       const float v = (k < 0) ? 0.f : (k == K ? 1.f : in[k * EH_TE + e]);
-      g[ge * a.kp + off] = round_tf32 ? tf32_rna(v) : v;
+      if (round_tf32 == 2) reinterpret_cast<__half*>(g)[ge * a.kp + off] = __float2half_rn(v);
+      else g[ge * a.kp + off] = round_tf32 ? tf32_rna(v) : v;
     }
     __syncthreads();
   }
@@ -316,7 +317,7 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
   if (d.n_hidden == 2 && d.hidden[0] == d.w && d.hidden[1] == d.w) {
     FESR_CHECK_ARG(p.mlp_w[0] && p.mlp_b[0] && p.mlp_w[1] && p.mlp_b[1], "NULL edge-MLP parameter");
     static const bool ffma_only = getenv("FESR_EDGE_FFMA") != nullptr;    // A/B switch for profiling
-    if (!ffma_only) return launch_edge_hidden2_mma(d, p, edge_attr, perm, E, g, s, round_tf32);
+    if (!ffma_only || round_tf32 == 2) return launch_edge_hidden2_mma(d, p, edge_attr, perm, E, g, s, round_tf32);
     const int64_t blocks = ceil_div(E, 128);
     const int grid = (int)(blocks < 16 * (int64_t)num_sms() ? blocks : 16 * (int64_t)num_sms());
     const size_t stage_bytes = (size_t)4 * 32 * (d.kp + 4) * sizeof(float);
@@ -394,6 +395,14 @@ __global__ void fc_in_kernel(const float* __restrict__ x, const float* __restric
     acc.z = fmaf(xv, wv.z, acc.z);
     acc.w = fmaf(xv, wv.w, acc.w);
   }
+  if (round_tf32 == 2) {
+    __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(h) + i * wp + b4) = pk;
+    return;
+  }
   if (round_tf32) {
     acc.x = tf32_rna(acc.x);
     acc.y = tf32_rna(acc.y);
@@ -414,25 +423,31 @@ int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, in
 }
 
 // y[i, c] = h[i, :w] . W2[c, :] + b2[c]   (models/model.py:561 / :284); one warp per 8 nodes
-__global__ void fc_out_kernel(const float* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2,
-                              int w, int wp, int out_ch, int64_t n, float* __restrict__ y) {
+__global__ void fc_out_kernel(const void* __restrict__ hv, const float* __restrict__ w2, const float* __restrict__ b2,
+                              int w, int wp, int out_ch, int64_t n, int h_half, float* __restrict__ y) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= n * out_ch) return;
   const int64_t i = idx / out_ch;
   const int c = (int)(idx % out_ch);
-  const float* hr = h + i * wp;
   const float* wr = w2 + c * w;
   float acc = b2[c];
-  for (int b = 0; b < w; ++b) acc = fmaf(hr[b], wr[b], acc);
+  if (h_half) {
+    const __half* hr = static_cast<const __half*>(hv) + i * wp;
+    for (int b = 0; b < w; ++b) acc = fmaf(__half2float(hr[b]), wr[b], acc);
+  } else {
+    const float* hr = static_cast<const float*>(hv) + i * wp;
+    for (int b = 0; b < w; ++b) acc = fmaf(hr[b], wr[b], acc);
+  }
   y[idx] = acc;
 }
 
-int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const float* h, int64_t n, float* y, cudaStream_t s) {
+int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const void* h, int64_t n, float* y, cudaStream_t s,
+                  int h_half) {
   if (n == 0) return FESR_OK;
   FESR_CHECK_ARG(p.fc2_w && p.fc2_b, "NULL fc2 parameter");
   const int64_t total = n * d.out_ch;
   ProfScope prof(PROF_FC_OUT, s);
-  fc_out_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(h, p.fc2_w, p.fc2_b, d.w, d.wp, d.out_ch, n, y);
+  fc_out_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(h, p.fc2_w, p.fc2_b, d.w, d.wp, d.out_ch, n, h_half, y);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
