@@ -317,7 +317,15 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
   if (d.n_hidden == 2 && d.hidden[0] == d.w && d.hidden[1] == d.w) {
     FESR_CHECK_ARG(p.mlp_w[0] && p.mlp_b[0] && p.mlp_w[1] && p.mlp_b[1], "NULL edge-MLP parameter");
     static const bool ffma_only = getenv("FESR_EDGE_FFMA") != nullptr;    // A/B switch for profiling
-    if (!ffma_only || round_tf32 == 2) return launch_edge_hidden2_mma(d, p, edge_attr, perm, E, g, s, round_tf32);
+    int covered = 1;
+    if (!ffma_only || round_tf32 == 2) {
+      covered = launch_edge_hidden2_mma(d, p, edge_attr, perm, E, g, s, round_tf32);
+      if (covered != 1) return covered;
+    }
+  }
+  // shapes the tensor-core kernel does not cover: fp32 / tf32 rows from the thread-per-edge kernel,
+  // fp16 rows from the generic tiled kernel below
+  if (d.n_hidden == 2 && d.hidden[0] == d.w && d.hidden[1] == d.w && round_tf32 != 2 && d.w <= 64) {
     const int64_t blocks = ceil_div(E, 128);
     const int grid = (int)(blocks < 16 * (int64_t)num_sms() ? blocks : 16 * (int64_t)num_sms());
     const size_t stage_bytes = (size_t)4 * 32 * (d.kp + 4) * sizeof(float);
