@@ -78,6 +78,7 @@ struct Prepared {
   float* ttilde_t;   // [wp, zk]  K-major tf32 copy of T~
   void* tprime_t_h;  // [wp, zk]  K-major fp16 copy of T'   (FESR_PREC_F16)
   void* ttilde_t_h;  // [wp, zk]  K-major fp16 copy of T~
+  void* tfused_h;    // [parts, 48, 832] fp16 T' in the fused layer kernel's K order (layer_fused.cu), or NULL
   float* bias_p;     // [wp]
   float* fc1_wp;     // [in_ch, wp] transposed + padded
   float* fc1_bp;     // [wp] (TEECNet: constant-1 column set here)

@@ -27,7 +27,7 @@ __device__ __forceinline__ void em_mma(float (&c)[4], const uint32_t (&a)[4], ui
 __device__ __forceinline__ float em_act(float v, int leaky) { return leaky ? (v > 0.f ? v : 0.01f * v) : fmaxf(v, 0.f); }
 
 // WPAD: padded input width (K of the GEMM); NTO: output n-tiles = kp / 8; TERMS: 1 or 3; OMODE: 0 fp32,
-// 1 fp32 rounded to tf32, 2 fp16
+// 1 fp32 rounded to tf32, 2 fp16, 3 fp16 planar [KP/16][E][16] (the fused layer kernel's slot groups)
 template <int WPAD, int NTO, int TERMS, int OMODE>
 __global__ void __launch_bounds__(128)
 edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
@@ -39,7 +39,7 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
   __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1p[KP];
   __shared__ __align__(16) uint32_t whi[WPAD][SB];                     // [in][slot], tf32 bit patterns
   __shared__ __align__(16) uint32_t wlo[TERMS == 3 ? WPAD : 1][SB];
-  __shared__ __align__(16) float stage[4][32][SST];
+  extern __shared__ __align__(16) float stage_dyn[];                   // [4 warps][32 edges][SST]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, tq = lane & 3;
   for (int i = tid; i < WPAD; i += blockDim.x) {
@@ -60,7 +60,7 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
   }
   __syncthreads();
 
-  float (*wst)[SST] = stage[warp];
+  float (*wst)[SST] = reinterpret_cast<float (*)[SST]>(stage_dyn + (size_t)warp * 32 * SST);
   const int64_t n_groups = (E + 31) / 32;
   for (int64_t grp = (int64_t)blockIdx.x * 4 + warp; grp < n_groups; grp += (int64_t)gridDim.x * 4) {
     const int64_t e_base = grp * 32;
@@ -134,7 +134,7 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
         }
     }
     __syncwarp();
-    if (OMODE == 2) {                            // fp16 rows: 8 halfs = 16 bytes per store
+    if (OMODE >= 2) {                            // fp16 rows: 8 halfs = 16 bytes per store
       __half* gh = static_cast<__half*>(gv);
       constexpr int Q8 = KP / 8;
       for (int t = lane; t < 32 * Q8; t += 32) {
@@ -149,7 +149,8 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
           pk.y = *reinterpret_cast<uint32_t*>(&p1);
           pk.z = *reinterpret_cast<uint32_t*>(&p2);
           pk.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(gh + (e_base + r) * KP + 8 * c8) = pk;
+          if (OMODE == 3) *reinterpret_cast<uint4*>(gh + ((int64_t)(c8 >> 1) * E + e_base + r) * 16 + (c8 & 1) * 8) = pk;
+          else *reinterpret_cast<uint4*>(gh + (e_base + r) * KP + 8 * c8) = pk;
         }
       }
     } else {
@@ -171,12 +172,22 @@ static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const flo
   const int64_t blocks = ceil_div(ceil_div(E, 32), 4);
   const int grid = (int)(blocks < 8ll * num_sms() ? blocks : 8ll * num_sms());
   ProfScope prof(PROF_EDGE_HIDDEN, s);
+  constexpr size_t stage_bytes = (size_t)4 * 32 * (NTO * 8 + 4) * sizeof(float);
 #define FESR_EH(TERMS, OMODE)                                                                                   \
-  edge_hidden2_mma_kernel<WPAD, NTO, TERMS, OMODE><<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], \
+  edge_hidden2_mma_kernel<WPAD, NTO, TERMS, OMODE><<<grid, 128, stage_bytes, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], \
                                                                         d.w, d.leaky, d.kt, d.ktp, d.k1, edge_attr, perm, E, g)
+  static bool attr_set = false;
+  if (!attr_set) {   // static + dynamic shared memory exceeds 48 KB for the widest rows
+    FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_mma_kernel<WPAD, NTO, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_mma_kernel<WPAD, NTO, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_mma_kernel<WPAD, NTO, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_mma_kernel<WPAD, NTO, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    attr_set = true;
+  }
   if (omode == 0) FESR_EH(3, 0);
   else if (omode == 1) FESR_EH(1, 1);
-  else FESR_EH(1, 2);
+  else if (omode == 2) FESR_EH(1, 2);
+  else FESR_EH(1, 3);
 #undef FESR_EH
   FESR_LAUNCH_CHECK();
   return FESR_OK;

@@ -57,13 +57,26 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   // reduced-precision arms: g and h are rounded to tf32 by their producers, so the gather kernel
   // feeds them to the tensor cores without converting
   const int rnd_in = precision == FESR_PREC_FP32 ? 0 : (precision == FESR_PREC_F16 ? 2 : 1);   // 2: fp16 g and h
-  if ((rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s, rnd_in))) return rc;
+  // FESR_PREC_F16 predict of the KernelNN shape: one fused kernel per layer (layer_fused.cu), Z stays on chip.
+  // FESR_FUSE=0 selects the two-kernel path (A/B switch for profiling); 1..3 = parts per launch
+  const char* fuse_env = getenv("FESR_FUSE");
+  const int fuse_mode = fuse_env ? atoi(fuse_env) : 3;
+  const bool fused = precision == FESR_PREC_F16 && !keep_for_backward && fuse_mode > 0 && layer_fused_supported(d) &&
+                     ws.prep.tfused_h != nullptr && E > 0;
+  if ((rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s, fused ? 3 : rnd_in))) return rc;
   if ((rc = launch_fc_in(d, ws.prep, x, n, ws.h[0], s, rnd_in))) return rc;
   const float* h_last = ws.h[0];
   for (int l = 0; l < d.layers; ++l) {
     const float* h_in = keep_for_backward ? ws.h[l] : ws.h[l & 1];
     float* h_out = keep_for_backward ? ws.h[l + 1] : ws.h[(l + 1) & 1];
     float* Z = keep_for_backward ? ws.Z[l] : ws.Z[0];
+    if (fused) {
+      if ((rc = launch_layer_fused_f16(d, rowptr, src_sorted, ws.g, E, h_in, n, ws.prep.tfused_h, ws.prep.bias_p, Z, h_out,
+                                       d.w <= 43 ? fuse_mode : (fuse_mode > 2 ? 2 : fuse_mode), s)))
+        return rc;
+      h_last = h_out;
+      continue;
+    }
     const int zmode = precision == FESR_PREC_FP32 ? 0 : (precision == FESR_PREC_F16 ? 2 : 1);
     if (zmode == 2)
       rc = launch_zbuild_f16(d, rowptr, src_sorted, ws.g, h_in, n, Z, s);

@@ -35,6 +35,16 @@ int launch_zbuild_mma(const fesr_model_dims& d, const int32_t* rowptr, const int
 int launch_zbuild_f16(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted,
                       const void* g_half, const void* h_half, int64_t n, void* Z_half, cudaStream_t s);
 
+// layer_fused.cu: zbuild + node contraction + epilogue of one layer in one kernel (FESR_PREC_F16)
+bool layer_fused_supported(const fesr_model_dims& d);
+size_t layer_fused_tf_elems(const fesr_model_dims& d);
+int launch_prepare_tfused(const fesr_model_dims& d, const float* tprime, void* tf, cudaStream_t s);
+// g3: fp16 planar [kp/16][E][16] (launch_edge_hidden with round mode 3); P: fp32 [n, 48] scratch;
+// mode: parts per launch (0 = as many as the TMEM lanes hold)
+int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* g3,
+                           int64_t E, const void* h_in, int64_t n, const void* tf, const float* bias_p, float* P,
+                           void* h_out, int mode, cudaStream_t s);
+
 // gemm_simt.cu ------------------------------------------------------------------------
 // h_out[n, wp] = epilogue(Z[n, zk] x tprime[zk, wp] + bias)
 // epilogue modes

@@ -27,6 +27,7 @@ Prepared carve_prepared(Carver& c, const fesr_model_dims& d) {
   w.ttilde_t = c.take<float>((size_t)d.zk * d.wp);
   w.tprime_t_h = c.take<__half>((size_t)d.zk * d.wp);
   w.ttilde_t_h = c.take<__half>((size_t)d.zk * d.wp);
+  w.tfused_h = layer_fused_supported(d) ? c.take<__half>(layer_fused_tf_elems(d)) : nullptr;
   w.bias_p = c.take<float>(d.wp);
   w.fc1_wp = c.take<float>((size_t)d.in_ch * d.wp);
   w.fc1_bp = c.take<float>(d.wp);
@@ -119,6 +120,7 @@ int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const
   FESR_LAUNCH_CHECK();
   prepare_small_kernel<<<1, 64, 0, s>>>(d, p.fc1_w, p.fc1_b, p.bias, w.bias_p, w.fc1_wp, w.fc1_bp);
   FESR_LAUNCH_CHECK();
+  if (w.tfused_h) return launch_prepare_tfused(d, w.tprime, w.tfused_h, s);
   return FESR_OK;
 }
 
@@ -318,11 +320,12 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
     FESR_CHECK_ARG(p.mlp_w[0] && p.mlp_b[0] && p.mlp_w[1] && p.mlp_b[1], "NULL edge-MLP parameter");
     static const bool ffma_only = getenv("FESR_EDGE_FFMA") != nullptr;    // A/B switch for profiling
     int covered = 1;
-    if (!ffma_only || round_tf32 == 2) {
+    if (!ffma_only || round_tf32 >= 2) {
       covered = launch_edge_hidden2_mma(d, p, edge_attr, perm, E, g, s, round_tf32);
       if (covered != 1) return covered;
     }
   }
+  FESR_CHECK_ARG(round_tf32 != 3, "planar fp16 g rows are only produced for the shapes the fused layer kernel covers");
   // shapes the tensor-core kernel does not cover: fp32 / tf32 rows from the thread-per-edge kernel,
   // fp16 rows from the generic tiled kernel below
   if (d.n_hidden == 2 && d.hidden[0] == d.w && d.hidden[1] == d.w && round_tf32 != 2 && d.w <= 64) {

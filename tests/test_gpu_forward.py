@@ -156,3 +156,78 @@ def test_tf32_small_widths(golden, name, kind, w, L):
     for prec in ("tf32", "f16"):
         y = _run(m, golden["x"], golden["ref_edge_index"], golden["ref_edge_attr"], precision=prec)
         assert rel_l2(y, golden[name + "_y"]) < TOL[prec], prec
+
+
+# ----------------------------------------------------------------------------- fused layer kernel
+def _run_fuse_mode(monkeypatch, mode, m, x, ei, ea):
+    monkeypatch.setenv("FESR_FUSE", str(mode))
+    return _run(m, x, ei, ea, precision="f16")
+
+
+def test_fused_layer_kernel_all_launch_modes_50k(shipped, monkeypatch):
+    """layer_fused.cu (Z kept on chip, T' in TMEM) in its 1-, 2- and 3-launch-per-layer forms against the
+    two-kernel f16 path (FESR_FUSE=0) and the fp32 CPU oracle, 52 728-cell duct, shipped w=43 weights."""
+    from fesr_b200.dataset.synthetic import make_duct_mesh
+    mesh = make_duct_mesh("50k")
+    src, dst, ea = og.build_edges(mesh.cells, mesh.pos)
+    ei = np.stack([src, dst])
+    m, o = _models("neuralop", 43, 5)
+    sd = shipped_state_dict(shipped, "neuralop")
+    m.load_state_dict(sd)
+    o.load_state_dict(sd)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        yo = o(torch.from_numpy(mesh.x), torch.from_numpy(ei), torch.from_numpy(ea)).numpy()
+    y0 = _run_fuse_mode(monkeypatch, 0, m, mesh.x, ei, ea)
+    assert rel_l2(y0, yo) < TOL["f16"]
+    for mode in (1, 2, 3):
+        y = _run_fuse_mode(monkeypatch, mode, m, mesh.x, ei, ea)
+        err, dev = rel_l2(y, yo), rel_l2(y, y0)
+        print(f"fused mode {mode}: rel-L2 vs oracle {err:.3e}, vs two-kernel path {dev:.3e}")
+        assert err < TOL["f16"], mode
+        assert dev < 5e-4, mode
+        assert np.array_equal(y, _run_fuse_mode(monkeypatch, mode, m, mesh.x, ei, ea)), "not deterministic"
+
+
+def test_fused_layer_kernel_ragged_graph(shipped, monkeypatch):
+    """isolated nodes, in-degrees above one 16-edge chunk, a node count that is not a multiple of the tile."""
+    rng = np.random.default_rng(7)
+    n = 16 * 37 + 5
+    deg = rng.integers(0, 40, size=n)
+    deg[rng.random(n) < 0.2] = 0
+    dst = np.repeat(np.arange(n), deg)
+    src = rng.integers(0, n, size=dst.size)
+    order = rng.permutation(dst.size)
+    ei = np.stack([src[order], dst[order]]).astype(np.int64)
+    ea = rng.uniform(2e-3, 6e-3, size=dst.size).astype(np.float32)
+    x = rng.uniform(0.0, 1.0, size=(n, 4)).astype(np.float32)     # normalised fields, as the datasets produce
+    m, o = _models("neuralop", 43, 5)
+    sd = shipped_state_dict(shipped, "neuralop")
+    m.load_state_dict(sd)
+    o.load_state_dict(sd)
+    with torch.no_grad():
+        yo = o(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ea)).numpy()
+    for mode in (0, 1, 2, 3):
+        y = _run_fuse_mode(monkeypatch, mode, m, x, ei, ea)
+        err = rel_l2(y, yo)
+        print(f"ragged, fused mode {mode}: rel-L2 {err:.3e}")
+        assert err < TOL["f16"], mode
+
+
+@pytest.mark.parametrize("w", [40, 36])
+def test_fused_layer_kernel_narrower_widths(monkeypatch, w):
+    """widths below 43 use the same kernel without the CUDA-core fix-up row."""
+    torch.manual_seed(w)
+    m, o = _models("neuralop", w, 3)
+    o.load_state_dict(m.state_dict())
+    rng = np.random.default_rng(w)
+    n = 700
+    dst = np.repeat(np.arange(n), rng.integers(1, 14, size=n))
+    src = rng.integers(0, n, size=dst.size)
+    ei = np.stack([src, dst]).astype(np.int64)
+    ea = rng.uniform(2e-3, 6e-3, size=dst.size).astype(np.float32)
+    x = rng.normal(size=(n, 4)).astype(np.float32)
+    with torch.no_grad():
+        yo = o(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ea)).numpy()
+    for mode in (0, 3):
+        assert rel_l2(_run_fuse_mode(monkeypatch, mode, m, x, ei, ea), yo) < TOL["f16"], mode
