@@ -3,30 +3,37 @@
 //   h'_i = act( sum_{(s,a)} Z_i[s,a] T'[(s,a), :] + h_i root + bias ),   Z_i = 1/deg_i sum_{e->i} g_e (x) h[src_e]
 //
 // (reference: NNConv_old.forward/message/update + PyG mean aggregation, models/model.py:521-536, and
-// the last Linear of the edge MLP, :311-315 -- reordered as in DESIGN.md section 2.)  The unfused
-// path writes Z (4.4 KB per node) to HBM and reads it back in the node GEMM; that round trip is
-// two thirds of a layer's time.  Here Z never leaves the SM:
+// the last Linear of the edge MLP, :311-315 -- reordered as in DESIGN.md section 2.)  The two-kernel
+// path (zbuild_f16.cu + gemm_tc.cu) writes Z (4.4 KB per node) to HBM and reads it back; that round
+// trip is two thirds of a layer's time.  Here Z never leaves the SM.  Warp-specialised CTA, one per SM,
+// tiles of 8 consecutive nodes:
 //
-//   builder warps   stage 16 edges at a time (cp.async: the g slots of this launch's parts + the
-//                   gathered h[src] row), form the per-node outer-product sum on mma.sync.m16n8k16
-//                   (D = H_i^T [a x edges] . G_i [edges x slots], fp32 accumulate), scale by 1/deg
-//                   and write the fp16 result straight into the B-operand tile of the node
-//                   contraction in shared memory (K-major, SWIZZLE_128B, K ordered so that every
-//                   warp-wide store is one conflict-free 128-byte row);
-//   MMA warp        tcgen05.mma kind::f16, M = 128, N = 16 nodes x PPL parts, A = T' FROM TENSOR
-//                   MEMORY (loaded once per CTA with tcgen05.st), B = the Z tile, D in TMEM;
-//   epilogue warps  tcgen05.ld, combine the parts, (+ partial sums of earlier launches), bias,
-//                   ReLU, fp16 h' rows.
+//   producers (3 warps)   stage the tile's CSR edge range into a shared-memory ring: one cp.async.bulk per
+//                         g slot group, cp.async gathers of the h[src] rows, the 8 own h rows, a header;
+//   consumers (2 x 8)     two groups play ping-pong over the tiles, warp j = node j: per 16 edges 6
+//                         ldmatrix + 18 mma.sync.m16n8k16 (D = H_i^T [a x edges] . G_i [edges x slots],
+//                         fp16 accumulate), then 9 stmatrix.x4 straight into the B-operand tile of the node
+//                         contraction (K-major, SWIZZLE_128B, K ordered so that one 8x8 accumulator
+//                         fragment is one 16-byte chunk of a k-block row: conflict-free);
+//   MMA issuer (1 warp)   tcgen05.mma kind::f16, M = 128, N = 8 nodes x PPL parts, A = T' FROM TENSOR
+//                         MEMORY (loaded once per CTA with tcgen05.st), B = the Z tile, D in TMEM;
+//   epilogue (4 warps)    tcgen05.ld, combine the parts, 1/deg, (+ partial sums of earlier launches),
+//                         bias, ReLU, fp16 h' rows.
 //
 // Nodes sit on the MMA N dimension because a full-K Z tile of >= 64 nodes (what M would need)
 // does not fit in shared memory, and T' sits in TMEM because re-reading it from shared memory for
-// every 16-node tile would cost more shared-memory bandwidth than Z itself.  TMEM holds 512
-// columns = 1024 fp16 of K per lane, so K (2304 + 48) is cut into PARTS of 16 g-slots
-// (768 = 12 k-blocks of 64) plus one root k-block.  Several parts share the 128 TMEM lanes
-// (rows) at once: part p lives in lanes [p*RS, p*RS + w) and multiplies only the B columns that
-// hold part p of the tile's nodes.  With w <= 43 all three parts of the shipped model fit
-// (3*43 = 129: the single row that does not fit, (part 2, channel 42), is evaluated on CUDA
-// cores from the builder's registers), so a layer is ONE launch and every edge is staged once.
+// every tile would cost more shared-memory bandwidth than Z itself.  TMEM holds 512 columns = 1024
+// fp16 of K per lane, so K (2304 + 48) is cut into PARTS of 16 g-slots (768 = 12 k-blocks of 64)
+// plus one root k-block.  Several parts share the 128 TMEM lanes (rows) at once: part p lives in
+// lanes [p*RS, p*RS + w) and multiplies only the B columns that hold part p of the tile's nodes.
+// With w <= 43 all three parts of the shipped model fit (3*43 = 129: the single row that does not
+// fit, (part 2, channel 42), is evaluated on CUDA cores from the consumer's accumulator registers),
+// so a layer is ONE launch and every edge is staged once.
+//
+// What bounds it (B200, 526 848-cell duct, clock64 accounting per role, profiles/r01_layer_fused_*):
+// every role is a latency-bound instruction stream (about one instruction per 12-17 cycles per warp
+// with 6 warps per scheduler), so the structure minimises instructions on the critical path and hands
+// nothing between roles except through mbarriers that the next tile's work has already covered.
 #include <cuda_fp16.h>
 
 #include "kernels.cuh"
@@ -34,11 +41,11 @@
 namespace fesr {
 
 constexpr int FL_NODES = 8;                   // nodes per tile
+constexpr int FL_CAP = 128;                   // staged edges per ring slot (a tile with more edges takes several)
 constexpr int FL_DEGC = 16;                   // edges per staged chunk = one m16n8k16 k-step
 constexpr int FL_NKB = 13;                    // k-blocks per part: 12 outer-product blocks + root block
 constexpr int FL_KP = FL_NKB * 64;            // 832 fp16 of K per part
 constexpr int FL_ACOLS = FL_KP / 2;           // TMEM columns of the A operand
-constexpr int FL_SHB = 112;                   // staged h row stride in bytes (96 + 16: conflict-free ldmatrix)
 constexpr int FL_WP = 48;
 
 __device__ __forceinline__ uint32_t fl_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -53,11 +60,11 @@ __device__ __forceinline__ void fl_mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "FL_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra FL_DONE;\n\t"
       "bra FL_WAIT;\n\t"
       "FL_DONE:\n\t"
-      "}" ::"r"(bar), "r"(parity)
+      "}" ::"r"(bar), "r"(parity), "r"(0x989680)     // suspend-time hint: a waiting warp sleeps instead of spinning
       : "memory");
 }
 __device__ __forceinline__ bool fl_elect_one() {
@@ -76,25 +83,23 @@ __device__ __forceinline__ void fl_ldsm4t(uint32_t addr, uint32_t (&r)[4]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(addr));
 }
-__device__ __forceinline__ void fl_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+// fp16-accumulate MMA: D/C are two f16x2 registers (rows gq and gq + 8, columns 2tq, 2tq + 1)
+__device__ __forceinline__ void fl_mma16(uint32_t (&c)[2], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm(
+      "mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%0,%1};"
+      : "+r"(c[0]), "+r"(c[1])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void fl_mma0(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
-      : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+__device__ __forceinline__ __half2 fl_as_h2(uint32_t u) { return *reinterpret_cast<const __half2*>(&u); }
+__device__ __forceinline__ uint32_t fl_lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ uint32_t fl_h2_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
-}
-__device__ __forceinline__ float2 fl_h2_to_f2(uint32_t u) {
-  return __half22float2(*reinterpret_cast<const __half2*>(&u));
 }
 __device__ __forceinline__ uint32_t fl_hmul2(uint32_t a, __half2 b) {
   const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&a), b);
@@ -168,39 +173,61 @@ __global__ void prepare_tfused_kernel(fesr_model_dims d, int n_parts, const floa
   tf[idx] = __float2half_rn(v);
 }
 
-// PPL: parts per launch (1..3); NBUF: staged nodes in flight per node slot.  A tile is FL_NODES = 8 nodes;
-// node slot j is served by a GROUP of PPL builder warps (warp j*PPL + pp builds part pp: 6 MMAs, 12 row
-// stores), so 8*PPL builder warps hide each other's load / ldmatrix / MMA latencies.  MMA N = 8 * PPL
-// rounded up to 16 (row pp*8 + j of the Z tile = part pp of node j).
+// PPL: parts per launch (1..3); NBUF: staged tile segments in flight.
+//
+// A tile is FL_NODES = 8 consecutive nodes; their CSR edges are one contiguous range, staged as one
+// SEGMENT (<= FL_CAP edges; a tile with more edges takes several) into a ring of NBUF buffers:
+//   * FL_NPROD PRODUCER warps work on a segment together: producer p bulk-copies the g slot group of
+//     part p (planar [part][E][16] fp16 -> one cp.async.bulk of 32 B x edges) and issues every
+//     FL_NPROD-th block of 32 sixteen-byte h[src] gather chunks (cp.async, rows of 96 B with chunk c
+//     stored at c ^ bit 2 of the row index: conflict-free ldmatrix without padding) plus, on the tile's
+//     last segment, the 8 nodes' own h rows.  Completion lands on the ring's `sfull` mbarrier
+//     (complete_tx / cp.async.mbarrier.arrive.noinc); a header carries the 9 row bounds of the tile.
+//   * two GROUPS of 8 CONSUMER warps play ping-pong over the tiles (group = tile parity, warp j = node j).
+//     Per tile a group: per 16 edges of its node 6 ldmatrix (row addresses inside the segment, rows past the
+//     node's range read a zero row) and 18 mma.sync.m16n8k16 (fp16 accumulate: one rounding, exactly what
+//     the fp16 Z tile gets); then -- once the tensor core has finished the group's PREVIOUS tile, a wait that
+//     the gather work above has already covered -- the epilogue of that previous tile (tcgen05.ld, combine
+//     the parts, 1/deg, bias, ReLU, fp16 h' rows), 9 stmatrix.x4 of the new Z rows into the group's B-operand
+//     tile, a group barrier, and one elected lane issues the tile's tcgen05.mma chain (A = T' in TMEM,
+//     D = the group's TMEM accumulator) + commit.  No role hands anything to another role except the ring.
+// MMA N = 8 * PPL rounded up to 16 (row pp*8 + j of the Z tile = part pp of node j).
 template <int PPL, int NBUF>
-__global__ void __launch_bounds__((8 * PPL + 5) * 32, 1)
+__global__ void __launch_bounds__((16 + 3 + 1 + 4) * 32, 1)
 layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
                        const __half* __restrict__ g3, int64_t E, const __half* __restrict__ h_in, int64_t n,
                        int part0, int has_root, const __half* __restrict__ tf, const float* __restrict__ bias_p,
                        const float* p_in, float* p_out, __half* __restrict__ h_out,
                        int rs, int fix_b, int relu) {
-  constexpr int FL_BW = FL_NODES * PPL;                // builder warps
-  constexpr int FL_THREADS = (FL_BW + 5) * 32;         // + 4 epilogue warps + 1 MMA warp
+  constexpr int FL_BW = 2 * FL_NODES;                  // consumer warps: two groups of 8
+  constexpr int FL_NPROD = 3;                          // producer warps
+  constexpr int FL_THREADS = (FL_BW + FL_NPROD + 1 + 4) * 32;   // + the MMA issuer warp + 4 epilogue warps
   constexpr int N = (PPL * FL_NODES + 15) / 16 * 16;   // MMA N
   constexpr int SLAB = N * 128;                        // bytes per k-block of the Z tile
   constexpr int ZBYTES = FL_NKB * SLAB;
-  constexpr int SGB = 32 * PPL + 16;                   // staged g row stride (bytes), odd multiple of 16
-  constexpr int GSZ = FL_DEGC * SGB;
-  constexpr int STG = GSZ + (FL_DEGC + 1) * FL_SHB;    // + 16 gathered h rows + the node's own h row
-  constexpr int HI = (FL_DEGC * 6 + 32 * PPL - 1) / (32 * PPL);   // h cp.async instructions per warp per chunk
+  constexpr int GPL = FL_CAP * 32;                     // bytes of one staged g plane
+  constexpr int HOFF = PPL * GPL;                      // gathered h rows (96 B each)
+  constexpr int OWN = HOFF + FL_CAP * 96;              // the 8 nodes' own h rows
+  constexpr int HDR = OWN + FL_NODES * 96;             // header: 9 row bounds, segment begin / end, last flag
+  constexpr int STG = HDR + 64;
+  constexpr int CMB = PPL * FL_NODES * FL_WP;          // floats of one group's combine buffer
 
   extern __shared__ __align__(1024) uint8_t fl_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fl_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* zbuf = smem;                                            // [2][ZBYTES]
-  uint8_t* stage = zbuf + 2 * ZBYTES;                              // [FL_NODES][NBUF][STG]
-  float* comb = reinterpret_cast<float*>(stage + FL_NODES * NBUF * STG);   // [PPL][8][48]
-  float* fixs = comb + PPL * FL_NODES * FL_WP;                     // [4][8]  fix-up row values
-  float* invs = fixs + 4 * FL_NODES;                               // [4][8]  1 / max(deg, 1)
-  uint32_t* wfs = reinterpret_cast<uint32_t*>(invs + 4 * FL_NODES);       // [12][32] + [8][4]  fix-up row weights
+  uint8_t* zbuf = smem;                                            // [2 groups][ZBYTES]
+  uint8_t* stage = zbuf + 2 * ZBYTES;                              // [NBUF][STG]
+  float* comb = reinterpret_cast<float*>(stage + NBUF * STG);      // [PPL][8][48]
+  float* fixs = comb + CMB;                                        // [2 groups][2][8]  fix-up row values
+  float* invs = fixs + 4 * FL_NODES;                               // [2 groups][2][8]  1 / max(deg, 1)
+  uint32_t* zrow = reinterpret_cast<uint32_t*>(invs + 4 * FL_NODES);    // 32 B of zeros: masked g rows
+  uint32_t* wfs = zrow + 8;                                        // [12][32] + [8][4]  fix-up row weights (PPL == 3)
   uint64_t* bars = reinterpret_cast<uint64_t*>(wfs + (PPL == 3 ? 12 * 32 + 32 : 0));
-  const uint32_t zfull = fl_smem(&bars[0]), zempty = fl_smem(&bars[2]), dfull = fl_smem(&bars[4]),
-                 dempty = fl_smem(&bars[6]), aready = fl_smem(&bars[8]);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[9]);
+  const uint32_t mdone = fl_smem(&bars[0]);                        // [2]  tensor core done with a group's tile
+  const uint32_t zready = fl_smem(&bars[2]);                       // [2]  a group's Z tile is written (8 warps)
+  const uint32_t dfree = fl_smem(&bars[4]);                        // [2]  a group's TMEM accumulator has been read (4 warps)
+  const uint32_t sfull = fl_smem(&bars[6]);                        // [NBUF]
+  const uint32_t sempty = sfull + 8 * NBUF;                        // [NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(&bars[6 + 2 * NBUF]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
@@ -211,21 +238,12 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
   // tail of the root block are never written afterwards
   for (int t = threadIdx.x; t < 2 * ZBYTES / 16; t += FL_THREADS)
     reinterpret_cast<uint4*>(zbuf)[t] = make_uint4(0u, 0u, 0u, 0u);
-  for (int t = threadIdx.x; t < FL_NODES * NBUF * STG / 16; t += FL_THREADS)
+  for (int t = threadIdx.x; t < NBUF * STG / 16; t += FL_THREADS)
     reinterpret_cast<uint4*>(stage)[t] = make_uint4(0u, 0u, 0u, 0u);       // stale slab contents stay finite
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
-      fl_mbar_init(zfull + 8 * s, FL_BW);
-      fl_mbar_init(zempty + 8 * s, 1);
-      fl_mbar_init(dfull + 8 * s, 1);
-      fl_mbar_init(dempty + 8 * s, 4);
-    }
-    fl_mbar_init(aready, 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  if (threadIdx.x < 8) zrow[threadIdx.x] = 0u;
   if (PPL == 3 && fix_b >= 0) {
-    // fix-up row (see header): weights of output channel fix_b against a builder lane's last-part values,
-    // in the order the lane holds them: wfs[(mt*2+hh)*2+nl][lane], then the root block as 6 x 16 bytes
+    // fix-up row (see header): weights of output channel fix_b against a consumer lane's last-part values,
+    // in the order the lane holds them: wfs[(mt*2+hh)*2+nl][lane], then the root block as 6 x 16 bytes (+ zeros)
     const __half* wr = tf + ((size_t)(part0 + PPL - 1) * FL_WP + fix_b) * FL_KP;
     for (int t = threadIdx.x; t < 12 * 32; t += FL_THREADS) {
       const int q = t >> 5, l = t & 31;
@@ -234,7 +252,20 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     for (int t = threadIdx.x; t < 32; t += FL_THREADS)
       wfs[12 * 32 + t] = t < 24 ? *reinterpret_cast<const uint32_t*>(wr + 12 * 64 + 2 * t) : 0u;
   }
-  if (warp == FL_BW) {   // TMEM: all 512 columns (A operand 416, two D stages of N)
+  if (threadIdx.x == 0) {
+    fl_mbar_init(mdone, 1);
+    fl_mbar_init(mdone + 8, 1);
+    fl_mbar_init(zready, FL_NODES);
+    fl_mbar_init(zready + 8, FL_NODES);
+    fl_mbar_init(dfree, 4);
+    fl_mbar_init(dfree + 8, 4);
+    for (int s = 0; s < NBUF; ++s) {
+      fl_mbar_init(sfull + 8 * s, FL_NPROD * 32 + FL_NPROD);   // cp.async completions of every producer lane + one arrive per producer
+      fl_mbar_init(sempty + 8 * s, FL_NODES);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {   // TMEM: all 512 columns (A operand 416, one D stage of N per group)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(fl_smem(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -244,369 +275,409 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < FL_BW) {
-    // =========================================================================== builders
-    // Group j = warp / PPL owns node j of every tile of this CTA; this warp builds part pp = warp % PPL.
-    // Item = one node (its first 16 edges are prefetched NBUF - 1 items ahead; the rare longer rows
-    // finish synchronously).  Each warp of a group stages its own share of an item: the g slot group of
-    // its part and every PPL-th block of 32 h-row chunks.
-    const int j = warp / PPL, pp = warp % PPL;
-    const int gq = lane >> 2, tq = lane & 3;
-    const uint32_t st_u32 = fl_smem(stage + (size_t)j * NBUF * STG);
-    const int lr = lane & 7, lm = lane >> 3;
-    // ldmatrix row addresses (bytes, relative to a staged chunk):
-    //   A = H^T tile mt: matrices {a 0-7, e 0-7}, {a 8-15, e 0-7}, {a 0-7, e 8-15}, {a 8-15, e 8-15}
-    //   B = G of this part: matrices {e 0-7, nt 0}, {e 8-15, nt 0}, {e 0-7, nt 1}, {e 8-15, nt 1}
-    const uint32_t a_off = (uint32_t)(GSZ + ((lm >> 1) * 8 + lr) * FL_SHB + (lm & 1) * 16);
-    const uint32_t b_off = (uint32_t)(((lm & 1) * 8 + lr) * SGB + (lm >> 1) * 16 + pp * 32);
-    // this lane's row of the Z tile: row pp*8 + j, 16-byte chunk gq (swizzled), bytes 4*tq
-    const uint32_t zlane = fl_smem(zbuf) + (uint32_t)((pp * FL_NODES + j) * 128 + ((gq ^ j) << 4) + (tq << 2));
-
-    // staging constants of this lane
-    const int gj = lane >> 1;                                        // g: chunk (lane & 1) of edge row gj
-    const uint32_t gdst = (uint32_t)(gj * SGB + pp * 32 + (lane & 1) * 16);
-    const __half* gsrc = g3 + ((size_t)(part0 + pp) * E + gj) * 16 + (lane & 1) * 8;
-    int hj[HI];
-    uint32_t hdst[HI], hsrc[HI];
+  // TMEM lane L holds row (p, b) = (L / rs, L % rs): part p, output channel b
+  // ---- T' rows of this launch's parts into TMEM (A operand): lane L <- TF[part0 + p][b][:]; warps 0-3 load
+  // the first half of the columns, warps 8-11 the second half (a warp reaches the TMEM lanes 32*(warp%4)...)
+  if (warp < FL_BW && (warp & 7) < 4) {
+    const int L = (warp & 3) * 32 + lane;
+    const int p = L / rs, b = L % rs;
+    const bool row_ok = p < PPL && b < FL_WP;
+    const __half* src = tf + ((size_t)(part0 + (row_ok ? p : 0)) * FL_WP + (row_ok ? b : 0)) * FL_KP;
+    const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int cbeg = (warp >> 3) * (FL_ACOLS / 2);
+#pragma unroll 1
+    for (int c0 = cbeg; c0 < cbeg + FL_ACOLS / 2; c0 += 16) {
+      uint32_t r[16];
 #pragma unroll
-    for (int i = 0; i < HI; ++i) {
-      const int t = (i * PPL + pp) * 32 + lane, r = t / 6, c = t % 6;
-      hj[i] = (t < FL_DEGC * 6) ? r : FL_DEGC;                       // FL_DEGC: no such row
-      hdst[i] = (uint32_t)(GSZ + r * FL_SHB + c * 16);
-      hsrc[i] = (uint32_t)(c * 8);
+      for (int v4 = 0; v4 < 4; ++v4) {
+        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+        if (row_ok) t = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0) + v4);
+        r[4 * v4] = t.x;
+        r[4 * v4 + 1] = t.y;
+        r[4 * v4 + 2] = t.z;
+        r[4 * v4 + 3] = t.w;
+      }
+      fl_tmem_st16(taddr + c0, r);
     }
-    const bool last_part = pp == PPL - 1;
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
+  if (warp < FL_BW) {
+    // =========================================================================== consumers
+    const int grp = warp >> 3, j = warp & 7;
+    const int lr = lane & 7, lm = lane >> 3;
+    const uint32_t zrow_u32 = fl_smem(zrow) + (uint32_t)((lm >> 1) * 16);
+    // ldmatrix rows supplied by this lane (edge index within the 16-edge k-step):
+    //   A = H^T tile mt: matrices {a 0-7, e 0-7}, {a 8-15, e 0-7}, {a 0-7, e 8-15}, {a 8-15, e 8-15}
+    //   B = G of part pp: matrices {e 0-7, nt 0}, {e 8-15, nt 0}, {e 0-7, nt 1}, {e 8-15, nt 1}
+    const int ka = (lm >> 1) * 8 + lr, kb = (lm & 1) * 8 + lr;
+    // stmatrix row address: the 4 matrices of a-tile mt are stored in accumulator register order
+    // (nl 0, hh 0), (nl 0, hh 1), (nl 1, hh 0), (nl 1, hh 1); matrix lm = (nl, hh) is k-block mt*4 + hh*2 + nl;
+    // this lane supplies row lr (= a within the octet) -> 16-byte chunk lr (swizzled) of Z-tile row pp*8 + j
+    const uint32_t zgrp = fl_smem(zbuf) + (uint32_t)(grp * ZBYTES);
+    const uint32_t zst = zgrp + (uint32_t)(((lm & 1) * 2 + (lm >> 1)) * SLAB + j * 128 + ((lr ^ j) << 4));
+    const uint32_t zroot = zgrp + (uint32_t)(12 * SLAB + ((PPL - 1) * FL_NODES + j) * 128 + ((lane ^ j) << 4));
+    const uint32_t md = mdone + 8 * grp;
+    const bool do_fix = PPL == 3 && fix_b >= 0;
+    const uint32_t wfl = fl_smem(wfs) + (uint32_t)(lane * 4);
 
-    // rowptr of this group's nodes: 16 tile iterations per register (lanes 2i, 2i+1 = begin, end)
-    auto load_block = [&](int blk) {
-      const int itx = blk * 16 + (lane >> 1);
-      int64_t node = ((int64_t)blockIdx.x + (int64_t)itx * gridDim.x) * FL_NODES + j + (lane & 1);
+    // the group's own ring: buffers grp*NBG .. grp*NBG + NBG - 1 hold the segments of its tiles
+    constexpr int NBG = NBUF / 2;
+    const uint32_t rg_stage = fl_smem(stage) + (uint32_t)(grp * NBG * STG);
+    const uint32_t rg_full = sfull + 8 * grp * NBG, rg_empty = sempty + 8 * grp * NBG;
+    int buf = 0;
+    uint32_t par = 0;             // parity of the ring's current pass
+    int n_mine = 0;               // own tiles issued so far
+    for (int it = grp; it < n_it; it += 2) {
+      // D[pp][mt][nl][hh]: fp16x2 accumulators (rows gq + 8*hh of a-tile mt, slots 2tq, 2tq+1 of n-tile nl)
+      uint32_t d[PPL][3][2][2];
+#pragma unroll
+      for (int pp = 0; pp < PPL; ++pp)
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) d[pp][mt][0][0] = d[pp][mt][0][1] = d[pp][mt][1][0] = d[pp][mt][1][1] = 0u;
+      int deg = 0;
+      int lastw;
+      uint4 hv = make_uint4(0u, 0u, 0u, 0u);       // own h row chunk (root block)
+      do {
+        const uint32_t base = rg_stage + (uint32_t)(buf * STG);
+        fl_mbar_wait(rg_full + 8 * buf, par);
+        int seg_lo, seg_hi, pad;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(seg_lo), "=r"(seg_hi), "=r"(lastw), "=r"(pad) : "r"(base + (uint32_t)(HDR + 48)));
+        {
+          int eb, ee;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(eb) : "r"(base + (uint32_t)(HDR + 4 * j)));
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ee) : "r"(base + (uint32_t)(HDR + 4 * j + 4)));
+          deg = ee - eb;
+          const int lo = max(eb, seg_lo), hi = min(ee, seg_hi);
+          for (int c = lo; c < hi; c += FL_DEGC) {
+            const int rem = hi - c;
+            const int r0 = c - seg_lo;
+            const int ra = min(r0 + ka, seg_hi - seg_lo - 1);            // rows past the node's range: any finite row
+            const uint32_t a_addr = base + (uint32_t)(HOFF + ra * 96 + (((lm & 1) ^ ((ra >> 2) & 1)) << 4));
+            const uint32_t b_addr = kb < rem ? base + (uint32_t)((r0 + kb) * 32 + (lm >> 1) * 16) : zrow_u32;
+            const uint32_t b_step = kb < rem ? (uint32_t)GPL : 0u;
+            uint32_t a[3][4];
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt) fl_ldsm4t(a_addr + (uint32_t)(mt * 32), a[mt]);
+#pragma unroll
+            for (int pp = 0; pp < PPL; ++pp) {
+              uint32_t b[4];
+              fl_ldsm4t(b_addr + pp * b_step, b);
+#pragma unroll
+              for (int mt = 0; mt < 3; ++mt) {
+                fl_mma16(d[pp][mt][0], a[mt], b[0], b[1]);
+                fl_mma16(d[pp][mt][1], a[mt], b[2], b[3]);
+              }
+            }
+          }
+          if (lastw != 0 && has_root && lane < 6)
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hv.x), "=r"(hv.y), "=r"(hv.z), "=r"(hv.w) : "r"(base + (uint32_t)(OWN + j * 96 + lane * 16)));
+        }
+        __syncwarp();
+        if (lane == 0) fl_mbar_arrive(rg_empty + 8 * buf);     // this warp is done reading the segment
+        if (++buf == NBG) {
+          buf = 0;
+          par ^= 1;
+        }
+      } while (lastw == 0);
+      // ---- once the tensor core has finished this group's previous tile (a wait the gather work above has
+      // covered) the Z buffer is free: this tile's Z rows, raw sums (the epilogue applies 1/deg)
+      if (n_mine > 0) fl_mbar_wait(md, (uint32_t)((n_mine - 1) & 1));
+#pragma unroll
+      for (int pp = 0; pp < PPL; ++pp)
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt)
+          asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(zst + (uint32_t)(pp * FL_NODES * 128 + mt * 4 * SLAB)),
+                       "r"(d[pp][mt][0][0]), "r"(d[pp][mt][0][1]), "r"(d[pp][mt][1][0]), "r"(d[pp][mt][1][1])
+                       : "memory");
+      __half2 f0 = __float2half2_rn(0.f), f1 = f0;
+      if (do_fix) {
+#pragma unroll
+        for (int mt = 0; mt < 3; ++mt) {
+          f0 = __hfma2(fl_as_h2(d[PPL - 1][mt][0][0]), fl_as_h2(fl_lds32(wfl + (mt * 4 + 0) * 128)), f0);     // (hh 0, nl 0)
+          f1 = __hfma2(fl_as_h2(d[PPL - 1][mt][1][0]), fl_as_h2(fl_lds32(wfl + (mt * 4 + 1) * 128)), f1);     // (hh 0, nl 1)
+          f0 = __hfma2(fl_as_h2(d[PPL - 1][mt][0][1]), fl_as_h2(fl_lds32(wfl + (mt * 4 + 2) * 128)), f0);     // (hh 1, nl 0)
+          f1 = __hfma2(fl_as_h2(d[PPL - 1][mt][1][1]), fl_as_h2(fl_lds32(wfl + (mt * 4 + 3) * 128)), f1);     // (hh 1, nl 1)
+        }
+      }
+      if (has_root && lane < 8) {
+        // root block: h_i * max(deg, 1) so that the epilogue's 1/deg leaves h_i (lanes 6, 7: the zero tail)
+        const __half2 dg = __float2half2_rn((float)(deg > 0 ? deg : 1));
+        uint4 hs;
+        hs.x = fl_hmul2(hv.x, dg);
+        hs.y = fl_hmul2(hv.y, dg);
+        hs.z = fl_hmul2(hv.z, dg);
+        hs.w = fl_hmul2(hv.w, dg);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(zroot), "r"(hs.x), "r"(hs.y), "r"(hs.z), "r"(hs.w) : "memory");
+        if (do_fix) {
+          uint4 wr;     // root weights of this lane's chunk (lanes 6, 7: zeros)
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(wr.x), "=r"(wr.y), "=r"(wr.z), "=r"(wr.w) : "r"(wfl + (uint32_t)(12 * 128 + lane * 12)));
+          f0 = __hfma2(fl_as_h2(hs.x), fl_as_h2(wr.x), f0);
+          f1 = __hfma2(fl_as_h2(hs.y), fl_as_h2(wr.y), f1);
+          f0 = __hfma2(fl_as_h2(hs.z), fl_as_h2(wr.z), f0);
+          f1 = __hfma2(fl_as_h2(hs.w), fl_as_h2(wr.w), f1);
+        }
+      }
+      float fsum = 0.f;
+      __syncwarp();          // reconverge after the lane < 8 branch: the shuffles below must not take the divergent path
+      if (do_fix) {
+        const float2 a0 = __half22float2(f0), a1 = __half22float2(f1);
+        fsum = (a0.x + a0.y) + (a1.x + a1.y);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fsum += __shfl_xor_sync(FULL, fsum, o);
+      }
+      if (lane == 0) {
+        fixs[(grp * 2 + (n_mine & 1)) * FL_NODES + j] = fsum;
+        invs[(grp * 2 + (n_mine & 1)) * FL_NODES + j] = __frcp_rn((float)(deg > 0 ? deg : 1));
+      }
+      // Z rows visible to the tensor core (and this warp's TMEM loads of the previous epilogue retired):
+      // tell the group's MMA issuer warp
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) fl_mbar_arrive(zready + 8 * grp);
+      ++n_mine;
+    }
+  } else if (warp >= FL_BW + FL_NPROD + 1) {
+    // =========================================================================== epilogue (4 warps, every tile)
+    const int qd = warp - (FL_BW + FL_NPROD + 1);     // TMEM lane quadrant (== warp % 4)
+    const int L = qd * 32 + lane;                     // TMEM lane = row (p, b) = (L / rs, L % rs)
+    const int ep = L / rs, eb_ = L % rs;
+    const bool row_ok = ep < PPL && eb_ < FL_WP;
+    const int te = qd * 32 + lane;
+    constexpr int OUTI = (FL_NODES * 24 + 127) / 128;      // (node, channel pair) outputs per thread
+    const uint32_t cmb = fl_smem(comb);
+    int oj[OUTI], oc[OUTI];
+    float ob0[OUTI], ob1[OUTI];
+#pragma unroll
+    for (int i = 0; i < OUTI; ++i) {
+      const int o = te + 128 * i;
+      oj[i] = o < FL_NODES * 24 ? o / 24 : -1;
+      oc[i] = (o % 24) * 2;
+      ob0[i] = bias_p[oc[i]];
+      ob1[i] = bias_p[oc[i] + 1];
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int grp = it & 1, k = it >> 1;
+      fl_mbar_wait(mdone + 8 * grp, (uint32_t)(k & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t r[N / 16][16];
+#pragma unroll
+      for (int c = 0; c < N / 16; ++c) fl_tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + FL_ACOLS + grp * N + c * 16, r[c]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // per-node scalars of this thread's outputs, read BEFORE the accumulator is handed back (the consumers
+      // reuse the slot two own tiles later, which needs that arrival first)
+      float fxv[OUTI], inv[OUTI];
+#pragma unroll
+      for (int i = 0; i < OUTI; ++i) {
+        const int q = oj[i] < 0 ? 0 : oj[i];
+        fxv[i] = fixs[(grp * 2 + (k & 1)) * FL_NODES + q];
+        inv[i] = invs[(grp * 2 + (k & 1)) * FL_NODES + q];
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) fl_mbar_arrive(dfree + 8 * grp);
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < FL_NODES; ++q) {
+          uint32_t v = r[q / 16][q % 16];
+          if (PPL > 1 && ep == 1) v = r[(FL_NODES + q) / 16][(FL_NODES + q) % 16];
+          if (PPL > 2 && ep == 2) v = r[(2 * FL_NODES + q) / 16][(2 * FL_NODES + q) % 16];
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(cmb + (uint32_t)(((ep * FL_NODES + q) * FL_WP + eb_) * 4)), "r"(v) : "memory");
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FL_NODES;
+#pragma unroll
+      for (int i = 0; i < OUTI; ++i) {
+        const int64_t row = row0 + oj[i];
+        if (oj[i] >= 0 && row < n) {
+          const int c0 = oc[i];
+          float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+          for (int pp = 0; pp < PPL; ++pp) {
+            float2 cv;
+            asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(cv.x), "=f"(cv.y) : "r"(cmb + (uint32_t)(((pp * FL_NODES + oj[i]) * FL_WP + c0) * 4)));
+            if (c0 < rs) v0 += (PPL == 3 && pp == PPL - 1 && c0 == fix_b) ? fxv[i] : cv.x;
+            if (c0 + 1 < rs) v1 += (PPL == 3 && pp == PPL - 1 && c0 + 1 == fix_b) ? fxv[i] : cv.y;
+          }
+          v0 *= inv[i];
+          v1 *= inv[i];
+          if (p_in) {
+            const float2 pv = *reinterpret_cast<const float2*>(p_in + row * FL_WP + c0);
+            v0 += pv.x;
+            v1 += pv.y;
+          }
+          if (p_out) {
+            *reinterpret_cast<float2*>(p_out + row * FL_WP + c0) = make_float2(v0, v1);
+          } else {
+            v0 += ob0[i];
+            v1 += ob1[i];
+            if (relu & 1) {
+              v0 = fmaxf(v0, 0.f);
+              v1 = fmaxf(v1, 0.f);
+            }
+            *reinterpret_cast<uint32_t*>(h_out + row * FL_WP + c0) = fl_h2_sat(v0, v1);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+  } else if (warp == FL_BW + FL_NPROD) {
+    // =========================================================================== MMA issuer
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // D = F32, A = B = F16 K-major, N, M = 128
+    const int nkb = has_root ? FL_NKB : FL_NKB - 1;
+    for (int it = 0; it < n_it; ++it) {
+      const int grp = it & 1;
+      fl_mbar_wait(dfree + 8 * grp, (uint32_t)(((it >> 1) & 1) ^ 1));     // the epilogue has read the previous result
+      fl_mbar_wait(zready + 8 * grp, (uint32_t)((it >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (fl_elect_one()) {
+        const uint32_t zgrp = fl_smem(zbuf) + (uint32_t)(grp * ZBYTES);
+        const uint32_t tmem_d = tmem_base + FL_ACOLS + grp * N;
+        for (int kk = 0; kk < nkb; ++kk) {
+          const uint64_t bdesc = fl_sw128_desc(zgrp + (uint32_t)(kk * SLAB));
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            fl_umma_ts(tmem_d, tmem_base + (uint32_t)(kk * 32 + q * 8), bdesc + 2 * q, idesc, (kk | q) != 0);
+        }
+        fl_umma_commit(mdone + 8 * grp);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =========================================================================== producers
+    const int pw = warp - FL_BW;
+    const uint32_t st_u32 = fl_smem(stage);
+    // This lane's gather chunk-ops of a segment: op i is 16-byte chunk tc of staged row tr[i]; the flat index
+    // t = (i * FL_NPROD + pw) * 32 + lane runs over rows x 6 chunks.  Destination offsets are lane constants.
+    // (One 96-byte cp.async.bulk per row was tried: ~30 cycles per small bulk copy, slower than these.)
+    constexpr int GOPS = (FL_CAP * 6 + 32 * FL_NPROD - 1) / (32 * FL_NPROD);
+    int tr[GOPS];
+    uint32_t tc[GOPS], gdst[GOPS];
+#pragma unroll
+    for (int i = 0; i < GOPS; ++i) {
+      const int t = (i * FL_NPROD + pw) * 32 + lane;
+      tr[i] = t / 6;
+      tc[i] = (uint32_t)(t % 6);
+      gdst[i] = (uint32_t)(HOFF + tr[i] * 96) + ((tc[i] ^ (uint32_t)((tr[i] >> 2) & 1)) << 4);
+    }
+    // the 8 nodes' own rows: 48 chunk-ops, lanes of producers 0 and 1
+    const int ot = pw * 32 + lane;
+    const bool own_lane = ot < FL_NODES * 6;
+    const int orow = ot / 6;
+    const uint32_t odst = (uint32_t)(OWN + orow * 96 + (ot % 6) * 16);
+    const uint4* h16 = reinterpret_cast<const uint4*>(h_in);         // h rows as 6 sixteen-byte chunks
+    // rowptr of the tile's 9 node boundaries in lanes 0..8
+    auto load_rp = [&](int itx) {
+      int64_t node = ((int64_t)blockIdx.x + (int64_t)itx * gridDim.x) * FL_NODES + (lane < 9 ? lane : 8);
       node = node < n ? node : n;
       return __ldg(rowptr + node);
     };
-    int rpb0 = load_block(0), rpb1 = load_block(1);
-    auto bounds = [&](int itx, int& eb, int& ee) {
-      const int rpv = ((itx >> 4) & 1) ? rpb1 : rpb0;
-      eb = __shfl_sync(FULL, rpv, (itx & 15) * 2);
-      ee = __shfl_sync(FULL, rpv, (itx & 15) * 2 + 1);
-    };
-    // source ids of item itx (lanes 0..15; clamped address: the value is not looked at before it is used)
-    auto load_src = [&](int itx) {
-      int eb, ee;
-      bounds(itx, eb, ee);
-      int e = eb + (lane & 15);
-      e = e < ee ? e : (ee > 0 ? ee - 1 : 0);
-      return __ldg(src_sorted + e);
-    };
-    // this warp's share of edges [c0, c0 + m) of a node: g slot group of its part (planar [part][E][16]; a
-    // miss pulls 256 B into L2, i.e. the rows of the next edges of the same stream) and gathered h chunks
-    auto stage_chunk = [&](uint32_t base, int c0, int m, int src_reg) {
-      if (gj < m) {
-        asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(base + gdst), "l"(gsrc + (size_t)c0 * 16) : "memory");
-      } else {   // unused edge slots of the k-step: g = 0 (the stale h row is finite)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + gdst), "r"(0) : "memory");
-      }
+    // source ids of this lane's gather ops for the first segment of a tile (clamped addresses)
+    auto load_srcs = [&](int rpv, int (&sv)[GOPS]) {
+      const int e_lo = __shfl_sync(FULL, rpv, 0), e_max = max(__shfl_sync(FULL, rpv, 8) - 1, 0);
 #pragma unroll
-      for (int i = 0; i < HI; ++i) {
-        const int s = __shfl_sync(FULL, src_reg, hj[i] & 15);
-        if (hj[i] < m)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + hdst[i]), "l"(h_in + (size_t)s * FL_WP + hsrc[i]) : "memory");
-      }
+      for (int i = 0; i < GOPS; ++i) sv[i] = __ldg(src_sorted + min(e_lo + tr[i], e_max));
     };
-    auto issue = [&](int itx, int buf, int src_reg) {
-      if (itx < n_it) {
-        int eb, ee;
-        bounds(itx, eb, ee);
-        const uint32_t base = st_u32 + (uint32_t)(buf * STG);
-        stage_chunk(base, eb, min(FL_DEGC, ee - eb), src_reg);
-        const int64_t node = ((int64_t)blockIdx.x + (int64_t)itx * gridDim.x) * FL_NODES + j;
-        if (last_part && lane < 6 && node < n)   // the node's own row: root block (+ fix-up)
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + (uint32_t)(GSZ + FL_DEGC * FL_SHB + lane * 16)),
-                       "l"(h_in + (size_t)node * FL_WP + lane * 8)
-                       : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto group_sync = [&]() {   // the PPL warps of node slot j
-      if (PPL > 1) asm volatile("bar.sync %0, %1;" ::"r"(2 + j), "n"(32 * PPL) : "memory");
-      else __syncwarp();
-    };
-
+    // Prefetch registers, indexed by (tile & 3) inside a loop unrolled by 4 so that no in-flight load is ever
+    // moved between registers (a move would wait for it): rowptr of tile t is requested 3 tiles ahead, the
+    // source ids of tile t 2 tiles ahead (their addresses need rowptr(t), one tile old by then).
+    int rp[4];
+    int sc[4][GOPS];
+    rp[0] = load_rp(0);
+    rp[1] = load_rp(1);
+    rp[2] = load_rp(2);
+    load_srcs(rp[0], sc[0]);
+    load_srcs(rp[1], sc[1]);
+    constexpr int NBG = NBUF / 2; // ring of the tile-parity group: buffers g*NBG ..
+    int bufs[2] = {0, 0};
+    uint32_t pars[2] = {1u, 1u};  // a fresh `sempty` barrier passes a parity-1 wait
+    for (int it0 = 0; it0 < n_it; it0 += 4) {
 #pragma unroll
-    for (int i = 0; i < NBUF - 1; ++i) issue(i, i, load_src(i));
-    // source ids are fetched three iterations before their gathers are issued: the dependent load never
-    // sits on the critical path
-    int src_a = load_src(NBUF - 1), src_b = load_src(NBUF), src_c = load_src(NBUF + 1);
-    int buf = 0;
-    float acc[3][2][4];
-    for (int it = 0; it < n_it; ++it) {
-      const int src_n = load_src(it + NBUF + 2);
-      asm volatile("cp.async.wait_group %0;" ::"n"(NBUF - 2) : "memory");   // this warp's share of item `it` has landed
-      group_sync();          // ... and everyone's; every warp of the group is also done reading item it - 1,
-      {                      // whose buffer the next prefetch overwrites
-        const int bl = buf == 0 ? NBUF - 1 : buf - 1;
-        issue(it + NBUF - 1, bl, src_a);
-      }
-      if ((it & 15) == 0 && it > 0) {          // rowptr of the block after this one
-        const int nb = load_block((it >> 4) + 1);
-        if (((it >> 4) + 1) & 1) rpb1 = nb;
-        else rpb0 = nb;
-      }
-      int eb, ee;
-      bounds(it, eb, ee);
-      const uint32_t base = st_u32 + (uint32_t)(buf * STG);
-      if (ee > eb) {
-        uint32_t b[4];
-        fl_ldsm4t(base + b_off, b);
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt) {
-          uint32_t a[4];
-          fl_ldsm4t(base + a_off + (uint32_t)(mt * 32), a);
-          fl_mma0(acc[mt][0], a, b[0], b[1]);
-          fl_mma0(acc[mt][1], a, b[2], b[3]);
-        }
-        for (int c0 = eb + FL_DEGC; c0 < ee; c0 += FL_DEGC) {   // rows longer than one chunk (not prefetched)
-          group_sync();
-          const int m = min(FL_DEGC, ee - c0);
-          const int sr = __ldg(src_sorted + c0 + min(lane & 15, m - 1));
-          stage_chunk(base, c0, m, sr);
-          asm volatile("cp.async.commit_group;" ::: "memory");
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-          group_sync();
-          fl_ldsm4t(base + b_off, b);
-#pragma unroll
-          for (int mt = 0; mt < 3; ++mt) {
-            uint32_t a[4];
-            fl_ldsm4t(base + a_off + (uint32_t)(mt * 32), a);
-            fl_mma(acc[mt][0], a, b[0], b[1]);
-            fl_mma(acc[mt][1], a, b[2], b[3]);
+      for (int u = 0; u < 4; ++u) {
+        const int it = it0 + u;
+        if (it >= n_it) break;
+        rp[(u + 3) & 3] = load_rp(it + 3);
+        load_srcs(rp[(u + 2) & 3], sc[(u + 2) & 3]);
+        const int rp0 = rp[u];
+        const int64_t node0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FL_NODES;
+        const int e_lo = __shfl_sync(FULL, rp0, 0), e_hi = __shfl_sync(FULL, rp0, 8);
+        int seg_lo = e_lo;
+        bool last;
+        do {
+          const int seg_hi = min(seg_lo + FL_CAP, e_hi);
+          last = seg_hi == e_hi;
+          const int nseg = seg_hi - seg_lo;
+          const int sl = (u & 1) * NBG + bufs[u & 1];
+          const uint32_t base = st_u32 + (uint32_t)(sl * STG);
+          const uint32_t fb = sfull + 8 * sl;
+          fl_mbar_wait(sempty + 8 * sl, pars[u & 1]);
+          if (pw == 0) {   // header: rp[0..8] | .. | seg_lo, seg_hi, last
+            int hw = rp0;
+            if (lane == 12) hw = seg_lo;
+            if (lane == 13) hw = seg_hi;
+            if (lane == 14) hw = last ? 1 : 0;
+            if (lane < 16) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)(HDR + 4 * lane)), "r"(hw) : "memory");
           }
-        }
-      } else {   // zero in-degree
-#pragma unroll
-        for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-          for (int nl = 0; nl < 2; ++nl)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[mt][nl][r] = 0.f;
-      }
-      // ---- this part's row of the Z tile: raw sums (the epilogue applies 1/deg), fp16, one conflict-free
-      // 128-byte row per store instruction
-      const int zb = it & 1;
-      const int deg = ee - eb;
-      fl_mbar_wait(zempty + 8 * zb, ((it >> 1) & 1) ^ 1);          // the tensor core is done with this buffer
-      const uint32_t zrow = zlane + (uint32_t)(zb * ZBYTES);
-      float fsum = 0.f;
-#pragma unroll
-      for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-          for (int nl = 0; nl < 2; ++nl) {
-            const uint32_t v = fl_h2_sat(acc[mt][nl][2 * hh], acc[mt][nl][2 * hh + 1]);
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(zrow + (uint32_t)(((mt * 2 + hh) * 2 + nl) * SLAB)), "r"(v) : "memory");
+          __syncwarp();
+          // g slot group of part pw: one bulk copy (the explicit arrive also releases the header stores)
+          if (lane == 0) {
+            if (pw < PPL && nseg > 0) {
+              const uint32_t bytes = (uint32_t)nseg * 32u;
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(bytes) : "memory");
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(base + (uint32_t)(pw * GPL)),
+                           "l"(g3 + ((size_t)(part0 + pw) * E + (size_t)seg_lo) * 16), "r"(bytes), "r"(fb)
+                           : "memory");
+            } else {
+              fl_mbar_arrive(fb);
+            }
           }
-      if (last_part) {
-        if (PPL == 3 && fix_b >= 0) {
+          // gathered h rows
+          if (seg_lo == e_lo) {
 #pragma unroll
-          for (int mt = 0; mt < 3; ++mt)
+            for (int i = 0; i < GOPS; ++i)
+              if (tr[i] < nseg)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + gdst[i]), "l"(h16 + (uint32_t)(sc[u][i] * 6) + tc[i]) : "memory");
+          } else {   // later segments of a big tile: source ids not prefetched
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-              for (int nl = 0; nl < 2; ++nl) {
-                const float2 wf = fl_h2_to_f2(wfs[((mt * 2 + hh) * 2 + nl) * 32 + lane]);
-                fsum = fmaf(acc[mt][nl][2 * hh], wf.x, fmaf(acc[mt][nl][2 * hh + 1], wf.y, fsum));
+            for (int i = 0; i < GOPS; ++i)
+              if (tr[i] < nseg) {
+                const int sidx = __ldg(src_sorted + seg_lo + tr[i]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + gdst[i]), "l"(h16 + (uint32_t)(sidx * 6) + tc[i]) : "memory");
               }
-        }
-        if (has_root && lane < 8) {
-          // root block: h_i * max(deg, 1) so that the epilogue's 1/deg leaves h_i
-          uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-          if (lane < 6) {
-            const uint32_t sa = base + (uint32_t)(GSZ + FL_DEGC * FL_SHB + lane * 16);
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(hv.x), "=r"(hv.y), "=r"(hv.z), "=r"(hv.w) : "r"(sa));
           }
-          const __half2 dg = __float2half2_rn((float)(deg > 0 ? deg : 1));
-          uint4 hs;
-          hs.x = fl_hmul2(hv.x, dg);
-          hs.y = fl_hmul2(hv.y, dg);
-          hs.z = fl_hmul2(hv.z, dg);
-          hs.w = fl_hmul2(hv.w, dg);
-          const uint32_t addr = fl_smem(zbuf) + (uint32_t)(zb * ZBYTES + 12 * SLAB + ((PPL - 1) * FL_NODES + j) * 128 + ((lane ^ j) << 4));
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(hs.x), "r"(hs.y), "r"(hs.z), "r"(hs.w) : "memory");
-          if (PPL == 3) {
-            const float2 h0 = fl_h2_to_f2(hs.x), h1 = fl_h2_to_f2(hs.y), h2 = fl_h2_to_f2(hs.z), h3 = fl_h2_to_f2(hs.w);
-            const uint4 wroot = *reinterpret_cast<const uint4*>(wfs + 12 * 32 + 4 * lane);     // lanes 6, 7: zeros
-            const float2 w0 = fl_h2_to_f2(wroot.x), w1 = fl_h2_to_f2(wroot.y), w2 = fl_h2_to_f2(wroot.z), w3 = fl_h2_to_f2(wroot.w);
-            fsum += h0.x * w0.x + h0.y * w0.y + h1.x * w1.x + h1.y * w1.y + h2.x * w2.x + h2.y * w2.y + h3.x * w3.x + h3.y * w3.y;
+          // the nodes' own rows ride with the tile's last segment
+          if (last && own_lane && node0 + orow < n)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + odst), "l"(h16 + (uint32_t)((int)(node0 + orow) * 6 + ot % 6)) : "memory");
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fb) : "memory");
+          if (++bufs[u & 1] == NBG) {
+            bufs[u & 1] = 0;
+            pars[u & 1] ^= 1;
           }
-        }
-        if (PPL == 3 && fix_b >= 0) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) fsum += __shfl_xor_sync(FULL, fsum, o);
-        }
-        if (lane == 0) {
-          fixs[(it & 3) * FL_NODES + j] = fsum;
-          invs[(it & 3) * FL_NODES + j] = 1.0f / (float)(deg > 0 ? deg : 1);
-        }
+          seg_lo = seg_hi;
+        } while (!last);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) fl_mbar_arrive(zfull + 8 * zb);
-      src_a = src_b;
-      src_b = src_c;
-      src_c = src_n;
-      buf = buf == NBUF - 1 ? 0 : buf + 1;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-  } else if (warp < FL_BW + 4) {
-    // =========================================================================== epilogue
-    const int qd = warp - FL_BW;                 // TMEM lane quadrant (== warp % 4)
-    const int L = qd * 32 + lane;                // TMEM lane = A/D row
-    const int p = L / rs, b = L % rs;
-    const bool row_ok = p < PPL && b < FL_WP;
-    // ---- T' rows of this launch's parts into TMEM (A operand): lane L <- TF[part0 + p][b][:]
-    {
-      const __half* src = tf + ((size_t)(part0 + (row_ok ? p : 0)) * FL_WP + (row_ok ? b : 0)) * FL_KP;
-      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < FL_ACOLS; c0 += 16) {
-        uint32_t r[16];
-#pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4) {
-          uint4 t = make_uint4(0u, 0u, 0u, 0u);
-          if (row_ok) t = __ldg(reinterpret_cast<const uint4*>(src + 2 * c0) + v4);
-          r[4 * v4] = t.x;
-          r[4 * v4 + 1] = t.y;
-          r[4 * v4 + 2] = t.z;
-          r[4 * v4 + 3] = t.w;
-        }
-        fl_tmem_st16(taddr + c0, r);
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) fl_mbar_arrive(aready);
-    }
-    const int te = threadIdx.x - FL_BW * 32;     // 0..127
-    constexpr int OUTI = (FL_NODES * 24 + 127) / 128;     // (node, channel pair) outputs per thread
-    for (int it = 0; it < n_it; ++it) {
-      const int as = it & 1;
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
-      fl_mbar_wait(dfull + 8 * as, (it >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + FL_ACOLS + as * N;
-      uint32_t r[N / 16][16];
-#pragma unroll
-      for (int c = 0; c < N / 16; ++c) fl_tmem_ld16(taddr + c * 16, r[c]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      // per-node scalars of this thread's outputs, read BEFORE the D stage is handed back (the builders
-      // reuse a slot four tiles later, which needs that arrival first)
-      float fxv[OUTI] = {}, inv[OUTI] = {};
-#pragma unroll
-      for (int i = 0; i < OUTI; ++i)
-        if (te + 128 * i < FL_NODES * 24) {
-          fxv[i] = fixs[(it & 3) * FL_NODES + (te + 128 * i) / 24];
-          inv[i] = invs[(it & 3) * FL_NODES + (te + 128 * i) / 24];
-        }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) fl_mbar_arrive(dempty + 8 * as);     // the D stage is free again
-      if (row_ok) {
-#pragma unroll
-        for (int j = 0; j < FL_NODES; ++j) {
-          uint32_t v = r[j / 16][j % 16];
-          if (PPL > 1 && p == 1) v = r[(FL_NODES + j) / 16][(FL_NODES + j) % 16];
-          if (PPL > 2 && p == 2) v = r[(2 * FL_NODES + j) / 16][(2 * FL_NODES + j) % 16];
-          comb[(p * FL_NODES + j) * FL_WP + b] = __uint_as_float(v);
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      // (node j, channel pair) outputs: 8 x 24 pairs over 128 threads
-#pragma unroll
-      for (int i = 0; i < OUTI; ++i) {
-        const int o = te + 128 * i;
-        if (o >= FL_NODES * 24) break;
-        const int j = o / 24, bb = (o % 24) * 2;
-        const int64_t row = tile * FL_NODES + j;
-        float v[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = bb + u;
-          float s = 0.f;
-          if (c < rs) {
-#pragma unroll
-            for (int pp = 0; pp < PPL; ++pp) {
-              if (PPL == 3 && pp == PPL - 1 && c == fix_b) s += fxv[i];
-              else s += comb[(pp * FL_NODES + j) * FL_WP + c];
-            }
-          }
-          v[u] = s * inv[i];
-        }
-        if (row < n) {
-          if (p_in) {
-            const float2 pv = *reinterpret_cast<const float2*>(p_in + row * FL_WP + bb);
-            v[0] += pv.x;
-            v[1] += pv.y;
-          }
-          if (p_out) {
-            *reinterpret_cast<float2*>(p_out + row * FL_WP + bb) = make_float2(v[0], v[1]);
-          } else {
-            v[0] += bias_p[bb];
-            v[1] += bias_p[bb + 1];
-            if (relu) {
-              v[0] = fmaxf(v[0], 0.f);
-              v[1] = fmaxf(v[1], 0.f);
-            }
-            *reinterpret_cast<uint32_t*>(h_out + row * FL_WP + bb) = fl_h2_sat(v[0], v[1]);
-          }
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-  } else {
-    // =========================================================================== MMA issuer
-    // instruction descriptor: D = F32, A = B = F16, both K-major, N, M = 128
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const int nkb = has_root ? FL_NKB : FL_NKB - 1;
-    fl_mbar_wait(aready, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int it = 0; it < n_it; ++it) {
-      const int zb = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      fl_mbar_wait(dempty + 8 * zb, ph ^ 1);
-      fl_mbar_wait(zfull + 8 * zb, ph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (fl_elect_one()) {
-        const uint32_t tmem_d = tmem_base + FL_ACOLS + zb * N;
-        const uint32_t zaddr = fl_smem(zbuf + (size_t)zb * ZBYTES);
-        for (int kb = 0; kb < nkb; ++kb) {
-          const uint64_t bdesc = fl_sw128_desc(zaddr + (uint32_t)(kb * SLAB));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            fl_umma_ts(tmem_d, tmem_base + (uint32_t)(kb * 32 + k * 8), bdesc + 2 * k, idesc, (kb | k) != 0);
-        }
-        fl_umma_commit(zempty + 8 * zb);
-        fl_umma_commit(dfull + 8 * zb);
-      }
-      __syncwarp();
-    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == FL_BW) {
+  if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
 template <int PPL, int NBUF>
 static size_t fl_smem_bytes() {
-  constexpr int NODES = FL_NODES;
-  constexpr int N = (PPL * NODES + 15) / 16 * 16;
+  constexpr int N = (PPL * FL_NODES + 15) / 16 * 16;
   constexpr size_t z = (size_t)2 * FL_NKB * N * 128;
-  constexpr size_t st = (size_t)FL_NODES * NBUF * (FL_DEGC * (32 * PPL + 16) + (FL_DEGC + 1) * FL_SHB);
-  constexpr size_t misc = (size_t)PPL * NODES * FL_WP * 4 + 8 * NODES * 4 + (PPL == 3 ? (12 * 32 + 32) * 4 : 0) + 10 * 8 + 16;
+  constexpr size_t st = (size_t)NBUF * (PPL * FL_CAP * 32 + FL_CAP * 96 + FL_NODES * 96 + 64);
+  constexpr size_t misc = (size_t)PPL * FL_NODES * FL_WP * 4 + 8 * FL_NODES * 4 + 32 + (PPL == 3 ? (12 * 32 + 32) * 4 : 0) + (6 + 2 * NBUF) * 8 + 16;
   return 1024 + z + st + misc;
 }
 
@@ -623,7 +694,7 @@ static int launch_fl(const int32_t* rowptr, const int32_t* src_sorted, const __h
   }
   const int64_t n_tiles = ceil_div(n, FL_NODES);
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  layer_fused_f16_kernel<PPL, NBUF><<<grid, (FL_NODES * PPL + 5) * 32, smem, s>>>(rowptr, src_sorted, g3, E, h_in, n, part0, has_root, tf,
+  layer_fused_f16_kernel<PPL, NBUF><<<grid, (2 * FL_NODES + 3 + 1 + 4) * 32, smem, s>>>(rowptr, src_sorted, g3, E, h_in, n, part0, has_root, tf,
                                                                   bias_p, p_in, p_out, h_out, rs, fix_b, relu);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
