@@ -334,7 +334,11 @@ def run_fesr(args):
         pass
     w = d.w
     zb = 2 if args.precision in ("f16", "fp16") else 4          # bytes per element of the Z intermediate
+    hb = 2 if args.precision in ("f16", "fp16") else 4          # bytes per element of g and h
     alg = {
+        # one fused layer (layer_fused.cu): src index, g row and gathered h row per edge; own h row read, h' row
+        # written and two row bounds per node.  Z stays on chip, so it is not in the byte count
+        "layer_fused": ("hbm", E_s * (4 + hb * d.kp + hb * d.wp) + n_s * (2 * hb * d.wp + 4) + 4),
         # gather + segmented mean: src index, g row, gathered h row per edge; h row read + Z row written per node
         "zbuild": ("hbm", E_s * (4 + 4 * d.k1 + 4 * w) + n_s * (4 * w + zb * (d.k1 * w + w)) + 4 * (n_s + 1)),
         # node contraction: Z row read, h row written; flops 2*n*zk*wp
@@ -366,7 +370,7 @@ def run_fesr(args):
     else:
         k = top if "gbs" in kernels[top] else "zbuild"
         roof = {"kernel": k, "bound": "hbm", "achieved": kernels[k]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": kernels[k]["gbs"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["src"]}
+                "frac": kernels[k]["gbs"] / peaks["hbm_gbs"], "traffic": ncu_traffic(k, args), "peak_source": peaks["src"]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -389,6 +393,17 @@ def run_fesr(args):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic(kind, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this same workload (profiles/*_traffic.json); None when there is none."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        key = f"{kind}:{args.precision}:n{args.mesh_n}"
+        return t[key]["dram_bytes_per_launch"] if key in t else None
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def run_cpu_baseline(args, levels):

@@ -105,7 +105,7 @@ def check(rc: int, what: str = ""):
 
 
 PROF_KINDS = ("prepare", "edge_hidden", "fc_in", "zbuild", "node_gemm", "fc_out", "node_weight", "stitch", "graph",
-              "backward")
+              "backward", "layer_fused")
 
 
 def profile_enable(on: bool):

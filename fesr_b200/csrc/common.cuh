@@ -38,7 +38,7 @@ void count_launch();
 // Optional per-kernel-class CUDA-event timing (bench.py's roofline numbers); off by default.
 enum ProfKind {
   PROF_PREPARE = 0, PROF_EDGE_HIDDEN, PROF_FC_IN, PROF_ZBUILD, PROF_NODE_GEMM, PROF_FC_OUT,
-  PROF_NODE_WEIGHT, PROF_STITCH, PROF_GRAPH, PROF_BACKWARD, PROF_NKINDS
+  PROF_NODE_WEIGHT, PROF_STITCH, PROF_GRAPH, PROF_BACKWARD, PROF_LAYER_FUSED, PROF_NKINDS
 };
 struct ProfScope {
   int slot;

@@ -730,7 +730,7 @@ int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, cons
   const __half* tfh = static_cast<const __half*>(tf);
   __half* ho = static_cast<__half*>(h_out);
   const int relu = 1;
-  ProfScope prof(PROF_ZBUILD, s);
+  ProfScope prof(PROF_LAYER_FUSED, s);
   int rc;
   if (mode == 0) mode = d.w <= 43 ? 3 : 2;
   if (mode == 3 && d.w <= 43) {

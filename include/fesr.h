@@ -58,7 +58,7 @@ long long fesr_launch_count(void);
  * roofline figures).  Classes: 0 prepare, 1 edge_hidden, 2 fc_in, 3 zbuild, 4 node_gemm,
  * 5 fc_out, 6 node_weight, 7 stitch, 8 graph, 9 backward.  _collect synchronises the recorded
  * events, sums milliseconds / scopes per class and clears the record. */
-#define FESR_PROF_NKINDS 10
+#define FESR_PROF_NKINDS 11
 int fesr_profile_enable(int on);
 int fesr_profile_collect(double* ms_by_kind, long long* launches_by_kind, int nkinds);
 
