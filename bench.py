@@ -199,7 +199,7 @@ def run_reference(args):
             "config": workload_config(args, world, levels, mesh.num_cells, sub, per_step),
             "cpu_baseline": {"value": value, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -389,7 +389,7 @@ def run_fesr(args):
                         "h2d_bytes_per_step": e2e_bytes["h2d"], "d2h_bytes_per_step": e2e_bytes["d2h"],
                         "api": "GNNPartitionScheduler.predict + dataset.reconstruct_from_partition"},
                 "gpu_launches": int(launches), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -416,6 +416,18 @@ def run_cpu_baseline(args, levels):
             "sample": f"{m} of {S} subdomains ({c} cells) in {t:.1f} s, torch CPU per-subdomain loop + numpy stitch"}
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints there (NCCL's version
+    banner, for one) has been routed to stderr."""
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     sys.exit(run_reference(a) if a.impl == "reference" else run_fesr(a))

@@ -188,14 +188,16 @@ class GNNPartitionScheduler():
         else:
             mine = torch.ones(S, dtype=torch.bool, device=dev)
 
-        pred = torch.zeros(csr.n, self.models[0].dims.out_ch, dtype=torch.float32, device=dev)
-        weight_s = torch.zeros(S, dtype=torch.float32, device=dev)
+        single = self.num_partitions == 1 and world == 1      # one model, every subdomain: nothing to select
+        if not single:
+            pred = torch.zeros(csr.n, self.models[0].dims.out_ch, dtype=torch.float32, device=dev)
+            weight_s = torch.zeros(S, dtype=torch.float32, device=dev)
         for i in range(self.num_partitions):
-            keep = (labels == i) & mine
-            if not bool(keep.any()):
+            keep = None if single else (labels == i) & mine
+            if keep is not None and not bool(keep.any()):
                 continue
             model = self.models[i]
-            if bool(keep.all()):
+            if keep is None or bool(keep.all()):
                 sub, ea, nptr, node_keep = csr, edge_attr, node_ptr, None
                 xi, yi = x_dev, y_dev
             else:
@@ -217,7 +219,7 @@ class GNNPartitionScheduler():
             cnt = [bounds[r + 1] - bounds[r] for r in range(world)]
             weight_s = all_gather_rows(weight_s[bounds[rank]:bounds[rank + 1]].contiguous(), cnt)
 
-        host = torch.empty(pred.numel() + S, dtype=torch.float32, pin_memory=True)    # one packed D2H copy
+        host = torch.empty(pred.numel() + S, dtype=torch.float32, pin_memory=True)    # one packed D2H copy (cached host allocator)
         host.copy_(torch.cat([pred.reshape(-1), weight_s]), non_blocking=True)
         torch.cuda.current_stream().synchronize()
         pred_cpu = host[:pred.numel()].view(pred.shape)
@@ -230,7 +232,7 @@ class GNNPartitionScheduler():
         ref_y_list.dev = y_dev
         w_cpu = host[pred.numel():]
         weights_list = [w_cpu[s].expand(sizes[s]) for s in range(S)]
-        model_idx = labels.cpu().numpy().astype(int)
+        model_idx = np.zeros(S, dtype=int) if self.num_partitions == 1 else labels.cpu().numpy().astype(int)
         return pred_y_list, ref_y_list, model_idx, weights_list
 
     # ----------------------------------------------------------------------------- train
