@@ -305,7 +305,9 @@ def run_fesr(args):
     def step_e2e():
         p, r, mi, wl = sched.predict(sample_h)
         out = ds.reconstruct_from_partition(p, r, 0, mi, wl)
-        return out.field                     # the stitched prediction on the fine mesh, on the host
+        f = out.field                        # the stitched prediction on the fine mesh, on the host
+        p.wait()                             # ... and the per-subdomain predictions + weights (packed copy)
+        return f
 
     sampler = ClockSampler(local)
     if rank == 0:

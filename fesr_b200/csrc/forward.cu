@@ -30,13 +30,14 @@ extern "C" {
 
 size_t fesr_forward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E, int keep_for_backward) {
   if (!dims || n < 0 || E < 0 || dims->layers > FESR_MAX_LAYERS) return 0;
-  return carve_forward(nullptr, *dims, n, E, keep_for_backward).bytes;
+  return carve_forward(nullptr, *dims, n, E, keep_for_backward & FESR_FWD_KEEP).bytes;
 }
 
 int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, const float* x,
                         const int32_t* rowptr, const int32_t* src_sorted, const int32_t* perm,
-                        const float* edge_attr, int64_t n, int64_t E, int precision, int keep_for_backward,
+                        const float* edge_attr, int64_t n, int64_t E, int precision, int fwd_flags,
                         float* y, void* workspace, size_t workspace_bytes, void* stream_) {
+  const int keep_for_backward = fwd_flags & FESR_FWD_KEEP;
   FESR_CHECK_ARG(dims && params, "dims/params NULL");
   FESR_CHECK_ARG(n >= 0 && E >= 0 && n < (1ll << 31) && E < (1ll << 31), "n/E out of range");
   FESR_CHECK_ARG(dims->layers <= FESR_MAX_LAYERS, "too many layers");
@@ -52,7 +53,7 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   }
   cudaStream_t s = as_stream(stream_);
   int rc;
-  if ((rc = launch_prepare_weights(d, *params, ws.prep, s))) return rc;
+  if (!(fwd_flags & FESR_FWD_WEIGHTS_PREPARED) && (rc = launch_prepare_weights(d, *params, ws.prep, s))) return rc;
   static const bool ffma_only = getenv("FESR_ZBUILD_FFMA") != nullptr;   // A/B switch for profiling
   // reduced-precision arms: g and h are rounded to tf32 by their producers, so the gather kernel
   // feeds them to the tensor cores without converting

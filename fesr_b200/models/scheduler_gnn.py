@@ -25,8 +25,24 @@ from ..dataset.GraphDataset import SubdomainSample
 
 
 class TensorList(list):
-    """list of per-subdomain CPU tensors that remembers the device-resident concatenation."""
+    """list of per-subdomain CPU tensors that remembers the device-resident concatenation.  The host buffer
+    behind the elements may still be filling (asynchronous device -> host copy on a side stream): the first
+    element access waits for it."""
     dev = None
+    ready = None          # torch.cuda.Event recorded after the device -> host copy, or None
+
+    def wait(self):
+        if self.ready is not None:
+            self.ready.synchronize()
+            self.ready = None
+
+    def __getitem__(self, i):
+        self.wait()
+        return super().__getitem__(i)
+
+    def __iter__(self):
+        self.wait()
+        return super().__iter__()
 
 
 def _dist():
@@ -66,8 +82,15 @@ def _as_batch(x, device):
         if getattr(b, "_sizes", None) is None:
             b._sizes = np.diff(b.node_ptr.cpu().numpy()).tolist()
         if x.x_host is not None:          # new input / reference fields arriving from the host
-            return (b.csr, b.edge_attr, b.node_ptr, x.x_host.to(device, non_blocking=True),
-                    x.y_host.to(device, non_blocking=True), b._sizes)
+            # x on the compute stream; the reference field is only needed by the node weight at the very end,
+            # so its copy rides on a side stream underneath the forward pass
+            main, side = torch.cuda.current_stream(device), _side_stream(device)
+            x_dev = x.x_host.to(device, non_blocking=True)
+            with torch.cuda.stream(side):
+                y_dev = x.y_host.to(device, non_blocking=True)
+                y_dev.ready = side.record_event()
+            y_dev.record_stream(main)
+            return b.csr, b.edge_attr, b.node_ptr, x_dev, y_dev, b._sizes
         return b.csr, b.edge_attr, b.node_ptr, x.x_dev, x.y_dev, b._sizes
     sizes = [int(d.x.shape[0]) for d in x]
     offs = np.concatenate([[0], np.cumsum(sizes)])
@@ -78,6 +101,16 @@ def _as_batch(x, device):
     csr = ops.csr_build(ei, int(offs[-1]))
     node_ptr = torch.from_numpy(offs.astype(np.int32)).to(device)
     return csr, ea, node_ptr, xs, ys, sizes
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device)
+    return _SIDE[key]
 
 
 def select_subdomains(csr, edge_attr, node_ptr, keep_sub):
@@ -173,6 +206,7 @@ class GNNPartitionScheduler():
             raise ValueError('Models are not trained yet')
         dev = self.device
         csr, edge_attr, node_ptr, x_dev, y_dev, sizes = _as_batch(x, dev)
+        y_ready = getattr(y_dev, "ready", None)
         S = len(sizes)
         dist, rank, world = _dist()
         labels = self._route(x_dev, node_ptr)
@@ -201,9 +235,15 @@ class GNNPartitionScheduler():
                 sub, ea, nptr, node_keep = csr, edge_attr, node_ptr, None
                 xi, yi = x_dev, y_dev
             else:
+                if y_ready is not None:                 # the selection below reads y before the forward
+                    torch.cuda.current_stream(dev).wait_event(y_ready)
+                    y_ready = None
                 sub, ea, nptr, node_keep = select_subdomains(csr, edge_attr, node_ptr, keep)
                 xi, yi = x_dev[node_keep], y_dev[node_keep]
             pi = model(xi, sub, ea)
+            if y_ready is not None:
+                torch.cuda.current_stream(dev).wait_event(y_ready)
+                y_ready = None
             wi = ops.node_weight(pi, yi, sub, ea, nptr)
             if node_keep is None:
                 pred, weight_s = pi, wi
@@ -219,19 +259,29 @@ class GNNPartitionScheduler():
             cnt = [bounds[r + 1] - bounds[r] for r in range(world)]
             weight_s = all_gather_rows(weight_s[bounds[rank]:bounds[rank + 1]].contiguous(), cnt)
 
-        host = torch.empty(pred.numel() + S, dtype=torch.float32, pin_memory=True)    # one packed D2H copy (cached host allocator)
-        host.copy_(torch.cat([pred.reshape(-1), weight_s]), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        # one packed device -> host copy on the side stream: reconstruct_from_partition works from the device
+        # copy (`.dev`), so the host lists only have to be complete when somebody reads them
+        host = torch.empty(pred.numel() + S, dtype=torch.float32, pin_memory=True)    # (cached host allocator)
+        packed = torch.cat([pred.reshape(-1), weight_s])
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        produced = main.record_event()
+        with torch.cuda.stream(side):
+            side.wait_event(produced)
+            host.copy_(packed, non_blocking=True)
+            copied = side.record_event()
+        packed.record_stream(side)
         pred_cpu = host[:pred.numel()].view(pred.shape)
         pred_y_list = TensorList(torch.split(pred_cpu, sizes))
         pred_y_list.dev = pred
+        pred_y_list.ready = copied
         if isinstance(x, SubdomainSample) and x.y_host is not None:
             ref_y_list = TensorList(torch.split(x.y_host, sizes))
         else:
             ref_y_list = TensorList([d.y for d in x])
         ref_y_list.dev = y_dev
         w_cpu = host[pred.numel():]
-        weights_list = [w_cpu[s].expand(sizes[s]) for s in range(S)]
+        weights_list = TensorList([w_cpu[s].expand(sizes[s]) for s in range(S)])
+        weights_list.ready = copied
         model_idx = np.zeros(S, dtype=int) if self.num_partitions == 1 else labels.cpu().numpy().astype(int)
         return pred_y_list, ref_y_list, model_idx, weights_list
 

@@ -52,14 +52,17 @@ class _Workspace:
         buf = self.bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             self.bufs.pop(key, None)
+            _prepared.pop(key, None)          # a new buffer holds no prepared weights
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
             self.bufs[key] = buf
         return buf
 
     def clear(self):
         self.bufs.clear()
+        _prepared.clear()
 
 
+_prepared = {}          # (device, workspace tag) -> (workspace ptr, dims, parameter (ptr, version) pairs) last prepared there
 workspace = _Workspace()
 
 
@@ -131,13 +134,22 @@ def nnconv_forward(dims: ModelDims, tensors: dict, x: torch.Tensor, csr: Csr, ed
     y = torch.empty(n, dims.out_ch, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         nbytes = lib.fesr_forward_workspace_bytes(C.byref(dims), n, E, int(keep_for_backward))
+        flags = int(keep_for_backward)
         if keep_for_backward:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         else:
             ws = workspace.get(dev, ws_tag, nbytes)
+            # the prepared weight copies at the head of the cached workspace stay valid as long as the same
+            # parameter tensors hold the same values (predict loops): skip the preparation kernels then
+            state = (ws.data_ptr(), bytes(dims), tuple((t.data_ptr(), t._version) for t in keep))
+            if _prepared.get((dev.index, ws_tag)) == state:
+                flags |= _lib.FWD_WEIGHTS_PREPARED
+            _prepared[(dev.index, ws_tag)] = None
         check(lib.fesr_nnconv_forward(C.byref(dims), C.byref(p), _ptr(x), _ptr(csr.rowptr), _ptr(csr.src),
-                                      _ptr(csr.perm), _ptr(edge_attr), n, E, precision, int(keep_for_backward),
+                                      _ptr(csr.perm), _ptr(edge_attr), n, E, precision, flags,
                                       _ptr(y), _ptr(ws), ws.numel(), _stream(dev)), "fesr_nnconv_forward")
+        if not keep_for_backward:
+            _prepared[(dev.index, ws_tag)] = state
     del keep
     return (y, ws) if keep_for_backward else y
 

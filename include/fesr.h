@@ -137,9 +137,15 @@ int fesr_csr_build(const int64_t* edge_index, int64_t E, int64_t n,
  *   edge_attr  : [E] fp32 in ORIGINAL edge order (perm maps CSR slot -> original id);
  *                perm == NULL means edge_attr is already in CSR order
  *   y          : [n, out_ch] fp32
- *   workspace  : fesr_forward_workspace_bytes(dims, n, E, keep) bytes.  With keep != 0 the
+ *   workspace  : fesr_forward_workspace_bytes(dims, n, E, keep) bytes.  With FESR_FWD_KEEP the
  *                per-layer activations needed by fesr_nnconv_backward stay in it.
+ *   keep_for_backward : bit flags.  FESR_FWD_KEEP (1) as above.  FESR_FWD_WEIGHTS_PREPARED (2): the
+ *                head of this workspace still holds the padded / permuted weight copies that an
+ *                earlier call made from the SAME parameter values (predict loops: the weights do
+ *                not change between calls), so the preparation kernels are skipped.
  * ---------------------------------------------------------------------------------- */
+#define FESR_FWD_KEEP 1
+#define FESR_FWD_WEIGHTS_PREPARED 2
 size_t fesr_forward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E, int keep_for_backward);
 int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params,
                         const float* x, const int32_t* rowptr, const int32_t* src_sorted,

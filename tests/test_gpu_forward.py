@@ -231,3 +231,29 @@ def test_fused_layer_kernel_narrower_widths(monkeypatch, w):
         yo = o(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ea)).numpy()
     for mode in (0, 3):
         assert rel_l2(_run_fuse_mode(monkeypatch, mode, m, x, ei, ea), yo) < TOL["f16"], mode
+
+
+def test_prepared_weights_are_reused_and_invalidated(golden):
+    """Predict loops skip the weight preparation kernels when the parameters did not change
+    (FESR_FWD_WEIGHTS_PREPARED); an in-place update of any parameter must prepare again."""
+    from fesr_b200 import _lib
+    m, _ = _models("neuralop", 16, 3)
+    m.load_state_dict(state_dict_from(golden, "kernelnn_w16"))
+    args = (golden["x"], golden["ref_edge_index"], golden["ref_edge_attr"])
+    y1 = _run(m, *args)
+    n0 = _lib.launch_count()
+    y2 = _run(m, *args)
+    n_cached = _lib.launch_count() - n0
+    assert np.array_equal(y1, y2)
+    with torch.no_grad():
+        m.fc2.bias.add_(1.0)                      # fc2 is not a prepared weight, but the version check is conservative
+        m.conv1.root.mul_(0.5)
+    n0 = _lib.launch_count()
+    y3 = _run(m, *args)
+    n_fresh = _lib.launch_count() - n0
+    assert n_fresh > n_cached, (n_fresh, n_cached)
+    with torch.no_grad():
+        m.fc2.bias.sub_(1.0)
+        m.conv1.root.mul_(2.0)
+    assert rel_l2(_run(m, *args), y1) < 1e-6
+    assert rel_l2(y3, y1) > 1e-3
