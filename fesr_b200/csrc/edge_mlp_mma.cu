@@ -9,6 +9,7 @@
 // channel gets zero weights and bias 1), so the accumulator fragments are g rows already: bias,
 // activation, rounding, one shared-memory transpose for coalesced 128-bit stores.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -166,6 +167,132 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
   }
 }
 
+
+// fp16 arms (OMODE 2: fp16 rows [E][KP]; 3: fp16 planar [KP/16][E][16], the fused layer kernel's slot groups):
+// the same product on mma.sync.m16n8k16 (fp16 operands -- 11-bit mantissa like the tf32 leading term -- fp32
+// accumulate): half the MMAs, weights as B fragments through ldmatrix from a [slot][in] fp16 copy, and the
+// accumulator tiles leave through stmatrix into row-per-edge staging (no fp32 round trip).
+__device__ __forceinline__ uint32_t em_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void em_mma16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t em_pack(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <int WPAD, int NTO, int OMODE>
+__global__ void __launch_bounds__(128)
+edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
+                        const float* __restrict__ b1g, int w, int leaky, int kt, int ktp, int k1,
+                        const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int64_t E,
+                        __half* __restrict__ gh) {
+  constexpr int KS = WPAD / 16, KP = NTO * 8;
+  constexpr int WST = WPAD + 8, SST = KP + 8;                          // row strides in halfs (+16 B: conflict-free)
+  __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1p[KP];
+  __shared__ __align__(16) __half wsm[KP][WST];                        // [slot][in]: K contiguous
+  __shared__ __align__(16) __half stage[4][32][SST];                   // [warp][edge][slot]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3, lr = lane & 7, lm = lane >> 3;
+  for (int i = tid; i < WPAD; i += blockDim.x) {
+    w0[i] = i < w ? w0g[i] : 0.f;
+    b0[i] = i < w ? b0g[i] : 0.f;
+  }
+  for (int slot = tid; slot < KP; slot += blockDim.x) {
+    const int q = slot / ktp, r = slot % ktp, ch = q * kt + r;
+    b1p[slot] = (r < kt && ch < k1 - 1 && ch < w) ? b1g[ch] : ((r < kt && ch == k1 - 1) ? 1.f : 0.f);
+  }
+  for (int i = tid; i < KP * WPAD; i += blockDim.x) {
+    const int slot = i / WPAD, in = i % WPAD;
+    const int q = slot / ktp, r = slot % ktp, ch = q * kt + r;
+    wsm[slot][in] = __float2half_rn((in < w && r < kt && ch < k1 - 1 && ch < w) ? w1g[ch * w + in] : 0.f);
+  }
+  __syncthreads();
+  // ldmatrix rows of the B fragments: matrices (n-tile 2np, k lo), (2np, k hi), (2np + 1, k lo), (2np + 1, k hi)
+  const uint32_t b_addr = em_smem(&wsm[(lm >> 1) * 8 + lr][(lm & 1) * 8]);
+  // stmatrix rows of the C tiles of m-tile mt: matrices (hh 0, nt), (hh 1, nt), (hh 0, nt + 1), (hh 1, nt + 1)
+  const uint32_t s_addr = em_smem(&stage[warp][(lm & 1) * 8 + lr][(lm >> 1) * 8]);
+
+  const int64_t n_groups = (E + 31) / 32;
+  for (int64_t grp = (int64_t)blockIdx.x * 4 + warp; grp < n_groups; grp += (int64_t)gridDim.x * 4) {
+    const int64_t e_base = grp * 32;
+    const int64_t e = e_base + lane;
+    const float d_lane = (e < E) ? edge_attr[perm ? perm[e] : e] : 0.f;
+    float dr[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      dr[mt][0] = __shfl_sync(0xffffffffu, d_lane, mt * 16 + gq);
+      dr[mt][1] = __shfl_sync(0xffffffffu, d_lane, mt * 16 + gq + 8);
+    }
+    float acc[2][NTO][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NTO; ++nt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[mt][nt][r] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      // layer 0 straight into A fragments: rows gq / gq + 8 (edges), columns 2tq, 2tq + 1 (+ 8) of this k-step
+      uint32_t a[2][4];
+      const int c = ks * 16 + 2 * tq;
+      const float2 wl = *reinterpret_cast<const float2*>(&w0[c]), bl = *reinterpret_cast<const float2*>(&b0[c]);
+      const float2 wh = *reinterpret_cast<const float2*>(&w0[c + 8]), bh = *reinterpret_cast<const float2*>(&b0[c + 8]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const float d = dr[mt][hh];
+          a[mt][hh] = em_pack(em_act(fmaf(d, wl.x, bl.x), leaky), em_act(fmaf(d, wl.y, bl.y), leaky));
+          a[mt][2 + hh] = em_pack(em_act(fmaf(d, wh.x, bh.x), leaky), em_act(fmaf(d, wh.y, bh.y), leaky));
+        }
+#pragma unroll
+      for (int np = 0; np < NTO / 2; ++np) {
+        uint32_t b[4];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
+                     : "r"(b_addr + (uint32_t)((np * 16 * WST + ks * 16) * 2)));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          em_mma16(acc[mt][2 * np], a[mt], b[0], b[1]);
+          em_mma16(acc[mt][2 * np + 1], a[mt], b[2], b[3]);
+        }
+      }
+    }
+    // epilogue: + bias, activation, fp16, 8x8 tiles transposed into rows through stmatrix
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int np = 0; np < NTO / 2; ++np) {
+        uint32_t h[2][2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int nt = 2 * np + q;
+          const float2 bz = *reinterpret_cast<const float2*>(&b1p[nt * 8 + 2 * tq]);
+          h[q][0] = em_pack(em_act(acc[mt][nt][0] + bz.x, leaky), em_act(acc[mt][nt][1] + bz.y, leaky));
+          h[q][1] = em_pack(em_act(acc[mt][nt][2] + bz.x, leaky), em_act(acc[mt][nt][3] + bz.y, leaky));
+        }
+        asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(s_addr + (uint32_t)((mt * 16 * SST + np * 16) * 2)),
+                     "r"(h[0][0]), "r"(h[0][1]), "r"(h[1][0]), "r"(h[1][1])
+                     : "memory");
+      }
+    __syncwarp();
+    constexpr int Q8 = KP / 8;
+    for (int t = lane; t < 32 * Q8; t += 32) {
+      const int r = t / Q8, c8 = t - r * Q8;
+      if (e_base + r < E) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(&stage[warp][r][8 * c8]);
+        if (OMODE == 3) *reinterpret_cast<uint4*>(gh + ((int64_t)(c8 >> 1) * E + e_base + r) * 16 + (c8 & 1) * 8) = pk;
+        else *reinterpret_cast<uint4*>(gh + (e_base + r) * KP + 8 * c8) = pk;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int WPAD, int NTO>
 static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr, const int32_t* perm,
                        int64_t E, float* g, cudaStream_t s, int omode) {
@@ -184,8 +311,15 @@ static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const flo
     FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_mma_kernel<WPAD, NTO, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
     attr_set = true;
   }
+  static const bool tf32_only = getenv("FESR_EDGE_TF32") != nullptr;     // A/B switch for profiling
   if (omode == 0) FESR_EH(3, 0);
   else if (omode == 1) FESR_EH(1, 1);
+  else if (!tf32_only && omode == 2)
+    edge_hidden2_f16_kernel<WPAD, NTO, 2><<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.leaky, d.kt, d.ktp,
+                                                              d.k1, edge_attr, perm, E, reinterpret_cast<__half*>(g));
+  else if (!tf32_only)
+    edge_hidden2_f16_kernel<WPAD, NTO, 3><<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.leaky, d.kt, d.ktp,
+                                                              d.k1, edge_attr, perm, E, reinterpret_cast<__half*>(g));
   else if (omode == 2) FESR_EH(1, 2);
   else FESR_EH(1, 3);
 #undef FESR_EH
