@@ -555,33 +555,30 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     // This lane's gather chunk-ops of a segment: op i is 16-byte chunk tc of staged row tr[i]; the flat index
     // t = (i * FL_NPROD + pw) * 32 + lane runs over rows x 6 chunks.  Destination offsets are lane constants.
     // (One 96-byte cp.async.bulk per row was tried: ~30 cycles per small bulk copy, slower than these.)
+    // With 32 * FL_NPROD = 96 = 16 rows x 6 chunks per round, op i of a lane is chunk c0 of row r0 + 16 i, and its
+    // swizzled destination (chunk ^ bit 2 of the row) is g0 + 1536 i: three lane constants describe all ops.
     constexpr int GOPS = (FL_CAP * 6 + 32 * FL_NPROD - 1) / (32 * FL_NPROD);
-    int tr[GOPS];
-    uint32_t tc[GOPS], gdst[GOPS];
-#pragma unroll
-    for (int i = 0; i < GOPS; ++i) {
-      const int t = (i * FL_NPROD + pw) * 32 + lane;
-      tr[i] = t / 6;
-      tc[i] = (uint32_t)(t % 6);
-      gdst[i] = (uint32_t)(HOFF + tr[i] * 96) + ((tc[i] ^ (uint32_t)((tr[i] >> 2) & 1)) << 4);
-    }
+    static_assert(FL_NPROD == 3, "the lane constants below assume 96 chunk-ops per round");
+    const int t0 = pw * 32 + lane;
+    const int r0 = t0 / 6;
+    const uint32_t c0 = (uint32_t)(t0 % 6);
+    const uint32_t g0 = (uint32_t)(HOFF + ((t0 ^ ((r0 >> 2) & 1)) << 4));
     // the 8 nodes' own rows: 48 chunk-ops, lanes of producers 0 and 1
     const int ot = pw * 32 + lane;
     const bool own_lane = ot < FL_NODES * 6;
     const int orow = ot / 6;
     const uint32_t odst = (uint32_t)(OWN + orow * 96 + (ot % 6) * 16);
     const uint4* h16 = reinterpret_cast<const uint4*>(h_in);         // h rows as 6 sixteen-byte chunks
-    // rowptr of the tile's 9 node boundaries in lanes 0..8
-    auto load_rp = [&](int itx) {
-      int64_t node = ((int64_t)blockIdx.x + (int64_t)itx * gridDim.x) * FL_NODES + (lane < 9 ? lane : 8);
-      node = node < n ? node : n;
-      return __ldg(rowptr + node);
-    };
+    const __half* gplane = g3 + (size_t)(part0 + (pw < PPL ? pw : 0)) * E * 16;   // this producer's g slot group
+    const int n32 = (int)n, lane9 = lane < 9 ? lane : 8;
+    const int tile0 = (int)blockIdx.x, tstep = (int)gridDim.x;
+    // rowptr of the tile's 9 node boundaries in lanes 0..8 (node ids fit 31 bits)
+    auto load_rp = [&](int itx) { return __ldg(rowptr + min((tile0 + itx * tstep) * FL_NODES + lane9, n32)); };
     // source ids of this lane's gather ops for the first segment of a tile (clamped addresses)
     auto load_srcs = [&](int rpv, int (&sv)[GOPS]) {
       const int e_lo = __shfl_sync(FULL, rpv, 0), e_max = max(__shfl_sync(FULL, rpv, 8) - 1, 0);
 #pragma unroll
-      for (int i = 0; i < GOPS; ++i) sv[i] = __ldg(src_sorted + min(e_lo + tr[i], e_max));
+      for (int i = 0; i < GOPS; ++i) sv[i] = __ldg(src_sorted + min(e_lo + r0 + 16 * i, e_max));
     };
     // Prefetch registers, indexed by (tile & 3) inside a loop unrolled by 4 so that no in-flight load is ever
     // moved between registers (a move would wait for it): rowptr of tile t is requested 3 tiles ahead, the
@@ -604,7 +601,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
         rp[(u + 3) & 3] = load_rp(it + 3);
         load_srcs(rp[(u + 2) & 3], sc[(u + 2) & 3]);
         const int rp0 = rp[u];
-        const int64_t node0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FL_NODES;
+        const int node0 = (tile0 + it * tstep) * FL_NODES;
         const int e_lo = __shfl_sync(FULL, rp0, 0), e_hi = __shfl_sync(FULL, rp0, 8);
         int seg_lo = e_lo;
         bool last;
@@ -616,12 +613,12 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
           const uint32_t base = st_u32 + (uint32_t)(sl * STG);
           const uint32_t fb = sfull + 8 * sl;
           fl_mbar_wait(sempty + 8 * sl, pars[u & 1]);
-          if (pw == 0) {   // header: rp[0..8] | .. | seg_lo, seg_hi, last
+          if (pw == 0 && lane < 16) {   // header: rp[0..8] | .. | seg_lo, seg_hi, last
             int hw = rp0;
             if (lane == 12) hw = seg_lo;
             if (lane == 13) hw = seg_hi;
             if (lane == 14) hw = last ? 1 : 0;
-            if (lane < 16) asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)(HDR + 4 * lane)), "r"(hw) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + (uint32_t)(HDR + 4 * lane)), "r"(hw) : "memory");
           }
           __syncwarp();
           // g slot group of part pw: one bulk copy (the explicit arrive also releases the header stores)
@@ -630,29 +627,30 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
               const uint32_t bytes = (uint32_t)nseg * 32u;
               asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(bytes) : "memory");
               asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(base + (uint32_t)(pw * GPL)),
-                           "l"(g3 + ((size_t)(part0 + pw) * E + (size_t)seg_lo) * 16), "r"(bytes), "r"(fb)
+                           "l"(gplane + (size_t)seg_lo * 16), "r"(bytes), "r"(fb)
                            : "memory");
             } else {
               fl_mbar_arrive(fb);
             }
           }
-          // gathered h rows
-          if (seg_lo == e_lo) {
+          __syncwarp();
+          // gathered h rows (later segments of a big tile: source ids not prefetched)
+          int sidx[GOPS];
 #pragma unroll
-            for (int i = 0; i < GOPS; ++i)
-              if (tr[i] < nseg)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + gdst[i]), "l"(h16 + (uint32_t)(sc[u][i] * 6) + tc[i]) : "memory");
-          } else {   // later segments of a big tile: source ids not prefetched
+          for (int i = 0; i < GOPS; ++i) sidx[i] = sc[u][i];
+          if (seg_lo != e_lo) {
 #pragma unroll
-            for (int i = 0; i < GOPS; ++i)
-              if (tr[i] < nseg) {
-                const int sidx = __ldg(src_sorted + seg_lo + tr[i]);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + gdst[i]), "l"(h16 + (uint32_t)(sidx * 6) + tc[i]) : "memory");
-              }
+            for (int i = 0; i < GOPS; ++i) sidx[i] = __ldg(src_sorted + min(seg_lo + r0 + 16 * i, seg_hi - 1));
           }
+#pragma unroll
+          const uint32_t gb = base + g0;
+#pragma unroll
+          for (int i = 0; i < GOPS; ++i)
+            if (r0 + 16 * i < nseg)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(gb + (uint32_t)(1536 * i)), "l"(h16 + ((uint32_t)sidx[i] * 6u + c0)) : "memory");
           // the nodes' own rows ride with the tile's last segment
-          if (last && own_lane && node0 + orow < n)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + odst), "l"(h16 + (uint32_t)((int)(node0 + orow) * 6 + ot % 6)) : "memory");
+          if (last && own_lane && node0 + orow < n32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + odst), "l"(h16 + (uint32_t)((node0 + orow) * 6 + ot % 6)) : "memory");
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fb) : "memory");
           if (++bufs[u & 1] == NBG) {
             bufs[u & 1] = 0;
