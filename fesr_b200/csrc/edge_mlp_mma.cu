@@ -184,11 +184,11 @@ __device__ __forceinline__ uint32_t em_pack(float lo, float hi) {
   return r;
 }
 
-template <int WPAD, int NTO, int OMODE>
+template <int WPAD, int NTO, int OMODE>     // ReLU only (KernelNN); LeakyReLU shapes use the tf32 kernel above
 __global__ void __launch_bounds__(128)
 edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
-                        const float* __restrict__ b1g, int w, int leaky, int kt, int ktp, int k1,
-                        const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int64_t E,
+                        const float* __restrict__ b1g, int w, int kt, int ktp, int k1,
+                        const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int E,
                         __half* __restrict__ gh) {
   constexpr int KS = WPAD / 16, KP = NTO * 8;
   constexpr int WST = WPAD + 8, SST = KP + 8;                          // row strides in halfs (+16 B: conflict-free)
@@ -216,11 +216,22 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
   // stmatrix rows of the C tiles of m-tile mt: matrices (hh 0, nt), (hh 1, nt), (hh 0, nt + 1), (hh 1, nt + 1)
   const uint32_t s_addr = em_smem(&stage[warp][(lm & 1) * 8 + lr][(lm >> 1) * 8]);
 
-  const int64_t n_groups = (E + 31) / 32;
-  for (int64_t grp = (int64_t)blockIdx.x * 4 + warp; grp < n_groups; grp += (int64_t)gridDim.x * 4) {
-    const int64_t e_base = grp * 32;
-    const int64_t e = e_base + lane;
-    const float d_lane = (e < E) ? edge_attr[perm ? perm[e] : e] : 0.f;
+  // coalesced row stores: lanes 0..23 move 4 rows x 6 sixteen-byte chunks per round
+  constexpr int Q8 = KP / 8, RPR = 32 / Q8;                            // chunks per row, rows per round
+  const int sr = lane / Q8, sc8 = lane % Q8;
+  const bool st_lane = lane < RPR * Q8;
+  __half* const sdst = OMODE == 3 ? gh + (int64_t)(sc8 >> 1) * E * 16 + (sc8 & 1) * 8 : gh + 8 * sc8;
+  constexpr int RSTR = OMODE == 3 ? 16 : KP;                           // row stride of the destination (halfs)
+  const int n_groups = (E + 31) / 32;
+  auto load_d = [&](int g) {      // edge length of this lane's edge of group g (clamped: the value of a missing edge is unused)
+    const int e = min(g * 32 + lane, E - 1);
+    return __ldg(edge_attr + (perm ? __ldg(perm + e) : e));
+  };
+  float d_next = load_d(min((int)(blockIdx.x * 4 + warp), n_groups - 1));
+  for (int grp = blockIdx.x * 4 + warp; grp < n_groups; grp += gridDim.x * 4) {
+    const int e_base = grp * 32;
+    const float d_lane = d_next;
+    d_next = load_d(min(grp + (int)gridDim.x * 4, n_groups - 1));     // next group's lengths fly under this group's math
     float dr[2][2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -246,8 +257,8 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const float d = dr[mt][hh];
-          a[mt][hh] = em_pack(em_act(fmaf(d, wl.x, bl.x), leaky), em_act(fmaf(d, wl.y, bl.y), leaky));
-          a[mt][2 + hh] = em_pack(em_act(fmaf(d, wh.x, bh.x), leaky), em_act(fmaf(d, wh.y, bh.y), leaky));
+          a[mt][hh] = em_pack(fmaxf(fmaf(d, wl.x, bl.x), 0.f), fmaxf(fmaf(d, wl.y, bl.y), 0.f));
+          a[mt][2 + hh] = em_pack(fmaxf(fmaf(d, wh.x, bh.x), 0.f), fmaxf(fmaf(d, wh.y, bh.y), 0.f));
         }
 #pragma unroll
       for (int np = 0; np < NTO / 2; ++np) {
@@ -272,22 +283,19 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
         for (int q = 0; q < 2; ++q) {
           const int nt = 2 * np + q;
           const float2 bz = *reinterpret_cast<const float2*>(&b1p[nt * 8 + 2 * tq]);
-          h[q][0] = em_pack(em_act(acc[mt][nt][0] + bz.x, leaky), em_act(acc[mt][nt][1] + bz.y, leaky));
-          h[q][1] = em_pack(em_act(acc[mt][nt][2] + bz.x, leaky), em_act(acc[mt][nt][3] + bz.y, leaky));
+          h[q][0] = em_pack(fmaxf(acc[mt][nt][0] + bz.x, 0.f), fmaxf(acc[mt][nt][1] + bz.y, 0.f));
+          h[q][1] = em_pack(fmaxf(acc[mt][nt][2] + bz.x, 0.f), fmaxf(acc[mt][nt][3] + bz.y, 0.f));
         }
         asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(s_addr + (uint32_t)((mt * 16 * SST + np * 16) * 2)),
                      "r"(h[0][0]), "r"(h[0][1]), "r"(h[1][0]), "r"(h[1][1])
                      : "memory");
       }
     __syncwarp();
-    constexpr int Q8 = KP / 8;
-    for (int t = lane; t < 32 * Q8; t += 32) {
-      const int r = t / Q8, c8 = t - r * Q8;
-      if (e_base + r < E) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(&stage[warp][r][8 * c8]);
-        if (OMODE == 3) *reinterpret_cast<uint4*>(gh + ((int64_t)(c8 >> 1) * E + e_base + r) * 16 + (c8 & 1) * 8) = pk;
-        else *reinterpret_cast<uint4*>(gh + (e_base + r) * KP + 8 * c8) = pk;
-      }
+    if (st_lane) {
+#pragma unroll
+      for (int r = sr; r < 32; r += RPR)
+        if (e_base + r < E)
+          *reinterpret_cast<uint4*>(sdst + (int64_t)(e_base + r) * RSTR) = *reinterpret_cast<const uint4*>(&stage[warp][r][8 * sc8]);
     }
     __syncwarp();
   }
@@ -314,12 +322,12 @@ static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const flo
   static const bool tf32_only = getenv("FESR_EDGE_TF32") != nullptr;     // A/B switch for profiling
   if (omode == 0) FESR_EH(3, 0);
   else if (omode == 1) FESR_EH(1, 1);
-  else if (!tf32_only && omode == 2)
-    edge_hidden2_f16_kernel<WPAD, NTO, 2><<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.leaky, d.kt, d.ktp,
-                                                              d.k1, edge_attr, perm, E, reinterpret_cast<__half*>(g));
-  else if (!tf32_only)
-    edge_hidden2_f16_kernel<WPAD, NTO, 3><<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.leaky, d.kt, d.ktp,
-                                                              d.k1, edge_attr, perm, E, reinterpret_cast<__half*>(g));
+  else if (!tf32_only && !d.leaky && omode == 2)
+    edge_hidden2_f16_kernel<WPAD, NTO, 2><<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
+                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g));
+  else if (!tf32_only && !d.leaky)
+    edge_hidden2_f16_kernel<WPAD, NTO, 3><<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
+                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g));
   else if (omode == 2) FESR_EH(1, 2);
   else FESR_EH(1, 3);
 #undef FESR_EH
