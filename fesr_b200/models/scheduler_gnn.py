@@ -205,10 +205,12 @@ class GNNPartitionScheduler():
         if not hasattr(self, 'models'):
             raise ValueError('Models are not trained yet')
         dev = self.device
+        dist, rank, world = _dist()
+        if world > 1 and self.num_partitions == 1 and isinstance(x, SubdomainSample):
+            return self._predict_sharded(x, rank, world)
         csr, edge_attr, node_ptr, x_dev, y_dev, sizes = _as_batch(x, dev)
         y_ready = getattr(y_dev, "ready", None)
         S = len(sizes)
-        dist, rank, world = _dist()
         labels = self._route(x_dev, node_ptr)
 
         # this rank's contiguous, edge-balanced share of the subdomain list
@@ -259,8 +261,56 @@ class GNNPartitionScheduler():
             cnt = [bounds[r + 1] - bounds[r] for r in range(world)]
             weight_s = all_gather_rows(weight_s[bounds[rank]:bounds[rank + 1]].contiguous(), cnt)
 
+        return self._to_host_lists(x, pred, weight_s, y_dev, sizes, labels)
+
+    def _predict_sharded(self, x, rank, world):
+        """One model, several ranks, device-resident decomposition: every rank runs its contiguous edge-balanced
+        share of the subdomains (the shard's CSR slice is built once per (mesh, world) and cached on the batch),
+        copies only ITS rows of the input field host -> device, and one packed all-gather brings the predictions
+        and subdomain weights of the other ranks (reference fan-out / fan-in: models/scheduler_gnn.py:254-311)."""
+        from ..pipeline import all_gather_packed, make_shard, shard_bounds
+        dev = self.device
+        b = x.batch
+        cache = b.__dict__.setdefault("_shards", {})
+        if world not in cache:
+            node_ptr_h = b.node_ptr.cpu().numpy().astype(np.int64)
+            bounds = shard_bounds(b.edge_ptr.cpu().numpy().astype(np.int64), world)
+            cache[world] = {"shard": make_shard(b, bounds[rank], bounds[rank + 1]),
+                            "rows": [int(node_ptr_h[bounds[r + 1]] - node_ptr_h[bounds[r]]) for r in range(world)],
+                            "cnt": [bounds[r + 1] - bounds[r] for r in range(world)],
+                            "sizes": np.diff(node_ptr_h).tolist()}
+        c = cache[world]
+        sh, sizes = c["shard"], c["sizes"]
+        lo, hi = sh.node_lo, sh.node_hi
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        y_ready = None
+        if x.x_host is not None:
+            xi = x.x_host[lo:hi].to(dev, non_blocking=True)
+            with torch.cuda.stream(side):        # the whole reference field: the stitch of ref_y_list needs all of it
+                y_dev = x.y_host.to(dev, non_blocking=True)
+                y_ready = side.record_event()
+            y_dev.record_stream(main)
+        else:
+            xi, y_dev = x.x_dev[lo:hi], x.y_dev
+        model = self.models[0]
+        if hi > lo:
+            pi = model(xi, sh.csr, sh.edge_attr)
+            if y_ready is not None:
+                main.wait_event(y_ready)
+            wi = ops.node_weight(pi, y_dev[lo:hi], sh.csr, sh.edge_attr, sh.node_ptr)
+        else:                                    # more ranks than subdomains
+            if y_ready is not None:
+                main.wait_event(y_ready)
+            pi = torch.zeros(0, model.dims.out_ch, dtype=torch.float32, device=dev)
+            wi = torch.zeros(0, dtype=torch.float32, device=dev)
+        pred, weight_s = all_gather_packed(pi, wi, c["rows"], c["cnt"])
+        return self._to_host_lists(x, pred, weight_s, y_dev, sizes, None)
+
+    def _to_host_lists(self, x, pred, weight_s, y_dev, sizes, labels):
         # one packed device -> host copy on the side stream: reconstruct_from_partition works from the device
         # copy (`.dev`), so the host lists only have to be complete when somebody reads them
+        dev = self.device
+        S = len(sizes)
         host = torch.empty(pred.numel() + S, dtype=torch.float32, pin_memory=True)    # (cached host allocator)
         packed = torch.cat([pred.reshape(-1), weight_s])
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
@@ -282,7 +332,7 @@ class GNNPartitionScheduler():
         w_cpu = host[pred.numel():]
         weights_list = TensorList([w_cpu[s].expand(sizes[s]) for s in range(S)])
         weights_list.ready = copied
-        model_idx = np.zeros(S, dtype=int) if self.num_partitions == 1 else labels.cpu().numpy().astype(int)
+        model_idx = np.zeros(S, dtype=int) if labels is None or self.num_partitions == 1 else labels.cpu().numpy().astype(int)
         return pred_y_list, ref_y_list, model_idx, weights_list
 
     # ----------------------------------------------------------------------------- train

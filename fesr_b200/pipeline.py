@@ -60,6 +60,28 @@ def all_gather_rows(local: torch.Tensor, rows, group=None) -> torch.Tensor:
     return torch.cat([parts[r][:rows[r]] for r in range(world)], dim=0)
 
 
+def all_gather_packed(pred_local: torch.Tensor, w_local: torch.Tensor, rows, cnt, group=None):
+    """Predictions [rows[r], c] and subdomain weights [cnt[r]] of every rank in ONE collective: each rank packs
+    both into one flat fp32 buffer padded to the largest rank, `all_gather_into_tensor`, then the rank blocks
+    are unpacked in rank (= subdomain) order.  -> (pred [sum rows, c], weights [sum cnt])."""
+    import torch.distributed as dist
+    world = len(rows)
+    c = int(pred_local.shape[1])
+    if world == 1:
+        return pred_local, w_local
+    mx = max(rows[r] * c + cnt[r] for r in range(world))
+    rank = dist.get_rank(group)
+    buf = pred_local.new_empty(world, mx)
+    mine = buf[rank]
+    np_, nw = rows[rank] * c, cnt[rank]
+    mine[:np_] = pred_local.reshape(-1)
+    mine[np_:np_ + nw] = w_local
+    dist.all_gather_into_tensor(buf.view(-1), mine.clone(), group=group)
+    pred = torch.cat([buf[r, :rows[r] * c] for r in range(world)]).view(-1, c)
+    w = torch.cat([buf[r, rows[r] * c:rows[r] * c + cnt[r]] for r in range(world)])
+    return pred, w
+
+
 def make_shard(batch: ops.SubdomainBatch, s0: int, s1: int) -> Shard:
     node_ptr_h = batch.node_ptr[[s0, s1]].cpu().numpy()
     edge_ptr_h = batch.edge_ptr[[s0, s1]].cpu().numpy()

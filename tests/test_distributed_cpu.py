@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fesr_b200.pipeline import all_gather_rows, shard_bounds
+from fesr_b200.pipeline import all_gather_packed, all_gather_rows, shard_bounds
 
 
 def _free_port():
@@ -32,6 +32,11 @@ def _worker(rank, world, port, edge_ptr, node_ptr, ret):
         mine = full[lo:lo + rows[rank]].clone()
         got = all_gather_rows(mine, rows)
         ok_gather = bool(torch.equal(got, full))
+        # predictions + per-subdomain weights in one packed collective
+        cnt = [bounds[r + 1] - bounds[r] for r in range(world)]
+        w_full = torch.arange(len(node_ptr) - 1, dtype=torch.float32) + 0.5
+        p2, w2 = all_gather_packed(mine, w_full[bounds[rank]:bounds[rank + 1]].clone(), rows, cnt)
+        ok_gather = ok_gather and bool(torch.equal(p2, full)) and bool(torch.equal(w2, w_full))
         # gradient averaging as FlatAdam.step does it (sum / world)
         g = torch.full((10,), float(rank + 1))
         dist.all_reduce(g, op=dist.ReduceOp.SUM)

@@ -132,3 +132,39 @@ def test_gradient_loss_forward(golden):
         assert abs(v - float(golden[key])) <= 2e-5 * abs(float(golden[key])) + 1e-9
     nw = GradientbasedLoss().compute_node_weight(pred, y, ei, ea, y.shape[0])
     assert nw.shape == (y.shape[0],)
+
+
+def test_sharded_predict_matches_single_rank(tmp_path, shipped, monkeypatch):
+    """The multi-rank predict path (cached shard + packed all-gather), both ranks of a world of 2 played one after
+    the other on this GPU: the union of what the ranks contribute equals the single-rank result bit for bit."""
+    from fesr_b200 import pipeline
+    from fesr_b200.models import scheduler_gnn as sg
+    ds, model, sds = _setup(tmp_path, 1, shipped, monkeypatch)
+    sched = sg.GNNPartitionScheduler("t", 1, ds, model, train=False)
+    base = ds.get_one_full_sample(0)
+    p1, _, _, w1 = sched.predict(base)
+    full_p, full_w = p1.dev.clone(), torch.stack([w[0] for w in w1])
+    # host-input variant of the same sample (the sharded path copies only its own rows of x)
+    c = ds._mesh(0)
+    xh, yh = c["x"].cpu().pin_memory(), c["y"].cpu().pin_memory()
+    contributed = {}
+
+    def fake_gather(pi, wi, rows, cnt, group=None):
+        contributed[fake_gather.rank] = (pi.clone(), wi.clone(), list(rows), list(cnt))
+        return full_p, full_w.cuda()
+
+    monkeypatch.setattr(pipeline, "all_gather_packed", fake_gather)
+    for sample in (base, base.with_host_inputs(xh, yh)):
+        contributed.clear()
+        base.batch.__dict__.pop("_shards", None)
+        for rank in range(2):
+            fake_gather.rank = rank
+            monkeypatch.setattr(sg, "_dist", lambda r=rank: (None, r, 2))
+            base.batch.__dict__.pop("_shards", None)          # the cache is per process; here one process plays both
+            p, r, mi, w = sched.predict(sample)
+            assert len(p) == 16 and mi.shape == (16,)
+            assert torch.equal(torch.cat(list(p)), full_p.cpu())
+        (pa, wa, rows, cnt), (pb, wb, _, _) = contributed[0], contributed[1]
+        assert pa.shape[0] == rows[0] and pb.shape[0] == rows[1] and sum(cnt) == 16 and min(cnt) > 0
+        assert torch.equal(torch.cat([pa, pb]), full_p)
+        assert torch.equal(torch.cat([wa, wb]).cpu(), full_w.cpu())
