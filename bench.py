@@ -342,10 +342,10 @@ def run_fesr(args):
         # written and two row bounds per node.  Z stays on chip, so it is not in the byte count
         "layer_fused": ("hbm", E_s * (4 + hb * d.kp + hb * d.wp) + n_s * (2 * hb * d.wp + 4) + 4),
         # gather + segmented mean: src index, g row, gathered h row per edge; h row read + Z row written per node
-        "zbuild": ("hbm", E_s * (4 + 4 * d.k1 + 4 * w) + n_s * (4 * w + zb * (d.k1 * w + w)) + 4 * (n_s + 1)),
+        "zbuild": ("hbm", E_s * (4 + hb * d.k1 + hb * w) + n_s * (hb * w + zb * (d.k1 * w + w)) + 4 * (n_s + 1)),
         # node contraction: Z row read, h row written; flops 2*n*zk*wp
         "node_gemm": ("hbm" if args.precision != "fp32" else "fp32", n_s * (zb * (d.k1 * w + w) + 4 * w)),
-        "edge_hidden": ("hbm", E_s * (4 + 4 * d.k1)),
+        "edge_hidden": ("hbm", E_s * (4 + hb * d.k1)),
         "stitch": ("hbm", pred.batch.n_tot * 20 + pred.N * 20),
         "node_weight": ("hbm", E_s * (4 + 4 + 32) + n_s * 36),
     }

@@ -301,6 +301,261 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
   }
 }
 
+// TEECNet's edge MLP (DenseNet([1, 32, 64, 128, w*w], LeakyReLU), reference models/model.py:403 + :311-315): the
+// three hidden layers 1 -> 32 -> 64 -> 128 for the reduced-precision arms.  One warp owns 32 consecutive CSR edges and
+// the activations never leave its registers: layer 0 is evaluated straight into A fragments, the fp32 accumulator
+// tiles of layer 1 (two adjacent n-tiles = one k-step) are re-packed into the A fragments of layer 2, and layer 2's
+// 144 output slots (128 channels + the constant-1 channel in the padded / channel-grouped g row layout, the columns
+// of W2 permuted at load time) are produced in three chunks of 48 so that the accumulators stay at 48 registers.
+// Arithmetic: mma.sync.m16n8k16 on SPLIT fp16 operands, a = a_hi + a_lo and W = W_hi + W_lo with the three
+// significant products accumulated in fp32 (the fp16 twin of 3xTF32, ~2^-21).  Plain fp16 operands are not enough
+// here: the shipped TEECNet is sensitive to the hidden layers (single-term products move the predicted field by
+// 1.3e-2 rel-L2, rounding W1 alone by 1.27e-2; the split form by 4e-5 -- measured on the CPU restatement).
+// OMODE 1: fp32 rows rounded to tf32 [E][144]; OMODE 2: fp16 rows [E][144].
+__device__ __forceinline__ void em_split(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  hi = em_pack(v0, v1);
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = em_pack(v0 - f.x, v1 - f.y);
+}
+__device__ __forceinline__ void em_ldsm4(uint32_t addr, uint32_t (&b)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3])
+               : "r"(addr));
+}
+
+template <int OMODE>
+__global__ void __launch_bounds__(128)
+edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
+                        const float* __restrict__ b1g, const float* __restrict__ w2g, const float* __restrict__ b2g,
+                        int kt, int ktp, int k1, const float* __restrict__ edge_attr,
+                        const int32_t* __restrict__ perm, int E, void* __restrict__ gv) {
+  constexpr int H0 = 32, H1 = 64, KP = 144;
+  constexpr int CW = 48, NCH = KP / CW, NTC = CW / 8;                  // slots per chunk, chunks, n-tiles per chunk
+  constexpr int KS0 = H0 / 16, KS1 = H1 / 16, NT1 = H1 / 8;
+  constexpr int W1S = H0 + 8, W2S = H1 + 8;                            // row strides in halfs (+16 B: conflict-free)
+  constexpr int SST = OMODE == 2 ? (CW + 8) * 2 : (CW + 4) * 4;        // staged row stride in BYTES
+  __shared__ __align__(16) float w0[H0], b0[H0], b1[H1], b2p[KP];
+  extern __shared__ __align__(16) uint8_t eh3_dyn[];
+  __half (*w1h)[W1S] = reinterpret_cast<__half (*)[W1S]>(eh3_dyn);     // [out][in]: K contiguous
+  __half (*w1l)[W1S] = w1h + H1;
+  __half (*w2h)[W2S] = reinterpret_cast<__half (*)[W2S]>(w1l + H1);    // [slot][in]
+  __half (*w2l)[W2S] = w2h + KP;
+  uint8_t* stage = reinterpret_cast<uint8_t*>(w2l + KP);               // [4 warps][32 edges][SST]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, tq = lane & 3, lr = lane & 7, lm = lane >> 3;
+  for (int i = tid; i < H0; i += blockDim.x) {
+    w0[i] = w0g[i];
+    b0[i] = b0g[i];
+  }
+  for (int i = tid; i < H1; i += blockDim.x) b1[i] = b1g[i];
+  for (int i = tid; i < H1 * H0; i += blockDim.x) {
+    const float v = w1g[i];
+    const __half hi = __float2half_rn(v);
+    w1h[i / H0][i % H0] = hi;
+    w1l[i / H0][i % H0] = __float2half_rn(v - __half2float(hi));
+  }
+  for (int slot = tid; slot < KP; slot += blockDim.x) {
+    const int q = slot / ktp, r = slot % ktp, ch = q * kt + r;
+    b2p[slot] = (r < kt && ch < k1 - 1) ? b2g[ch] : ((r < kt && ch == k1 - 1) ? 1.f : 0.f);
+  }
+  for (int i = tid; i < KP * H1; i += blockDim.x) {
+    const int slot = i / H1, in = i % H1;
+    const int q = slot / ktp, r = slot % ktp, ch = q * kt + r;
+    const float v = (r < kt && ch < k1 - 1) ? w2g[ch * H1 + in] : 0.f;
+    const __half hi = __float2half_rn(v);
+    w2h[slot][in] = hi;
+    w2l[slot][in] = __float2half_rn(v - __half2float(hi));
+  }
+  __syncthreads();
+  auto lrelu = [](float v) { return v > 0.f ? v : 0.01f * v; };
+  // ldmatrix rows of the B fragments: matrices (n-tile 2np, k lo), (2np, k hi), (2np + 1, k lo), (2np + 1, k hi)
+  const uint32_t b1_addr = em_smem(&w1h[(lm >> 1) * 8 + lr][(lm & 1) * 8]);
+  const uint32_t b2_addr = em_smem(&w2h[(lm >> 1) * 8 + lr][(lm & 1) * 8]);
+  constexpr uint32_t LO1 = H1 * W1S * 2, LO2 = KP * W2S * 2;           // byte distance hi -> lo copy
+  uint8_t* const wstage = stage + (size_t)warp * 32 * SST;
+  // fp16 rows: stmatrix rows of the C tiles of m-tile mt: matrices (hh 0, nt), (hh 1, nt), (hh 0, nt + 1), (hh 1, nt + 1)
+  const uint32_t s_addr = em_smem(wstage) + (uint32_t)(((lm & 1) * 8 + lr) * SST + (lm >> 1) * 16);
+  constexpr int QB = OMODE == 2 ? CW / 8 : CW / 4;                     // 16-byte chunks per staged row
+  const int n_groups = (E + 31) / 32;
+  auto load_d = [&](int g) {
+    const int e = min(g * 32 + lane, E - 1);
+    return __ldg(edge_attr + (perm ? __ldg(perm + e) : e));
+  };
+  float d_next = load_d(min((int)(blockIdx.x * 4 + warp), n_groups - 1));
+  for (int grp = blockIdx.x * 4 + warp; grp < n_groups; grp += gridDim.x * 4) {
+    const int e_base = grp * 32;
+    const float d_lane = d_next;
+    d_next = load_d(min(grp + (int)gridDim.x * 4, n_groups - 1));
+    float dr[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      dr[mt][0] = __shfl_sync(0xffffffffu, d_lane, mt * 16 + gq);
+      dr[mt][1] = __shfl_sync(0xffffffffu, d_lane, mt * 16 + gq + 8);
+    }
+    // ---- layer 1: [32 edges, H0] x [H0, H1], layer 0 evaluated into the A fragments
+    float acc1[2][NT1][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < NT1; ++nt)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc1[mt][nt][r] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS0; ++ks) {
+      uint32_t ah[2][4], al[2][4];
+      const int c = ks * 16 + 2 * tq;
+      const float2 wl = *reinterpret_cast<const float2*>(&w0[c]), bl = *reinterpret_cast<const float2*>(&b0[c]);
+      const float2 wh = *reinterpret_cast<const float2*>(&w0[c + 8]), bh = *reinterpret_cast<const float2*>(&b0[c + 8]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const float d = dr[mt][hh];
+          em_split(lrelu(fmaf(d, wl.x, bl.x)), lrelu(fmaf(d, wl.y, bl.y)), ah[mt][hh], al[mt][hh]);
+          em_split(lrelu(fmaf(d, wh.x, bh.x)), lrelu(fmaf(d, wh.y, bh.y)), ah[mt][2 + hh], al[mt][2 + hh]);
+        }
+#pragma unroll
+      for (int np = 0; np < NT1 / 2; ++np) {
+        uint32_t bh_[4], bl_[4];
+        const uint32_t ad = b1_addr + (uint32_t)((np * 16 * W1S + ks * 16) * 2);
+        em_ldsm4(ad, bh_);
+        em_ldsm4(ad + LO1, bl_);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          em_mma16(acc1[mt][2 * np], al[mt], bh_[0], bh_[1]);
+          em_mma16(acc1[mt][2 * np + 1], al[mt], bh_[2], bh_[3]);
+          em_mma16(acc1[mt][2 * np], ah[mt], bl_[0], bl_[1]);
+          em_mma16(acc1[mt][2 * np + 1], ah[mt], bl_[2], bl_[3]);
+          em_mma16(acc1[mt][2 * np], ah[mt], bh_[0], bh_[1]);
+          em_mma16(acc1[mt][2 * np + 1], ah[mt], bh_[2], bh_[3]);
+        }
+      }
+    }
+    // ---- layer-1 activations as the A fragments of layer 2: n-tiles (2ks, 2ks + 1) of the accumulator are the
+    // (k lo, k hi) halves of k-step ks; rows gq / gq + 8 sit in accumulator elements {0,1} / {2,3}
+    uint32_t a1h[2][KS1][4], a1l[2][KS1][4];
+#pragma unroll
+    for (int ks = 0; ks < KS1; ++ks) {
+      const float2 bl = *reinterpret_cast<const float2*>(&b1[ks * 16 + 2 * tq]);
+      const float2 bh = *reinterpret_cast<const float2*>(&b1[ks * 16 + 8 + 2 * tq]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        em_split(lrelu(acc1[mt][2 * ks][0] + bl.x), lrelu(acc1[mt][2 * ks][1] + bl.y), a1h[mt][ks][0], a1l[mt][ks][0]);
+        em_split(lrelu(acc1[mt][2 * ks][2] + bl.x), lrelu(acc1[mt][2 * ks][3] + bl.y), a1h[mt][ks][1], a1l[mt][ks][1]);
+        em_split(lrelu(acc1[mt][2 * ks + 1][0] + bh.x), lrelu(acc1[mt][2 * ks + 1][1] + bh.y), a1h[mt][ks][2], a1l[mt][ks][2]);
+        em_split(lrelu(acc1[mt][2 * ks + 1][2] + bh.x), lrelu(acc1[mt][2 * ks + 1][3] + bh.y), a1h[mt][ks][3], a1l[mt][ks][3]);
+      }
+    }
+    // ---- layer 2 in chunks of CW output slots
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+      float acc[2][NTC][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NTC; ++nt)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[mt][nt][r] = 0.f;
+      const uint32_t bch = b2_addr + (uint32_t)(ch * CW * W2S * 2);
+#pragma unroll
+      for (int ks = 0; ks < KS1; ++ks)
+#pragma unroll
+        for (int np = 0; np < NTC / 2; ++np) {
+          uint32_t bh_[4], bl_[4];
+          const uint32_t ad = bch + (uint32_t)((np * 16 * W2S + ks * 16) * 2);
+          em_ldsm4(ad, bh_);
+          em_ldsm4(ad + LO2, bl_);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            em_mma16(acc[mt][2 * np], a1l[mt][ks], bh_[0], bh_[1]);
+            em_mma16(acc[mt][2 * np + 1], a1l[mt][ks], bh_[2], bh_[3]);
+            em_mma16(acc[mt][2 * np], a1h[mt][ks], bl_[0], bl_[1]);
+            em_mma16(acc[mt][2 * np + 1], a1h[mt][ks], bl_[2], bl_[3]);
+            em_mma16(acc[mt][2 * np], a1h[mt][ks], bh_[0], bh_[1]);
+            em_mma16(acc[mt][2 * np + 1], a1h[mt][ks], bh_[2], bh_[3]);
+          }
+        }
+      if (OMODE == 2) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int np = 0; np < NTC / 2; ++np) {
+            uint32_t h[2][2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int nt = 2 * np + q;
+              const float2 bz = *reinterpret_cast<const float2*>(&b2p[ch * CW + nt * 8 + 2 * tq]);
+              h[q][0] = em_pack(lrelu(acc[mt][nt][0] + bz.x), lrelu(acc[mt][nt][1] + bz.y));
+              h[q][1] = em_pack(lrelu(acc[mt][nt][2] + bz.x), lrelu(acc[mt][nt][3] + bz.y));
+            }
+            asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(s_addr + (uint32_t)(mt * 16 * SST + np * 32)),
+                         "r"(h[0][0]), "r"(h[0][1]), "r"(h[1][0]), "r"(h[1][1])
+                         : "memory");
+          }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < NTC; ++nt) {
+          const float2 bz = *reinterpret_cast<const float2*>(&b2p[ch * CW + nt * 8 + 2 * tq]);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const float v0 = __uint_as_float(em_tf32(lrelu(acc[mt][nt][2 * hh] + bz.x)));
+              const float v1 = __uint_as_float(em_tf32(lrelu(acc[mt][nt][2 * hh + 1] + bz.y)));
+              *reinterpret_cast<float2*>(wstage + (size_t)(mt * 16 + gq + 8 * hh) * SST + (nt * 8 + 2 * tq) * 4) = make_float2(v0, v1);
+            }
+        }
+      }
+      __syncwarp();
+      {
+        constexpr int ESZ = OMODE == 2 ? 2 : 4;
+        uint8_t* const dst = static_cast<uint8_t*>(gv) + (size_t)ch * CW * ESZ;
+        for (int t = lane; t < 32 * QB; t += 32) {
+          const int r = t / QB, c = t - r * QB;
+          if (e_base + r < E)
+            *reinterpret_cast<uint4*>(dst + (size_t)(e_base + r) * KP * ESZ + c * 16) =
+                *reinterpret_cast<const uint4*>(wstage + (size_t)r * SST + c * 16);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// returns 1 when the shape is not covered here (the caller then uses the generic CUDA-core kernel)
+int launch_edge_hidden3_mma(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr, const int32_t* perm,
+                            int64_t E, float* g, cudaStream_t s, int omode) {
+  if (E == 0) return FESR_OK;
+  if (!(d.n_hidden == 3 && d.hidden[0] == 32 && d.hidden[1] == 64 && d.hidden[2] == 128 && d.kp == 144 && d.leaky)) return 1;
+  if (omode != 1 && omode != 2) return 1;
+  static const bool off = getenv("FESR_EDGE_FFMA") != nullptr;            // A/B switch for profiling
+  if (off) return 1;
+  for (int l = 0; l < 3; ++l)
+    if (!p.mlp_w[l] || !p.mlp_b[l]) {
+      set_error("NULL edge-MLP parameter %d", l);
+      return FESR_EINVAL;
+    }
+  const int64_t blocks = ceil_div(ceil_div(E, 32), 4);
+  const int grid = (int)(blocks < 3ll * num_sms() ? blocks : 3ll * num_sms());
+  const size_t wbytes = (size_t)2 * 64 * 40 * 2 + (size_t)2 * 144 * 72 * 2;
+  const size_t smem16 = wbytes + (size_t)4 * 32 * (48 + 8) * 2, smem32 = wbytes + (size_t)4 * 32 * (48 + 4) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FESR_CUDA(cudaFuncSetAttribute(edge_hidden3_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
+    FESR_CUDA(cudaFuncSetAttribute(edge_hidden3_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    attr_set = true;
+  }
+  ProfScope prof(PROF_EDGE_HIDDEN, s);
+  if (omode == 2)
+    edge_hidden3_mma_kernel<2><<<grid, 128, smem16, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
+                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g);
+  else
+    edge_hidden3_mma_kernel<1><<<grid, 128, smem32, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
+                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
 template <int WPAD, int NTO>
 static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr, const int32_t* perm,
                        int64_t E, float* g, cudaStream_t s, int omode) {

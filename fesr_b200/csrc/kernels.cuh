@@ -14,6 +14,10 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
 // edge_mlp_mma.cu: the two-hidden-layer (KernelNN) case on mma.sync 3xTF32 (fp32-class accuracy)
 int launch_edge_hidden2_mma(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
                             const int32_t* perm, int64_t E, float* g, cudaStream_t s, int round_tf32);
+// edge_mlp_mma.cu: TEECNet's three hidden layers (1 -> 32 -> 64 -> 128, LeakyReLU) on mma.sync split-fp16 (3 terms);
+// omode 1: tf32-rounded fp32 rows, 2: fp16 rows
+int launch_edge_hidden3_mma(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
+                            const int32_t* perm, int64_t E, float* g, cudaStream_t s, int omode);
 int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s,
                  int round_tf32 = 0);
 int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const void* h, int64_t n, float* y, cudaStream_t s,

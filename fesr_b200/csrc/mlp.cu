@@ -325,6 +325,10 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
       if (covered != 1) return covered;
     }
   }
+  if ((round_tf32 == 1 || round_tf32 == 2) && d.n_hidden == 3) {
+    const int covered = launch_edge_hidden3_mma(d, p, edge_attr, perm, E, g, s, round_tf32);
+    if (covered != 1) return covered;
+  }
   FESR_CHECK_ARG(round_tf32 != 3, "planar fp16 g rows are only produced for the shapes the fused layer kernel covers");
   // shapes the tensor-core kernel does not cover: fp32 / tf32 rows from the thread-per-edge kernel,
   // fp16 rows from the generic tiled kernel below

@@ -1,7 +1,10 @@
 set -x
-python -m pytest tests -m gpu -x -q > gpurun_out/s3_tests.log 2>&1; tail -3 gpurun_out/s3_tests.log
-python bench.py --model teecnet --precision f16 --steps 20 --no-cpu-baseline > gpurun_out/s3_teec_f16.json 2> gpurun_out/s3_teec_f16.err; tail -c 600 gpurun_out/s3_teec_f16.err
-python bench.py --model teecnet --precision tf32 --steps 20 --no-cpu-baseline > gpurun_out/s3_teec_tf32.json 2> gpurun_out/s3_teec_tf32.err
-python tools/bench_train.py --mesh-n 28 --precision tf32 --steps 5 --profile > gpurun_out/s3_train28.json 2> gpurun_out/s3_train28.err; cat gpurun_out/s3_train28.json
-python tools/bench_train.py --mesh-n 28 --precision tf32 --steps 5 --model teecnet --profile > gpurun_out/s3_train28_teec.json 2> gpurun_out/s3_train28_teec.err; cat gpurun_out/s3_train28_teec.json
-python tools/bench_train.py --mesh-n 44 --levels 9 --precision tf32 --steps 5 --profile > gpurun_out/s3_train44.json 2> gpurun_out/s3_train44.err; cat gpurun_out/s3_train44.json
+python -m pytest tests/test_gpu_forward.py tests/test_gpu_backward.py tests/test_gpu_scheduler.py -m gpu -q -s > gpurun_out/s5_tests.log 2>&1; tail -3 gpurun_out/s5_tests.log; grep "rel-L2" gpurun_out/s5_tests.log
+for prec in f16 tf32; do
+python bench.py --model teecnet --precision $prec --steps 20 --no-cpu-baseline > gpurun_out/s5_teec_$prec.json 2> gpurun_out/s5_teec_$prec.err; tail -c 300 gpurun_out/s5_teec_$prec.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/s5_teec_$prec.json').read().strip().splitlines()[-1])
+print('%.1fM'%(d['value']/1e6), d['ms_per_step'], {k:round(v['ms_per_launch'],3) for k,v in d['kernels'].items()})
+PY
+done
