@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--levels", type=int, default=-1)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="fixed mesh (--mesh-n, --levels) sharded over the ranks instead of an N-times longer duct "
+                         "(BASELINE configs 3 / 5: one 2 M / 5 M-cell mesh over 8 GPUs)")
     return ap.parse_args()
 
 
@@ -73,6 +76,9 @@ def load_weights(kind):
 def levels_for(args, world):
     if args.levels >= 0:
         return args.levels
+    if getattr(args, "strong", False):
+        from fesr_b200.dataset import synthetic as syn
+        return syn.default_kd_levels((args.mesh_n + 1) ** 2 * (4 * args.mesh_n + 1))
     lv = BASE_LEVELS
     w = world
     while w > 1:
@@ -175,7 +181,8 @@ def run_reference(args):
         return 0
     world = args.gpus
     levels = levels_for(args, world)
-    mesh, sub, home_cells, model = cpu_setup(args, world, levels)
+    lf = 1 if args.strong else world
+    mesh, sub, home_cells, model = cpu_setup(args, lf, levels)
     S = 1 << levels
     # size the per-step sample so that one step is ~1/3 of the budget
     t1, c1 = oracle_subdomain_pass(model, sub, mesh, [0], home_cells)
@@ -194,9 +201,10 @@ def run_reference(args):
     sample = f"{per_step} of {S} subdomains ({cells} cells) per step, best of {steps}, torch CPU + numpy stitch"
     line = {"impl": "reference", "metric": "super-resolved mesh cells/s (predict pass: forward + node weight + stitch)",
             "value": value, "unit": "cells/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": best * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": best * 1e3, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
+            "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world, levels, mesh.num_cells, sub, per_step),
+            "config": workload_config(args, lf, levels, mesh.num_cells, sub, per_step),
             "cpu_baseline": {"value": value, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -233,7 +241,8 @@ def run_fesr(args):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     levels = levels_for(args, world)
-    mesh = make_mesh(args.mesh_n, world)
+    lf = 1 if args.strong else world
+    mesh = make_mesh(args.mesh_n, lf)
     pos = torch.from_numpy(mesh.pos).to(dev)
     cells = torch.from_numpy(mesh.cells).to(dev)
     if args.model == "neuralop":
@@ -291,7 +300,7 @@ def run_fesr(args):
     # (run_ALDS_3D.py:17-26); both return host tensors, so every step pays its H2D and D2H copies.
     from fesr_b200.dataset.GraphDataset import SyntheticDuctDataset
     from fesr_b200.models.scheduler_gnn import GNNPartitionScheduler
-    ds = SyntheticDuctDataset(mesh_n=args.mesh_n, num_meshes=1, sub_size=1 << levels, length_factor=world, device=dev)
+    ds = SyntheticDuctDataset(mesh_n=args.mesh_n, num_meshes=1, sub_size=1 << levels, length_factor=lf, device=dev)
     sched = GNNPartitionScheduler("bench", 1, ds, model, train=True)
     sched.models = [model]
     base = ds.get_one_full_sample(0, materialize=False)
@@ -379,13 +388,15 @@ def run_fesr(args):
         cpu_baseline = run_cpu_baseline(args, levels)
 
     if rank == 0:
-        cfg = workload_config(args, world, levels, total_cells, pred.batch)
+        cfg = workload_config(args, lf, levels, total_cells, pred.batch)
+        cfg["parallelism"] = f"subdomain-sharded x{world}"
         cfg.update({"assembly_ms": assembly_ms, "batch_nodes": pred.batch.n_tot, "batch_edges": pred.batch.e_tot,
                     "precision": args.precision})
         line = {"metric": "super-resolved mesh cells/s (predict pass: forward + node weight + stitch)",
                 "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32"}.get(args.precision, "f16"),
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "tf32": "tf32"}.get(args.precision, "f16"),
                 "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": e2e_bytes["h2d"], "d2h_bytes_per_step": e2e_bytes["d2h"],

@@ -168,7 +168,7 @@ class SyntheticDuctDataset:
     def get(self, idx):
         mesh_idx, sub_idx = divmod(int(idx), self.sub_size)
         c = self._mesh(mesh_idx)
-        if "datas" not in c:
+        if not c.get("datas"):              # also after get_one_full_sample(materialize=False) left it empty
             c["datas"] = self._datas(c)
         return c["datas"][sub_idx]
 
@@ -178,7 +178,7 @@ class SyntheticDuctDataset:
         """All subdomains of mesh ``idx`` (reference :1464-1484), with the device batch attached.
         materialize=False skips building the per-subdomain CPU ``Data`` list (large meshes)."""
         c = self._mesh(idx)
-        if "datas" not in c:
+        if not c.get("datas"):
             c["datas"] = self._datas(c) if materialize else []
         return SubdomainSample(c["datas"], c["batch"], c["x"], c["y"], idx, c["mesh"].num_nodes)
 

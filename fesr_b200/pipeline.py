@@ -82,6 +82,16 @@ def all_gather_packed(pred_local: torch.Tensor, w_local: torch.Tensor, rows, cnt
     return pred, w
 
 
+def padded_positions(idx: torch.Tensor, rows) -> torch.Tensor:
+    """Row index into the rank-order concatenation of the shards -> row index into the padded [world, max(rows)]
+    all-gather buffer (int32)."""
+    mx = max(rows)
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(rows)]), dtype=torch.int64, device=idx.device)
+    i = idx.long()
+    r = torch.bucketize(i, offs[1:], right=True)
+    return (i + r * mx - offs[r]).to(torch.int32).contiguous()
+
+
 def make_shard(batch: ops.SubdomainBatch, s0: int, s1: int) -> Shard:
     node_ptr_h = batch.node_ptr[[s0, s1]].cpu().numpy()
     edge_ptr_h = batch.edge_ptr[[s0, s1]].cpu().numpy()
@@ -132,9 +142,31 @@ class MeshPredictor:
     def stitch(self, pred_all: torch.Tensor, want_merged=False):
         return ops.stitch_mean(pred_all, self.occ, self.batch.global_ids, want_merged=want_merged, want_count=False)
 
+    def _padded_gather(self, pred_shard: torch.Tensor) -> torch.Tensor:
+        """The all-gather of step(): every rank's block lands at [r, :rows[r]] of one persistent [world, max rows, c]
+        buffer (one copy into the send block + one `all_gather_into_tensor`); the stitch then reads the padded
+        buffer directly through an occurrence index remapped once to padded positions, so there is no pad / split /
+        concatenate traffic around the collective."""
+        import torch.distributed as dist
+        c = int(pred_shard.shape[1])
+        if getattr(self, "_gbuf", None) is None or self._gbuf.shape[2] != c:
+            dev = pred_shard.device
+            mx = max(self.shard_rows)
+            self._gbuf = torch.zeros(self.world, mx, c, dtype=torch.float32, device=dev)
+            self._send = torch.zeros(mx, c, dtype=torch.float32, device=dev)
+            self._occ_padded = ops.Occurrence(self.occ.occ_ptr, padded_positions(self.occ.occ_idx, self.shard_rows),
+                                              self.occ.N, self.world * mx)
+        self._send[:pred_shard.shape[0]].copy_(pred_shard)
+        dist.all_gather_into_tensor(self._gbuf.view(-1), self._send.view(-1), group=self.group)
+        return self._gbuf.view(-1, c)
+
     def step(self, x_shard, y_shard=None):
         """forward (+ node weight) + all-gather + stitch; returns (field [N,c], weights [S_shard] | None)."""
         pred = self.forward_shard(x_shard)
         w = self.node_weight(pred, y_shard) if y_shard is not None else None
-        field, _, _ = self.stitch(self.all_gather(pred))
+        if self.world > 1:
+            field, _, _ = ops.stitch_mean(self._padded_gather(pred), self._occ_padded, None, want_merged=False,
+                                          want_count=False)
+        else:
+            field, _, _ = self.stitch(pred)
         return field, w, pred

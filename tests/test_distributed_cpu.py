@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fesr_b200.pipeline import all_gather_packed, all_gather_rows, shard_bounds
+from fesr_b200.pipeline import all_gather_packed, all_gather_rows, padded_positions, shard_bounds
 
 
 def _free_port():
@@ -76,3 +76,18 @@ def test_two_rank_gather_and_grad_average():
         ok_gather, ok_grad, bounds = ret[r]
         assert ok_gather and ok_grad
     assert ret[0][2] == ret[1][2]
+
+
+def test_padded_positions_address_the_gather_buffer():
+    rows = [5, 0, 9, 3]
+    mx, c = max(rows), 4
+    full = torch.arange(sum(rows) * c, dtype=torch.float32).reshape(-1, c)
+    buf = torch.full((len(rows), mx, c), -1.0)
+    o = 0
+    for r, n in enumerate(rows):
+        buf[r, :n] = full[o:o + n]
+        o += n
+    idx = torch.randperm(sum(rows)).to(torch.int32)
+    pos = padded_positions(idx, rows)
+    assert pos.dtype == torch.int32
+    assert torch.equal(buf.view(-1, c)[pos.long()], full[idx.long()])
