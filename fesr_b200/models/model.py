@@ -112,7 +112,10 @@ class _MeshModel(nn.Module):
             return NNConvFunction.apply(self, csr, edge_attr, prec, x, *self._flat_params())
         detached = {k: (None if v is None else v.detach() if torch.is_tensor(v) else [t.detach() for t in v])
                     for k, v in tensors.items()}
-        return ops.nnconv_forward(self.dims, detached, x.detach(), csr, edge_attr.detach(), prec)
+        # `ws_tag`: the scheduler gives every per-cluster model its own workspace so that each keeps its prepared
+        # weights between predict calls (one shared workspace would re-prepare on every model switch)
+        return ops.nnconv_forward(self.dims, detached, x.detach(), csr, edge_attr.detach(), prec,
+                                  ws_tag=getattr(self, "ws_tag", "fwd"))
 
     def _flat_params(self):
         t = self.param_tensors()

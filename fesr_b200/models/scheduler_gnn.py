@@ -164,7 +164,10 @@ class GNNPartitionScheduler():
             model = self._initialize_model()
             path = os.path.join(self._model_dir(), 'partition_{}.pth'.format(i))
             model.load_state_dict(torch.load(path, map_location=torch.device('cpu'), weights_only=True))
-            models.append(model.to(self.device).eval())
+            model = model.to(self.device).eval()
+            if self.num_partitions > 1:
+                model.ws_tag = f"fwd{i}"
+            models.append(model)
         return models
 
     def _train_partitions(self, num_partitions, train):
@@ -212,56 +215,66 @@ class GNNPartitionScheduler():
         y_ready = getattr(y_dev, "ready", None)
         S = len(sizes)
         labels = self._route(x_dev, node_ptr)
-
-        # this rank's contiguous, edge-balanced share of the subdomain list
-        if world > 1:
-            from ..pipeline import shard_bounds
-            node_ptr_h = node_ptr.cpu().numpy().astype(np.int64)
-            edge_cum = csr.rowptr[node_ptr.long()].cpu().numpy().astype(np.int64)
-            bounds = shard_bounds(edge_cum, world)
-            mine = torch.zeros(S, dtype=torch.bool, device=dev)
-            mine[bounds[rank]:bounds[rank + 1]] = True
-        else:
-            mine = torch.ones(S, dtype=torch.bool, device=dev)
-
-        single = self.num_partitions == 1 and world == 1      # one model, every subdomain: nothing to select
-        if not single:
-            pred = torch.zeros(csr.n, self.models[0].dims.out_ch, dtype=torch.float32, device=dev)
-            weight_s = torch.zeros(S, dtype=torch.float32, device=dev)
-        for i in range(self.num_partitions):
-            keep = None if single else (labels == i) & mine
-            if keep is not None and not bool(keep.any()):
-                continue
-            model = self.models[i]
-            if keep is None or bool(keep.all()):
-                sub, ea, nptr, node_keep = csr, edge_attr, node_ptr, None
-                xi, yi = x_dev, y_dev
-            else:
-                if y_ready is not None:                 # the selection below reads y before the forward
-                    torch.cuda.current_stream(dev).wait_event(y_ready)
-                    y_ready = None
-                sub, ea, nptr, node_keep = select_subdomains(csr, edge_attr, node_ptr, keep)
-                xi, yi = x_dev[node_keep], y_dev[node_keep]
-            pi = model(xi, sub, ea)
+        if self.num_partitions == 1 and world == 1:          # one model, every subdomain: nothing to select
+            pred = self.models[0](x_dev, csr, edge_attr)
             if y_ready is not None:
                 torch.cuda.current_stream(dev).wait_event(y_ready)
-                y_ready = None
-            wi = ops.node_weight(pi, yi, sub, ea, nptr)
-            if node_keep is None:
-                pred, weight_s = pi, wi
-            else:
-                pred[node_keep] = pi
-                weight_s[keep] = wi
-        if world > 1:
-            # predictions of the other ranks: one all-gather(v) in rank = subdomain order
-            rows = [int(node_ptr_h[bounds[r + 1]] - node_ptr_h[bounds[r]]) for r in range(world)]
-            lo = int(node_ptr_h[bounds[rank]])
-            from ..pipeline import all_gather_rows
-            pred = all_gather_rows(pred[lo:lo + rows[rank]].contiguous(), rows)
-            cnt = [bounds[r + 1] - bounds[r] for r in range(world)]
-            weight_s = all_gather_rows(weight_s[bounds[rank]:bounds[rank + 1]].contiguous(), cnt)
+            weight_s = ops.node_weight(pred, y_dev, csr, edge_attr, node_ptr)
+            return self._to_host_lists(x, pred, weight_s, y_dev, sizes, labels)
 
+        # Routed and / or sharded: the plan -- this rank's contiguous edge-balanced share of the subdomain list and,
+        # per cluster, the block-diagonal sub-batch of its subdomains -- depends only on the labels, so it is kept
+        # on the device batch and rebuilt only when the routing of this sample changes.
+        labels_h = labels.cpu().numpy()
+        holder = x.batch.__dict__ if isinstance(x, SubdomainSample) else {}
+        plan = holder.get("_alds_plan")
+        if (plan is None or plan["world"] != world or plan["rank"] != rank or plan["k"] != self.num_partitions
+                or not np.array_equal(plan["labels"], labels_h)):
+            plan = self._routing_plan(csr, edge_attr, node_ptr, labels_h, rank, world)
+            holder["_alds_plan"] = plan
+        if y_ready is not None:
+            torch.cuda.current_stream(dev).wait_event(y_ready)
+        out_ch = self.models[0].dims.out_ch
+        pred = torch.zeros(csr.n, out_ch, dtype=torch.float32, device=dev)
+        weight_s = torch.zeros(S, dtype=torch.float32, device=dev)
+        for i, c in plan["clusters"]:
+            xi, yi = x_dev.index_select(0, c["nodes"]), y_dev.index_select(0, c["nodes"])
+            pi = self.models[i](xi, c["csr"], c["edge_attr"])
+            wi = ops.node_weight(pi, yi, c["csr"], c["edge_attr"], c["node_ptr"])
+            pred.index_copy_(0, c["nodes"], pi)
+            weight_s.index_copy_(0, c["subs"], wi)
+        if world > 1:
+            # predictions of the other ranks: one packed all-gather in rank = subdomain order
+            from ..pipeline import all_gather_packed
+            rows, cnt, lo, b0 = plan["rows"], plan["cnt"], plan["lo"], plan["b0"]
+            pred, weight_s = all_gather_packed(pred[lo:lo + rows[rank]], weight_s[b0:b0 + cnt[rank]], rows, cnt)
         return self._to_host_lists(x, pred, weight_s, y_dev, sizes, labels)
+
+    def _routing_plan(self, csr, edge_attr, node_ptr, labels_h, rank, world):
+        from ..pipeline import shard_bounds
+        dev = self.device
+        S = node_ptr.numel() - 1
+        node_ptr_h = node_ptr.cpu().numpy().astype(np.int64)
+        if world > 1:
+            edge_cum = csr.rowptr[node_ptr.long()].cpu().numpy().astype(np.int64)
+            bounds = shard_bounds(edge_cum, world)
+        else:
+            bounds = [0, S]
+        mine = np.zeros(S, dtype=bool)
+        mine[bounds[rank]:bounds[rank + 1]] = True
+        clusters = []
+        for i in range(self.num_partitions):
+            keep_h = (labels_h == i) & mine
+            if not keep_h.any():
+                continue
+            keep = torch.from_numpy(keep_h).to(dev)
+            sub, ea, nptr, node_keep = select_subdomains(csr, edge_attr, node_ptr, keep)
+            clusters.append((i, {"csr": sub, "edge_attr": ea, "node_ptr": nptr,
+                                 "nodes": node_keep.nonzero().squeeze(1), "subs": keep.nonzero().squeeze(1)}))
+        return {"world": world, "rank": rank, "k": self.num_partitions, "labels": labels_h.copy(), "clusters": clusters,
+                "rows": [int(node_ptr_h[bounds[r + 1]] - node_ptr_h[bounds[r]]) for r in range(world)],
+                "cnt": [bounds[r + 1] - bounds[r] for r in range(world)],
+                "lo": int(node_ptr_h[bounds[rank]]), "b0": bounds[rank]}
 
     def _predict_sharded(self, x, rank, world):
         """One model, several ranks, device-resident decomposition: every rank runs its contiguous edge-balanced
