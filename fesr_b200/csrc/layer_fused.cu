@@ -35,6 +35,7 @@
 // with 6 warps per scheduler), so the structure minimises instructions on the critical path and hands
 // nothing between roles except through mbarriers that the next tile's work has already covered.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 
@@ -231,6 +232,10 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
+  // Programmatic dependent launch: the next launch in the stream (the next layer) may be scheduled onto an SM as
+  // soon as this CTA has left it, and runs its prologue (zero fill, barriers, TMEM allocation, T' into TMEM --
+  // nothing that depends on this layer) under the tail of this grid; it waits for this grid's completion below.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int64_t n_tiles = (n + FL_NODES - 1) / FL_NODES;
   const int n_it = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // grid <= n_tiles
 
@@ -304,6 +309,9 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // everything above touched only this launch's constants; h_in / P / h_out belong to the previous launch until it
+  // has completed (no-op when this kernel was not launched as a programmatic dependent)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp < FL_BW) {
     // =========================================================================== consumers
@@ -692,9 +700,20 @@ static int launch_fl(const int32_t* rowptr, const int32_t* src_sorted, const __h
   }
   const int64_t n_tiles = ceil_div(n, FL_NODES);
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
-  layer_fused_f16_kernel<PPL, NBUF><<<grid, (2 * FL_NODES + 3 + 1 + 4) * 32, smem, s>>>(rowptr, src_sorted, g3, E, h_in, n, part0, has_root, tf,
-                                                                  bias_p, p_in, p_out, h_out, rs, fix_b, relu);
-  FESR_LAUNCH_CHECK();
+  static const bool pdl = !(getenv("FESR_PDL") && atoi(getenv("FESR_PDL")) == 0);     // A/B switch for profiling
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((2 * FL_NODES + 3 + 1 + 4) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  FESR_CUDA(cudaLaunchKernelEx(&cfg, layer_fused_f16_kernel<PPL, NBUF>, rowptr, src_sorted, g3, E, h_in, n, part0, has_root, tf, bias_p,
+                               p_in, p_out, h_out, rs, fix_b, relu));
+  count_launch();
   return FESR_OK;
 }
 
