@@ -427,11 +427,53 @@ __global__ void fc_in_kernel(const float* __restrict__ x, const float* __restric
   *reinterpret_cast<float4*>(h + i * wp + b4) = acc;
 }
 
+// fp16 rows, 4 input channels: one thread per 8 outputs (one 16-byte store), x row as one 128-bit load; the fmaf
+// chain per output is the one of the generic kernel above
+__global__ void __launch_bounds__(256)
+fc_in_c4h_kernel(const float* __restrict__ x, const float* __restrict__ wp_, const float* __restrict__ bp, int wp, int64_t n,
+                 __half* __restrict__ h) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // eight halfs of h per thread
+  const int q = wp / 8;
+  if (idx >= n * q) return;
+  const int64_t i = idx / q;
+  const int b8 = (int)(idx - i * q) * 8;
+  const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+  const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+  float acc[8];
+  {
+    const float4 b0 = *reinterpret_cast<const float4*>(bp + b8), b1 = *reinterpret_cast<const float4*>(bp + b8 + 4);
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w;
+    acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp_ + c * wp + b8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp_ + c * wp + b8 + 4));
+    acc[0] = fmaf(xs[c], w0.x, acc[0]); acc[1] = fmaf(xs[c], w0.y, acc[1]);
+    acc[2] = fmaf(xs[c], w0.z, acc[2]); acc[3] = fmaf(xs[c], w0.w, acc[3]);
+    acc[4] = fmaf(xs[c], w1.x, acc[4]); acc[5] = fmaf(xs[c], w1.y, acc[5]);
+    acc[6] = fmaf(xs[c], w1.z, acc[6]); acc[7] = fmaf(xs[c], w1.w, acc[7]);
+  }
+  __half2 p0 = __floats2half2_rn(acc[0], acc[1]), p1 = __floats2half2_rn(acc[2], acc[3]);
+  __half2 p2 = __floats2half2_rn(acc[4], acc[5]), p3 = __floats2half2_rn(acc[6], acc[7]);
+  uint4 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&p0);
+  pk.y = *reinterpret_cast<uint32_t*>(&p1);
+  pk.z = *reinterpret_cast<uint32_t*>(&p2);
+  pk.w = *reinterpret_cast<uint32_t*>(&p3);
+  *reinterpret_cast<uint4*>(h + i * wp + b8) = pk;
+}
+
 int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, int64_t n, float* h, cudaStream_t s,
                  int round_tf32) {
   if (n == 0) return FESR_OK;
   const int64_t total = n * (d.wp / 4);
   ProfScope prof(PROF_FC_IN, s);
+  if (round_tf32 == 2 && d.in_ch == 4 && d.wp % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    fc_in_c4h_kernel<<<(unsigned)ceil_div(n * (d.wp / 8), 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.wp, n, reinterpret_cast<__half*>(h));
+    FESR_LAUNCH_CHECK();
+    return FESR_OK;
+  }
   fc_in_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.in_ch, d.wp, n, round_tf32, h);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
@@ -456,12 +498,56 @@ __global__ void fc_out_kernel(const void* __restrict__ hv, const float* __restri
   y[idx] = acc;
 }
 
+// fp16 rows of 48, 4 output channels: one thread per node reads its row as six 16-byte words and keeps the four
+// dot products in registers (W2 staged in shared memory as [b][4] so that a row element meets its four weights in
+// one 128-bit broadcast load); the node's four outputs leave as one float4.  Same fp32 fmaf chain per output, in
+// channel order, as the generic kernel below.
+__global__ void __launch_bounds__(256)
+fc_out_h48c4_kernel(const __half* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2, int w,
+                    int64_t n, float* __restrict__ y) {
+  __shared__ __align__(16) float wt[48][4];
+  for (int t = threadIdx.x; t < 48 * 4; t += blockDim.x) {
+    const int b = t >> 2, c = t & 3;
+    wt[b][c] = b < w ? w2[c * w + b] : 0.f;
+  }
+  __syncthreads();
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 acc = make_float4(b2[0], b2[1], b2[2], b2[3]);
+  const uint4* row = reinterpret_cast<const uint4*>(h + i * 48);
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const uint4 v = __ldg(row + q);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
+      const float4 w0 = *reinterpret_cast<const float4*>(wt[q * 8 + 2 * k]);
+      const float4 w1 = *reinterpret_cast<const float4*>(wt[q * 8 + 2 * k + 1]);
+      acc.x = fmaf(f.x, w0.x, acc.x);
+      acc.y = fmaf(f.x, w0.y, acc.y);
+      acc.z = fmaf(f.x, w0.z, acc.z);
+      acc.w = fmaf(f.x, w0.w, acc.w);
+      acc.x = fmaf(f.y, w1.x, acc.x);
+      acc.y = fmaf(f.y, w1.y, acc.y);
+      acc.z = fmaf(f.y, w1.z, acc.z);
+      acc.w = fmaf(f.y, w1.w, acc.w);
+    }
+  }
+  reinterpret_cast<float4*>(y)[i] = acc;
+}
+
 int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const void* h, int64_t n, float* y, cudaStream_t s,
                   int h_half) {
   if (n == 0) return FESR_OK;
   FESR_CHECK_ARG(p.fc2_w && p.fc2_b, "NULL fc2 parameter");
   const int64_t total = n * d.out_ch;
   ProfScope prof(PROF_FC_OUT, s);
+  if (h_half && d.wp == 48 && d.out_ch == 4 && d.w <= 48 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    fc_out_h48c4_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(static_cast<const __half*>(h), p.fc2_w, p.fc2_b, d.w, n, y);
+    FESR_LAUNCH_CHECK();
+    return FESR_OK;
+  }
   fc_out_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(h, p.fc2_w, p.fc2_b, d.w, d.wp, d.out_ch, n, h_half, y);
   FESR_LAUNCH_CHECK();
   return FESR_OK;

@@ -73,20 +73,33 @@ __global__ void node_weight_partial_kernel(const float* __restrict__ pred, const
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float pd[C], yd[C];
+  auto load_row = [&](const float* base, int64_t r, float (&v)[C]) {
+    if (C == 4) {      // one 128-bit load per gathered row
+      const float4 t = __ldg(reinterpret_cast<const float4*>(base) + r);
+      v[0] = t.x;
+      v[1] = t.y;
+      v[2] = t.z;
+      v[3] = t.w;
+    } else {
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    pd[c] = pred[i * C + c];
-    yd[c] = target[i * C + c];
-  }
+      for (int c = 0; c < C; ++c) v[c] = base[r * C + c];
+    }
+  };
+  load_row(pred, i, pd);
+  load_row(target, i, yd);
   float acc = 0.f;
-  for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+  const int e_end = rowptr[i + 1];
+  for (int e = rowptr[i]; e < e_end; ++e) {
     const int64_t s = src_sorted[e];
     const float d = edge_attr[perm ? perm[e] : e];
+    float ps[C], ys[C];
+    load_row(pred, s, ps);
+    load_row(target, s, ys);
     float m = -INFINITY;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const float gp = __fdiv_rn(__fsub_rn(pred[s * C + c], pd[c]), d);
-      const float gd = __fdiv_rn(__fsub_rn(target[s * C + c], yd[c]), d);
+      const float gp = __fdiv_rn(__fsub_rn(ps[c], pd[c]), d);
+      const float gd = __fdiv_rn(__fsub_rn(ys[c], yd[c]), d);
       m = fmaxf(m, __fsub_rn(gp, gd));
     }
     acc = __fadd_rn(acc, m);
@@ -201,6 +214,8 @@ int fesr_node_weight(const float* pred, const float* target, int32_t channels, c
   FESR_CHECK_ARG(out && (n == 0 || (pred && target && rowptr && node_scratch)), "NULL pointer");
   FESR_CHECK_ARG(E == 0 || (src_sorted && edge_attr), "NULL edge arrays");
   FESR_CHECK_ARG(node_ptr || n_sub == 1, "node_ptr is required for n_sub > 1");
+  FESR_CHECK_ARG(((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target)) & 15) == 0,
+                 "pred / target rows must be 16-byte aligned");
   cudaStream_t s = as_stream(stream_);
   ProfScope prof(PROF_NODE_WEIGHT, s);
   if (n > 0) {
