@@ -1,7 +1,7 @@
-timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/s14_tests.log 2>&1; tail -3 gpurun_out/s14_tests.log
-timeout 300 python bench.py --steps 100 --no-cpu-baseline > gpurun_out/s14_bench.json 2> gpurun_out/s14_bench.err; tail -c 300 gpurun_out/s14_bench.err
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/s14_bench.json').read().strip().splitlines()[-1])
-print('%.1fM'%(d['value']/1e6), d['ms_per_step'], d['ms_per_step_instrumented'], 'e2e %.1fM'%(d['e2e']['value']/1e6), d['e2e']['ms_per_step'], {k:round(v['ms_per_launch'],4) for k,v in d['kernels'].items()})
-PY
+set -x
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/r01c_plain.json 2> gpurun_out/r01c_plain.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r01c_launches.csv $CMD > gpurun_out/r01c_ncu1.log 2>&1
+$CMD > gpurun_out/r01c_plain2.json 2> gpurun_out/r01c_plain2.err &&
+ncu --set full --clock-control none --import-source on -k regex:layer_fused -s 10 -c 2 -o gpurun_out/r01c_top -f $CMD > gpurun_out/r01c_ncu2.log 2>&1
+ls -la gpurun_out/ | tail -8
