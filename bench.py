@@ -308,14 +308,16 @@ def run_fesr(args):
     xa_host = torch.from_numpy(mesh.x[gid_all]).pin_memory()
     ya_host = torch.from_numpy(mesh.y[gid_all]).pin_memory()
     sample_h = base.with_host_inputs(xa_host, ya_host)
+    # whole-job bytes per step: every rank copies ITS rows of x and y in, its rows of the predictions + its subdomain
+    # weights out, and the stitched field of the whole mesh out (the other ranks' rows stay on their hosts until asked for)
     e2e_bytes = {"h2d": int(xa_host.numel() * 4 + ya_host.numel() * 4),
-                 "d2h": int(base.batch.n_tot * 16 + (1 << levels) * 4 + mesh.num_nodes * 16)}
+                 "d2h": int(base.batch.n_tot * 16 + (1 << levels) * 4 + world * mesh.num_nodes * 16)}
 
     def step_e2e():
         p, r, mi, wl = sched.predict(sample_h)
         out = ds.reconstruct_from_partition(p, r, 0, mi, wl)
         f = out.field                        # the stitched prediction on the fine mesh, on the host
-        p.wait()                             # ... and the per-subdomain predictions + weights (packed copy)
+        p.wait()                             # ... and this rank's per-subdomain predictions + weights (packed copy)
         return f
 
     sampler = ClockSampler(local)

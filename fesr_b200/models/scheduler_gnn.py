@@ -27,21 +27,35 @@ from ..dataset.GraphDataset import SubdomainSample
 class TensorList(list):
     """list of per-subdomain CPU tensors that remembers the device-resident concatenation.  The host buffer
     behind the elements may still be filling (asynchronous device -> host copy on a side stream): the first
-    element access waits for it."""
+    element access waits for it.  On a multi-rank run only this rank's own subdomains (`own` = index range) are
+    copied eagerly; the first access to any other element fetches the rest (`rest`, a one-shot callable)."""
     dev = None
-    ready = None          # torch.cuda.Event recorded after the device -> host copy, or None
+    ready = None          # torch.cuda.Event recorded after the (own part of the) device -> host copy, or None
+    own = None            # (s0, s1): the subdomains that `ready` covers; None = all of them
+    rest = None           # callable that copies everything else and blocks until it is there; None = nothing left
 
     def wait(self):
+        """Blocks until this rank's own part is on the host."""
         if self.ready is not None:
             self.ready.synchronize()
             self.ready = None
 
+    def wait_all(self):
+        if self.rest is not None:
+            self.rest()
+            self.rest = None
+        self.wait()
+
     def __getitem__(self, i):
+        if self.rest is not None:
+            j = i + len(self) if isinstance(i, int) and i < 0 else i
+            if not (isinstance(j, int) and self.own is not None and self.own[0] <= j < self.own[1]):
+                self.wait_all()
         self.wait()
         return super().__getitem__(i)
 
     def __iter__(self):
-        self.wait()
+        self.wait_all()
         return super().__iter__()
 
 
@@ -297,46 +311,78 @@ class GNNPartitionScheduler():
         lo, hi = sh.node_lo, sh.node_hi
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
         y_ready = None
-        if x.x_host is not None:
+        host_in = x.x_host is not None
+        if host_in:
+            # only this rank's rows cross PCIe; the other ranks' rows of the reference field (the stitch of
+            # ref_y_list needs all of it) arrive over NVLink, packed into the all-gather of the predictions
             xi = x.x_host[lo:hi].to(dev, non_blocking=True)
-            with torch.cuda.stream(side):        # the whole reference field: the stitch of ref_y_list needs all of it
-                y_dev = x.y_host.to(dev, non_blocking=True)
+            with torch.cuda.stream(side):
+                yi = x.y_host[lo:hi].to(dev, non_blocking=True)
                 y_ready = side.record_event()
-            y_dev.record_stream(main)
+            yi.record_stream(main)
         else:
-            xi, y_dev = x.x_dev[lo:hi], x.y_dev
+            xi, yi = x.x_dev[lo:hi], x.y_dev[lo:hi]
         model = self.models[0]
         if hi > lo:
             pi = model(xi, sh.csr, sh.edge_attr)
             if y_ready is not None:
                 main.wait_event(y_ready)
-            wi = ops.node_weight(pi, y_dev[lo:hi], sh.csr, sh.edge_attr, sh.node_ptr)
+            wi = ops.node_weight(pi, yi, sh.csr, sh.edge_attr, sh.node_ptr)
         else:                                    # more ranks than subdomains
             if y_ready is not None:
                 main.wait_event(y_ready)
             pi = torch.zeros(0, model.dims.out_ch, dtype=torch.float32, device=dev)
             wi = torch.zeros(0, dtype=torch.float32, device=dev)
-        pred, weight_s = all_gather_packed(pi, wi, c["rows"], c["cnt"])
-        return self._to_host_lists(x, pred, weight_s, y_dev, sizes, None)
+        if host_in:
+            oc = pi.shape[1]
+            both, weight_s = all_gather_packed(torch.cat([pi, yi], dim=1), wi, c["rows"], c["cnt"])
+            pred, y_dev = both[:, :oc].contiguous(), both[:, oc:].contiguous()
+        else:
+            pred, weight_s = all_gather_packed(pi, wi, c["rows"], c["cnt"])
+            y_dev = x.y_dev
+        b0 = sum(c["cnt"][:rank])
+        return self._to_host_lists(x, pred, weight_s, y_dev, sizes, None, own=(lo, hi, b0, b0 + c["cnt"][rank]))
 
-    def _to_host_lists(self, x, pred, weight_s, y_dev, sizes, labels):
+    def _to_host_lists(self, x, pred, weight_s, y_dev, sizes, labels, own=None):
         # one packed device -> host copy on the side stream: reconstruct_from_partition works from the device
-        # copy (`.dev`), so the host lists only have to be complete when somebody reads them
+        # copy (`.dev`), so the host lists only have to be complete when somebody reads them.  `own` =
+        # (node_lo, node_hi, sub_lo, sub_hi) on a multi-rank run: only this rank's rows are copied now, the other
+        # ranks' rows (they hold them on their own hosts) on first access.
         dev = self.device
         S = len(sizes)
         host = torch.empty(pred.numel() + S, dtype=torch.float32, pin_memory=True)    # (cached host allocator)
         packed = torch.cat([pred.reshape(-1), weight_s])
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
         produced = main.record_event()
+        rest = None
         with torch.cuda.stream(side):
             side.wait_event(produced)
-            host.copy_(packed, non_blocking=True)
+            if own is None:
+                host.copy_(packed, non_blocking=True)
+            else:
+                oc, np_ = pred.shape[1], pred.numel()
+                host[own[0] * oc:own[1] * oc].copy_(packed[own[0] * oc:own[1] * oc], non_blocking=True)
+                host[np_ + own[2]:np_ + own[3]].copy_(packed[np_ + own[2]:np_ + own[3]], non_blocking=True)
+
+                def rest(host=host, packed=packed, side=side):
+                    with torch.cuda.stream(side):
+                        host.copy_(packed, non_blocking=True)
+                    side.synchronize()
             copied = side.record_event()
         packed.record_stream(side)
         pred_cpu = host[:pred.numel()].view(pred.shape)
         pred_y_list = TensorList(torch.split(pred_cpu, sizes))
         pred_y_list.dev = pred
         pred_y_list.ready = copied
+        if own is not None:
+            state = {"rest": rest}
+
+            def rest_once(state=state):          # the two lists share one buffer: whoever asks first fetches for both
+                if state["rest"] is not None:
+                    state["rest"]()
+                    state["rest"] = None
+            pred_y_list.own = (own[2], own[3])
+            pred_y_list.rest = rest_once
         if isinstance(x, SubdomainSample) and x.y_host is not None:
             ref_y_list = TensorList(torch.split(x.y_host, sizes))
         else:
@@ -345,6 +391,9 @@ class GNNPartitionScheduler():
         w_cpu = host[pred.numel():]
         weights_list = TensorList([w_cpu[s].expand(sizes[s]) for s in range(S)])
         weights_list.ready = copied
+        if own is not None:
+            weights_list.own = (own[2], own[3])
+            weights_list.rest = rest_once
         model_idx = np.zeros(S, dtype=int) if labels is None or self.num_partitions == 1 else labels.cpu().numpy().astype(int)
         return pred_y_list, ref_y_list, model_idx, weights_list
 

@@ -149,22 +149,36 @@ def test_sharded_predict_matches_single_rank(tmp_path, shipped, monkeypatch):
     xh, yh = c["x"].cpu().pin_memory(), c["y"].cpu().pin_memory()
     contributed = {}
 
+    y_full = c["y"]
+
     def fake_gather(pi, wi, rows, cnt, group=None):
         contributed[fake_gather.rank] = (pi.clone(), wi.clone(), list(rows), list(cnt))
+        if pi.shape[1] == 8:          # host inputs: the reference-field rows ride in the same collective
+            return torch.cat([full_p, y_full], dim=1), full_w.cuda()
         return full_p, full_w.cuda()
 
     monkeypatch.setattr(pipeline, "all_gather_packed", fake_gather)
     for sample in (base, base.with_host_inputs(xh, yh)):
         contributed.clear()
-        base.batch.__dict__.pop("_shards", None)
         for rank in range(2):
             fake_gather.rank = rank
             monkeypatch.setattr(sg, "_dist", lambda r=rank: (None, r, 2))
             base.batch.__dict__.pop("_shards", None)          # the cache is per process; here one process plays both
             p, r, mi, w = sched.predict(sample)
             assert len(p) == 16 and mi.shape == (16,)
-            assert torch.equal(torch.cat(list(p)), full_p.cpu())
+            # only the rank's own subdomains were copied to the host eagerly; touching one of them does not fetch the rest
+            s0, s1 = p.own
+            assert 0 <= s0 < s1 <= 16 and p.rest is not None
+            own_first = p[s0]
+            assert p.rest is not None
+            off = sum(int(t.shape[0]) for t in list(list.__iter__(p))[:s0])
+            assert torch.equal(own_first, full_p[off:off + own_first.shape[0]].cpu())
+            assert torch.equal(torch.cat(list(p)), full_p.cpu())          # iterating fetches everything
+            assert p.rest is None
+            assert torch.equal(torch.stack([t[0] for t in w]).cpu(), full_w.cpu())
+            out = ds.reconstruct_from_partition(p, r, 0, mi, w)
+            assert rel_l2(out.ref_field.numpy(), c["mesh"].y) < 1e-6
         (pa, wa, rows, cnt), (pb, wb, _, _) = contributed[0], contributed[1]
         assert pa.shape[0] == rows[0] and pb.shape[0] == rows[1] and sum(cnt) == 16 and min(cnt) > 0
-        assert torch.equal(torch.cat([pa, pb]), full_p)
+        assert torch.equal(torch.cat([pa, pb])[:, :4], full_p)
         assert torch.equal(torch.cat([wa, wb]).cpu(), full_w.cpu())
