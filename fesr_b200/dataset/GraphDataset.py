@@ -182,6 +182,26 @@ class SyntheticDuctDataset:
             c["datas"] = self._datas(c) if materialize else []
         return SubdomainSample(c["datas"], c["batch"], c["x"], c["y"], idx, c["mesh"].num_nodes)
 
+    # -- low-res -> high-res transfer ---------------------------------------------------------
+    @staticmethod
+    def _lagrangian_interpolation(mesh, physics, new_mesh, mesh_spacing=0.012, sharpness=2.0):
+        """Field of `mesh` interpolated at the points of `new_mesh` (reference :1041-1105: vtkPointInterpolator with
+        a Gaussian kernel of radius 3 * mesh_spacing and sharpness 2; mesh_spacing is hard-coded to 0.012 there and a
+        keyword here).  `mesh` / `new_mesh`: anything with a `.pos` [n, 3] array (or the array itself); `physics`:
+        [n] or [n, 1] values at the points of `mesh`.  -> float tensor [n_new, 1] on the current CUDA device."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+
+        def pts(m):
+            return torch.as_tensor(np.asarray(getattr(m, "pos", m)), dtype=torch.float32).to(dev)
+
+        src, dst = pts(mesh), pts(new_mesh)
+        vals = torch.as_tensor(np.asarray(physics), dtype=torch.float32).reshape(-1).to(dev)
+        if vals.shape[0] != src.shape[0]:
+            raise ValueError("Mismatch: physics array length must match the number of points in the original mesh.")
+        if dst.shape[0] == 0:
+            raise ValueError("New mesh has no points to interpolate.")
+        return ops.interp_gaussian(src, vals, dst, 3.0 * float(mesh_spacing), sharpness).reshape(-1, 1)
+
     # -- stitch -----------------------------------------------------------------------------
     def reconstruct_from_partition(self, subdomain_data_list, subdomain_ref_list, subdomain_idx, model_idx=None,
                                    weights_list=None):

@@ -413,3 +413,27 @@ def nnconv_backward(dims: ModelDims, tensors: dict, x, csr: Csr, edge_attr, prec
                                        _ptr(grad_x), _ptr(ws), ws.numel(), _stream(dev)), "fesr_nnconv_backward")
     del keep, keep_g
     return gt, grad_x
+
+
+# ---------------------------------------------------------------------------------- low-res -> high-res transfer
+def interp_gaussian(src_pos: torch.Tensor, src_val: torch.Tensor, dst_pos: torch.Tensor, radius: float,
+                    sharpness: float = 2.0, null_value: float = 0.0, want_count: bool = False):
+    """Gaussian-kernel point interpolation (fesr_interp_gaussian): src_val [n_src, c] at src_pos [n_src, 3] ->
+    [n_dst, c] at dst_pos.  c in {1, 3, 4}; a 1-D src_val is treated as one channel and comes back 1-D."""
+    dev = _require_cuda(src_pos, src_val, dst_pos)
+    src_pos, dst_pos = _f32c(src_pos), _f32c(dst_pos)
+    flat = src_val.dim() == 1
+    src_val = _f32c(src_val.unsqueeze(1) if flat else src_val.flatten(1))
+    n_src, c, n_dst = int(src_pos.shape[0]), int(src_val.shape[1]), int(dst_pos.shape[0])
+    if src_pos.shape[1:] != (3,) or dst_pos.shape[1:] != (3,) or src_val.shape[0] != n_src:
+        raise FesrError("interp_gaussian: positions must be [n, 3] and src_val [n_src, c]")
+    lib = _lib.load()
+    out = torch.empty(n_dst, c, dtype=torch.float32, device=dev)
+    count = torch.empty(n_dst, dtype=torch.int32, device=dev) if want_count else None
+    with torch.cuda.device(dev):
+        ws = workspace.get(dev, "sort", lib.fesr_interp_workspace_bytes(n_src, c))
+        check(lib.fesr_interp_gaussian(_ptr(src_pos), _ptr(src_val), c, n_src, _ptr(dst_pos), n_dst, float(radius),
+                                       float(sharpness), float(null_value), _ptr(out), _ptr(count), _ptr(ws),
+                                       ws.numel(), _stream(dev)), "fesr_interp_gaussian")
+    out = out.reshape(-1) if flat else out
+    return (out, count) if want_count else out

@@ -271,6 +271,20 @@ int fesr_cluster(const double* latent, int32_t n_sub, int32_t n_comp, const doub
                  const double* scaler_scale, const double* centroids, int32_t n_clusters,
                  int32_t* labels, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Low-resolution -> high-resolution field transfer (the step BEFORE the path).  Replaces
+ * AnsysDataset._lagrangian_interpolation (dataset/GraphDataset.py:1041-1105), i.e.
+ * vtkPointInterpolator + vtkGaussianKernel(radius = 3 * mesh_spacing, sharpness = 2):
+ *   out[t, :] = sum_j w_j src_val[j, :] / sum_j w_j  over source points with |p_j - q_t| <= radius,
+ *   w_j = exp(-(sharpness / radius)^2 |p_j - q_t|^2); no source point in range -> null_value (VTK: 0).
+ *   src_pos [n_src, 3], src_val [n_src, channels], dst_pos [n_dst, 3], out [n_dst, channels] fp32;
+ *   channels 1, 3 or 4; count [n_dst] int32 (optional) = source points used per target.
+ * ---------------------------------------------------------------------------------- */
+size_t fesr_interp_workspace_bytes(int64_t n_src, int32_t channels);
+int fesr_interp_gaussian(const float* src_pos, const float* src_val, int32_t channels, int64_t n_src,
+                         const float* dst_pos, int64_t n_dst, float radius, float sharpness, float null_value,
+                         float* out, int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -240,3 +240,39 @@ def stitch_mean(values: np.ndarray, global_ids: np.ndarray, N: int):
     field[nz] = acc[nz] / count[nz, None].astype(np.float32)
     merged = field[np.asarray(global_ids, dtype=np.int64)]
     return field, count, merged
+
+
+# --------------------------------------------------------------------------------------
+# low-res -> high-res transfer (the step before the path)
+# --------------------------------------------------------------------------------------
+def interp_gaussian(src_pos, src_val, dst_pos, radius, sharpness=2.0, null_value=0.0):
+    """AnsysDataset._lagrangian_interpolation (dataset/GraphDataset.py:1041-1105): vtkPointInterpolator with a
+    vtkGaussianKernel(radius, sharpness) -- vtk==9.4.1, not vendored: restated from the published algorithm
+    (vtkGaussianKernel::ComputeWeights: w = exp(-(sharpness / radius)^2 d^2), normalised; points gathered with
+    FindPointsWithinRadius, d^2 <= radius^2; no point in range -> NULL_VALUE strategy, value 0).  PARITY UNPINNED
+    (no VTK here).  fp64 arithmetic on the fp32 inputs; returns (values float32 [n_dst, c], count int32 [n_dst])."""
+    from scipy.spatial import cKDTree
+    sp = np.asarray(src_pos, dtype=np.float32).astype(np.float64)
+    dp = np.asarray(dst_pos, dtype=np.float32).astype(np.float64)
+    sv = np.asarray(src_val, dtype=np.float32).astype(np.float64).reshape(sp.shape[0], -1)
+    r = float(np.float32(radius))
+    r2 = r * r
+    f2 = (float(np.float32(sharpness)) / r) ** 2
+    out = np.full((dp.shape[0], sv.shape[1]), float(null_value), dtype=np.float64)
+    cnt = np.zeros(dp.shape[0], dtype=np.int32)
+    if sp.shape[0]:
+        tree = cKDTree(sp)
+        cand = tree.query_ball_point(dp, r * (1 + 1e-9) + 1e-300)      # superset; the exact test follows
+        for t, js in enumerate(cand):
+            if not js:
+                continue
+            js = np.asarray(sorted(js))
+            e = sp[js] - dp[t]
+            d2 = e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1] + e[:, 2] * e[:, 2]
+            keep = d2 <= r2
+            if not keep.any():
+                continue
+            w = np.exp(-f2 * d2[keep])
+            out[t] = (w[:, None] * sv[js[keep]]).sum(0) / w.sum()
+            cnt[t] = int(keep.sum())
+    return out.astype(np.float32), cnt

@@ -70,3 +70,19 @@ def test_routing_matches_reference_sklearn(golden):
                                golden["route_scaler_mean"], golden["route_scaler_scale"], golden["route_centroids"])
     assert rel_l2(latent, golden["route_latent"]) < 1e-5
     assert np.array_equal(labels, golden["route_labels"])
+
+
+def test_oracle_interp_gaussian_properties():
+    """The restated vtkGaussianKernel interpolation (parity unpinned: no VTK here): partition of unity, null value,
+    the rim of the radius is inclusive, weights follow exp(-(sharpness / radius)^2 d^2)."""
+    from oracle import graph as og
+    src = np.array([[0, 0, 0], [1, 0, 0], [0, 2, 0]], dtype=np.float32)
+    val = np.array([1.0, 3.0, 10.0], dtype=np.float32)
+    dst = np.array([[0, 0, 0], [0.5, 0, 0], [5, 5, 5], [2, 0, 0]], dtype=np.float32)
+    out, cnt = og.interp_gaussian(src, val, dst, radius=1.0, sharpness=2.0, null_value=-1.0)
+    assert cnt.tolist() == [2, 2, 0, 1]                       # (1,0,0) is exactly on the rim of (0,0,0) and of (2,0,0)
+    w = np.exp(-4.0)
+    assert abs(out[0, 0] - (1.0 + 3.0 * w) / (1.0 + w)) < 1e-6
+    assert abs(out[1, 0] - 2.0) < 1e-6 and out[2, 0] == -1.0 and abs(out[3, 0] - 3.0) < 1e-6
+    ones, _ = og.interp_gaussian(src, np.ones(3, np.float32), dst[:2], 1.5)
+    assert np.allclose(ones, 1.0)
