@@ -313,11 +313,20 @@ def run_fesr(args):
     e2e_bytes = {"h2d": int(xa_host.numel() * 4 + ya_host.numel() * 4),
                  "d2h": int(base.batch.n_tot * 16 + (1 << levels) * 4 + world * mesh.num_nodes * 16)}
 
+    host_t = {"predict": [], "reconstruct": [], "wait": []}
+
     def step_e2e():
+        t0 = time.perf_counter()
         p, r, mi, wl = sched.predict(sample_h)
+        t1 = time.perf_counter()
         out = ds.reconstruct_from_partition(p, r, 0, mi, wl)
+        t2 = time.perf_counter()
         f = out.field                        # the stitched prediction on the fine mesh, on the host
         p.wait()                             # ... and this rank's per-subdomain predictions + weights (packed copy)
+        t3 = time.perf_counter()
+        host_t["predict"].append(t1 - t0)    # host time to ISSUE the pass (nothing here waits for the GPU)
+        host_t["reconstruct"].append(t2 - t1)
+        host_t["wait"].append(t3 - t2)
         return f
 
     sampler = ClockSampler(local)
@@ -406,7 +415,8 @@ def run_fesr(args):
                 "data": "synthetic", "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "cells/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": e2e_bytes["h2d"], "d2h_bytes_per_step": e2e_bytes["d2h"],
-                        "api": "GNNPartitionScheduler.predict + dataset.reconstruct_from_partition"},
+                        "api": "GNNPartitionScheduler.predict + dataset.reconstruct_from_partition",
+                        "host_ms_median": {k: 1e3 * statistics.median(v) for k, v in host_t.items() if v}},
                 "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
                 "ms_per_step_instrumented": ms_prof / min(args.steps, 50), "cpu_baseline": cpu_baseline}
         emit(line)

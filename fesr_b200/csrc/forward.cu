@@ -44,7 +44,9 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   FESR_CHECK_ARG(precision == FESR_PREC_FP32 || precision == FESR_PREC_TF32 || precision == FESR_PREC_F16,
                  "unsupported precision %d (fp32 | tf32 | f16)", precision);
   if (n == 0) return FESR_OK;
-  FESR_CHECK_ARG(x && y && rowptr && (E == 0 || (src_sorted && edge_attr)), "NULL pointer");
+  const bool edge_only = (fwd_flags & FESR_FWD_EDGE_ONLY) != 0, edge_done = (fwd_flags & FESR_FWD_EDGE_DONE) != 0;
+  FESR_CHECK_ARG(!(edge_only && edge_done), "FESR_FWD_EDGE_ONLY and FESR_FWD_EDGE_DONE exclude each other");
+  FESR_CHECK_ARG((edge_only || (x && y)) && rowptr && (E == 0 || (src_sorted && edge_attr)), "NULL pointer");
   const fesr_model_dims& d = *dims;
   ForwardWs ws = carve_forward(workspace, d, n, E, keep_for_backward);
   if (!workspace || workspace_bytes < ws.bytes) {
@@ -53,7 +55,7 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   }
   cudaStream_t s = as_stream(stream_);
   int rc;
-  if (!(fwd_flags & FESR_FWD_WEIGHTS_PREPARED) && (rc = launch_prepare_weights(d, *params, ws.prep, s))) return rc;
+  if (!(fwd_flags & FESR_FWD_WEIGHTS_PREPARED) && !edge_done && (rc = launch_prepare_weights(d, *params, ws.prep, s))) return rc;
   static const bool ffma_only = getenv("FESR_ZBUILD_FFMA") != nullptr;   // A/B switch for profiling
   // reduced-precision arms: g and h are rounded to tf32 by their producers, so the gather kernel
   // feeds them to the tensor cores without converting
@@ -64,7 +66,8 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   const int fuse_mode = fuse_env ? atoi(fuse_env) : 3;
   const bool fused = precision == FESR_PREC_F16 && !keep_for_backward && fuse_mode > 0 && layer_fused_supported(d) &&
                      ws.prep.tfused_h != nullptr && E > 0;
-  if ((rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s, fused ? 3 : rnd_in))) return rc;
+  if (!edge_done && (rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s, fused ? 3 : rnd_in))) return rc;
+  if (edge_only) return FESR_OK;
   if ((rc = launch_fc_in(d, ws.prep, x, n, ws.h[0], s, rnd_in))) return rc;
   const float* h_last = ws.h[0];
   for (int l = 0; l < d.layers; ++l) {

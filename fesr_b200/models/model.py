@@ -100,14 +100,55 @@ class _MeshModel(nn.Module):
     def param_tensors(self):
         raise NotImplementedError
 
-    def forward(self, x, edge_index, edge_attr):
+    _CACHE_KEYS = ("_plist", "_plan", "_plan_key")
+
+    def __deepcopy__(self, memo):
+        # (the scheduler deep-copies its model once per cluster) the predict-time launch plan holds device tensors and
+        # ctypes structs that belong to THIS instance: the copy starts without one
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k not in self._CACHE_KEYS:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def _predict_plan(self, csr, edge_attr, prec):
+        """The validated launch plan of the predict-time forward, kept as long as the graph, the edge lengths, the
+        precision and the parameter storages / versions are the ones it was made for."""
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = self.__dict__["_plist"] = list(self.parameters())
+        key = (csr.rowptr.data_ptr(), csr.src.data_ptr(), csr.n, csr.E, edge_attr.data_ptr(), edge_attr._version, prec,
+               getattr(self, "ws_tag", "fwd"), tuple((p.data_ptr(), p._version) for p in plist))
+        if self.__dict__.get("_plan_key") != key:
+            detached = {k: (None if v is None else v.detach() if torch.is_tensor(v) else [t.detach() for t in v])
+                        for k, v in self.param_tensors().items()}
+            self.__dict__["_plan"] = ops.make_forward_plan(self.dims, detached, csr, edge_attr.detach(), prec,
+                                                           getattr(self, "ws_tag", "fwd"))
+            self.__dict__["_plan_key"] = key
+        return self.__dict__["_plan"]
+
+    @torch.no_grad()
+    def edge_phase(self, csr, edge_attr):
+        """Extension (predict only): issues the part of the next forward on (csr, edge_attr) that does not read x --
+        weight preparation + edge MLP -- so that a caller whose x is still on the host can start the GPU before it
+        issues the copies.  The next forward on the same graph picks the edge features up from the workspace."""
+        ops.run_forward_plan(self._predict_plan(csr, edge_attr, _lib.PRECISIONS[self.precision]), None, edge_only=True)
+
+    def forward(self, x, edge_index, edge_attr, x_ready=None):
+        """x_ready (extension, predict only): CUDA event after which `x` is valid -- see ops.run_forward_plan."""
         if not x.is_cuda:
             raise FesrError(f"{type(self).__name__}.forward needs CUDA tensors on a B200; fesr_b200 has no CPU path")
         csr = self._graphs.get(edge_index, x.shape[0])
         prec = _lib.PRECISIONS[self.precision]
+        if not torch.is_grad_enabled():
+            return ops.run_forward_plan(self._predict_plan(csr, edge_attr, prec), x.detach(), x_ready)
         tensors = self.param_tensors()
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
+            if x_ready is not None:
+                torch.cuda.current_stream(x.device).wait_event(x_ready)
             from .autograd import NNConvFunction
             return NNConvFunction.apply(self, csr, edge_attr, prec, x, *self._flat_params())
         detached = {k: (None if v is None else v.detach() if torch.is_tensor(v) else [t.detach() for t in v])
@@ -115,7 +156,7 @@ class _MeshModel(nn.Module):
         # `ws_tag`: the scheduler gives every per-cluster model its own workspace so that each keeps its prepared
         # weights between predict calls (one shared workspace would re-prepare on every model switch)
         return ops.nnconv_forward(self.dims, detached, x.detach(), csr, edge_attr.detach(), prec,
-                                  ws_tag=getattr(self, "ws_tag", "fwd"))
+                                  ws_tag=getattr(self, "ws_tag", "fwd"), x_ready=x_ready)
 
     def _flat_params(self):
         t = self.param_tensors()

@@ -96,13 +96,15 @@ def _as_batch(x, device):
         if getattr(b, "_sizes", None) is None:
             b._sizes = np.diff(b.node_ptr.cpu().numpy()).tolist()
         if x.x_host is not None:          # new input / reference fields arriving from the host
-            # x on the compute stream; the reference field is only needed by the node weight at the very end,
-            # so its copy rides on a side stream underneath the forward pass
+            # both copies ride on a side stream: x hides under the edge MLP (which does not read it: the model gets
+            # `x_ready`), the reference field -- only needed by the node weight at the very end -- under the layers
             main, side = torch.cuda.current_stream(device), _side_stream(device)
-            x_dev = x.x_host.to(device, non_blocking=True)
             with torch.cuda.stream(side):
+                x_dev = x.x_host.to(device, non_blocking=True)
+                x_dev.ready = side.record_event()
                 y_dev = x.y_host.to(device, non_blocking=True)
                 y_dev.ready = side.record_event()
+            x_dev.record_stream(main)
             y_dev.record_stream(main)
             return b.csr, b.edge_attr, b.node_ptr, x_dev, y_dev, b._sizes
         return b.csr, b.edge_attr, b.node_ptr, x.x_dev, x.y_dev, b._sizes
@@ -225,17 +227,23 @@ class GNNPartitionScheduler():
         dist, rank, world = _dist()
         if world > 1 and self.num_partitions == 1 and isinstance(x, SubdomainSample):
             return self._predict_sharded(x, rank, world)
+        if self.num_partitions == 1 and isinstance(x, SubdomainSample) and x.x_host is not None:
+            # inputs still on the host: start the GPU on the part of the pass that does not need them first
+            self.models[0].edge_phase(x.batch.csr, x.batch.edge_attr)
         csr, edge_attr, node_ptr, x_dev, y_dev, sizes = _as_batch(x, dev)
-        y_ready = getattr(y_dev, "ready", None)
+        y_ready, x_ready = getattr(y_dev, "ready", None), getattr(x_dev, "ready", None)
         S = len(sizes)
-        labels = self._route(x_dev, node_ptr)
         if self.num_partitions == 1 and world == 1:          # one model, every subdomain: nothing to select
-            pred = self.models[0](x_dev, csr, edge_attr)
+            labels = self._route(x_dev, node_ptr)
+            pred = self.models[0](x_dev, csr, edge_attr, x_ready=x_ready)
             if y_ready is not None:
                 torch.cuda.current_stream(dev).wait_event(y_ready)
             weight_s = ops.node_weight(pred, y_dev, csr, edge_attr, node_ptr)
             return self._to_host_lists(x, pred, weight_s, y_dev, sizes, labels)
 
+        if x_ready is not None:
+            torch.cuda.current_stream(dev).wait_event(x_ready)
+        labels = self._route(x_dev, node_ptr)
         # Routed and / or sharded: the plan -- this rank's contiguous edge-balanced share of the subdomain list and,
         # per cluster, the block-diagonal sub-batch of its subdomains -- depends only on the labels, so it is kept
         # on the device batch and rebuilt only when the routing of this sample changes.
@@ -310,21 +318,25 @@ class GNNPartitionScheduler():
         sh, sizes = c["shard"], c["sizes"]
         lo, hi = sh.node_lo, sh.node_hi
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-        y_ready = None
+        y_ready = x_ready = None
         host_in = x.x_host is not None
+        if host_in and hi > lo:
+            self.models[0].edge_phase(sh.csr, sh.edge_attr)
         if host_in:
             # only this rank's rows cross PCIe; the other ranks' rows of the reference field (the stitch of
             # ref_y_list needs all of it) arrive over NVLink, packed into the all-gather of the predictions
-            xi = x.x_host[lo:hi].to(dev, non_blocking=True)
             with torch.cuda.stream(side):
+                xi = x.x_host[lo:hi].to(dev, non_blocking=True)
+                x_ready = side.record_event()
                 yi = x.y_host[lo:hi].to(dev, non_blocking=True)
                 y_ready = side.record_event()
+            xi.record_stream(main)
             yi.record_stream(main)
         else:
             xi, yi = x.x_dev[lo:hi], x.y_dev[lo:hi]
         model = self.models[0]
         if hi > lo:
-            pi = model(xi, sh.csr, sh.edge_attr)
+            pi = model(xi, sh.csr, sh.edge_attr, x_ready=x_ready)
             if y_ready is not None:
                 main.wait_event(y_ready)
             wi = ops.node_weight(pi, yi, sh.csr, sh.edge_attr, sh.node_ptr)

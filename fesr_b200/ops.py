@@ -119,8 +119,12 @@ def make_params(struct_cls, tensors: dict):
 
 
 def nnconv_forward(dims: ModelDims, tensors: dict, x: torch.Tensor, csr: Csr, edge_attr: torch.Tensor,
-                   precision: int = _lib.PREC_FP32, keep_for_backward: bool = False, ws_tag: str = "fwd"):
-    """Runs fesr_nnconv_forward.  Returns y [n, out_ch] (and the workspace tensor when kept)."""
+                   precision: int = _lib.PREC_FP32, keep_for_backward: bool = False, ws_tag: str = "fwd",
+                   x_ready=None):
+    """Runs fesr_nnconv_forward.  Returns y [n, out_ch] (and the workspace tensor when kept).
+    x_ready: a CUDA event after which `x` is valid (its host -> device copy is still running on another stream).
+    The pass is then issued in two phases -- the edge MLP, which does not read x, first; the stream waits for the
+    event; the rest -- so that the copy hides under the edge MLP (predict only)."""
     dev = _require_cuda(x, edge_attr, csr.rowptr)
     x = _f32c(x)
     edge_attr = _f32c(edge_attr.reshape(-1))
@@ -145,6 +149,14 @@ def nnconv_forward(dims: ModelDims, tensors: dict, x: torch.Tensor, csr: Csr, ed
             if _prepared.get((dev.index, ws_tag)) == state:
                 flags |= _lib.FWD_WEIGHTS_PREPARED
             _prepared[(dev.index, ws_tag)] = None
+        if x_ready is not None and not keep_for_backward and n > 0:
+            check(lib.fesr_nnconv_forward(C.byref(dims), C.byref(p), None, _ptr(csr.rowptr), _ptr(csr.src),
+                                          _ptr(csr.perm), _ptr(edge_attr), n, E, precision, flags | _lib.FWD_EDGE_ONLY,
+                                          None, _ptr(ws), ws.numel(), _stream(dev)), "fesr_nnconv_forward (edge phase)")
+            torch.cuda.current_stream(dev).wait_event(x_ready)
+            flags |= _lib.FWD_EDGE_DONE
+        elif x_ready is not None:
+            torch.cuda.current_stream(dev).wait_event(x_ready)
         check(lib.fesr_nnconv_forward(C.byref(dims), C.byref(p), _ptr(x), _ptr(csr.rowptr), _ptr(csr.src),
                                       _ptr(csr.perm), _ptr(edge_attr), n, E, precision, flags,
                                       _ptr(y), _ptr(ws), ws.numel(), _stream(dev)), "fesr_nnconv_forward")
@@ -152,6 +164,71 @@ def nnconv_forward(dims: ModelDims, tensors: dict, x: torch.Tensor, csr: Csr, ed
             _prepared[(dev.index, ws_tag)] = state
     del keep
     return (y, ws) if keep_for_backward else y
+
+
+class ForwardPlan:
+    """Everything of a predict-time forward that does not change from call to call (validated once): the ctypes
+    parameter struct, the graph, the workspace size.  `run_forward_plan` then costs one tensor allocation and one
+    or two C calls -- the host time before the first kernel is enqueued is GPU idle time in an end-to-end step."""
+    __slots__ = ("dims", "params", "keep", "csr", "edge_attr", "n", "E", "precision", "ws_tag", "nbytes", "state_tail",
+                 "dev", "edge_in")
+
+
+def make_forward_plan(dims: ModelDims, tensors: dict, csr: Csr, edge_attr: torch.Tensor, precision: int,
+                      ws_tag: str = "fwd") -> ForwardPlan:
+    dev = _require_cuda(edge_attr, csr.rowptr)
+    edge_attr = _f32c(edge_attr.reshape(-1))
+    if edge_attr.numel() != csr.E:
+        raise FesrError(f"edge_attr must have {csr.E} entries, got {edge_attr.numel()}")
+    pl = ForwardPlan()
+    pl.dims, pl.csr, pl.edge_attr, pl.n, pl.E, pl.precision, pl.ws_tag, pl.dev = dims, csr, edge_attr, csr.n, csr.E, precision, ws_tag, dev
+    pl.params, pl.keep = make_params(Params, tensors)
+    with torch.cuda.device(dev):
+        pl.nbytes = _lib.load().fesr_forward_workspace_bytes(C.byref(dims), csr.n, csr.E, 0)
+    pl.state_tail = (bytes(dims), tuple((t.data_ptr(), t._version) for t in pl.keep))
+    pl.edge_in = None
+    return pl
+
+
+def run_forward_plan(pl: ForwardPlan, x: torch.Tensor | None, x_ready=None, edge_only: bool = False):
+    """edge_only: issue just the edge phase (FESR_FWD_EDGE_ONLY: weight preparation + edge MLP, nothing that reads x)
+    and return None -- the caller does so BEFORE it starts the host -> device copies of a step, so that the GPU is
+    busy while the host is still issuing them; the next call on this plan then runs the rest (FESR_FWD_EDGE_DONE)."""
+    dev, lib, csr = pl.dev, _lib.load(), pl.csr
+    if not edge_only:
+        if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous() or x.shape != (pl.n, pl.dims.in_ch):
+            raise FesrError(f"x must be a contiguous fp32 CUDA tensor of shape [{pl.n}, {pl.dims.in_ch}], got "
+                            f"{tuple(x.shape)} {x.dtype} on {x.device}")
+        y = torch.empty(pl.n, pl.dims.out_ch, dtype=torch.float32, device=dev)
+    if pl.n == 0:
+        return None if edge_only else y
+    ws = workspace.get(dev, pl.ws_tag, pl.nbytes)
+    key = (dev.index, pl.ws_tag)
+    state = (ws.data_ptr(),) + pl.state_tail
+    flags = _lib.FWD_WEIGHTS_PREPARED if _prepared.get(key) == state else 0
+    stream = torch.cuda.current_stream(dev)
+    sp = C.c_void_p(stream.cuda_stream)
+    args = (C.byref(pl.dims), C.byref(pl.params))
+    graph = (_ptr(csr.rowptr), _ptr(csr.src), _ptr(csr.perm), _ptr(pl.edge_attr), pl.n, pl.E, pl.precision)
+    edge_in = pl.edge_in == ws.data_ptr() and flags != 0      # an edge phase of THIS plan is the last thing in the workspace
+    pl.edge_in = None
+    _prepared[key] = None
+    with torch.cuda.device(dev):
+        if edge_only or (x_ready is not None and not edge_in):
+            check(lib.fesr_nnconv_forward(*args, None, *graph, flags | _lib.FWD_EDGE_ONLY, None, _ptr(ws), ws.numel(), sp),
+                  "fesr_nnconv_forward (edge phase)")
+            edge_in = True
+            if edge_only:
+                pl.edge_in = ws.data_ptr()
+                _prepared[key] = state
+                return None
+        if x_ready is not None:
+            stream.wait_event(x_ready)
+        if edge_in:
+            flags |= _lib.FWD_EDGE_DONE
+        check(lib.fesr_nnconv_forward(*args, _ptr(x), *graph, flags, _ptr(y), _ptr(ws), ws.numel(), sp), "fesr_nnconv_forward")
+    _prepared[key] = state
+    return y
 
 
 # ---------------------------------------------------------------------------------- node weight

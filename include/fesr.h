@@ -146,6 +146,12 @@ int fesr_csr_build(const int64_t* edge_index, int64_t E, int64_t n,
  * ---------------------------------------------------------------------------------- */
 #define FESR_FWD_KEEP 1
 #define FESR_FWD_WEIGHTS_PREPARED 2
+/* Two-phase call, so that the caller can overlap the host -> device copy of x with the part of the pass that does
+ * not read x: FESR_FWD_EDGE_ONLY (4) runs the weight preparation and the edge MLP (x and y are not touched and may
+ * be NULL) and leaves the edge features in the workspace; a following call with FESR_FWD_EDGE_DONE (8) on the SAME
+ * workspace, dims, parameters, graph, edge_attr and precision runs the rest (fc1, the layers, fc2). */
+#define FESR_FWD_EDGE_ONLY 4
+#define FESR_FWD_EDGE_DONE 8
 size_t fesr_forward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E, int keep_for_backward);
 int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params,
                         const float* x, const int32_t* rowptr, const int32_t* src_sorted,

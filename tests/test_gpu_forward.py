@@ -257,3 +257,56 @@ def test_prepared_weights_are_reused_and_invalidated(golden):
         m.conv1.root.mul_(2.0)
     assert rel_l2(_run(m, *args), y1) < 1e-6
     assert rel_l2(y3, y1) > 1e-3
+
+
+@pytest.mark.parametrize("prec", ["fp32", "f16"])
+def test_two_phase_forward_equals_single_call(golden, shipped, prec):
+    """FESR_FWD_EDGE_ONLY + FESR_FWD_EDGE_DONE (x arrives on another stream while the edge MLP runs) give the bits
+    of the single call."""
+    m, _ = _models("neuralop", 43, 5)
+    m.load_state_dict(shipped_state_dict(shipped, "neuralop"))
+    m = m.cuda().eval()
+    m.precision = prec
+    ei = torch.from_numpy(golden["ref_edge_index"]).cuda()
+    ea = torch.from_numpy(golden["ref_edge_attr"]).cuda()
+    x_host = torch.from_numpy(golden["x"]).pin_memory()
+    with torch.no_grad():
+        a = m(x_host.cuda(), ei, ea)
+        side = torch.cuda.Stream()
+        for _ in range(2):                      # second round: prepared weights + two-phase
+            with torch.cuda.stream(side):
+                x_dev = x_host.to("cuda", non_blocking=True)
+                ready = side.record_event()
+            x_dev.record_stream(torch.cuda.current_stream())
+            b = m(x_dev, ei, ea, x_ready=ready)
+            assert torch.equal(a, b)
+
+
+def test_edge_phase_issued_ahead_of_the_forward(golden, shipped):
+    """model.edge_phase(...) then model(x, ...) == model(x, ...) alone, also when another graph ran in between (the
+    edge features in the workspace are then stale and must be recomputed)."""
+    from fesr_b200 import ops
+    m, _ = _models("neuralop", 43, 5)
+    m.load_state_dict(shipped_state_dict(shipped, "neuralop"))
+    m = m.cuda().eval()
+    m.precision = "f16"
+    x = torch.from_numpy(golden["x"]).cuda()
+    n = x.shape[0]
+    csr = ops.csr_build(torch.from_numpy(golden["ref_edge_index"]).cuda(), n)
+    ea = torch.from_numpy(golden["ref_edge_attr"]).cuda()
+    half = n // 2
+    ei2 = torch.stack([torch.arange(1, half, device="cuda"), torch.arange(0, half - 1, device="cuda")])
+    csr2 = ops.csr_build(ei2, half)
+    ea2 = torch.full((half - 1,), 3e-3, device="cuda")
+    with torch.no_grad():
+        ref = m(x, csr, ea)
+        ref2 = m(x[:half].contiguous(), csr2, ea2)
+        m.edge_phase(csr, ea)
+        assert torch.equal(m(x, csr, ea), ref)
+        m.edge_phase(csr, ea)
+        assert torch.equal(m(x[:half].contiguous(), csr2, ea2), ref2)      # a different graph: plan replaced
+        assert torch.equal(m(x, csr, ea), ref)
+        m.edge_phase(csr, ea)
+        m.edge_phase(csr, ea)                                              # twice in a row is harmless
+        ev = torch.cuda.current_stream().record_event()
+        assert torch.equal(m(x, csr, ea, x_ready=ev), ref)
