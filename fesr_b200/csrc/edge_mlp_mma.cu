@@ -185,7 +185,7 @@ __device__ __forceinline__ uint32_t em_pack(float lo, float hi) {
 }
 
 template <int WPAD, int NTO, int OMODE>     // ReLU only (KernelNN); LeakyReLU shapes use the tf32 kernel above
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
                         const float* __restrict__ b1g, int w, int kt, int ktp, int k1,
                         const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int E,
@@ -575,13 +575,21 @@ static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const flo
     attr_set = true;
   }
   static const bool tf32_only = getenv("FESR_EDGE_TF32") != nullptr;     // A/B switch for profiling
+  // the fp16 kernels are persistent over edge groups: exactly one wave of resident blocks (a grid of 8 blocks per SM
+  // with 5 resident ran as a full wave plus a 60 % one)
+  static int occ16 = 0;
+  if (occ16 == 0) {
+    FESR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ16, edge_hidden2_f16_kernel<WPAD, NTO, 3>, 128, 0));
+    if (occ16 < 1) occ16 = 1;
+  }
+  const int grid16 = (int)(blocks < (int64_t)occ16 * num_sms() ? blocks : (int64_t)occ16 * num_sms());
   if (omode == 0) FESR_EH(3, 0);
   else if (omode == 1) FESR_EH(1, 1);
   else if (!tf32_only && !d.leaky && omode == 2)
-    edge_hidden2_f16_kernel<WPAD, NTO, 2><<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
+    edge_hidden2_f16_kernel<WPAD, NTO, 2><<<grid16, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
                                                               edge_attr, perm, (int)E, reinterpret_cast<__half*>(g));
   else if (!tf32_only && !d.leaky)
-    edge_hidden2_f16_kernel<WPAD, NTO, 3><<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
+    edge_hidden2_f16_kernel<WPAD, NTO, 3><<<grid16, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
                                                               edge_attr, perm, (int)E, reinterpret_cast<__half*>(g));
   else if (omode == 2) FESR_EH(1, 2);
   else FESR_EH(1, 3);
