@@ -311,7 +311,8 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
 // significant products accumulated in fp32 (the fp16 twin of 3xTF32, ~2^-21).  Plain fp16 operands are not enough
 // here: the shipped TEECNet is sensitive to the hidden layers (single-term products move the predicted field by
 // 1.3e-2 rel-L2, rounding W1 alone by 1.27e-2; the split form by 4e-5 -- measured on the CPU restatement).
-// OMODE 1: fp32 rows rounded to tf32 [E][144]; OMODE 2: fp16 rows [E][144].
+// OMODE 1: fp32 rows rounded to tf32 [E][144]; OMODE 2: fp16 rows [E][144]; OMODE 3: fp16 planar [9][E][16] (the
+// fused layer kernel's slot groups).
 __device__ __forceinline__ void em_split(float v0, float v1, uint32_t& hi, uint32_t& lo) {
   hi = em_pack(v0, v1);
   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
@@ -333,7 +334,7 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
   constexpr int CW = 48, NCH = KP / CW, NTC = CW / 8;                  // slots per chunk, chunks, n-tiles per chunk
   constexpr int KS0 = H0 / 16, KS1 = H1 / 16, NT1 = H1 / 8;
   constexpr int W1S = H0 + 8, W2S = H1 + 8;                            // row strides in halfs (+16 B: conflict-free)
-  constexpr int SST = OMODE == 2 ? (CW + 8) * 2 : (CW + 4) * 4;        // staged row stride in BYTES
+  constexpr int SST = OMODE >= 2 ? (CW + 8) * 2 : (CW + 4) * 4;        // staged row stride in BYTES
   __shared__ __align__(16) float w0[H0], b0[H0], b1[H1], b2p[KP];
   extern __shared__ __align__(16) uint8_t eh3_dyn[];
   __half (*w1h)[W1S] = reinterpret_cast<__half (*)[W1S]>(eh3_dyn);     // [out][in]: K contiguous
@@ -375,7 +376,7 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
   uint8_t* const wstage = stage + (size_t)warp * 32 * SST;
   // fp16 rows: stmatrix rows of the C tiles of m-tile mt: matrices (hh 0, nt), (hh 1, nt), (hh 0, nt + 1), (hh 1, nt + 1)
   const uint32_t s_addr = em_smem(wstage) + (uint32_t)(((lm & 1) * 8 + lr) * SST + (lm >> 1) * 16);
-  constexpr int QB = OMODE == 2 ? CW / 8 : CW / 4;                     // 16-byte chunks per staged row
+  constexpr int QB = OMODE >= 2 ? CW / 8 : CW / 4;                     // 16-byte chunks per staged row
   const int n_groups = (E + 31) / 32;
   auto load_d = [&](int g) {
     const int e = min(g * 32 + lane, E - 1);
@@ -475,7 +476,7 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
             em_mma16(acc[mt][2 * np + 1], a1h[mt][ks], bh_[2], bh_[3]);
           }
         }
-      if (OMODE == 2) {
+      if (OMODE >= 2) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -507,7 +508,15 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
         }
       }
       __syncwarp();
-      {
+      if (OMODE == 3) {          // planar: 16-byte chunk c of the 48-slot chunk ch = half (c & 1) of part 3 ch + c / 2
+        __half* const gh = static_cast<__half*>(gv);
+        for (int t = lane; t < 32 * QB; t += 32) {
+          const int r = t / QB, c = t - r * QB;
+          if (e_base + r < E)
+            *reinterpret_cast<uint4*>(gh + ((size_t)(ch * 3 + (c >> 1)) * E + e_base + r) * 16 + (c & 1) * 8) =
+                *reinterpret_cast<const uint4*>(wstage + (size_t)r * SST + c * 16);
+        }
+      } else {
         constexpr int ESZ = OMODE == 2 ? 2 : 4;
         uint8_t* const dst = static_cast<uint8_t*>(gv) + (size_t)ch * CW * ESZ;
         for (int t = lane; t < 32 * QB; t += 32) {
@@ -527,7 +536,7 @@ int launch_edge_hidden3_mma(const fesr_model_dims& d, const fesr_params& p, cons
                             int64_t E, float* g, cudaStream_t s, int omode) {
   if (E == 0) return FESR_OK;
   if (!(d.n_hidden == 3 && d.hidden[0] == 32 && d.hidden[1] == 64 && d.hidden[2] == 128 && d.kp == 144 && d.leaky)) return 1;
-  if (omode != 1 && omode != 2) return 1;
+  if (omode < 1 || omode > 3) return 1;
   static const bool off = getenv("FESR_EDGE_FFMA") != nullptr;            // A/B switch for profiling
   if (off) return 1;
   for (int l = 0; l < 3; ++l)
@@ -543,10 +552,14 @@ int launch_edge_hidden3_mma(const fesr_model_dims& d, const fesr_params& p, cons
   if (!attr_set) {
     FESR_CUDA(cudaFuncSetAttribute(edge_hidden3_mma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem32));
     FESR_CUDA(cudaFuncSetAttribute(edge_hidden3_mma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
+    FESR_CUDA(cudaFuncSetAttribute(edge_hidden3_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16));
     attr_set = true;
   }
   ProfScope prof(PROF_EDGE_HIDDEN, s);
-  if (omode == 2)
+  if (omode == 3)
+    edge_hidden3_mma_kernel<3><<<grid, 128, smem16, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
+                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g);
+  else if (omode == 2)
     edge_hidden3_mma_kernel<2><<<grid, 128, smem16, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
                                                         d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g);
   else

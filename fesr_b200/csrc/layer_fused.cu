@@ -717,9 +717,12 @@ static int launch_fl(const int32_t* rowptr, const int32_t* src_sorted, const __h
   return FESR_OK;
 }
 
-// Shapes the fused layer covers: KernelNN-like rows (one pass of 48 g slots, padded width 48).
+// Shapes the fused layer covers: KernelNN-like rows (one pass of 48 g slots, padded width 48) in one launch (w <= 43)
+// or two / three; TEECNet rows (129 channels -> 144 slots = 9 parts, w + 1 <= 44 columns incl. the constant-1 column)
+// in three launches of three parts that accumulate through the fp32 scratch P.
 bool layer_fused_supported(const fesr_model_dims& d) {
-  return d.kind == FESR_KERNELNN && d.passes == 1 && d.kp == 48 && d.wp == FL_WP;
+  if (d.kind == FESR_KERNELNN) return d.passes == 1 && d.kp == 48 && d.wp == FL_WP;
+  return d.kind == FESR_TEECNET && d.kp == 144 && d.wp == FL_WP && d.w <= 43;
 }
 int layer_fused_parts(const fesr_model_dims& d) { return d.kp / 16; }
 size_t layer_fused_tf_elems(const fesr_model_dims& d) { return (size_t)layer_fused_parts(d) * FL_WP * FL_KP; }
@@ -746,9 +749,17 @@ int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, cons
   const __half* hh = static_cast<const __half*>(h_in);
   const __half* tfh = static_cast<const __half*>(tf);
   __half* ho = static_cast<__half*>(h_out);
-  const int relu = 1;
+  const int relu = d.kind == FESR_KERNELNN ? 1 : 0;      // TEECNet: no activation between the layers (models/model.py:280-282)
   ProfScope prof(PROF_LAYER_FUSED, s);
   int rc;
+  if (d.kind == FESR_TEECNET) {
+    // 9 parts, three per launch, partial sums through P; the constant-1 column h[:, w] comes out of the epilogue as
+    // 0 (no T'' row feeds it) + bias_p[w], which prepare_small_kernel sets to 1 for TEECNet
+    const int fix_b = d.w == 43 ? 42 : -1;
+    if ((rc = launch_fl<3, 4>(rowptr, src_sorted, gh, E, hh, n, 0, 0, tfh, bias_p, nullptr, P, nullptr, 43, fix_b, relu, s))) return rc;
+    if ((rc = launch_fl<3, 4>(rowptr, src_sorted, gh, E, hh, n, 3, 0, tfh, bias_p, P, P, nullptr, 43, fix_b, relu, s))) return rc;
+    return launch_fl<3, 4>(rowptr, src_sorted, gh, E, hh, n, 6, 1, tfh, bias_p, P, nullptr, ho, 43, fix_b, relu, s);
+  }
   if (mode == 0) mode = d.w <= 43 ? 3 : 2;
   if (mode == 3 && d.w <= 43) {
     // all three parts in one launch: part p in TMEM lanes [43p, 43p + 43); (part 2, channel 42) on CUDA cores

@@ -97,7 +97,9 @@ __global__ void prepare_small_kernel(fesr_model_dims d, const float* __restrict_
                                      float* __restrict__ fc1_bp) {
   const int t = threadIdx.x;
   for (int b = t; b < d.wp; b += blockDim.x) {
-    bias_p[b] = (b < d.w) ? bias[b] : 0.f;
+    // TEECNet: h[:, w] is a constant-1 column; the GEMM epilogues set it explicitly (EPI_BIAS_CONST1), the fused
+    // layer kernel gets it as 0 + bias_p[w]
+    bias_p[b] = (b < d.w) ? bias[b] : ((d.kind == FESR_TEECNET && b == d.w) ? 1.f : 0.f);
     fc1_bp[b] = (b < d.w) ? fc1_b[b] : ((d.kind == FESR_TEECNET && b == d.w) ? 1.f : 0.f);
     for (int c = 0; c < d.in_ch; ++c) fc1_wp[c * d.wp + b] = (b < d.w) ? fc1_w[b * d.in_ch + c] : 0.f;
   }
@@ -325,7 +327,7 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
       if (covered != 1) return covered;
     }
   }
-  if ((round_tf32 == 1 || round_tf32 == 2) && d.n_hidden == 3) {
+  if (round_tf32 >= 1 && round_tf32 <= 3 && d.n_hidden == 3) {
     const int covered = launch_edge_hidden3_mma(d, p, edge_attr, perm, E, g, s, round_tf32);
     if (covered != 1) return covered;
   }

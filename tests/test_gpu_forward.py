@@ -310,3 +310,26 @@ def test_edge_phase_issued_ahead_of_the_forward(golden, shipped):
         m.edge_phase(csr, ea)                                              # twice in a row is harmless
         ev = torch.cuda.current_stream().record_event()
         assert torch.equal(m(x, csr, ea, x_ready=ev), ref)
+
+
+def test_teecnet_fused_layer_vs_two_kernel_50k(shipped, monkeypatch):
+    """TEECNet, f16 arm: the fused layer kernel (9 slot groups, three launches of three accumulating through the fp32
+    scratch, constant-1 column from the bias) against the two-kernel layer (FESR_FUSE=0) and the fp32 CPU oracle."""
+    from fesr_b200.dataset.synthetic import make_duct_mesh
+    mesh = make_duct_mesh("50k")
+    src, dst, ea = og.build_edges(mesh.cells, mesh.pos)
+    ei = np.stack([src, dst])
+    m, o = _models("teecnet", 43, 5)
+    sd = shipped_state_dict(shipped, "teecnet")
+    m.load_state_dict(sd)
+    o.load_state_dict(sd)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        yo = o(torch.from_numpy(mesh.x), torch.from_numpy(ei), torch.from_numpy(ea)).numpy()
+    y0 = _run_fuse_mode(monkeypatch, 0, m, mesh.x, ei, ea)
+    y3 = _run_fuse_mode(monkeypatch, 3, m, mesh.x, ei, ea)
+    print(f"teecnet f16: two-kernel {rel_l2(y0, yo):.3e}, fused {rel_l2(y3, yo):.3e}, fused vs two-kernel {rel_l2(y3, y0):.3e}")
+    assert rel_l2(y0, yo) < TOL["f16"] and rel_l2(y3, yo) < TOL["f16"]
+    assert rel_l2(y3, y0) < TOL["f16"]
+    y3b = _run_fuse_mode(monkeypatch, 3, m, mesh.x, ei, ea)
+    assert np.array_equal(y3, y3b)
