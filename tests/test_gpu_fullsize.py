@@ -158,3 +158,23 @@ def test_forward_properties_full_size(tag, shipped, monkeypatch):
         w2 = ops.node_weight(2.0 * again, 2.0 * y, b.csr, b.edge_attr, b.node_ptr)
         assert w1.shape == (b.n_sub,) and bool(torch.isfinite(w1).all())
         assert float(((w2 - 2.0 * w1).abs() / w1.abs().clamp(min=1e-6)).max()) < 1e-4
+
+
+def test_teecnet_arms_agree_full_size(shipped, monkeypatch):
+    """TEECNet at 526 848 cells: f16 fused / f16 two-kernel / tf32 against the fp32 arm (north_star gate 1e-3 is
+    stated against the fp32 CPU result, which the fp32 arm matches to 1e-5 at the sizes the oracle can run)."""
+    mesh, pos, cells, part, b, levels = _assembled("500k")
+    x = torch.from_numpy(mesh.x).cuda()[b.global_ids]
+    m = _model(shipped, "teecnet")
+    out = {}
+    with torch.no_grad():
+        for prec, fuse in (("fp32", "3"), ("tf32", "3"), ("f16", "0"), ("f16", "3")):
+            monkeypatch.setenv("FESR_FUSE", fuse)
+            m.precision = prec
+            out[(prec, fuse)] = m(x, b.csr, b.edge_attr).cpu().numpy()
+    ref = out[("fp32", "3")]
+    assert np.isfinite(ref).all()
+    for k, v in out.items():
+        err = rel_l2(v, ref)
+        print("teecnet 500k", k, f"rel-L2 vs fp32 arm: {err:.3e}")
+        assert err < 1.5e-3, k
