@@ -129,15 +129,17 @@ __global__ void bias_act_kernel(float* __restrict__ a, const float* __restrict__
   a[idx] = act_f(a[idx] + b[idx % D], leaky);
 }
 
-// da_last[e, k] = dg[e, off(k)] * act'(a_last[e, k])   (un-permute the padded g layout)
-__global__ void dg_to_dpre_kernel(const float* __restrict__ dg, const float* __restrict__ a_last, int64_t E, int K,
+// da_last[e, k] = dg[e, off(k)] * act'(a_last[e, k])   (un-permute the padded g layout).  The last hidden layer's
+// activations ARE the forward's edge features g (same padded layout; rounding to tf32 keeps the sign the derivative
+// depends on), so they are read from there instead of being recomputed with one more [E, K] x [K, K] product.
+__global__ void dg_to_dpre_kernel(const float* __restrict__ dg, const float* __restrict__ g, int64_t E, int K,
                                   int kt, int ktp, int kp, int leaky, float* __restrict__ dpre) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= E * K) return;
   const int64_t e = idx / K;
   const int k = (int)(idx % K);
   const int off = (k / kt) * ktp + (k % kt);
-  dpre[idx] = dg[e * kp + off] * act_grad(a_last[idx], leaky);
+  dpre[idx] = dg[e * kp + off] * act_grad(g[e * kp + off], leaky);
 }
 
 __global__ void act_grad_kernel(float* __restrict__ da, const float* __restrict__ a, int64_t count, int leaky) {
@@ -333,15 +335,14 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     mlp_layer0_kernel<<<(unsigned)ceil_div(E * d.hidden[0], T), T, 0, s>>>(w.dattr, p.mlp_w[0], p.mlp_b[0], E,
                                                                          d.hidden[0], leaky, w.act[0]);
     FESR_LAUNCH_CHECK();
-    for (int l = 1; l < nh; ++l) {
+    for (int l = 1; l < nh - 1; ++l) {      // (the last hidden layer's activations are g: not recomputed)
       const int din = d.hidden[l - 1], dout = d.hidden[l];
       GEMM(w.act[l - 1], din, 1, p.mlp_w[l], 1, din, w.act[l], dout, 1, E, dout, din, 0);
       bias_act_kernel<<<(unsigned)ceil_div(E * dout, T), T, 0, s>>>(w.act[l], p.mlp_b[l], E, dout, leaky);
       FESR_LAUNCH_CHECK();
     }
     const int K = d.hidden[nh - 1];
-    dg_to_dpre_kernel<<<(unsigned)ceil_div(E * K, T), T, 0, s>>>(w.dg, w.act[nh - 1], E, K, d.kt, d.ktp, d.kp, leaky,
-                                                                w.da[0]);
+    dg_to_dpre_kernel<<<(unsigned)ceil_div(E * K, T), T, 0, s>>>(w.dg, fw.g, E, K, d.kt, d.ktp, d.kp, leaky, w.da[0]);
     FESR_LAUNCH_CHECK();
     int dc = 0;
     for (int l = nh - 1; l >= 0; --l) {

@@ -35,8 +35,18 @@ edge_grad_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
       for (int e = eb; e < ee; ++e) {
         const int64_t s = src_sorted[e];
         float ha[AT];
+        if (AT % 2 == 0) {            // the lane's AT consecutive floats as 8-byte loads (ag * AT floats is 8-byte aligned)
+          const float2* hp = reinterpret_cast<const float2*>(h + s * WP + ag * AT);
 #pragma unroll
-        for (int t = 0; t < AT; ++t) ha[t] = __ldg(h + s * WP + ag * AT + t);
+          for (int t = 0; t < AT / 2; ++t) {
+            const float2 v = __ldg(hp + t);
+            ha[2 * t] = v.x;
+            ha[2 * t + 1] = v.y;
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < AT; ++t) ha[t] = __ldg(h + s * WP + ag * AT + t);
+        }
         float part[KT];
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
@@ -49,9 +59,18 @@ edge_grad_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
           part[k] = v;
         }
         if (ag == 0) {
-          float* out = dg + (int64_t)e * kp + (p * 4 + q) * KTP;
+          // the lane group's KTP slots of the dg row are one 16-byte-aligned run: read-modify-write as float4
+          // (the pad slots get + 0); 2 * KTP / 4 transactions per edge and group instead of 2 * KT scalar ones
+          float4* out = reinterpret_cast<float4*>(dg + (int64_t)e * kp + (p * 4 + q) * KTP);
 #pragma unroll
-          for (int k = 0; k < KT; ++k) out[k] += part[k];
+          for (int k4 = 0; k4 < KTP / 4; ++k4) {
+            float4 v = out[k4];
+            v.x += part[4 * k4];
+            if (4 * k4 + 1 < KT) v.y += part[4 * k4 + 1];
+            if (4 * k4 + 2 < KT) v.z += part[4 * k4 + 2];
+            if (4 * k4 + 3 < KT) v.w += part[4 * k4 + 3];
+            out[k4] = v;
+          }
         }
       }
     }

@@ -1,10 +1,5 @@
 set -x
-timeout 900 python -m pytest tests -m gpu -q -x -s > gpurun_out/s22_tests.log 2>&1; tail -3 gpurun_out/s22_tests.log; grep "teecnet 500k" gpurun_out/s22_tests.log
-timeout 300 python __graft_entry__.py smoke 2>&1 | tail -1
-timeout 400 python bench.py > gpurun_out/s22_bench.json 2> gpurun_out/s22_bench.err; tail -c 300 gpurun_out/s22_bench.err
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/s22_bench.json').read().strip().splitlines()[-1])
-print('%.1fM'%(d['value']/1e6), d['ms_per_step'], 'e2e %.1fM'%(d['e2e']['value']/1e6), d['roofline'], d['cpu_baseline'], d['clocks'])
-PY
-timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/s22_ref.json 2> gpurun_out/s22_ref.err; cut -c 1-300 gpurun_out/s22_ref.json
+timeout 600 python -m pytest tests/test_gpu_backward.py -m gpu -q -x > gpurun_out/s23_tests.log 2>&1; tail -3 gpurun_out/s23_tests.log
+python tools/bench_train.py --mesh-n 28 --precision tf32 --steps 5 --profile > gpurun_out/s23_train28.json 2> gpurun_out/s23_train28.err; cat gpurun_out/s23_train28.json; tail -c 300 gpurun_out/s23_train28.err
+python tools/bench_train.py --mesh-n 28 --precision tf32 --steps 5 --model teecnet > gpurun_out/s23_train28_teec.json 2> gpurun_out/s23_train28_teec.err; cat gpurun_out/s23_train28_teec.json
+python tools/bench_train.py --mesh-n 28 --precision fp32 --steps 3 > gpurun_out/s23_train28_fp32.json 2> gpurun_out/s23_train28_fp32.err; cat gpurun_out/s23_train28_fp32.json
