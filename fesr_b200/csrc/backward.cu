@@ -284,7 +284,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
       } else {
         GEMM(w.dpre, d.wp, 1, fw.prep.tprime, 1, d.wp, w.BZ, d.zk, 1, n, d.zk, d.wp, 0);
       }
-      if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, 1, w.dg, s))) return rc;
+      if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, rnd, w.dg, s))) return rc;
     }
     // dh_l = [sum over out-edges of g (x) dpre[dst]/deg[dst]  ++  dpre] T~
     if (rnd)

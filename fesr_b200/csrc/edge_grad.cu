@@ -4,6 +4,8 @@
 // writes Z with (lane = 8*q + ag), loops over the node's incoming edges in CSR order, reduces the
 // partial dot products over the 8 column groups with shuffles and the ag == 0 lanes accumulate
 // into dg (one writer per element => deterministic).
+#include <stdlib.h>
+
 #include "backward.cuh"
 
 namespace fesr {
@@ -77,6 +79,103 @@ edge_grad_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   }
 }
 
+// Reduced-precision arm: the same contraction on mma.sync.m16n8k8 tf32 (fp32 accumulate), one warp per destination node:
+//   dG_i [16 edges x channels] = H_i [16 edges x wp] . dZ_i^T [wp x channels]
+// A fragments are the gathered h[src] rows, B fragments the node's dZ row block (channel-major, wp contiguous: the
+// lane pattern 8 channels x 4 consecutive floats reads whole 32-byte sectors across the two halves of a k-step), the
+// accumulators go straight into dg (one writer per element: deterministic).  ~9x fewer instructions than the
+// shuffle-reduce kernel above, which stays the fp32 arm.
+__device__ __forceinline__ uint32_t eg_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+template <int WP>
+__global__ void __launch_bounds__(128)
+edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
+                     const float* __restrict__ dZ, const float* __restrict__ h, int64_t n, int k1p, int kt, int ktp, int kp,
+                     int zk, float* __restrict__ dg) {
+  constexpr int KS = WP / 8;                // k-steps over the node-feature index a
+  constexpr int NTC = 6;                    // channel n-tiles per pass (24 accumulator registers)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int64_t warp_global = (int64_t)blockIdx.x * 4 + warp, warp_stride = (int64_t)gridDim.x * 4;
+  const int n_nt = (k1p + 7) / 8;
+  // the 16 x kp tile of dg contributions of a chunk is staged per warp, so that dg is updated with coalesced
+  // 16-byte read-modify-writes of whole rows instead of scattered 4-byte ones
+  extern __shared__ __align__(16) float eg_tile[];
+  float* tile = eg_tile + (size_t)warp * 16 * kp;
+  const int q4 = kp >> 2;
+  for (int64_t i = warp_global; i < n; i += warp_stride) {
+    const int eb = rowptr[i], ee = rowptr[i + 1];
+    if (ee == eb) continue;
+    const float inv = 1.0f / (float)(ee - eb);
+    const float* zrow = dZ + i * (int64_t)zk;
+    for (int c0 = eb; c0 < ee; c0 += 16) {
+      const int e0 = c0 + gq, e1 = c0 + gq + 8;
+      const float* h0 = h + (int64_t)__ldg(src_sorted + min(e0, ee - 1)) * WP + tq;
+      const float* h1 = h + (int64_t)__ldg(src_sorted + min(e1, ee - 1)) * WP + tq;
+      uint32_t a[KS][4];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        a[ks][0] = eg_tf32(__ldg(h0 + ks * 8));
+        a[ks][1] = eg_tf32(__ldg(h1 + ks * 8));
+        a[ks][2] = eg_tf32(__ldg(h0 + ks * 8 + 4));
+        a[ks][3] = eg_tf32(__ldg(h1 + ks * 8 + 4));
+      }
+      for (int t = lane; t < 16 * q4; t += 32) reinterpret_cast<float4*>(tile)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncwarp();
+      for (int nt0 = 0; nt0 < n_nt; nt0 += NTC) {
+        float acc[NTC][4];
+#pragma unroll
+        for (int t = 0; t < NTC; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+#pragma unroll
+        for (int t = 0; t < NTC; ++t) {
+          if (nt0 + t < n_nt) {
+            // B[a][channel]: b0 = dZ[chan = (nt0 + t) * 8 + gq][a = ks * 8 + tq], b1 = ... [a + 4]
+            // (channels past k1p in the last tile: clamped row, masked on store)
+            const float* zp = zrow + (int64_t)min((nt0 + t) * 8 + gq, k1p - 1) * WP + tq;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const uint32_t b0 = eg_tf32(__ldg(zp + ks * 8)), b1 = eg_tf32(__ldg(zp + ks * 8 + 4));
+              asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                  : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                  : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1));
+            }
+          }
+        }
+        // accumulator (row gq / gq + 8, channels 2 tq, 2 tq + 1 of tile t) -> dg[edge][slot(channel)]
+#pragma unroll
+        for (int t = 0; t < NTC; ++t) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int chan = (nt0 + t) * 8 + 2 * tq + j;
+            if (nt0 + t < n_nt && chan < k1p) {
+              const int off = (chan / kt) * ktp + (chan % kt);
+              tile[gq * kp + off] = acc[t][j] * inv;
+              tile[(gq + 8) * kp + off] = acc[t][2 + j] * inv;
+            }
+          }
+        }
+      }
+      __syncwarp();
+      const int nrow = min(16, ee - c0);
+      float4* drow = reinterpret_cast<float4*>(dg + (int64_t)c0 * kp);
+      for (int t = lane; t < nrow * q4; t += 32) {
+        float4 v = drow[t];
+        const float4 u = reinterpret_cast<const float4*>(tile)[t];
+        v.x += u.x;
+        v.y += u.y;
+        v.z += u.z;
+        v.w += u.w;
+        drow[t] = v;
+      }
+      __syncwarp();
+    }
+  }
+}
+
 template <int KT>
 static int eg_dispatch(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src, const float* dZ,
                        const float* h, int64_t n, float* dg, cudaStream_t s) {
@@ -94,10 +193,19 @@ static int eg_dispatch(const fesr_model_dims& d, const int32_t* rowptr, const in
 }
 
 int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* dZ,
-                     const float* h, int64_t n, int accumulate, float* dg, cudaStream_t s) {
-  (void)accumulate;   // dg is zero-initialised by the caller and always accumulated into
+                     const float* h, int64_t n, int use_mma, float* dg, cudaStream_t s) {
+  // dg is zero-initialised by the caller and always accumulated into
   if (n == 0) return FESR_OK;
   ProfScope prof(PROF_BACKWARD, s);
+  static const bool no_mma = getenv("FESR_EDGE_GRAD_FFMA") != nullptr;      // A/B switch for profiling
+  if (use_mma && !no_mma && d.wp == 48) {
+    const int64_t blocks = ceil_div(n, 4);
+    const int grid = (int)(blocks < 16ll * num_sms() ? blocks : 16ll * num_sms());
+    const size_t smem = (size_t)4 * 16 * d.kp * sizeof(float);      // <= 36.9 KB (kp = 144)
+    edge_grad_mma_kernel<48><<<grid, 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+    FESR_LAUNCH_CHECK();
+    return FESR_OK;
+  }
   switch (d.kt) {
     case 4: return eg_dispatch<4>(d, rowptr, src_sorted, dZ, h, n, dg, s);
     case 8: return eg_dispatch<8>(d, rowptr, src_sorted, dZ, h, n, dg, s);
