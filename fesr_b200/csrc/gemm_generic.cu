@@ -113,14 +113,29 @@ int launch_gemm(const GemmArgs& a, float* ws, size_t ws_bytes, cudaStream_t s) {
 }
 
 // out[j] (+)= sum_i X[i*ld + j], j < cols; deterministic two-stage (rows split over blocks)
-__global__ void colsum_partial_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld, int64_t rchunk,
-                                      float* __restrict__ partial) {
-  const int j = blockIdx.y * blockDim.x + threadIdx.x;
-  if (j >= cols) return;
-  const int64_t r0 = (int64_t)blockIdx.x * rchunk, r1 = min(rows, r0 + rchunk);
-  float s = 0.f;
-  for (int64_t i = r0; i < r1; ++i) s += X[i * ld + j];
-  partial[(int64_t)blockIdx.x * cols + j] = s;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ X, int64_t rows, int cols, int64_t ld, int64_t rchunk,
+                      float* __restrict__ partial) {
+  // 64 columns x 4 row groups per block; a thread walks its rows 16 apart with four independent accumulators (four
+  // loads in flight), the groups are combined in a fixed order: deterministic
+  __shared__ float red[4][64];
+  const int jl = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int j = blockIdx.y * 64 + jl;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (j < cols) {
+    const int64_t r0 = (int64_t)blockIdx.x * rchunk, r1 = min(rows, r0 + rchunk);
+    int64_t i = r0 + rg;
+    for (; i + 12 < r1; i += 16) {
+      s0 += X[i * ld + j];
+      s1 += X[(i + 4) * ld + j];
+      s2 += X[(i + 8) * ld + j];
+      s3 += X[(i + 12) * ld + j];
+    }
+    for (; i < r1; i += 4) s0 += X[i * ld + j];
+  }
+  red[rg][jl] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (rg == 0 && j < cols) partial[(int64_t)blockIdx.x * cols + j] = (red[0][jl] + red[1][jl]) + (red[2][jl] + red[3][jl]);
 }
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, int cols, int accumulate,
                                     float* __restrict__ out) {
@@ -140,7 +155,7 @@ int launch_colsum(const float* X, int64_t rows, int cols, int64_t ld, int accumu
   const int64_t rchunk = ceil_div(rows > 0 ? rows : 1, nb);
   nb = (int)ceil_div(rows > 0 ? rows : 1, rchunk);
   dim3 grid(nb, (unsigned)ceil_div(cols, 64));
-  colsum_partial_kernel<<<grid, 64, 0, s>>>(X, rows, cols, ld, rchunk, ws);
+  colsum_partial_kernel<<<grid, 256, 0, s>>>(X, rows, cols, ld, rchunk, ws);
   FESR_LAUNCH_CHECK();
   colsum_final_kernel<<<(unsigned)ceil_div(cols, 64), 64, 0, s>>>(ws, nb, cols, accumulate, out);
   FESR_LAUNCH_CHECK();
