@@ -11,6 +11,8 @@
 // then the edge-MLP hidden layers, fc1 / fc2.  Replaces loss.backward() of the reference's train
 // step (models/scheduler_gnn.py:407) -- where autograd materialises the [E, w*w] edge matrices
 // and their gradients -- for the same parameters, named as in the state_dict.
+#include <stdlib.h>
+
 #include "backward.cuh"
 #include "workspace.cuh"
 
@@ -193,6 +195,7 @@ static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n
     const size_t b = gemm_ws_bytes(d.hidden[l], l > 0 ? d.hidden[l - 1] : 1, E);
     if (b > g) g = b;
   }
+  if (edge_mlp_bwd_ws_bytes(d, E) > g) g = edge_mlp_bwd_ws_bytes(d, E);
   size_t b2 = gemm_ws_bytes(d.out_ch, d.w, n);
   if (b2 > g) g = b2;
   b2 = gemm_ws_bytes(d.w, d.in_ch, n);
@@ -328,7 +331,10 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   if (grad_x) GEMM(dh0, d.wp, 1, p.fc1_w, d.in_ch, 1, grad_x, d.in_ch, 1, n, d.in_ch, d.w, 0);
 
   // ---- edge MLP hidden layers
-  if (E > 0) {
+  static const bool no_fused_mlp = getenv("FESR_EDGE_MLP_BWD_GENERIC") != nullptr;       // A/B switch for profiling
+  if (E > 0 && rnd && !no_fused_mlp && edge_mlp_bwd_supported(d)) {
+    if ((rc = launch_edge_mlp_bwd(d, p, edge_attr, perm, w.dg, fw.g, E, grads, w.gemm_ws, s))) return rc;
+  } else if (E > 0) {
     const int nh = d.n_hidden, leaky = d.leaky;
     gather_scalar_kernel<<<(unsigned)ceil_div(E, T), T, 0, s>>>(edge_attr, perm, E, w.dattr);
     FESR_LAUNCH_CHECK();

@@ -33,4 +33,10 @@ int launch_wgrad_mma(const fesr_model_dims& d, const float* Z, const float* dpre
                      cudaStream_t s);
 int launch_dz_mma(const fesr_model_dims& d, const float* dpre, const float* tprime, int64_t n, float* dZ, cudaStream_t s);
 
+// edge_mlp_bwd.cu (tf32 arm, KernelNN shape): the whole backward of the edge-MLP hidden layers in one kernel
+bool edge_mlp_bwd_supported(const fesr_model_dims& d);
+size_t edge_mlp_bwd_ws_bytes(const fesr_model_dims& d, int64_t E);
+int launch_edge_mlp_bwd(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr, const int32_t* perm,
+                        const float* dg, const float* g, int64_t E, fesr_param_grads* grads, float* ws, cudaStream_t s);
+
 }  // namespace fesr
