@@ -1,6 +1,5 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_backward.py -m gpu -q -x > gpurun_out/s28_tests.log 2>&1; tail -3 gpurun_out/s28_tests.log
-for m in neuralop teecnet; do
-python tools/bench_train.py --mesh-n 28 --precision tf32 --steps 5 --model $m > gpurun_out/s28_train28_$m.json 2> gpurun_out/s28_train28.err; python -c "
-import json;d=json.loads(open('gpurun_out/s28_train28_$m.json').read().strip().splitlines()[-1]);print('$m', d['ms_per_step'], d['value'], d['loss'])"
-done
+CMD="python tools/bench_train.py --mesh-n 28 --precision tf32 --steps 2 --warmup 1 --model teecnet"
+$CMD > gpurun_out/r01c_train_teec_plain.json 2> gpurun_out/r01c_train_teec_plain.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/r01c_train_teec_launches.csv $CMD > gpurun_out/r01c_train_teec_ncu.log 2>&1
+tail -1 gpurun_out/r01c_train_teec_ncu.log
