@@ -157,16 +157,19 @@ class MeshPredictor:
             self._occ_padded = ops.Occurrence(self.occ.occ_ptr, padded_positions(self.occ.occ_idx, self.shard_rows),
                                               self.occ.N, self.world * mx)
         self._send[:pred_shard.shape[0]].copy_(pred_shard)
-        dist.all_gather_into_tensor(self._gbuf.view(-1), self._send.view(-1), group=self.group)
-        return self._gbuf.view(-1, c)
+        work = dist.all_gather_into_tensor(self._gbuf.view(-1), self._send.view(-1), group=self.group, async_op=True)
+        return self._gbuf.view(-1, c), work
 
     def step(self, x_shard, y_shard=None):
         """forward (+ node weight) + all-gather + stitch; returns (field [N,c], weights [S_shard] | None)."""
         pred = self.forward_shard(x_shard)
-        w = self.node_weight(pred, y_shard) if y_shard is not None else None
         if self.world > 1:
-            field, _, _ = ops.stitch_mean(self._padded_gather(pred), self._occ_padded, None, want_merged=False,
-                                          want_count=False)
-        else:
-            field, _, _ = self.stitch(pred)
+            # the collective runs on NCCL's stream underneath the node-weight kernels (they only need this rank's rows)
+            gathered, work = self._padded_gather(pred)
+            w = self.node_weight(pred, y_shard) if y_shard is not None else None
+            work.wait()
+            field, _, _ = ops.stitch_mean(gathered, self._occ_padded, None, want_merged=False, want_count=False)
+            return field, w, pred
+        w = self.node_weight(pred, y_shard) if y_shard is not None else None
+        field, _, _ = self.stitch(pred)
         return field, w, pred
