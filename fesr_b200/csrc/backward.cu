@@ -249,6 +249,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
 #define GEMM(...)                                                     \
   do {                                                                \
     GemmArgs ga__ = {__VA_ARGS__};                                    \
+    ga__.tf32 = rnd;                                                  \
     if ((rc = launch_gemm(ga__, w.gemm_ws, w.gemm_ws_bytes, s))) return rc; \
   } while (0)
 

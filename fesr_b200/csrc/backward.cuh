@@ -13,6 +13,7 @@ struct GemmArgs {
   int64_t sCm, sCn;
   int64_t M, N, K;
   int accumulate;
+  int tf32;          // 1: products on mma.sync tf32 (fp32 accumulate) -- the reduced-precision arm
 };
 
 size_t gemm_ws_bytes(int64_t M, int64_t N, int64_t K);

@@ -7,6 +7,15 @@ namespace fesr {
 
 constexpr int GG_BM = 64, GG_BN = 64, GG_BK = 16, GG_THREADS = 256;
 
+__device__ __forceinline__ uint32_t gg_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+// TF32 = true: the 64 x 64 x 16 slab product on mma.sync.m16n8k8 (warp = 16 rows x 32 columns) instead of the 4 x 4
+// register tiles; same tiles, same split-K, same fixed-order reduce
+template <bool TF32>
 __global__ void __launch_bounds__(GG_THREADS)
 gemm_generic_kernel(GemmArgs a, int64_t kchunk, float* __restrict__ partial) {
   __shared__ __align__(16) float As[GG_BK][GG_BM + 4];
@@ -16,7 +25,9 @@ gemm_generic_kernel(GemmArgs a, int64_t kchunk, float* __restrict__ partial) {
   const int64_t kb = (int64_t)blockIdx.z * kchunk;
   const int64_t ke = min(a.K, kb + kchunk);
   const int tm = (tid >> 4) * 4, tn = (tid & 15) * 4;
-  float acc[4][4];
+  const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;      // TF32: this warp's corner of the tile
+  float acc[4][4];                                            // TF32: acc[n-tile][c0..c3]
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -40,6 +51,23 @@ gemm_generic_kernel(GemmArgs a, int64_t kchunk, float* __restrict__ partial) {
       Bs[kk][nn] = (gn < a.N && gk < ke) ? a.B[gk * a.sBk + gn * a.sBn] : 0.f;
     }
     __syncthreads();
+    if (TF32) {
+#pragma unroll
+      for (int ks = 0; ks < GG_BK / 8; ++ks) {
+        const uint32_t a0 = gg_tf32(As[ks * 8 + tq][wm + gq]), a1 = gg_tf32(As[ks * 8 + tq][wm + gq + 8]);
+        const uint32_t a2 = gg_tf32(As[ks * 8 + tq + 4][wm + gq]), a3 = gg_tf32(As[ks * 8 + tq + 4][wm + gq + 8]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const uint32_t b0 = gg_tf32(Bs[ks * 8 + tq][wn + nt * 8 + gq]), b1 = gg_tf32(Bs[ks * 8 + tq + 4][wn + nt * 8 + gq]);
+          asm volatile(
+              "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+              : "+f"(acc[nt][0]), "+f"(acc[nt][1]), "+f"(acc[nt][2]), "+f"(acc[nt][3])
+              : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+      }
+      __syncthreads();
+      continue;
+    }
 #pragma unroll
     for (int kk = 0; kk < GG_BK; ++kk) {
       const float4 av = *reinterpret_cast<const float4*>(&As[kk][tm]);
@@ -55,12 +83,12 @@ gemm_generic_kernel(GemmArgs a, int64_t kchunk, float* __restrict__ partial) {
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int64_t gm = m0 + tm + i;
-    if (gm >= a.M) continue;
+    // TF32: i = n-tile, j = accumulator element (rows gq / gq + 8, columns 2 tq / 2 tq + 1)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int64_t gn = n0 + tn + j;
-      if (gn >= a.N) continue;
+      const int64_t gm = TF32 ? m0 + wm + gq + 8 * (j >> 1) : m0 + tm + i;
+      const int64_t gn = TF32 ? n0 + wn + i * 8 + 2 * tq + (j & 1) : n0 + tn + j;
+      if (gm >= a.M || gn >= a.N) continue;
       if (partial) {
         partial[((int64_t)blockIdx.z * a.M + gm) * a.N + gn] = acc[i][j];
       } else {
@@ -103,7 +131,8 @@ int launch_gemm(const GemmArgs& a, float* ws, size_t ws_bytes, cudaStream_t s) {
   if (kchunk == 0) kchunk = GG_BK;
   ks = (int)ceil_div(a.K > 0 ? a.K : 1, kchunk);
   dim3 grid((unsigned)ceil_div(a.M, GG_BM), (unsigned)ceil_div(a.N, GG_BN), (unsigned)ks);
-  gemm_generic_kernel<<<grid, GG_THREADS, 0, s>>>(a, kchunk, ks > 1 ? ws : nullptr);
+  if (a.tf32) gemm_generic_kernel<true><<<grid, GG_THREADS, 0, s>>>(a, kchunk, ks > 1 ? ws : nullptr);
+  else gemm_generic_kernel<false><<<grid, GG_THREADS, 0, s>>>(a, kchunk, ks > 1 ? ws : nullptr);
   FESR_LAUNCH_CHECK();
   if (ks > 1) {
     splitk_reduce_kernel<<<(unsigned)ceil_div(a.M * a.N, 256), 256, 0, s>>>(ws, ks, a);
