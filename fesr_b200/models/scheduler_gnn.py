@@ -34,6 +34,21 @@ class TensorList(list):
     own = None            # (s0, s1): the subdomains that `ready` covers; None = all of them
     rest = None           # callable that copies everything else and blocks until it is there; None = nothing left
 
+    def __init__(self, items=None, make=None, n=0):
+        """`make` (with `n` = the length): the per-subdomain views are built on first access -- slicing a host buffer
+        into a thousand tensors costs milliseconds of host time that a caller who only hands the list on to
+        reconstruct_from_partition (which works from `.dev`) never needs to spend."""
+        super().__init__(items if items is not None else ())
+        self._make, self._n = make, n
+
+    def _fill(self):
+        if self._make is not None:
+            mk, self._make = self._make, None
+            list.extend(self, mk())
+
+    def __len__(self):
+        return self._n if self._make is not None else list.__len__(self)
+
     def wait(self):
         """Blocks until this rank's own part is on the host."""
         if self.ready is not None:
@@ -47,6 +62,7 @@ class TensorList(list):
         self.wait()
 
     def __getitem__(self, i):
+        self._fill()
         if self.rest is not None:
             j = i + len(self) if isinstance(i, int) and i < 0 else i
             if not (isinstance(j, int) and self.own is not None and self.own[0] <= j < self.own[1]):
@@ -55,6 +71,7 @@ class TensorList(list):
         return super().__getitem__(i)
 
     def __iter__(self):
+        self._fill()
         self.wait_all()
         return super().__iter__()
 
@@ -383,7 +400,7 @@ class GNNPartitionScheduler():
             copied = side.record_event()
         packed.record_stream(side)
         pred_cpu = host[:pred.numel()].view(pred.shape)
-        pred_y_list = TensorList(torch.split(pred_cpu, sizes))
+        pred_y_list = TensorList(make=lambda: torch.split(pred_cpu, sizes), n=S)
         pred_y_list.dev = pred
         pred_y_list.ready = copied
         if own is not None:
@@ -396,12 +413,13 @@ class GNNPartitionScheduler():
             pred_y_list.own = (own[2], own[3])
             pred_y_list.rest = rest_once
         if isinstance(x, SubdomainSample) and x.y_host is not None:
-            ref_y_list = TensorList(torch.split(x.y_host, sizes))
+            y_host = x.y_host
+            ref_y_list = TensorList(make=lambda: torch.split(y_host, sizes), n=S)
         else:
-            ref_y_list = TensorList([d.y for d in x])
+            ref_y_list = TensorList(make=lambda: [d.y for d in x], n=S)
         ref_y_list.dev = y_dev
         w_cpu = host[pred.numel():]
-        weights_list = TensorList([w_cpu[s].expand(sizes[s]) for s in range(S)])
+        weights_list = TensorList(make=lambda: [w_cpu[s].expand(sizes[s]) for s in range(S)], n=S)
         weights_list.ready = copied
         if own is not None:
             weights_list.own = (own[2], own[3])
