@@ -91,3 +91,24 @@ def test_padded_positions_address_the_gather_buffer():
     pos = padded_positions(idx, rows)
     assert pos.dtype == torch.int32
     assert torch.equal(buf.view(-1, c)[pos.long()], full[idx.long()])
+
+
+def test_tensor_list_is_lazy_and_fetches_remote_rows_on_demand():
+    """Host logic of predict()'s return lists: the per-subdomain views are built on first access, a rank's own
+    subdomains never trigger the fetch of the other ranks' rows, anything else does exactly once."""
+    from fesr_b200.models.scheduler_gnn import TensorList
+    built, fetched = [], []
+    buf = torch.arange(12.0)
+    t = TensorList(make=lambda: (built.append(1), list(torch.split(buf, [3, 4, 5])))[1], n=3)
+    t.own = (1, 2)
+    t.rest = lambda: fetched.append(1)
+    assert isinstance(t, list) and len(t) == 3 and not built
+    assert t[1].tolist() == [3.0, 4.0, 5.0, 6.0] and built == [1] and not fetched      # own subdomain
+    assert t[-2].shape == (4,) and not fetched                                          # negative index, still own
+    assert t[0].shape == (3,) and fetched == [1]                                        # somebody else's rows
+    assert t[2].shape == (5,) and fetched == [1] and t.rest is None
+    assert [int(v.numel()) for v in t] == [3, 4, 5] and built == [1]
+    u = TensorList(make=lambda: [torch.zeros(1), torch.ones(1)], n=2)
+    u.rest = lambda: fetched.append(2)
+    assert torch.cat(list(u)).tolist() == [0.0, 1.0] and fetched == [1, 2]              # iteration needs everything
+    assert TensorList([1, 2])[1] == 2 and len(TensorList()) == 0
