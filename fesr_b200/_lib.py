@@ -77,6 +77,11 @@ SIGNATURES = {
     "fesr_cluster": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "fesr_interp_workspace_bytes": (_sz, [_i64, _i32]),
     "fesr_interp_gaussian": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
+    "fesr_tet_gradient": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "fesr_incident_mean": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i64, _i32, _vp, _vp]),
+    "fesr_boundary_faces_workspace_bytes": (_sz, [_i64]),
+    "fesr_boundary_faces": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp]),
+    "fesr_wall_shear_stress": (C.c_int, [_vp, _vp, _vp, _i64, _f, _vp, _vp, _vp]),
     "fesr_route": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
 }
 

@@ -514,3 +514,48 @@ def interp_gaussian(src_pos: torch.Tensor, src_val: torch.Tensor, dst_pos: torch
                                        ws.numel(), _stream(dev)), "fesr_interp_gaussian")
     out = out.reshape(-1) if flat else out
     return (out, count) if want_count else out
+
+
+# ---------------------------------------------------------------------------------- wall shear stress (post-processing)
+def wall_shear_stress(pos: torch.Tensor, cells: torch.Tensor, velocity: torch.Tensor, dynamic_viscosity: float = 1.0):
+    """compute_wss.compute_wall_shear_stress on a tetrahedral mesh: point gradients of `velocity` [N, 3] (mean of the
+    incident tets' gradients), boundary faces (outward), point normals, tau_wall = tau - (tau . n) n.
+    -> dict(surface_nodes [M] int64, faces [F, 3] int32, normals [M, 3], gradient [N, 9], wss [M, 3], wss_magnitude [M])."""
+    dev = _require_cuda(pos, cells, velocity)
+    if pos.dtype != torch.float32 or cells.dtype != torch.int32 or cells.dim() != 2 or cells.shape[1] != 4:
+        raise FesrError("pos must be fp32 [N, 3] and cells int32 [C, 4]")
+    pos, cells, velocity = pos.contiguous(), cells.contiguous(), _f32c(velocity)
+    N, Cn = int(pos.shape[0]), int(cells.shape[0])
+    if velocity.shape != (N, 3):
+        raise FesrError(f"velocity must be [{N}, 3], got {tuple(velocity.shape)}")
+    lib = _lib.load()
+    st = _stream(dev)
+    with torch.cuda.device(dev):
+        grad_c = torch.empty(Cn, 9, dtype=torch.float32, device=dev)
+        check(lib.fesr_tet_gradient(_ptr(pos), _ptr(cells), _ptr(velocity), Cn, _ptr(grad_c), st), "fesr_tet_gradient")
+        occ = occurrence_build(cells.reshape(-1).long(), N)                # node -> (cell, corner) incidences
+        grad_p = torch.empty(N, 9, dtype=torch.float32, device=dev)
+        check(lib.fesr_incident_mean(_ptr(grad_c), 9, _ptr(occ.occ_ptr), _ptr(occ.occ_idx), 4, N, 0, _ptr(grad_p), st),
+              "fesr_incident_mean")
+        faces = torch.empty(max(4 * Cn, 1), 3, dtype=torch.int32, device=dev)
+        face_cell = torch.empty(max(4 * Cn, 1), dtype=torch.int32, device=dev)
+        face_n = torch.empty(max(4 * Cn, 1), 3, dtype=torch.float32, device=dev)
+        ws = workspace.get(dev, "sort", lib.fesr_boundary_faces_workspace_bytes(Cn))
+        cnt = C.c_int64(0)
+        check(lib.fesr_boundary_faces(_ptr(pos), _ptr(cells), N, Cn, _ptr(faces), _ptr(face_cell), _ptr(face_n),
+                                      C.byref(cnt), _ptr(ws), ws.numel(), st), "fesr_boundary_faces")
+        F = int(cnt.value)
+        faces, face_n = faces[:F].contiguous(), face_n[:F].contiguous()
+        focc = occurrence_build(faces.reshape(-1).long(), N)               # node -> boundary-face incidences
+        normal_p = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        check(lib.fesr_incident_mean(_ptr(face_n), 3, _ptr(focc.occ_ptr), _ptr(focc.occ_idx), 3, N, 1, _ptr(normal_p), st),
+              "fesr_incident_mean")
+        surf = torch.nonzero(focc.occ_ptr[1:] > focc.occ_ptr[:-1]).reshape(-1)
+        M = int(surf.numel())
+        surf32 = surf.to(torch.int32)
+        tau = torch.empty(M, 3, dtype=torch.float32, device=dev)
+        mag = torch.empty(M, dtype=torch.float32, device=dev)
+        check(lib.fesr_wall_shear_stress(_ptr(grad_p), _ptr(normal_p), _ptr(surf32), M, float(dynamic_viscosity),
+                                         _ptr(tau), _ptr(mag), st), "fesr_wall_shear_stress")
+    return {"surface_nodes": surf, "faces": faces, "face_cell": face_cell[:F], "normals": normal_p[surf], "gradient": grad_p,
+            "wss": tau, "wss_magnitude": mag}

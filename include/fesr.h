@@ -291,6 +291,31 @@ int fesr_interp_gaussian(const float* src_pos, const float* src_val, int32_t cha
                          const float* dst_pos, int64_t n_dst, float radius, float sharpness, float null_value,
                          float* out, int32_t* count, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Wall shear stress of the (stitched) velocity field -- the step AFTER the path.  Replaces
+ * compute_wss.py:5-120 (vtkGradientFilter -> vtkDataSetSurfaceFilter -> vtkPolyDataNormals ->
+ * tau_wall = tau - (tau . n) n with tau = mu (grad u + grad u^T) n, :86-99) on a tetrahedral mesh:
+ *   fesr_tet_gradient      grad [C, 9]: the constant gradient of every tet, grad[3 i + j] = d u_i / d x_j
+ *   fesr_incident_mean     out[i, :] = mean (or, unit_vector = 1, normalised sum) of item_val[item, :] over the
+ *                          items incident to node i; the incidence list is fesr_occurrence_build over the
+ *                          flattened [items, verts] connectivity (entry j belongs to item occ_idx[j] / verts).
+ *                          width 9: point gradients from tet gradients (verts = 4); width 3 + unit_vector: point
+ *                          normals from boundary-face normals (verts = 3)
+ *   fesr_boundary_faces    tet faces owned by exactly one cell, oriented outward, with unit normals; outputs are
+ *                          capacity buffers of 4 C rows, the count goes to host_count (synchronises the stream);
+ *                          node ids must fit 21 bits
+ *   fesr_wall_shear_stress tau [M, 3], mag [M] at the nodes surf_nodes[M] (NULL: nodes 0..M-1)
+ * VTK differences (parity unpinned): outward orientation instead of traversal order, no feature-edge splitting.
+ * ---------------------------------------------------------------------------------- */
+int fesr_tet_gradient(const float* pos, const int32_t* cells, const float* field, int64_t C, float* grad, void* stream);
+int fesr_incident_mean(const float* item_val, int32_t width, const int32_t* occ_ptr, const int32_t* occ_idx,
+                       int32_t verts, int64_t N, int32_t unit_vector, float* out, void* stream);
+size_t fesr_boundary_faces_workspace_bytes(int64_t C);
+int fesr_boundary_faces(const float* pos, const int32_t* cells, int64_t N, int64_t C, int32_t* faces, int32_t* face_cell,
+                        float* face_normal, int64_t* host_count, void* workspace, size_t workspace_bytes, void* stream);
+int fesr_wall_shear_stress(const float* grad_pt, const float* normal_pt, const int32_t* surf_nodes, int64_t M, float mu,
+                           float* tau, float* mag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -276,3 +276,53 @@ def interp_gaussian(src_pos, src_val, dst_pos, radius, sharpness=2.0, null_value
             out[t] = (w[:, None] * sv[js[keep]]).sum(0) / w.sum()
             cnt[t] = int(keep.sum())
     return out.astype(np.float32), cnt
+
+
+# --------------------------------------------------------------------------------------
+# wall shear stress (the step after the path)
+# --------------------------------------------------------------------------------------
+def wall_shear_stress(pos, cells, velocity, dynamic_viscosity=1.0):
+    """compute_wss.py:5-120 restated for a tetrahedral mesh (vtk==9.4.1 filters, not vendored -> PARITY UNPINNED):
+    vtkGradientFilter = mean over the incident tets of their constant gradient (:36-42), vtkDataSetSurfaceFilter =
+    faces owned by one cell (:45-48), vtkPolyDataNormals = normalised sum of the unit face normals at a point
+    (:53-58), then tau = mu (G + G^T) n, tau_wall = tau - (tau . n) n and its norm (:86-99).  Faces are oriented
+    outward and sharp edges are not split (see fesr_b200/csrc/wss.cu).  fp64.
+    -> dict(surface_nodes, faces (sorted rows), normals, gradient [N, 9], wss, wss_magnitude)."""
+    p = np.asarray(pos, dtype=np.float32).astype(np.float64)
+    c = np.asarray(cells).astype(np.int64)
+    u = np.asarray(velocity, dtype=np.float32).astype(np.float64)
+    N = p.shape[0]
+    E = p[c[:, 1:]] - p[c[:, :1]]                       # [C, 3, 3] edge vectors (rows)
+    dU = u[c[:, 1:]] - u[c[:, :1]]                      # [C, 3, 3]: dU[k, i] = u_i(v_k) - u_i(v_0)
+    G = np.transpose(np.linalg.solve(E, dU), (0, 2, 1)) # solve E X = dU, X[j, i] = d u_i / d x_j -> G[i, j]
+    gsum = np.zeros((N, 9))
+    cnt = np.zeros(N)
+    for k in range(4):
+        np.add.at(gsum, c[:, k], G.reshape(-1, 9))
+        np.add.at(cnt, c[:, k], 1.0)
+    grad = gsum / np.maximum(cnt, 1.0)[:, None]
+    # boundary faces: the face opposite vertex f
+    tri, opp = [], []
+    for f in range(4):
+        keep = [q for q in range(4) if q != f]
+        tri.append(c[:, keep])
+        opp.append(c[:, f])
+    tri, opp = np.concatenate(tri), np.concatenate(opp)
+    key = np.sort(tri, axis=1)
+    _, inv, counts = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    b = counts[inv.reshape(-1)] == 1
+    tri, opp = tri[b], opp[b]
+    nrm = np.cross(p[tri[:, 1]] - p[tri[:, 0]], p[tri[:, 2]] - p[tri[:, 0]])
+    flip = np.einsum("ij,ij->i", nrm, p[tri[:, 0]] - p[opp]) < 0
+    nrm[flip] *= -1.0
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nsum = np.zeros((N, 3))
+    for k in range(3):
+        np.add.at(nsum, tri[:, k], nrm)
+    surf = np.unique(tri.reshape(-1))
+    n = nsum[surf] / np.linalg.norm(nsum[surf], axis=1, keepdims=True)
+    Gs = grad[surf].reshape(-1, 3, 3)
+    tau = dynamic_viscosity * np.einsum("sij,sj->si", Gs + np.transpose(Gs, (0, 2, 1)), n)
+    tw = tau - np.einsum("si,si->s", tau, n)[:, None] * n
+    return {"surface_nodes": surf, "faces": np.unique(np.sort(tri, axis=1), axis=0), "normals": n, "gradient": grad,
+            "wss": tw, "wss_magnitude": np.linalg.norm(tw, axis=1)}

@@ -86,3 +86,21 @@ def test_oracle_interp_gaussian_properties():
     assert abs(out[1, 0] - 2.0) < 1e-6 and out[2, 0] == -1.0 and abs(out[3, 0] - 3.0) < 1e-6
     ones, _ = og.interp_gaussian(src, np.ones(3, np.float32), dst[:2], 1.5)
     assert np.allclose(ones, 1.0)
+
+
+def test_oracle_wall_shear_stress_properties():
+    """The restated compute_wss.py chain (parity unpinned: no VTK here): a linear field's gradient is recovered at every
+    point, the boundary of the n x n x 4n duct has 2 (2 n^2 + 16 n^2) triangles, tau_wall is tangential."""
+    from fesr_b200.dataset.synthetic import make_duct_mesh
+    from oracle import graph as og
+    n = 3
+    m = make_duct_mesh(n)
+    A = np.array([[1.0, 2.0, 3.0], [0.5, -1.0, 2.0], [4.0, 0.0, -2.0]])
+    r = og.wall_shear_stress(m.pos, m.cells, (m.pos.astype(np.float64) @ A.T).astype(np.float32), 2.0)
+    assert np.abs(r["gradient"] - A.reshape(-1)).max() < 1e-4
+    assert r["faces"].shape[0] == 2 * (2 * n * n + 16 * n * n)
+    assert r["surface_nodes"].size == 2 * (n + 1) ** 2 + 4 * n * (4 * n - 1)
+    assert np.abs(np.einsum("ij,ij->i", r["wss"], r["normals"])).max() < 1e-9 * max(1.0, np.abs(r["wss"]).max()) + 1e-9
+    tau = 2.0 * (r["normals"] @ (A + A.T).T)
+    tw = tau - np.einsum("ij,ij->i", tau, r["normals"])[:, None] * r["normals"]
+    assert np.abs(r["wss"] - tw).max() < 1e-3
