@@ -40,6 +40,9 @@ def init_dataset(name, **kwargs):
         return AnsysDataset(**kwargs)
     elif name == 'synthetic':
         return SyntheticDuctDataset(**kwargs)
+    elif name == 'stored':              # the reference's partitioned store (mesh_*/subdomain_*), root = .npz / .h5 file
+        from .dataset.store import StoredSubdomainDataset
+        return StoredSubdomainDataset(**kwargs)
     raise ValueError(f'Invalid dataset name: {name}')
 
 

@@ -182,3 +182,37 @@ def test_sharded_predict_matches_single_rank(tmp_path, shipped, monkeypatch):
         assert pa.shape[0] == rows[0] and pb.shape[0] == rows[1] and sum(cnt) == 16 and min(cnt) > 0
         assert torch.equal(torch.cat([pa, pb])[:, :4], full_p)
         assert torch.equal(torch.cat([wa, wb]).cpu(), full_w.cpu())
+
+
+def test_stored_subdomains_flow_through_the_gpu_path(tmp_path, shipped, monkeypatch):
+    """The reference's on-disk layout (edges in arbitrary order, as its Python set leaves them) -> StoredSubdomainDataset
+    -> scheduler.predict + reconstruct_from_partition gives what the GPU-assembled dataset gives."""
+    from fesr_b200.dataset.store import StoredSubdomainDataset, save_partitioned
+    from fesr_b200.models.scheduler_gnn import GNNPartitionScheduler
+    from fesr_b200.utils import init_dataset
+    ds, model, sds = _setup(tmp_path, 1, shipped, monkeypatch)
+    rng = np.random.default_rng(0)
+    meshes = []
+    for m in range(2):
+        subs = []
+        for d in ds.get_one_full_sample(m):
+            p = torch.from_numpy(rng.permutation(d.edge_index.shape[1]))
+            subs.append({"x": d.x, "y": d.y, "pos": d.pos, "edge_index": d.edge_index[:, p], "edge_attr": d.edge_attr[p],
+                         "global_node_ids": d.global_node_ids})
+        meshes.append(subs)
+    path = str(tmp_path / "partitioned.npz")
+    save_partitioned(path, meshes)
+    stored = init_dataset("stored", root=path)
+    assert isinstance(stored, StoredSubdomainDataset) and len(stored) == 32 and stored[17].x.shape == ds[17].x.shape
+    sched = GNNPartitionScheduler("t", 1, ds, model, train=False)
+    sched2 = GNNPartitionScheduler("t", 1, stored, model, train=False)
+    for m in range(2):
+        p, r, mi, w = sched.predict(ds.get_one_full_sample(m))
+        out = ds.reconstruct_from_partition(p, r, m, mi, w)
+        p2, r2, mi2, w2 = sched2.predict(stored.get_one_full_sample(m))
+        out2 = stored.reconstruct_from_partition(p2, r2, m, mi2, w2)
+        assert rel_l2(torch.cat(list(p2)).numpy(), torch.cat(list(p)).numpy()) < 1e-6
+        assert rel_l2(out2.field.numpy(), out.field.numpy()) < 1e-6
+        assert rel_l2(out2.ref_field.numpy(), out.ref_field.numpy()) < 1e-6
+        assert np.allclose(out2.pos, ds._mesh(m)["mesh"].pos)
+        assert torch.allclose(torch.stack([t[0] for t in w2]), torch.stack([t[0] for t in w]), rtol=1e-4, atol=1e-6)
