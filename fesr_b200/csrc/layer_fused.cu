@@ -721,7 +721,7 @@ static int launch_fl(const int32_t* rowptr, const int32_t* src_sorted, const __h
 // or two / three; TEECNet rows (129 channels -> 144 slots = 9 parts, w + 1 <= 44 columns incl. the constant-1 column)
 // in three launches of three parts that accumulate through the fp32 scratch P.
 bool layer_fused_supported(const fesr_model_dims& d) {
-  if (d.kind == FESR_KERNELNN) return d.passes == 1 && d.kp == 48 && d.wp == FL_WP;
+  if (d.kind == FESR_KERNELNN) return d.passes == 1 && (d.kp == 48 || d.kp == 64) && d.wp == FL_WP;
   return d.kind == FESR_TEECNET && d.kp == 144 && d.wp == FL_WP && d.w <= 43;
 }
 int layer_fused_parts(const fesr_model_dims& d) { return d.kp / 16; }
@@ -759,6 +759,12 @@ int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, cons
     if ((rc = launch_fl<3, 4>(rowptr, src_sorted, gh, E, hh, n, 0, 0, tfh, bias_p, nullptr, P, nullptr, 43, fix_b, relu, s))) return rc;
     if ((rc = launch_fl<3, 4>(rowptr, src_sorted, gh, E, hh, n, 3, 0, tfh, bias_p, P, P, nullptr, 43, fix_b, relu, s))) return rc;
     return launch_fl<3, 4>(rowptr, src_sorted, gh, E, hh, n, 6, 1, tfh, bias_p, P, nullptr, ho, 43, fix_b, relu, s);
+  }
+  if (d.kp == 64) {
+    // w = 48 (the reference's default config width): 49 edge channels -> 64 slots = 4 parts, two launches of two
+    // parts (part p in TMEM lanes [64p, 64p + 48)), partial sums through P
+    if ((rc = launch_fl<2, 4>(rowptr, src_sorted, gh, E, hh, n, 0, 0, tfh, bias_p, nullptr, P, nullptr, 64, -1, relu, s))) return rc;
+    return launch_fl<2, 4>(rowptr, src_sorted, gh, E, hh, n, 2, 1, tfh, bias_p, P, nullptr, ho, 64, -1, relu, s);
   }
   if (mode == 0) mode = d.w <= 43 ? 3 : 2;
   if (mode == 3 && d.w <= 43) {
