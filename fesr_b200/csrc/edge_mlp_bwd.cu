@@ -38,12 +38,10 @@ edge_mlp_bwd_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g
   __shared__ __align__(16) float w0s[EB_W], b0s[EB_W];
   __shared__ __align__(16) float w1s[EB_W][EB_SW];          // [o][i], tf32 bit patterns
   __shared__ __align__(16) float da1s[4][32][EB_S1];        // [warp][edge][channel o] (un-permuted), tf32 bit patterns
-  __shared__ int offs[EB_W];                                // channel -> slot of the g / dg row (-1: padding)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   for (int i = tid; i < EB_W; i += blockDim.x) {
     w0s[i] = i < w ? w0g[i] : 0.f;
     b0s[i] = i < w ? b0g[i] : 0.f;
-    offs[i] = i < w ? (i / kt) * ktp + (i % kt) : -1;
   }
   for (int t = tid; t < EB_W * EB_W; t += blockDim.x) {
     const int o = t / EB_W, i = t % EB_W;

@@ -65,9 +65,7 @@ gemm_generic_kernel(GemmArgs a, int64_t kchunk, float* __restrict__ partial) {
               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
         }
       }
-      __syncthreads();
-      continue;
-    }
+    } else {
 #pragma unroll
     for (int kk = 0; kk < GG_BK; ++kk) {
       const float4 av = *reinterpret_cast<const float4*>(&As[kk][tm]);
@@ -78,6 +76,7 @@ gemm_generic_kernel(GemmArgs a, int64_t kchunk, float* __restrict__ partial) {
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
     }
     __syncthreads();
   }

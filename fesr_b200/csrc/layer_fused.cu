@@ -650,7 +650,6 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
 #pragma unroll
             for (int i = 0; i < GOPS; ++i) sidx[i] = __ldg(src_sorted + min(seg_lo + r0 + 16 * i, seg_hi - 1));
           }
-#pragma unroll
           const uint32_t gb = base + g0;
 #pragma unroll
           for (int i = 0; i < GOPS; ++i)
