@@ -277,7 +277,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     if ((rc = launch_colsum(w.dpre, n, d.wp, d.wp, 1, w.dbias, w.colsum_ws, s))) return rc;
     // dT' += Z_l^T dpre
     if (rnd) {
-      if ((rc = launch_wgrad_mma(d, fw.Z[l], w.dpre, n, w.dT, w.gemm_ws, s))) return rc;
+      if ((rc = launch_wgrad_mma(d, fw.Z[l], z_stash_half(precision), w.dpre, n, w.dT, w.gemm_ws, s))) return rc;
     } else {
       GEMM(fw.Z[l], 1, d.zk, w.dpre, d.wp, 1, w.dT, d.wp, 1, d.zk, d.wp, n, 1);
     }

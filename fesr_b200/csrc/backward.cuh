@@ -30,7 +30,7 @@ int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int3
 
 // bwd_gemm_mma.cu (tf32 arm): dT' += Z^T dpre (ws: wgrad_mma_ws_bytes) and dZ = dpre T'^T
 size_t wgrad_mma_ws_bytes(const fesr_model_dims& d);
-int launch_wgrad_mma(const fesr_model_dims& d, const float* Z, const float* dpre, int64_t n, float* dT, float* ws,
+int launch_wgrad_mma(const fesr_model_dims& d, const void* Z, int z_half, const float* dpre, int64_t n, float* dT, float* ws,
                      cudaStream_t s);
 int launch_dz_mma(const fesr_model_dims& d, const float* dpre, const float* tprime, int64_t n, float* dZ, cudaStream_t s);
 

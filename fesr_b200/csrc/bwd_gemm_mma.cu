@@ -5,6 +5,8 @@
 //   Z:  dZ[n, zk]    = dpre[n, wp] . T'^T[wp, zk]    thin K (= wp), bound by writing dZ.
 // Both are HBM-bound (24 flop/B): mma.sync.m16n8k8 tf32 leaves the tensor pipe far from
 // saturated, and unlike tcgen05 it reads MN-major operands without a transposing copy.
+#include <cuda_fp16.h>
+
 #include "backward.cuh"
 
 namespace fesr {
@@ -30,14 +32,16 @@ constexpr int WG_BM = 128;     // zk columns per CTA (8 warps x 16)
 constexpr int WG_BK = 32;      // nodes per stage
 constexpr int WG_THREADS = 256;
 
-template <int WP>
+// ZT = float, or __half for the fp16 Z stash of the tf32 arm (fp16 -> fp32 is exact and already tf32-representable)
+template <int WP, typename ZT>
 __global__ void __launch_bounds__(WG_THREADS)
-wgrad_mma_kernel(const float* __restrict__ Z, const float* __restrict__ dpre, int64_t n, int zk, int64_t nchunk,
+wgrad_mma_kernel(const ZT* __restrict__ Z, const float* __restrict__ dpre, int64_t n, int zk, int64_t nchunk,
                  float* __restrict__ partial) {
   constexpr int NT = WP / 8;
   constexpr int SZ = WG_BM + 8, SD = WP + 8;
+  constexpr int ZV = 16 / (int)sizeof(ZT);   // Z elements per 16-byte copy
   extern __shared__ __align__(16) float smem[];
-  float* Zs = smem;                          // [2][BK][SZ]
+  ZT* Zs = reinterpret_cast<ZT*>(smem);      // [2][BK][SZ]  (the float-sized region is kept for both element types)
   float* Ds = smem + 2 * WG_BK * SZ;         // [2][BK][SD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   const int m0 = blockIdx.x * WG_BM;
@@ -49,13 +53,13 @@ wgrad_mma_kernel(const float* __restrict__ Z, const float* __restrict__ dpre, in
     for (int r = 0; r < 4; ++r) acc[nt][r] = 0.f;
 
   auto load_stage = [&](int st, int64_t k0) {
-    float* zs = Zs + st * WG_BK * SZ;
+    ZT* zs = Zs + st * WG_BK * SZ;
     float* ds = Ds + st * WG_BK * SD;
-    for (int t = tid; t < WG_BK * (WG_BM / 4); t += WG_THREADS) {
-      const int r = t / (WG_BM / 4), c = (t % (WG_BM / 4)) * 4;
-      float* dst = zs + r * SZ + c;
+    for (int t = tid; t < WG_BK * (WG_BM / ZV); t += WG_THREADS) {
+      const int r = t / (WG_BM / ZV), c = (t % (WG_BM / ZV)) * ZV;
+      ZT* dst = zs + r * SZ + c;
       if (k0 + r < k_end && m0 + c < zk) bg_cp16(dst, Z + (k0 + r) * (int64_t)zk + m0 + c);
-      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
     }
     for (int t = tid; t < WG_BK * (WP / 4); t += WG_THREADS) {
       const int r = t / (WP / 4), c = (t % (WP / 4)) * 4;
@@ -74,16 +78,16 @@ wgrad_mma_kernel(const float* __restrict__ Z, const float* __restrict__ dpre, in
     if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
-    const float* zs = Zs + st * WG_BK * SZ + warp * 16;
+    const ZT* zs = Zs + st * WG_BK * SZ + warp * 16;
     const float* ds = Ds + st * WG_BK * SD;
 #pragma unroll
     for (int ks = 0; ks < WG_BK / 8; ++ks) {
       const int r0 = ks * 8 + tq, r1 = r0 + 4;
       uint32_t a[4];
-      a[0] = bg_tf32(zs[r0 * SZ + gq]);
-      a[1] = bg_tf32(zs[r0 * SZ + gq + 8]);
-      a[2] = bg_tf32(zs[r1 * SZ + gq]);
-      a[3] = bg_tf32(zs[r1 * SZ + gq + 8]);
+      a[0] = bg_tf32((float)zs[r0 * SZ + gq]);
+      a[1] = bg_tf32((float)zs[r0 * SZ + gq + 8]);
+      a[2] = bg_tf32((float)zs[r1 * SZ + gq]);
+      a[3] = bg_tf32((float)zs[r1 * SZ + gq + 8]);
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) bg_mma(acc[nt], a, bg_tf32(ds[r0 * SD + nt * 8 + gq]), bg_tf32(ds[r1 * SD + nt * 8 + gq]));
     }
@@ -120,7 +124,7 @@ int wgrad_mma_splits(int zk) {
 
 size_t wgrad_mma_ws_bytes(const fesr_model_dims& d) { return (size_t)wgrad_mma_splits(d.zk) * d.zk * d.wp * sizeof(float); }
 
-int launch_wgrad_mma(const fesr_model_dims& d, const float* Z, const float* dpre, int64_t n, float* dT, float* ws,
+int launch_wgrad_mma(const fesr_model_dims& d, const void* Z, int z_half, const float* dpre, int64_t n, float* dT, float* ws,
                      cudaStream_t s) {
   if (n == 0) return FESR_OK;
   const int ks = wgrad_mma_splits(d.zk);
@@ -132,10 +136,14 @@ int launch_wgrad_mma(const fesr_model_dims& d, const float* Z, const float* dpre
     constexpr size_t smem = (size_t)2 * WG_BK * (WG_BM + 8 + WPV + 8) * sizeof(float);                      \
     static bool attr = false;                                                                               \
     if (!attr) {                                                                                            \
-      FESR_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<WPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      FESR_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<WPV, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      FESR_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<WPV, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr = true;                                                                                          \
     }                                                                                                       \
-    wgrad_mma_kernel<WPV><<<grid, WG_THREADS, smem, s>>>(Z, dpre, n, d.zk, nchunk, ws);                     \
+    if (z_half)                                                                                             \
+      wgrad_mma_kernel<WPV, __half><<<grid, WG_THREADS, smem, s>>>(static_cast<const __half*>(Z), dpre, n, d.zk, nchunk, ws); \
+    else                                                                                                    \
+      wgrad_mma_kernel<WPV, float><<<grid, WG_THREADS, smem, s>>>(static_cast<const float*>(Z), dpre, n, d.zk, nchunk, ws);   \
   } while (0)
   switch (d.wp) {
     case 16: FESR_WG(16); break;

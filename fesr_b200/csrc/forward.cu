@@ -81,6 +81,14 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
       h_last = h_out;
       continue;
     }
+    if (keep_for_backward && z_stash_half(precision)) {
+      // training forward of the tf32 arm: fp16 Z stash (workspace.cuh), fp32 g / h as everywhere in this arm
+      if ((rc = launch_zbuild_mma(d, rowptr, src_sorted, ws.g, h_in, n, Z, 2, s))) return rc;
+      const int epi16 = d.kind == FESR_TEECNET ? EPI_BIAS_CONST1 : EPI_BIAS_RELU;
+      if ((rc = launch_node_gemm_f16(d, ws.prep.tprime_t_h, ws.prep.bias_p, epi16, Z, n, h_out, s, 1))) return rc;
+      h_last = h_out;
+      continue;
+    }
     const int zmode = precision == FESR_PREC_FP32 ? 0 : (precision == FESR_PREC_F16 ? 2 : 1);
     if (zmode == 2)
       rc = launch_zbuild_f16(d, rowptr, src_sorted, ws.g, h_in, n, Z, s);
