@@ -22,4 +22,9 @@ Parity pinning (see tests/golden/README.md and DESIGN.md section 3):
     vtkStaticPointLocator) that are neither vendored nor installable here and
     ships no golden outputs; the oracle defines them (exact-median kd bisection;
     mean over coincident points keyed by global node id).
+  * the two steps either side of the path are PARITY UNPINNED for the same reason: the
+    Gaussian-kernel point interpolation (graph.interp_gaussian: vtkPointInterpolator + vtkGaussianKernel) and the
+    wall-shear-stress chain (graph.wall_shear_stress: vtkGradientFilter, vtkDataSetSurfaceFilter,
+    vtkPolyDataNormals) are restated from the published algorithms of those filters; where the restatement
+    deliberately differs (outward face orientation, no feature-edge splitting) the docstring says so.
 """
