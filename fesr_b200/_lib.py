@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libfesr.so")
 KERNELNN, TEECNET = 0, 1
 PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16 = 0, 1, 2, 3
 ONE_REGION, ALL_INTERSECTING = 0, 1
-FWD_KEEP, FWD_WEIGHTS_PREPARED, FWD_EDGE_ONLY, FWD_EDGE_DONE = 1, 2, 4, 8
+FWD_KEEP, FWD_WEIGHTS_PREPARED, FWD_EDGE_ONLY, FWD_EDGE_DONE, FWD_KEEP_Z16 = 1, 2, 4, 8, 16
 REDUCE_WS_BYTES = 8192
 PRECISIONS = {"fp32": PREC_FP32, "tf32": PREC_TF32, "f16": PREC_F16, "fp16": PREC_F16}
 

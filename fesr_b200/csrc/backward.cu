@@ -233,7 +233,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   FESR_CHECK_ARG(E == 0 || (src_sorted && rowptr_t && src_t && rev_to_fwd && edge_attr), "NULL edge arrays");
   const fesr_model_dims& d = *dims;
   const fesr_params& p = *params;
-  ForwardWs fw = carve_forward(const_cast<void*>(forward_workspace), d, n, E, 1);
+  ForwardWs fw = carve_forward(const_cast<void*>(forward_workspace), d, n, E, 1, z_stash_half(precision));
   BackwardWs w = carve_backward(workspace, d, n, E);
   if (!workspace || workspace_bytes < w.bytes) {
     set_error("backward workspace too small: need %zu bytes, got %zu", w.bytes, workspace_bytes);

@@ -8,7 +8,7 @@ using namespace fesr;
 
 namespace fesr {
 
-ForwardWs carve_forward(void* base, const fesr_model_dims& d, int64_t n, int64_t E, int keep) {
+ForwardWs carve_forward(void* base, const fesr_model_dims& d, int64_t n, int64_t E, int keep, int z_half) {
   Carver c(base);
   ForwardWs ws;
   ws.prep = carve_prepared(c, d);
@@ -19,7 +19,8 @@ ForwardWs carve_forward(void* base, const fesr_model_dims& d, int64_t n, int64_t
   ws.n_z = nz;
   const size_t nn = (size_t)(n > 0 ? n : 1);
   for (int i = 0; i < nh; ++i) ws.h[i] = c.take<float>(nn * d.wp);
-  for (int i = 0; i < nz; ++i) ws.Z[i] = c.take<float>(nn * d.zk);
+  for (int i = 0; i < nz; ++i)
+    ws.Z[i] = (keep && z_half) ? reinterpret_cast<float*>(c.take<uint16_t>(nn * d.zk)) : c.take<float>(nn * d.zk);
   ws.bytes = c.used();
   return ws;
 }
@@ -30,7 +31,7 @@ extern "C" {
 
 size_t fesr_forward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E, int keep_for_backward) {
   if (!dims || n < 0 || E < 0 || dims->layers > FESR_MAX_LAYERS) return 0;
-  return carve_forward(nullptr, *dims, n, E, keep_for_backward & FESR_FWD_KEEP).bytes;
+  return carve_forward(nullptr, *dims, n, E, keep_for_backward & FESR_FWD_KEEP, (keep_for_backward & FESR_FWD_KEEP_Z16) != 0).bytes;
 }
 
 int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, const float* x,
@@ -48,7 +49,9 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   FESR_CHECK_ARG(!(edge_only && edge_done), "FESR_FWD_EDGE_ONLY and FESR_FWD_EDGE_DONE exclude each other");
   FESR_CHECK_ARG((edge_only || (x && y)) && rowptr && (E == 0 || (src_sorted && edge_attr)), "NULL pointer");
   const fesr_model_dims& d = *dims;
-  ForwardWs ws = carve_forward(workspace, d, n, E, keep_for_backward);
+  // (the layout of a kept workspace follows the precision, not the caller's size-query flag: fesr_nnconv_backward
+  // carves it the same way)
+  ForwardWs ws = carve_forward(workspace, d, n, E, keep_for_backward, keep_for_backward && z_stash_half(precision));
   if (!workspace || workspace_bytes < ws.bytes) {
     set_error("forward workspace too small: need %zu bytes, got %zu", ws.bytes, workspace_bytes);
     return FESR_EWORKSPACE;

@@ -25,6 +25,7 @@ inline bool z_stash_half(int precision) {
   return on && precision == FESR_PREC_TF32;
 }
 
-ForwardWs carve_forward(void* base, const fesr_model_dims& d, int64_t n, int64_t E, int keep);
+// z_half: the kept Z stash holds fp16 rows (z_stash_half) -- half the bytes per layer
+ForwardWs carve_forward(void* base, const fesr_model_dims& d, int64_t n, int64_t E, int keep, int z_half = 0);
 
 }  // namespace fesr

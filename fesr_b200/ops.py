@@ -5,6 +5,7 @@ Every function requires CUDA tensors on an sm_100 device and raises otherwise.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -137,7 +138,10 @@ def nnconv_forward(dims: ModelDims, tensors: dict, x: torch.Tensor, csr: Csr, ed
     p, keep = make_params(Params, tensors)
     y = torch.empty(n, dims.out_ch, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        nbytes = lib.fesr_forward_workspace_bytes(C.byref(dims), n, E, int(keep_for_backward))
+        qflags = int(keep_for_backward)
+        if keep_for_backward and precision == _lib.PREC_TF32 and os.environ.get("FESR_Z16", "1") != "0":
+            qflags |= _lib.FWD_KEEP_Z16          # the tf32 arm keeps its Z stash as fp16: half the bytes per layer
+        nbytes = lib.fesr_forward_workspace_bytes(C.byref(dims), n, E, qflags)
         flags = int(keep_for_backward)
         if keep_for_backward:
             ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)

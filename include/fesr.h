@@ -152,6 +152,10 @@ int fesr_csr_build(const int64_t* edge_index, int64_t E, int64_t n,
  * workspace, dims, parameters, graph, edge_attr and precision runs the rest (fc1, the layers, fc2). */
 #define FESR_FWD_EDGE_ONLY 4
 #define FESR_FWD_EDGE_DONE 8
+/* Size query only (fesr_forward_workspace_bytes): with FESR_FWD_KEEP and the FESR_PREC_TF32 arm the kept Z stash is
+ * fp16 (half the bytes per layer); a caller that will run that arm may pass FESR_FWD_KEEP | FESR_FWD_KEEP_Z16 to get
+ * the smaller size.  Without it the query returns the fp32-stash size, which is always enough. */
+#define FESR_FWD_KEEP_Z16 16
 size_t fesr_forward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E, int keep_for_backward);
 int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params,
                         const float* x, const int32_t* rowptr, const int32_t* src_sorted,
