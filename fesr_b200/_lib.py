@@ -55,6 +55,7 @@ SIGNATURES = {
     "fesr_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "fesr_csr_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fesr_forward_workspace_bytes": (_sz, [C.POINTER(ModelDims), _i64, _i64, C.c_int]),
+    "fesr_forward_overflow_offset": (_sz, [C.POINTER(ModelDims)]),
     "fesr_nnconv_forward": (C.c_int, [C.POINTER(ModelDims), C.POINTER(Params), _vp, _vp, _vp, _vp, _vp, _i64, _i64,
                                       C.c_int, C.c_int, _vp, _vp, _sz, _vp]),
     "fesr_backward_workspace_bytes": (_sz, [C.POINTER(ModelDims), _i64, _i64]),
@@ -82,6 +83,13 @@ SIGNATURES = {
     "fesr_boundary_faces_workspace_bytes": (_sz, [_i64]),
     "fesr_boundary_faces": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp]),
     "fesr_wall_shear_stress": (C.c_int, [_vp, _vp, _vp, _i64, _f, _vp, _vp, _vp]),
+    "fesr_comm_unique_id": (C.c_int, [_vp]),
+    "fesr_comm_init": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "fesr_comm_destroy": (C.c_int, []),
+    "fesr_comm_rank": (C.c_int, []),
+    "fesr_comm_world": (C.c_int, []),
+    "fesr_allgatherv_pred": (C.c_int, [_vp, _i64, _vp]),
+    "fesr_allreduce_grads": (C.c_int, [_vp, _i64, _vp]),
     "fesr_route": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
 }
 

@@ -60,7 +60,11 @@ def build(verbose: bool = False) -> str:
             if did:
                 print(f"[fesr build] compiled {os.path.basename(obj)}")
     if rebuilt or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-o", LIB, *[r[0] for r in results], "-gencode", "arch=compute_100a,code=sm_100a"]
+        # -cudart shared: the runtime is the libcudart.so.12 the host process already has (PyTorch loads one), not a
+        # private static copy inside libfesr.so; -ldl: comm.cu resolves NCCL with dlopen
+        cmd = [NVCC, "-shared", "-cudart", "shared", "-o", LIB, *[r[0] for r in results],
+               "-gencode", "arch=compute_100a,code=sm_100a", "-ldl",
+               "-Xlinker", "-rpath", "-Xlinker", "/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -14,6 +14,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local int* g_cur_ovf = nullptr;
+int* cur_ovf() { return g_cur_ovf; }
+void set_cur_ovf(int* flag) { g_cur_ovf = flag; }
+
 static long long g_launches = 0;
 void count_launch() { ++g_launches; }
 

@@ -29,6 +29,31 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 void count_launch();
+
+// fp16 range guard of the f16 arms.  Every kernel that packs fp32 results into fp16 notes the magnitudes it packs
+// and, if any exceeds the largest finite fp16 (65504) or is not a number, raises the forward's overflow flag (one
+// int32 in the workspace, zeroed at the start of the pass).  fc_out then poisons the output with NaN and the
+// host wrapper raises: a clipped intermediate can never come back as a plausible field.
+// The flag of the pass being issued is a host-side thread-local (cur_ovf) so that launch wrappers shared with the
+// backward (where it is NULL: no check) need no extra parameter.
+int* cur_ovf();
+void set_cur_ovf(int* flag);
+struct OvfScope {
+  explicit OvfScope(int* flag) { set_cur_ovf(flag); }
+  ~OvfScope() { set_cur_ovf(nullptr); }
+};
+#ifdef __CUDACC__
+struct F16Guard {
+  unsigned m;
+  __device__ __forceinline__ F16Guard() : m(0u) {}
+  __device__ __forceinline__ void note(float a, float b) {
+    m = max(m, max(__float_as_uint(a) & 0x7fffffffu, __float_as_uint(b) & 0x7fffffffu));
+  }
+  __device__ __forceinline__ void flush(int* flag) const {
+    if (flag != nullptr && m > 0x477fe000u) *flag = 1;      // 0x477fe000 = 65504.0f; inf / NaN bit patterns are larger
+  }
+};
+#endif
 #define FESR_LAUNCH_CHECK()          \
   do {                               \
     ::fesr::count_launch();          \
@@ -82,6 +107,7 @@ struct Prepared {
   float* bias_p;     // [wp]
   float* fc1_wp;     // [in_ch, wp] transposed + padded
   float* fc1_bp;     // [wp] (TEECNet: constant-1 column set here)
+  int* ovf;          // [1] fp16 overflow flag of the pass (F16Guard)
 };
 
 }  // namespace fesr

@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(128)
 edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
                         const float* __restrict__ b1g, int w, int leaky, int kt, int ktp, int k1,
                         const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int64_t E,
-                        void* __restrict__ gv) {
+                        void* __restrict__ gv, int* ovf) {
+  F16Guard guard;
   constexpr int KS = WPAD / 8, KP = NTO * 8, SB = KP + 8;
   constexpr int SST = KP + 4;                                          // stage row stride (floats)
   __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1p[KP];
@@ -143,6 +144,10 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
         if (e_base + r < E) {
           const float4 lo = *reinterpret_cast<const float4*>(&wst[r][8 * c8]);
           const float4 hi = *reinterpret_cast<const float4*>(&wst[r][8 * c8 + 4]);
+          guard.note(lo.x, lo.y);
+          guard.note(lo.z, lo.w);
+          guard.note(hi.x, hi.y);
+          guard.note(hi.z, hi.w);
           __half2 p0 = __floats2half2_rn(lo.x, lo.y), p1 = __floats2half2_rn(lo.z, lo.w);
           __half2 p2 = __floats2half2_rn(hi.x, hi.y), p3 = __floats2half2_rn(hi.z, hi.w);
           uint4 pk;
@@ -165,6 +170,7 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
     }
     __syncwarp();
   }
+  if (OMODE >= 2) guard.flush(ovf);
 }
 
 
@@ -183,13 +189,18 @@ __device__ __forceinline__ uint32_t em_pack(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ uint32_t em_pack(float lo, float hi, F16Guard& guard) {     // range-checked (common.cuh)
+  guard.note(lo, hi);
+  return em_pack(lo, hi);
+}
 
 template <int WPAD, int NTO, int OMODE>     // ReLU only (KernelNN); LeakyReLU shapes use the tf32 kernel above
 __global__ void __launch_bounds__(128, 6)
 edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
                         const float* __restrict__ b1g, int w, int kt, int ktp, int k1,
                         const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int E,
-                        __half* __restrict__ gh) {
+                        __half* __restrict__ gh, int* ovf) {
+  F16Guard guard;
   constexpr int KS = WPAD / 16, KP = NTO * 8;
   constexpr int WST = WPAD + 8, SST = KP + 8;                          // row strides in halfs (+16 B: conflict-free)
   __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1p[KP];
@@ -257,8 +268,8 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const float d = dr[mt][hh];
-          a[mt][hh] = em_pack(fmaxf(fmaf(d, wl.x, bl.x), 0.f), fmaxf(fmaf(d, wl.y, bl.y), 0.f));
-          a[mt][2 + hh] = em_pack(fmaxf(fmaf(d, wh.x, bh.x), 0.f), fmaxf(fmaf(d, wh.y, bh.y), 0.f));
+          a[mt][hh] = em_pack(fmaxf(fmaf(d, wl.x, bl.x), 0.f), fmaxf(fmaf(d, wl.y, bl.y), 0.f), guard);
+          a[mt][2 + hh] = em_pack(fmaxf(fmaf(d, wh.x, bh.x), 0.f), fmaxf(fmaf(d, wh.y, bh.y), 0.f), guard);
         }
 #pragma unroll
       for (int np = 0; np < NTO / 2; ++np) {
@@ -283,8 +294,8 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
         for (int q = 0; q < 2; ++q) {
           const int nt = 2 * np + q;
           const float2 bz = *reinterpret_cast<const float2*>(&b1p[nt * 8 + 2 * tq]);
-          h[q][0] = em_pack(fmaxf(acc[mt][nt][0] + bz.x, 0.f), fmaxf(acc[mt][nt][1] + bz.y, 0.f));
-          h[q][1] = em_pack(fmaxf(acc[mt][nt][2] + bz.x, 0.f), fmaxf(acc[mt][nt][3] + bz.y, 0.f));
+          h[q][0] = em_pack(fmaxf(acc[mt][nt][0] + bz.x, 0.f), fmaxf(acc[mt][nt][1] + bz.y, 0.f), guard);
+          h[q][1] = em_pack(fmaxf(acc[mt][nt][2] + bz.x, 0.f), fmaxf(acc[mt][nt][3] + bz.y, 0.f), guard);
         }
         asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(s_addr + (uint32_t)((mt * 16 * SST + np * 16) * 2)),
                      "r"(h[0][0]), "r"(h[0][1]), "r"(h[1][0]), "r"(h[1][1])
@@ -299,6 +310,7 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
     }
     __syncwarp();
   }
+  guard.flush(ovf);
 }
 
 // TEECNet's edge MLP (DenseNet([1, 32, 64, 128, w*w], LeakyReLU), reference models/model.py:403 + :311-315): the
@@ -313,8 +325,8 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
 // 1.3e-2 rel-L2, rounding W1 alone by 1.27e-2; the split form by 4e-5 -- measured on the CPU restatement).
 // OMODE 1: fp32 rows rounded to tf32 [E][144]; OMODE 2: fp16 rows [E][144]; OMODE 3: fp16 planar [9][E][16] (the
 // fused layer kernel's slot groups).
-__device__ __forceinline__ void em_split(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  hi = em_pack(v0, v1);
+__device__ __forceinline__ void em_split(float v0, float v1, uint32_t& hi, uint32_t& lo, F16Guard& guard) {
+  hi = em_pack(v0, v1, guard);
   const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   lo = em_pack(v0 - f.x, v1 - f.y);
 }
@@ -329,7 +341,8 @@ __global__ void __launch_bounds__(128)
 edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
                         const float* __restrict__ b1g, const float* __restrict__ w2g, const float* __restrict__ b2g,
                         int kt, int ktp, int k1, const float* __restrict__ edge_attr,
-                        const int32_t* __restrict__ perm, int E, void* __restrict__ gv) {
+                        const int32_t* __restrict__ perm, int E, void* __restrict__ gv, int* ovf) {
+  F16Guard guard;
   constexpr int H0 = 32, H1 = 64, KP = 144;
   constexpr int CW = 48, NCH = KP / CW, NTC = CW / 8;                  // slots per chunk, chunks, n-tiles per chunk
   constexpr int KS0 = H0 / 16, KS1 = H1 / 16, NT1 = H1 / 8;
@@ -412,8 +425,8 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const float d = dr[mt][hh];
-          em_split(lrelu(fmaf(d, wl.x, bl.x)), lrelu(fmaf(d, wl.y, bl.y)), ah[mt][hh], al[mt][hh]);
-          em_split(lrelu(fmaf(d, wh.x, bh.x)), lrelu(fmaf(d, wh.y, bh.y)), ah[mt][2 + hh], al[mt][2 + hh]);
+          em_split(lrelu(fmaf(d, wl.x, bl.x)), lrelu(fmaf(d, wl.y, bl.y)), ah[mt][hh], al[mt][hh], guard);
+          em_split(lrelu(fmaf(d, wh.x, bh.x)), lrelu(fmaf(d, wh.y, bh.y)), ah[mt][2 + hh], al[mt][2 + hh], guard);
         }
 #pragma unroll
       for (int np = 0; np < NT1 / 2; ++np) {
@@ -441,10 +454,10 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
       const float2 bh = *reinterpret_cast<const float2*>(&b1[ks * 16 + 8 + 2 * tq]);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        em_split(lrelu(acc1[mt][2 * ks][0] + bl.x), lrelu(acc1[mt][2 * ks][1] + bl.y), a1h[mt][ks][0], a1l[mt][ks][0]);
-        em_split(lrelu(acc1[mt][2 * ks][2] + bl.x), lrelu(acc1[mt][2 * ks][3] + bl.y), a1h[mt][ks][1], a1l[mt][ks][1]);
-        em_split(lrelu(acc1[mt][2 * ks + 1][0] + bh.x), lrelu(acc1[mt][2 * ks + 1][1] + bh.y), a1h[mt][ks][2], a1l[mt][ks][2]);
-        em_split(lrelu(acc1[mt][2 * ks + 1][2] + bh.x), lrelu(acc1[mt][2 * ks + 1][3] + bh.y), a1h[mt][ks][3], a1l[mt][ks][3]);
+        em_split(lrelu(acc1[mt][2 * ks][0] + bl.x), lrelu(acc1[mt][2 * ks][1] + bl.y), a1h[mt][ks][0], a1l[mt][ks][0], guard);
+        em_split(lrelu(acc1[mt][2 * ks][2] + bl.x), lrelu(acc1[mt][2 * ks][3] + bl.y), a1h[mt][ks][1], a1l[mt][ks][1], guard);
+        em_split(lrelu(acc1[mt][2 * ks + 1][0] + bh.x), lrelu(acc1[mt][2 * ks + 1][1] + bh.y), a1h[mt][ks][2], a1l[mt][ks][2], guard);
+        em_split(lrelu(acc1[mt][2 * ks + 1][2] + bh.x), lrelu(acc1[mt][2 * ks + 1][3] + bh.y), a1h[mt][ks][3], a1l[mt][ks][3], guard);
       }
     }
     // ---- layer 2 in chunks of CW output slots
@@ -486,8 +499,8 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
             for (int q = 0; q < 2; ++q) {
               const int nt = 2 * np + q;
               const float2 bz = *reinterpret_cast<const float2*>(&b2p[ch * CW + nt * 8 + 2 * tq]);
-              h[q][0] = em_pack(lrelu(acc[mt][nt][0] + bz.x), lrelu(acc[mt][nt][1] + bz.y));
-              h[q][1] = em_pack(lrelu(acc[mt][nt][2] + bz.x), lrelu(acc[mt][nt][3] + bz.y));
+              h[q][0] = em_pack(lrelu(acc[mt][nt][0] + bz.x), lrelu(acc[mt][nt][1] + bz.y), guard);
+              h[q][1] = em_pack(lrelu(acc[mt][nt][2] + bz.x), lrelu(acc[mt][nt][3] + bz.y), guard);
             }
             asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(s_addr + (uint32_t)(mt * 16 * SST + np * 32)),
                          "r"(h[0][0]), "r"(h[0][1]), "r"(h[1][0]), "r"(h[1][1])
@@ -529,6 +542,7 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
       __syncwarp();
     }
   }
+  guard.flush(ovf);
 }
 
 // returns 1 when the shape is not covered here (the caller then uses the generic CUDA-core kernel)
@@ -558,13 +572,13 @@ int launch_edge_hidden3_mma(const fesr_model_dims& d, const fesr_params& p, cons
   ProfScope prof(PROF_EDGE_HIDDEN, s);
   if (omode == 3)
     edge_hidden3_mma_kernel<3><<<grid, 128, smem16, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
-                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g);
+                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g, cur_ovf());
   else if (omode == 2)
     edge_hidden3_mma_kernel<2><<<grid, 128, smem16, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
-                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g);
+                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g, cur_ovf());
   else
     edge_hidden3_mma_kernel<1><<<grid, 128, smem32, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
-                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g);
+                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g, cur_ovf());
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
@@ -578,7 +592,7 @@ static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const flo
   constexpr size_t stage_bytes = (size_t)4 * 32 * (NTO * 8 + 4) * sizeof(float);
 #define FESR_EH(TERMS, OMODE)                                                                                   \
   edge_hidden2_mma_kernel<WPAD, NTO, TERMS, OMODE><<<grid, 128, stage_bytes, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], \
-                                                                        d.w, d.leaky, d.kt, d.ktp, d.k1, edge_attr, perm, E, g)
+                                                                        d.w, d.leaky, d.kt, d.ktp, d.k1, edge_attr, perm, E, g, cur_ovf())
   static bool attr_set = false;
   if (!attr_set) {   // static + dynamic shared memory exceeds 48 KB for the widest rows
     FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_mma_kernel<WPAD, NTO, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
@@ -600,10 +614,10 @@ static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const flo
   else if (omode == 1) FESR_EH(1, 1);
   else if (!tf32_only && !d.leaky && omode == 2)
     edge_hidden2_f16_kernel<WPAD, NTO, 2><<<grid16, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
-                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g));
+                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g), cur_ovf());
   else if (!tf32_only && !d.leaky)
     edge_hidden2_f16_kernel<WPAD, NTO, 3><<<grid16, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
-                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g));
+                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g), cur_ovf());
   else if (omode == 2) FESR_EH(1, 2);
   else FESR_EH(1, 3);
 #undef FESR_EH

@@ -34,6 +34,12 @@ size_t fesr_forward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int6
   return carve_forward(nullptr, *dims, n, E, keep_for_backward & FESR_FWD_KEEP, (keep_for_backward & FESR_FWD_KEEP_Z16) != 0).bytes;
 }
 
+size_t fesr_forward_overflow_offset(const fesr_model_dims* dims) {
+  if (!dims) return 0;
+  ForwardWs ws = carve_forward(nullptr, *dims, 1, 1, 0, 0);
+  return (size_t)reinterpret_cast<uintptr_t>(ws.prep.ovf);      // carved from a NULL base: the address IS the offset
+}
+
 int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, const float* x,
                         const int32_t* rowptr, const int32_t* src_sorted, const int32_t* perm,
                         const float* edge_attr, int64_t n, int64_t E, int precision, int fwd_flags,
@@ -58,6 +64,10 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   }
   cudaStream_t s = as_stream(stream_);
   int rc;
+  // fp16 range guard (common.cuh F16Guard): the flag starts at 0 with the pass (its edge phase when it is issued in
+  // two calls), every kernel that packs fp16 raises it on overflow, fc_out turns a raised flag into a NaN output
+  if (!edge_done) FESR_CUDA(cudaMemsetAsync(ws.prep.ovf, 0, sizeof(int), s));
+  OvfScope ovf_scope(ws.prep.ovf);
   if (!(fwd_flags & FESR_FWD_WEIGHTS_PREPARED) && !edge_done && (rc = launch_prepare_weights(d, *params, ws.prep, s))) return rc;
   static const bool ffma_only = getenv("FESR_ZBUILD_FFMA") != nullptr;   // A/B switch for profiling
   // reduced-precision arms: g and h are rounded to tf32 by their producers, so the gather kernel

@@ -115,7 +115,8 @@ template <int WP, bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const float* __restrict__ bias_p, int64_t n, int zk, int w, int epi, int round_out,
-                      float* __restrict__ h_out) {
+                      float* __restrict__ h_out, int* ovf) {
+  F16Guard guard;
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
   constexpr uint32_t B_BYTES = WP * TC_BK * 4;      // wp * 128 B
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
@@ -246,6 +247,7 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               x0 = fmaxf(x0, 0.f);
               x1 = fmaxf(x1, 0.f);
             }
+            guard.note(x0, x1);
             asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(pk[j / 2]) : "f"(x1), "f"(x0));
           }
           __half* hh = reinterpret_cast<__half*>(h_out) + row * WP + c0;
@@ -280,6 +282,7 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
+    guard.flush(ovf);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -341,7 +344,7 @@ static int launch_tc(const fesr_model_dims& d, const void* B_kmajor, const float
   const int64_t n_tiles = ceil_div(n, TC_BM);
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   ProfScope prof(PROF_NODE_GEMM, s);
-  node_gemm_tf32_kernel<WP, HALF><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, bias_p, n, d.zk, d.w, epi, round_out, h_out);
+  node_gemm_tf32_kernel<WP, HALF><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, bias_p, n, d.zk, d.w, epi, round_out, h_out, cur_ovf());
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }

@@ -199,7 +199,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
                        const __half* __restrict__ g3, int64_t E, const __half* __restrict__ h_in, int64_t n,
                        int part0, int has_root, const __half* __restrict__ tf, const float* __restrict__ bias_p,
                        const float* p_in, float* p_out, __half* __restrict__ h_out,
-                       int rs, int fix_b, int relu) {
+                       int rs, int fix_b, int relu, int* ovf) {
   constexpr int FL_BW = 2 * FL_NODES;                  // consumer warps: two groups of 8
   constexpr int FL_NPROD = 3;                          // producer warps
   constexpr int FL_THREADS = (FL_BW + FL_NPROD + 1 + 4) * 32;   // + the MMA issuer warp + 4 epilogue warps
@@ -528,6 +528,12 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
               v0 = fmaxf(v0, 0.f);
               v1 = fmaxf(v1, 0.f);
             }
+            {   // fp16 range guard (common.cuh): an inf / NaN out of the fp16-accumulated Z tile reaches these sums too;
+                // raised on the spot -- no loop-carried register in this role's 80-register budget
+              F16Guard guard;
+              guard.note(v0, v1);
+              guard.flush(ovf);
+            }
             *reinterpret_cast<uint32_t*>(h_out + row * FL_WP + c0) = fl_h2_sat(v0, v1);
           }
         }
@@ -690,6 +696,7 @@ template <int PPL, int NBUF>
 static int launch_fl(const int32_t* rowptr, const int32_t* src_sorted, const __half* g3, int64_t E, const __half* h_in,
                      int64_t n, int part0, int has_root, const __half* tf, const float* bias_p, const float* p_in,
                      float* p_out, __half* h_out, int rs, int fix_b, int relu, cudaStream_t s) {
+  int* ovf = cur_ovf();
   size_t smem = fl_smem_bytes<PPL, NBUF>();
   if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: the kernel owns all 512 TMEM columns
   static bool attr_set = false;
@@ -711,7 +718,7 @@ static int launch_fl(const int32_t* rowptr, const int32_t* src_sorted, const __h
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   FESR_CUDA(cudaLaunchKernelEx(&cfg, layer_fused_f16_kernel<PPL, NBUF>, rowptr, src_sorted, g3, E, h_in, n, part0, has_root, tf, bias_p,
-                               p_in, p_out, h_out, rs, fix_b, relu));
+                               p_in, p_out, h_out, rs, fix_b, relu, ovf));
   count_launch();
   return FESR_OK;
 }

@@ -31,6 +31,7 @@ Prepared carve_prepared(Carver& c, const fesr_model_dims& d) {
   w.bias_p = c.take<float>(d.wp);
   w.fc1_wp = c.take<float>((size_t)d.in_ch * d.wp);
   w.fc1_bp = c.take<float>(d.wp);
+  w.ovf = c.take<int>(1);
   return w;
 }
 
@@ -147,7 +148,7 @@ __device__ __forceinline__ float act_fn(float v, int leaky) {
 // Persistent CTAs; all hidden-layer weights stay in shared memory (transposed [in][outP]).
 __global__ void __launch_bounds__(EH_THREADS, 2)
 edge_hidden_kernel(EdgeHiddenArgs a, const float* __restrict__ edge_attr, const int32_t* __restrict__ perm,
-                   int64_t E, int round_tf32, float* __restrict__ g) {
+                   int64_t E, int round_tf32, float* __restrict__ g, int* ovf) {
   extern __shared__ __align__(16) float smem[];
   // layout: w0[D0] b0[D0] | for l>=1: WT_l[Din][DoutP], b_l[DoutP] | bufA[MAXD][TE] bufB[MAXD][TE] | chan_of[kp]
   float* w0 = smem;
@@ -166,6 +167,7 @@ edge_hidden_kernel(EdgeHiddenArgs a, const float* __restrict__ edge_attr, const 
   float* bufB = bufA + EH_MAXD * EH_TE;
   int* chan_of = reinterpret_cast<int*>(bufB + EH_MAXD * EH_TE);
   const int tid = threadIdx.x;
+  F16Guard guard;
 
   for (int i = tid; i < a.dims[0]; i += EH_THREADS) {
     w0[i] = a.w[0][i];
@@ -245,11 +247,16 @@ edge_hidden_kernel(EdgeHiddenArgs a, const float* __restrict__ edge_attr, const 
       if (ge >= E) break;
       const int k = chan_of[off];
       const float v = (k < 0) ? 0.f : (k == K ? 1.f : in[k * EH_TE + e]);
-      if (round_tf32 == 2) reinterpret_cast<__half*>(g)[ge * a.kp + off] = __float2half_rn(v);
-      else g[ge * a.kp + off] = round_tf32 ? tf32_rna(v) : v;
+      if (round_tf32 == 2) {
+        guard.note(v, 0.f);
+        reinterpret_cast<__half*>(g)[ge * a.kp + off] = __float2half_rn(v);
+      } else {
+        g[ge * a.kp + off] = round_tf32 ? tf32_rna(v) : v;
+      }
     }
     __syncthreads();
   }
+  guard.flush(ovf);
 }
 
 // Two-hidden-layer variant (KernelNN: Linear(1,w) act Linear(w,w) act): one thread per edge,
@@ -389,7 +396,7 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
   const int64_t n_tiles = ceil_div(E, EH_TE);
   const int grid = (int)(n_tiles < 2 * num_sms() ? n_tiles : 2 * num_sms());
   ProfScope prof(PROF_EDGE_HIDDEN, s);
-  edge_hidden_kernel<<<grid, EH_THREADS, smem, s>>>(a, edge_attr, perm, E, round_tf32, g);
+  edge_hidden_kernel<<<grid, EH_THREADS, smem, s>>>(a, edge_attr, perm, E, round_tf32, g, cur_ovf());
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
@@ -397,7 +404,7 @@ int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const flo
 // ----------------------------------------------------------------------------- fc1 / fc2
 // h0[i, :] = x[i, :] W1^T + b1 (models/model.py:557 / :279), padded columns 0 (TEECNet: h[w] = 1)
 __global__ void fc_in_kernel(const float* __restrict__ x, const float* __restrict__ wp_, const float* __restrict__ bp,
-                             int in_ch, int wp, int64_t n, int round_tf32, float* __restrict__ h) {
+                             int in_ch, int wp, int64_t n, int round_tf32, float* __restrict__ h, int* ovf) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // one float4 of h per thread
   const int q = wp / 4;
   if (idx >= n * q) return;
@@ -413,6 +420,10 @@ __global__ void fc_in_kernel(const float* __restrict__ x, const float* __restric
     acc.w = fmaf(xv, wv.w, acc.w);
   }
   if (round_tf32 == 2) {
+    F16Guard guard;
+    guard.note(acc.x, acc.y);
+    guard.note(acc.z, acc.w);
+    guard.flush(ovf);
     __half2 lo = __floats2half2_rn(acc.x, acc.y), hi = __floats2half2_rn(acc.z, acc.w);
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -433,7 +444,7 @@ __global__ void fc_in_kernel(const float* __restrict__ x, const float* __restric
 // chain per output is the one of the generic kernel above
 __global__ void __launch_bounds__(256)
 fc_in_c4h_kernel(const float* __restrict__ x, const float* __restrict__ wp_, const float* __restrict__ bp, int wp, int64_t n,
-                 __half* __restrict__ h) {
+                 __half* __restrict__ h, int* ovf) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;   // eight halfs of h per thread
   const int q = wp / 8;
   if (idx >= n * q) return;
@@ -456,6 +467,10 @@ fc_in_c4h_kernel(const float* __restrict__ x, const float* __restrict__ wp_, con
     acc[4] = fmaf(xs[c], w1.x, acc[4]); acc[5] = fmaf(xs[c], w1.y, acc[5]);
     acc[6] = fmaf(xs[c], w1.z, acc[6]); acc[7] = fmaf(xs[c], w1.w, acc[7]);
   }
+  F16Guard guard;
+#pragma unroll
+  for (int t = 0; t < 8; t += 2) guard.note(acc[t], acc[t + 1]);
+  guard.flush(ovf);
   __half2 p0 = __floats2half2_rn(acc[0], acc[1]), p1 = __floats2half2_rn(acc[2], acc[3]);
   __half2 p2 = __floats2half2_rn(acc[4], acc[5]), p3 = __floats2half2_rn(acc[6], acc[7]);
   uint4 pk;
@@ -472,20 +487,25 @@ int launch_fc_in(const fesr_model_dims& d, const Prepared& w, const float* x, in
   const int64_t total = n * (d.wp / 4);
   ProfScope prof(PROF_FC_IN, s);
   if (round_tf32 == 2 && d.in_ch == 4 && d.wp % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-    fc_in_c4h_kernel<<<(unsigned)ceil_div(n * (d.wp / 8), 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.wp, n, reinterpret_cast<__half*>(h));
+    fc_in_c4h_kernel<<<(unsigned)ceil_div(n * (d.wp / 8), 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.wp, n, reinterpret_cast<__half*>(h), cur_ovf());
     FESR_LAUNCH_CHECK();
     return FESR_OK;
   }
-  fc_in_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.in_ch, d.wp, n, round_tf32, h);
+  fc_in_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(x, w.fc1_wp, w.fc1_bp, d.in_ch, d.wp, n, round_tf32, h, cur_ovf());
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
 
 // y[i, c] = h[i, :w] . W2[c, :] + b2[c]   (models/model.py:561 / :284); one warp per 8 nodes
 __global__ void fc_out_kernel(const void* __restrict__ hv, const float* __restrict__ w2, const float* __restrict__ b2,
-                              int w, int wp, int out_ch, int64_t n, int h_half, float* __restrict__ y) {
+                              int w, int wp, int out_ch, int64_t n, int h_half, float* __restrict__ y,
+                              const int* __restrict__ ovf) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= n * out_ch) return;
+  if (ovf != nullptr && *ovf != 0) {      // an fp16 intermediate of this pass left the fp16 range: no plausible output
+    y[idx] = __int_as_float(0x7fc00000);
+    return;
+  }
   const int64_t i = idx / out_ch;
   const int c = (int)(idx % out_ch);
   const float* wr = w2 + c * w;
@@ -506,7 +526,7 @@ __global__ void fc_out_kernel(const void* __restrict__ hv, const float* __restri
 // channel order, as the generic kernel below.
 __global__ void __launch_bounds__(256)
 fc_out_h48c4_kernel(const __half* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2, int w,
-                    int64_t n, float* __restrict__ y) {
+                    int64_t n, float* __restrict__ y, const int* __restrict__ ovf) {
   __shared__ __align__(16) float wt[48][4];
   for (int t = threadIdx.x; t < 48 * 4; t += blockDim.x) {
     const int b = t >> 2, c = t & 3;
@@ -516,6 +536,11 @@ fc_out_h48c4_kernel(const __half* __restrict__ h, const float* __restrict__ w2, 
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 acc = make_float4(b2[0], b2[1], b2[2], b2[3]);
+  if (ovf != nullptr && *ovf != 0) {      // an fp16 intermediate of this pass left the fp16 range: no plausible output
+    const float qn = __int_as_float(0x7fc00000);
+    reinterpret_cast<float4*>(y)[i] = make_float4(qn, qn, qn, qn);
+    return;
+  }
   const uint4* row = reinterpret_cast<const uint4*>(h + i * 48);
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
@@ -546,11 +571,11 @@ int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const void* h,
   const int64_t total = n * d.out_ch;
   ProfScope prof(PROF_FC_OUT, s);
   if (h_half && d.wp == 48 && d.out_ch == 4 && d.w <= 48 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
-    fc_out_h48c4_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(static_cast<const __half*>(h), p.fc2_w, p.fc2_b, d.w, n, y);
+    fc_out_h48c4_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(static_cast<const __half*>(h), p.fc2_w, p.fc2_b, d.w, n, y, cur_ovf());
     FESR_LAUNCH_CHECK();
     return FESR_OK;
   }
-  fc_out_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(h, p.fc2_w, p.fc2_b, d.w, d.wp, d.out_ch, n, h_half, y);
+  fc_out_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(h, p.fc2_w, p.fc2_b, d.w, d.wp, d.out_ch, n, h_half, y, cur_ovf());
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }

@@ -53,7 +53,8 @@ template <int MT, int WP>
 __global__ void __launch_bounds__(ZH_WARPS * 32, 2)
 zbuild_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
                   const __half* __restrict__ g, const __half* __restrict__ h, int64_t n, int passes, int kp, int kt,
-                  int ktp, int zk_main, int zk, __half* __restrict__ Z) {
+                  int ktp, int zk_main, int zk, __half* __restrict__ Z, int* ovf) {
+  F16Guard guard;
   constexpr int GROW = 16 * MT;
   constexpr int NT = WP / 8;
   constexpr int SG = GROW + 8, SH = WP + 8;                 // slab row strides in halfs (+16 B: conflict-free ldmatrix)
@@ -205,7 +206,11 @@ zbuild_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
             uint32_t* row = reinterpret_cast<uint32_t*>(zh + (kbase + chan[mt][hh]) * WP + 2 * tq);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
-              row[nt * 4] = zh_h2_sat(acc[mt][nt][2 * hh] * inv, acc[mt][nt][2 * hh + 1] * inv);
+            {
+              const float z0 = acc[mt][nt][2 * hh] * inv, z1 = acc[mt][nt][2 * hh + 1] * inv;
+              guard.note(z0, z1);
+              row[nt * 4] = zh_h2_sat(z0, z1);
+            }
           }
         if (cur.p == passes - 1) {                  // root block (h_i is fp16 already) + zero tail
           const uint32_t* hi = reinterpret_cast<const uint32_t*>(h + i * WP);
@@ -222,6 +227,7 @@ zbuild_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
+  guard.flush(ovf);
 }
 
 template <int MT, int WP>
@@ -239,7 +245,7 @@ static int launch_zh(const fesr_model_dims& d, const int32_t* rowptr, const int3
   ProfScope prof(PROF_ZBUILD, s);
   zbuild_f16_kernel<MT, WP><<<grid, ZH_WARPS * 32, smem, s>>>(rowptr, src_sorted, static_cast<const __half*>(g),
                                                              static_cast<const __half*>(h), n, d.passes, d.kp, d.kt,
-                                                             d.ktp, d.zk_main, d.zk, static_cast<__half*>(Z));
+                                                             d.ktp, d.zk_main, d.zk, static_cast<__half*>(Z), cur_ovf());
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }

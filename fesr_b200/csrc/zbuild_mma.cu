@@ -82,7 +82,8 @@ template <int MT, int WP, int ZMODE, bool BWD>
 __global__ void __launch_bounds__(ZM_WARPS * 32, 2)
 zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
                   const float* __restrict__ g, const float* __restrict__ h, int64_t n, int passes, int kp, int kt,
-                  int ktp, int zk_main, int zk, const float* __restrict__ gather_scale, void* __restrict__ Zv) {
+                  int ktp, int zk_main, int zk, const float* __restrict__ gather_scale, void* __restrict__ Zv, int* ovf) {
+  F16Guard guard;
   constexpr int GROW = 16 * MT;
   constexpr int NT = WP / 8;
   // slab row strides (floats): h rows padded by 8 (conflict-free B fragments); g rows unpadded so
@@ -285,11 +286,16 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
               uint32_t* row = reinterpret_cast<uint32_t*>(zh + (kbase + chan[mt][hh]) * WP + 2 * tq);
 #pragma unroll
               for (int nt = 0; nt < NT; ++nt)
-                row[nt * 4] = zm_h2_sat(acc[mt][nt][2 * hh] * inv, acc[mt][nt][2 * hh + 1] * inv);
+              {
+                const float z0 = acc[mt][nt][2 * hh] * inv, z1 = acc[mt][nt][2 * hh + 1] * inv;
+                guard.note(z0, z1);
+                row[nt * 4] = zm_h2_sat(z0, z1);
+              }
             }
           if (cur.p == passes - 1) {
             for (int c = lane * 2; c < zk - zk_main; c += 64) {
               const float h0 = (c < WP) ? h[i * WP + c] : 0.f, h1 = (c + 1 < WP) ? h[i * WP + c + 1] : 0.f;
+              guard.note(h0, h1);
               *reinterpret_cast<uint32_t*>(zh + zk_main + c) = zm_h2_sat(h0, h1);
             }
           }
@@ -323,6 +329,7 @@ zbuild_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
       buf ^= 1;
     }
   }
+  if constexpr (ZMODE == 2) guard.flush(ovf);
 }
 
 template <int MT, int WP, int ZMODE, bool BWD>
@@ -341,7 +348,7 @@ static int launch_zm(const fesr_model_dims& d, const int32_t* rowptr, const int3
   const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
   ProfScope prof(PROF_ZBUILD, s);
   zbuild_mma_kernel<MT, WP, ZMODE, BWD><<<grid, ZM_WARPS * 32, smem, s>>>(rowptr, src_sorted, g, h, n, d.passes, d.kp, d.kt,
-                                                                         d.ktp, d.zk_main, d.zk, gsc, Z);
+                                                                         d.ktp, d.zk_main, d.zk, gsc, Z, cur_ovf());
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }

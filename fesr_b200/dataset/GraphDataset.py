@@ -44,16 +44,28 @@ class SubdomainSample(list):
 
 class StitchedMesh:
     """Result of reconstruct_from_partition: the appended partitions with averaged point data
-    (what the reference returns as a vtkUnstructuredGrid) plus the field on the original mesh."""
+    (what the reference returns as a vtkUnstructuredGrid) plus the field on the original mesh.
 
-    def __init__(self, pos, cells, dev_arrays, global_ids):
+    Every array is copied to the host on first access.  After a sharded (multi-rank) predict the stitched field is
+    DISTRIBUTED: this rank has stitched -- and `field_local` / `ref_field_local` return -- only its own contiguous
+    slice `node_range` of the mesh nodes; the whole-mesh arrays (`field`, `ref_field`, `merged`, ...) are computed
+    from the gathered predictions when somebody asks for them (`lazy`: name -> callable returning the device array)."""
+
+    def __init__(self, pos, cells, dev_arrays, global_ids, lazy=None, node_range=None):
         self.pos, self.cells = pos, cells            # original mesh (numpy)
-        self._dev = dev_arrays                       # name -> device tensor; copied to the host on first access
+        self._dev = dict(dev_arrays)                 # name -> device tensor; copied to the host on first access
+        self._lazy = dict(lazy or {})
         self._host = {}
         self.global_ids = global_ids
+        self.node_range = node_range if node_range is not None else (0, int(np.asarray(pos).shape[0]))
 
     def _get(self, name):
         if name not in self._host:
+            if name not in self._dev:
+                if name.endswith("_local") and name[:-6] in self._dev:          # one rank: the slice is everything
+                    self._dev[name] = self._dev[name[:-6]]
+                else:
+                    self._dev[name] = self._lazy[name]()
             t = self._dev[name]
             host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             host.copy_(t, non_blocking=True)
@@ -61,6 +73,8 @@ class StitchedMesh:
             self._host[name] = host
         return self._host[name]
 
+    field_local = property(lambda self: self._get("field_local"))          # [node_range, 4] this rank's slice
+    ref_field_local = property(lambda self: self._get("ref_field_local"))
     field = property(lambda self: self._get("field"))            # [N, 4] prediction on the original mesh
     ref_field = property(lambda self: self._get("ref_field"))
     merged = property(lambda self: self._get("merged"))          # [sum n_s, 4] appended partitions, averaged
@@ -73,7 +87,7 @@ class StitchedMesh:
         return {"velocity": m[:, :3], "pressure": m[:, 3], "ref_velocity": r[:, :3], "ref_pressure": r[:, 3]}
 
     def GetNumberOfPoints(self):
-        return int(self._dev["merged"].shape[0])
+        return int(self.global_ids.shape[0])
 
     def write_vtu(self, path):
         """ASCII .vtu of the ORIGINAL mesh with the stitched point arrays (run_ALDS_3D.py:33-38)."""
@@ -209,26 +223,75 @@ class SyntheticDuctDataset:
         5-argument call of run_ALDS_3D.py:26 (model_idx / weights are carried but, as in the
         reference, not used by the averaging)."""
         c = self._mesh(subdomain_idx)
-        b = c["batch"]
-        dev = self.device
-
-        def to_dev(lst):
-            dev_t = getattr(lst, "dev", None)
-            if dev_t is not None:
-                return dev_t
-            t = torch.cat([torch.as_tensor(v, dtype=torch.float32) for v in lst], dim=0)
-            if t.shape[0] != b.n_tot:
-                raise ValueError(f"expected {b.n_tot} rows over all subdomains, got {t.shape[0]}")
-            return t.to(dev)
-
-        pred, ref = to_dev(subdomain_data_list), to_dev(subdomain_ref_list)
-        field, count, merged = ops.stitch_mean(pred, c["occ"], b.global_ids, want_merged=True)
-        rfield, _, rmerged = ops.stitch_mean(ref, c["occ"], b.global_ids, want_merged=True)
         if "gids_cpu" not in c:
-            c["gids_cpu"] = b.global_ids.cpu()
-        return StitchedMesh(c["mesh"].pos, c["mesh"].cells,
-                            {"field": field, "ref_field": rfield, "merged": merged, "merged_ref": rmerged, "count": count},
-                            c["gids_cpu"])
+            c["gids_cpu"] = c["batch"].global_ids.cpu()
+        return stitch_lists(c["batch"], c["occ"], c["mesh"].pos, c["mesh"].cells, c["gids_cpu"], c,
+                            subdomain_data_list, subdomain_ref_list, self.device)
+
+
+def stitch_lists(b, occ, pos, cells, gids_cpu, cache, pred_list, ref_list, dev):
+    """The averaging of reconstruct_from_partition over predict()'s return lists (shared by the dataset classes).
+    Lists that came out of a sharded predict carry the padded all-gather buffer (`padded`): the stitch reads it in
+    place through an occurrence index remapped once per layout, and only this rank's slice of the mesh nodes is
+    stitched eagerly (StitchedMesh.field_local); everything else is computed on demand."""
+
+    def to_dev(lst):
+        dev_t = getattr(lst, "dev", None)
+        if dev_t is not None:
+            return dev_t
+        t = torch.cat([torch.as_tensor(v, dtype=torch.float32) for v in lst], dim=0)
+        if t.shape[0] != b.n_tot:
+            raise ValueError(f"expected {b.n_tot} rows over all subdomains, got {t.shape[0]}")
+        return t.to(dev)
+
+    lay = getattr(pred_list, "layout", None)
+    if lay is not None and getattr(pred_list, "padded", None) is not None and lay.world > 1:
+        from .. import comm
+        from ..pipeline import node_slice
+        rank = getattr(pred_list, "rank", None)
+        if rank is None:
+            rank = comm.rank() if comm.ready() else 0
+        rng = node_slice(occ.N, rank, lay.world)
+        rows_view = pred_list.padded[0]
+        key = ("occ_padded", lay.world, lay.c, lay.slot, lay.with_ref, tuple(lay.rows))
+        if key not in cache:
+            cache[key] = (ops.Occurrence(occ.occ_ptr, lay.row_positions(occ.occ_idx), occ.N, int(rows_view.shape[0])),
+                          ops.Occurrence(occ.occ_ptr, lay.row_positions(occ.occ_idx, ref=True), occ.N,
+                                         int(rows_view.shape[0])) if lay.with_ref else None)
+        occ_p, occ_r = cache[key]
+        ref_padded = getattr(ref_list, "padded", None) is not None and occ_r is not None
+
+        def stitched(which, full):
+            if which == "pred":
+                vals, oc_ = rows_view, occ_p
+            elif ref_padded:
+                vals, oc_ = ref_list.padded[0], occ_r
+            else:
+                vals, oc_ = to_dev(ref_list), occ
+            return ops.stitch_mean(vals, oc_, None, want_merged=False, want_count=True, node_range=None if full else rng)
+
+        f_loc, cnt_loc, _ = stitched("pred", False)
+        r_loc, _, _ = stitched("ref", False)
+        full = {}
+
+        def whole(which):
+            if which not in full:
+                full[which] = stitched(which, True)
+            return full[which]
+
+        def merged_of(which):
+            return whole(which)[0].index_select(0, b.global_ids)
+
+        lazy = {"field": lambda: whole("pred")[0], "ref_field": lambda: whole("ref")[0], "count": lambda: whole("pred")[1],
+                "merged": lambda: merged_of("pred"), "merged_ref": lambda: merged_of("ref")}
+        return StitchedMesh(pos, cells, {"field_local": f_loc, "ref_field_local": r_loc, "count_local": cnt_loc},
+                            gids_cpu, lazy=lazy, node_range=rng)
+
+    pred, ref = to_dev(pred_list), to_dev(ref_list)
+    field, count, merged = ops.stitch_mean(pred, occ, b.global_ids, want_merged=True)
+    rfield, _, rmerged = ops.stitch_mean(ref, occ, b.global_ids, want_merged=True)
+    return StitchedMesh(pos, cells, {"field": field, "ref_field": rfield, "merged": merged, "merged_ref": rmerged,
+                                     "count": count}, gids_cpu)
 
 
 class AnsysDataset(SyntheticDuctDataset):

@@ -179,18 +179,10 @@ class StoredSubdomainDataset:
 
     def reconstruct_from_partition(self, subdomain_data_list, subdomain_ref_list, subdomain_idx, model_idx=None,
                                    weights_list=None):
+        from .GraphDataset import stitch_lists
         c = self._mesh(subdomain_idx)
-        b = c["batch"]
-
-        def to_dev(lst):
-            dev_t = getattr(lst, "dev", None)
-            if dev_t is not None:
-                return dev_t
-            return torch.cat([torch.as_tensor(v, dtype=torch.float32) for v in lst], dim=0).to(self.device)
-
-        pred, ref = to_dev(subdomain_data_list), to_dev(subdomain_ref_list)
-        field, count, merged = ops.stitch_mean(pred, c["occ"], b.global_ids, want_merged=True)
-        rfield, _, rmerged = ops.stitch_mean(ref, c["occ"], b.global_ids, want_merged=True)
+        if "gids_cpu" not in c:
+            c["gids_cpu"] = c["batch"].global_ids.cpu()
         cells = np.zeros((0, 4), dtype=np.int32)            # the store keeps graphs, not cells
-        return StitchedMesh(c["pos"], cells, {"field": field, "ref_field": rfield, "merged": merged, "merged_ref": rmerged,
-                                              "count": count}, b.global_ids.cpu())
+        return stitch_lists(c["batch"], c["occ"], c["pos"], cells, c["gids_cpu"], c, subdomain_data_list,
+                            subdomain_ref_list, self.device)

@@ -46,6 +46,9 @@ class PCAEncoder(Encoder):
     def _train_graph(self, dataset, save_model=False, path=None):
         data_space = [d.x.cpu().detach().numpy() for d in self._iter(dataset)]
         min_length = min(d.shape[0] for d in data_space)
+        if min_length < self.min_length:
+            raise ValueError(f"every subdomain needs >= {self.min_length} nodes for the PCA routing features "
+                             f"(models/encoder.py:152 transforms the first {self.min_length}); the shortest has {min_length}")
         if min_length != self.min_length:
             # the reference fits on the shortest subdomain (:117) but transforms the first 280 nodes
             # (:152); the two only agree when they coincide, so the fit is cut to 280 as well
@@ -66,6 +69,8 @@ class PCAEncoder(Encoder):
         batch = getattr(dataset, "batch", None)
         if batch is not None:
             x_dev, node_ptr = dataset.x_dev, batch.node_ptr
+            if x_dev is None:          # a sample made by with_host_inputs(): the fields are on the host
+                x_dev = dataset.x_host.to(dev, dtype=torch.float32)
         else:
             xs = [d.x for d in self._iter(dataset)]
             sizes = np.array([int(t.shape[0]) for t in xs])

@@ -120,7 +120,7 @@ class _MeshModel(nn.Module):
         if plist is None:
             plist = self.__dict__["_plist"] = list(self.parameters())
         key = (csr.rowptr.data_ptr(), csr.src.data_ptr(), csr.n, csr.E, edge_attr.data_ptr(), edge_attr._version, prec,
-               getattr(self, "ws_tag", "fwd"), tuple((p.data_ptr(), p._version) for p in plist))
+               getattr(self, "ws_tag", "fwd"), ops.weights_generation(), tuple((p.data_ptr(), p._version) for p in plist))
         if self.__dict__.get("_plan_key") != key:
             detached = {k: (None if v is None else v.detach() if torch.is_tensor(v) else [t.detach() for t in v])
                         for k, v in self.param_tensors().items()}
@@ -136,14 +136,17 @@ class _MeshModel(nn.Module):
         issues the copies.  The next forward on the same graph picks the edge features up from the workspace."""
         ops.run_forward_plan(self._predict_plan(csr, edge_attr, _lib.PRECISIONS[self.precision]), None, edge_only=True)
 
-    def forward(self, x, edge_index, edge_attr, x_ready=None):
-        """x_ready (extension, predict only): CUDA event after which `x` is valid -- see ops.run_forward_plan."""
+    def forward(self, x, edge_index, edge_attr, x_ready=None, out=None):
+        """x_ready (extension, predict only): CUDA event after which `x` is valid -- see ops.run_forward_plan.
+        out (extension, predict only): [n, out_ch] fp32 block the result is written into."""
         if not x.is_cuda:
             raise FesrError(f"{type(self).__name__}.forward needs CUDA tensors on a B200; fesr_b200 has no CPU path")
         csr = self._graphs.get(edge_index, x.shape[0])
         prec = _lib.PRECISIONS[self.precision]
         if not torch.is_grad_enabled():
-            return ops.run_forward_plan(self._predict_plan(csr, edge_attr, prec), x.detach(), x_ready)
+            return ops.run_forward_plan(self._predict_plan(csr, edge_attr, prec), x.detach(), x_ready, out=out)
+        if out is not None:
+            raise FesrError("out= is a predict-time extension (torch.no_grad())")
         tensors = self.param_tensors()
         needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:

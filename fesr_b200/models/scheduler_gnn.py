@@ -29,7 +29,7 @@ class TensorList(list):
     behind the elements may still be filling (asynchronous device -> host copy on a side stream): the first
     element access waits for it.  On a multi-rank run only this rank's own subdomains (`own` = index range) are
     copied eagerly; the first access to any other element fetches the rest (`rest`, a one-shot callable)."""
-    dev = None
+    padded = None         # (rows view [world*slot/c, c] of the gathered buffer, int64 row position of every batch row)
     ready = None          # torch.cuda.Event recorded after the (own part of the) device -> host copy, or None
     own = None            # (s0, s1): the subdomains that `ready` covers; None = all of them
     rest = None           # callable that copies everything else and blocks until it is there; None = nothing left
@@ -40,6 +40,20 @@ class TensorList(list):
         reconstruct_from_partition (which works from `.dev`) never needs to spend."""
         super().__init__(items if items is not None else ())
         self._make, self._n = make, n
+        self._dev = None
+
+    @property
+    def dev(self):
+        """Device-resident concatenation [sum n_s, c] in subdomain order.  After a sharded predict the rows live in
+        the padded all-gather buffer (`padded`); the contiguous copy is only made if somebody asks for it."""
+        if self._dev is None and self.padded is not None:
+            rows, pos = self.padded
+            self._dev = rows.index_select(0, pos)
+        return self._dev
+
+    @dev.setter
+    def dev(self, t):
+        self._dev = t
 
     def _fill(self):
         if self._make is not None:
@@ -49,11 +63,18 @@ class TensorList(list):
     def __len__(self):
         return self._n if self._make is not None else list.__len__(self)
 
+    ovf_host = None       # pinned int32 [1]: the forward's fp16 range flag, copied with the results
+
     def wait(self):
-        """Blocks until this rank's own part is on the host."""
+        """Blocks until this rank's own part is on the host.  Raises if the forward that produced it left the fp16
+        range (its output is NaN-filled then: fesr.h, fesr_forward_overflow_offset)."""
         if self.ready is not None:
             self.ready.synchronize()
             self.ready = None
+            if self.ovf_host is not None and int(self.ovf_host[0]) != 0:
+                raise _lib.FesrError("fp16 overflow in the f16 / tf32 arm: an intermediate exceeded 65504 and the output "
+                                     "was discarded (NaN).  Normalise the inputs as the reference does "
+                                     "(dataset/GraphDataset.py:962-976) or run precision='fp32'.")
 
     def wait_all(self):
         if self.rest is not None:
@@ -208,11 +229,17 @@ class GNNPartitionScheduler():
             return [self.dataset]
         path = self._model_dir()
         if train:
-            os.makedirs(path, exist_ok=True)
-            self.encoder.train(self.dataset, save_model=True, path=path)
+            # every rank fits the same (deterministic) PCA / k-means on the same data; only rank 0 writes the files
+            dist, rank, world = _dist()
+            save = rank == 0
+            if save:
+                os.makedirs(path, exist_ok=True)
+            self.encoder.train(self.dataset, save_model=save, path=path)
             latent_space = self.encoder.get_latent_space(self.dataset)
-            self.classifier.train(latent_space, save_model=True, path=path)
+            self.classifier.train(latent_space, save_model=save, path=path)
             labels = self.classifier.cluster(latent_space)
+            if world > 1:
+                dist.barrier()
         else:
             self.encoder.load_model(path)
             self.classifier.load_model(path)
@@ -242,6 +269,9 @@ class GNNPartitionScheduler():
             raise ValueError('Models are not trained yet')
         dev = self.device
         dist, rank, world = _dist()
+        if world > 1:
+            from .. import comm
+            comm.init_from_torch_distributed()          # idempotent: libfesr's own NCCL communicator
         if world > 1 and self.num_partitions == 1 and isinstance(x, SubdomainSample):
             return self._predict_sharded(x, rank, world)
         if self.num_partitions == 1 and isinstance(x, SubdomainSample) and x.x_host is not None:
@@ -283,11 +313,27 @@ class GNNPartitionScheduler():
             pred.index_copy_(0, c["nodes"], pi)
             weight_s.index_copy_(0, c["subs"], wi)
         if world > 1:
-            # predictions of the other ranks: one packed all-gather in rank = subdomain order
-            from ..pipeline import all_gather_packed
-            rows, cnt, lo, b0 = plan["rows"], plan["cnt"], plan["lo"], plan["b0"]
-            pred, weight_s = all_gather_packed(pred[lo:lo + rows[rank]], weight_s[b0:b0 + cnt[rank]], rows, cnt)
+            # predictions of the other ranks: one in-place all-gather (libfesr's communicator) in rank = subdomain order
+            pred, weight_s = self._gather_routed(pred, weight_s, plan, rank, world)
         return self._to_host_lists(x, pred, weight_s, y_dev, sizes, labels)
+
+    def _gather_routed(self, pred, weight_s, plan, rank, world):
+        """ALDS on several ranks: this rank's rows of `pred` [n, c] / `weight_s` [S] -> the complete arrays."""
+        from .. import comm
+        from ..pipeline import SlotLayout
+        rows, cnt, lo, b0 = plan["rows"], plan["cnt"], plan["lo"], plan["b0"]
+        oc = int(pred.shape[1])
+        lay = plan.get("lay")
+        if lay is None:
+            lay = plan["lay"] = SlotLayout(rows, cnt, oc, with_ref=False)
+            plan["pos"] = lay.row_positions(torch.arange(pred.shape[0], device=pred.device)).long()
+            plan["wpos"] = lay.weight_positions(pred.device)
+        gbuf = torch.empty(world, lay.slot, dtype=torch.float32, device=pred.device)
+        nr, ns = rows[rank], cnt[rank]
+        gbuf[rank, :nr * oc].copy_(pred[lo:lo + nr].reshape(-1))
+        gbuf[rank, lay.weight_off(rank):lay.weight_off(rank) + ns].copy_(weight_s[b0:b0 + ns])
+        comm.allgatherv_pred(gbuf)
+        return gbuf.view(-1, oc).index_select(0, plan["pos"]), gbuf.view(-1).index_select(0, plan["wpos"])
 
     def _routing_plan(self, csr, edge_attr, node_ptr, labels_h, rank, world):
         from ..pipeline import shard_bounds
@@ -316,32 +362,48 @@ class GNNPartitionScheduler():
                 "lo": int(node_ptr_h[bounds[rank]]), "b0": bounds[rank]}
 
     def _predict_sharded(self, x, rank, world):
-        """One model, several ranks, device-resident decomposition: every rank runs its contiguous edge-balanced
-        share of the subdomains (the shard's CSR slice is built once per (mesh, world) and cached on the batch),
-        copies only ITS rows of the input field host -> device, and one packed all-gather brings the predictions
-        and subdomain weights of the other ranks (reference fan-out / fan-in: models/scheduler_gnn.py:254-311)."""
-        from ..pipeline import all_gather_packed, make_shard, shard_bounds
+        """One model, several ranks, device-resident decomposition (reference fan-out / fan-in:
+        models/scheduler_gnn.py:254-311).  Every rank runs its contiguous edge-balanced share of the subdomains (the
+        shard's CSR slice and the slot layout are built once per (mesh, world) and cached on the batch) and copies
+        only ITS rows of the input field host -> device.  The forward writes its predictions, and the node-weight
+        kernel its subdomain weights, straight into this rank's slot of one [world, slot] buffer; ONE in-place
+        fesr_allgatherv_pred on the compute stream (libfesr's NCCL communicator) fills the other slots -- no
+        pad / cat / clone, no torch.distributed call.  With host inputs the rank's rows of the reference field ride
+        in the same slot (the stitch of ref_y_list needs every rank's rows; they arrive over NVLink, not PCIe)."""
+        from .. import comm
+        from ..pipeline import SlotLayout, make_shard, shard_bounds
         dev = self.device
         b = x.batch
+        model = self.models[0]
+        oc = int(model.dims.out_ch)
+        host_in = x.x_host is not None
         cache = b.__dict__.setdefault("_shards", {})
-        if world not in cache:
+        key = (world, rank, oc, host_in)
+        c = cache.get(key)
+        if c is None:
             node_ptr_h = b.node_ptr.cpu().numpy().astype(np.int64)
             bounds = shard_bounds(b.edge_ptr.cpu().numpy().astype(np.int64), world)
-            cache[world] = {"shard": make_shard(b, bounds[rank], bounds[rank + 1]),
-                            "rows": [int(node_ptr_h[bounds[r + 1]] - node_ptr_h[bounds[r]]) for r in range(world)],
-                            "cnt": [bounds[r + 1] - bounds[r] for r in range(world)],
-                            "sizes": np.diff(node_ptr_h).tolist()}
-        c = cache[world]
-        sh, sizes = c["shard"], c["sizes"]
+            rows = [int(node_ptr_h[bounds[r + 1]] - node_ptr_h[bounds[r]]) for r in range(world)]
+            cnt = [bounds[r + 1] - bounds[r] for r in range(world)]
+            lay = SlotLayout(rows, cnt, oc, with_ref=host_in)
+            batch_rows = torch.arange(b.n_tot, device=dev)
+            c = cache[key] = {"shard": make_shard(b, bounds[rank], bounds[rank + 1]), "lay": lay,
+                              "sizes": np.diff(node_ptr_h).tolist(), "b0": bounds[rank],
+                              "pos_pred": lay.row_positions(batch_rows).long(),
+                              "pos_ref": lay.row_positions(batch_rows, ref=True).long() if host_in else None,
+                              "wpos": lay.weight_positions(dev)}
+        sh, lay, sizes = c["shard"], c["lay"], c["sizes"]
         lo, hi = sh.node_lo, sh.node_hi
+        nr, ns = hi - lo, lay.cnt[rank]
+        gbuf = torch.empty(world, lay.slot, dtype=torch.float32, device=dev)
+        mine = gbuf[rank]
+        pred_v = mine[:nr * oc].view(nr, oc)
+        w_v = mine[lay.weight_off(rank):lay.weight_off(rank) + ns]
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
         y_ready = x_ready = None
-        host_in = x.x_host is not None
-        if host_in and hi > lo:
-            self.models[0].edge_phase(sh.csr, sh.edge_attr)
         if host_in:
-            # only this rank's rows cross PCIe; the other ranks' rows of the reference field (the stitch of
-            # ref_y_list needs all of it) arrive over NVLink, packed into the all-gather of the predictions
+            if nr > 0:
+                model.edge_phase(sh.csr, sh.edge_attr)
             with torch.cuda.stream(side):
                 xi = x.x_host[lo:hi].to(dev, non_blocking=True)
                 x_ready = side.record_event()
@@ -351,26 +413,97 @@ class GNNPartitionScheduler():
             yi.record_stream(main)
         else:
             xi, yi = x.x_dev[lo:hi], x.y_dev[lo:hi]
-        model = self.models[0]
-        if hi > lo:
-            pi = model(xi, sh.csr, sh.edge_attr, x_ready=x_ready)
-            if y_ready is not None:
-                main.wait_event(y_ready)
-            wi = ops.node_weight(pi, yi, sh.csr, sh.edge_attr, sh.node_ptr)
-        else:                                    # more ranks than subdomains
-            if y_ready is not None:
-                main.wait_event(y_ready)
-            pi = torch.zeros(0, model.dims.out_ch, dtype=torch.float32, device=dev)
-            wi = torch.zeros(0, dtype=torch.float32, device=dev)
+        if nr > 0:
+            model(xi, sh.csr, sh.edge_attr, x_ready=x_ready, out=pred_v)
+        if y_ready is not None:
+            main.wait_event(y_ready)
+        if nr > 0:
+            ops.node_weight(pred_v, yi, sh.csr, sh.edge_attr, sh.node_ptr, out=w_v)
+            if host_in:
+                mine[nr * oc:2 * nr * oc].view(nr, oc).copy_(yi)
+        comm.allgatherv_pred(gbuf)
+        return self._sharded_lists(x, gbuf, c, rank, world, oc, host_in)
+
+    def _sharded_lists(self, x, gbuf, c, rank, world, oc, host_in):
+        """The 4-tuple of predict() over the gathered slot buffer.  Only this rank's rows of the predictions and its
+        subdomain weights are copied to the host now (one pinned buffer, side stream); the rows the other ranks
+        computed -- they hold them on their own hosts -- are fetched on first access."""
+        dev = self.device
+        lay, sizes, sh = c["lay"], c["sizes"], c["shard"]
+        S = len(sizes)
+        lo, hi, b0 = sh.node_lo, sh.node_hi, c["b0"]
+        nr, ns = hi - lo, lay.cnt[rank]
+        n_tot = int(lay.row_offs[-1])
+        host = torch.empty(n_tot * oc + S, dtype=torch.float32, pin_memory=True)
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        produced = main.record_event()
+        wo = lay.weight_off(rank)
+        with torch.cuda.stream(side):
+            side.wait_event(produced)
+            ovf_host = self._copy_flag(side)
+            if nr > 0:
+                host[lo * oc:hi * oc].copy_(gbuf[rank, :nr * oc], non_blocking=True)
+                host[n_tot * oc + b0:n_tot * oc + b0 + ns].copy_(gbuf[rank, wo:wo + ns], non_blocking=True)
+            copied = side.record_event()
+        gbuf.record_stream(side)
+
+        def rest(host=host, gbuf=gbuf, side=side):
+            with torch.cuda.stream(side):
+                for r in range(world):
+                    if r == rank or lay.rows[r] == 0:
+                        continue
+                    r0, r1 = int(lay.row_offs[r]), int(lay.row_offs[r + 1])
+                    host[r0 * oc:r1 * oc].copy_(gbuf[r, :(r1 - r0) * oc], non_blocking=True)
+                    s0, w0 = int(lay.sub_offs[r]), lay.weight_off(r)
+                    host[n_tot * oc + s0:n_tot * oc + s0 + lay.cnt[r]].copy_(gbuf[r, w0:w0 + lay.cnt[r]], non_blocking=True)
+            side.synchronize()
+
+        state = {"rest": rest}
+
+        def rest_once(state=state):          # the two lists share one buffer: whoever asks first fetches for both
+            if state["rest"] is not None:
+                state["rest"]()
+                state["rest"] = None
+
+        rows_view = gbuf.view(-1, oc)
+        pred_cpu = host[:n_tot * oc].view(n_tot, oc)
+        pred_y_list = TensorList(make=lambda: torch.split(pred_cpu, sizes), n=S)
+        pred_y_list.padded = (rows_view, c["pos_pred"])
+        pred_y_list.layout = lay
+        pred_y_list.rank = rank
+        pred_y_list.ready = copied
+        pred_y_list.ovf_host = ovf_host
+        pred_y_list.own = (b0, b0 + ns)
+        pred_y_list.rest = rest_once
         if host_in:
-            oc = pi.shape[1]
-            both, weight_s = all_gather_packed(torch.cat([pi, yi], dim=1), wi, c["rows"], c["cnt"])
-            pred, y_dev = both[:, :oc].contiguous(), both[:, oc:].contiguous()
+            y_host = x.y_host
+            ref_y_list = TensorList(make=lambda: torch.split(y_host, sizes), n=S)
+            ref_y_list.padded = (rows_view, c["pos_ref"])
+            ref_y_list.layout = lay
+            ref_y_list.is_ref = True
         else:
-            pred, weight_s = all_gather_packed(pi, wi, c["rows"], c["cnt"])
-            y_dev = x.y_dev
-        b0 = sum(c["cnt"][:rank])
-        return self._to_host_lists(x, pred, weight_s, y_dev, sizes, None, own=(lo, hi, b0, b0 + c["cnt"][rank]))
+            ref_y_list = TensorList(make=lambda: [d.y for d in x], n=S)
+            ref_y_list.dev = x.y_dev
+        w_cpu = host[n_tot * oc:]
+        weights_list = TensorList(make=lambda: [w_cpu[s].expand(sizes[s]) for s in range(S)], n=S)
+        weights_list.ready = copied
+        weights_list.own = (b0, b0 + ns)
+        weights_list.rest = rest_once
+        weights_list.padded_flat = (gbuf.view(-1), c["wpos"])
+        return pred_y_list, ref_y_list, np.zeros(S, dtype=int), weights_list
+
+    def _copy_flag(self, side):
+        """fp16 range flags of the models' last forwards -> one pinned int32 (max over the models), on `side`."""
+        flags = [f for f in (ops.overflow_flag(m.dims, self.device, getattr(m, "ws_tag", "fwd")) for m in self.models)
+                 if f is not None]
+        if not flags:
+            return None
+        host = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        if len(flags) == 1:
+            host.copy_(flags[0], non_blocking=True)
+        else:
+            host.copy_(torch.stack(flags).max(0).values, non_blocking=True)
+        return host
 
     def _to_host_lists(self, x, pred, weight_s, y_dev, sizes, labels, own=None):
         # one packed device -> host copy on the side stream: reconstruct_from_partition works from the device
@@ -386,6 +519,7 @@ class GNNPartitionScheduler():
         rest = None
         with torch.cuda.stream(side):
             side.wait_event(produced)
+            ovf_host = self._copy_flag(side)
             if own is None:
                 host.copy_(packed, non_blocking=True)
             else:
@@ -403,6 +537,7 @@ class GNNPartitionScheduler():
         pred_y_list = TensorList(make=lambda: torch.split(pred_cpu, sizes), n=S)
         pred_y_list.dev = pred
         pred_y_list.ready = copied
+        pred_y_list.ovf_host = ovf_host
         if own is not None:
             state = {"rest": rest}
 

@@ -41,6 +41,30 @@ class FlatAdam:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.t = 0
+        # gradient accumulators shaped like model.param_tensors(): views of the flat gradient buffer, so that
+        # fesr_nnconv_backward adds straight into it (no per-parameter pack copies before the all-reduce)
+        where = {id(p): (int(o), p) for p, o in zip(self.params, self.offsets[:-1])}
+
+        def view_of(t):
+            if t is None:
+                return None
+            o, p = where[id(t)]
+            return self.grad[o:o + p.numel()].view_as(p)
+
+        pt = model.param_tensors() if hasattr(model, "param_tensors") else None
+        self.grad_views = None
+        if pt is not None and all(id(t) in where for v in pt.values() if v is not None
+                                  for t in (v if isinstance(v, (list, tuple)) else [v])):
+            self.grad_views = {k: (None if v is None else [view_of(t) for t in v] if isinstance(v, (list, tuple)) else view_of(v))
+                               for k, v in pt.items()}
+        dist, _, world = _dist()
+        if world > 1:
+            # DistributedDataParallel broadcasts rank 0's parameters when it wraps the model (scheduler_gnn.py:386);
+            # every rank must start from the same point or the averaged gradients are taken at different points
+            from .. import comm
+            comm.init_from_torch_distributed()
+            dist.broadcast(self.flat, src=0)
+            ops.invalidate_prepared_weights()
 
     def zero_grad(self):
         for p in self.params:
@@ -54,12 +78,14 @@ class FlatAdam:
             else:
                 seg.copy_(p.grad.reshape(-1))
 
-    def step(self):
-        self.pack_grads()
+    def step(self, packed: bool = False):
+        """packed=True: the gradients are already in the flat buffer (train_step's direct path)."""
+        if not packed:
+            self.pack_grads()
         dist, _, world = _dist()
         if world > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)     # DDP averages: sum / world
-            self.grad.div_(world)
+            from .. import comm
+            comm.allreduce_grads(self.grad)          # DDP averages: sum / world, on the compute stream
         self.t += 1
         ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.t, self.betas[0],
                       self.betas[1], self.eps)
@@ -67,11 +93,23 @@ class FlatAdam:
 
 def train_step(model, opt: FlatAdam, x, graph, edge_attr, y):
     """zero_grad -> forward -> MSELoss -> backward -> (all-reduce) -> Adam.step, :402-409."""
-    opt.zero_grad()
-    out = model(x, graph, edge_attr)
-    loss, grad = ops.mse_loss(out.detach(), y)
-    out.backward(grad)
-    opt.step()
+    from .. import _lib
+    if opt.grad_views is None or not isinstance(graph, ops.Csr):
+        opt.zero_grad()
+        out = model(x, graph, edge_attr)
+        loss, grad = ops.mse_loss(out.detach(), y)
+        out.backward(grad)
+        opt.step()
+        return loss
+    # direct path: forward / backward are one C-ABI call each and the parameter gradients land in the flat buffer
+    opt.grad.zero_()
+    prec = _lib.PRECISIONS[model.precision]
+    tensors = {k: (None if v is None else v.detach() if torch.is_tensor(v) else [t.detach() for t in v])
+               for k, v in model.param_tensors().items()}
+    out, ws = ops.nnconv_forward(model.dims, tensors, x, graph, edge_attr, prec, keep_for_backward=True)
+    loss, grad = ops.mse_loss(out, y)
+    ops.nnconv_backward(model.dims, tensors, x, graph, edge_attr, prec, grad, ws, grads=opt.grad_views)
+    opt.step(packed=True)
     return loss
 
 

@@ -63,8 +63,28 @@ class _Workspace:
         _prepared.clear()
 
 
-_prepared = {}          # (device, workspace tag) -> (workspace ptr, dims, parameter (ptr, version) pairs) last prepared there
+# (device, workspace tag) -> (state, tensors): `state` = (workspace ptr, dims, weights generation, parameter (ptr, version)
+# pairs) last prepared there; `tensors` keeps those parameter tensors alive so that the caching allocator cannot hand
+# their addresses to another model while the entry says "prepared".
+_prepared = {}
 workspace = _Workspace()
+_weights_gen = 0        # bumped by every out-of-band parameter write (fesr_adam_step works through raw pointers)
+
+
+def weights_generation() -> int:
+    return _weights_gen
+
+
+def invalidate_prepared_weights():
+    """A parameter was written without PyTorch noticing (no `_version` bump): every cached prepared copy is stale."""
+    global _weights_gen
+    _weights_gen += 1
+    _prepared.clear()
+
+
+def _prepared_state(key):
+    ent = _prepared.get(key)
+    return None if ent is None else ent[0]
 
 
 # ---------------------------------------------------------------------------------- graph
@@ -149,8 +169,8 @@ def nnconv_forward(dims: ModelDims, tensors: dict, x: torch.Tensor, csr: Csr, ed
             ws = workspace.get(dev, ws_tag, nbytes)
             # the prepared weight copies at the head of the cached workspace stay valid as long as the same
             # parameter tensors hold the same values (predict loops): skip the preparation kernels then
-            state = (ws.data_ptr(), bytes(dims), tuple((t.data_ptr(), t._version) for t in keep))
-            if _prepared.get((dev.index, ws_tag)) == state:
+            state = (ws.data_ptr(), bytes(dims), _weights_gen, tuple((t.data_ptr(), t._version) for t in keep))
+            if _prepared_state((dev.index, ws_tag)) == state:
                 flags |= _lib.FWD_WEIGHTS_PREPARED
             _prepared[(dev.index, ws_tag)] = None
         if x_ready is not None and not keep_for_backward and n > 0:
@@ -165,9 +185,20 @@ def nnconv_forward(dims: ModelDims, tensors: dict, x: torch.Tensor, csr: Csr, ed
                                       _ptr(csr.perm), _ptr(edge_attr), n, E, precision, flags,
                                       _ptr(y), _ptr(ws), ws.numel(), _stream(dev)), "fesr_nnconv_forward")
         if not keep_for_backward:
-            _prepared[(dev.index, ws_tag)] = state
+            _prepared[(dev.index, ws_tag)] = (state, keep)
     del keep
     return (y, ws) if keep_for_backward else y
+
+
+def overflow_flag(dims: ModelDims, dev, ws_tag: str = "fwd"):
+    """int32 [1] view of the fp16 range flag of the last forward that ran in the cached workspace `ws_tag` (None if
+    no forward has run there yet).  Reading its value synchronises: predict() copies it to the host together with
+    the results instead and raises when they are first touched."""
+    buf = workspace.bufs.get((torch.device(dev).index, ws_tag))
+    if buf is None:
+        return None
+    off = int(_lib.load().fesr_forward_overflow_offset(C.byref(dims)))
+    return buf[off:off + 4].view(torch.int32)
 
 
 class ForwardPlan:
@@ -194,7 +225,7 @@ def make_forward_plan(dims: ModelDims, tensors: dict, csr: Csr, edge_attr: torch
     return pl
 
 
-def run_forward_plan(pl: ForwardPlan, x: torch.Tensor | None, x_ready=None, edge_only: bool = False):
+def run_forward_plan(pl: ForwardPlan, x: torch.Tensor | None, x_ready=None, edge_only: bool = False, out=None):
     """edge_only: issue just the edge phase (FESR_FWD_EDGE_ONLY: weight preparation + edge MLP, nothing that reads x)
     and return None -- the caller does so BEFORE it starts the host -> device copies of a step, so that the GPU is
     busy while the host is still issuing them; the next call on this plan then runs the rest (FESR_FWD_EDGE_DONE)."""
@@ -203,13 +234,19 @@ def run_forward_plan(pl: ForwardPlan, x: torch.Tensor | None, x_ready=None, edge
         if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous() or x.shape != (pl.n, pl.dims.in_ch):
             raise FesrError(f"x must be a contiguous fp32 CUDA tensor of shape [{pl.n}, {pl.dims.in_ch}], got "
                             f"{tuple(x.shape)} {x.dtype} on {x.device}")
-        y = torch.empty(pl.n, pl.dims.out_ch, dtype=torch.float32, device=dev)
+        if out is not None:
+            # `out`: the caller's [n, out_ch] block (the rank's slot of the all-gather buffer) -- no copy afterwards
+            if not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or out.shape != (pl.n, pl.dims.out_ch):
+                raise FesrError(f"out must be a contiguous fp32 CUDA tensor of shape [{pl.n}, {pl.dims.out_ch}]")
+            y = out
+        else:
+            y = torch.empty(pl.n, pl.dims.out_ch, dtype=torch.float32, device=dev)
     if pl.n == 0:
         return None if edge_only else y
     ws = workspace.get(dev, pl.ws_tag, pl.nbytes)
     key = (dev.index, pl.ws_tag)
-    state = (ws.data_ptr(),) + pl.state_tail
-    flags = _lib.FWD_WEIGHTS_PREPARED if _prepared.get(key) == state else 0
+    state = (ws.data_ptr(), _weights_gen) + pl.state_tail
+    flags = _lib.FWD_WEIGHTS_PREPARED if _prepared_state(key) == state else 0
     stream = torch.cuda.current_stream(dev)
     sp = C.c_void_p(stream.cuda_stream)
     args = (C.byref(pl.dims), C.byref(pl.params))
@@ -224,25 +261,28 @@ def run_forward_plan(pl: ForwardPlan, x: torch.Tensor | None, x_ready=None, edge
             edge_in = True
             if edge_only:
                 pl.edge_in = ws.data_ptr()
-                _prepared[key] = state
+                _prepared[key] = (state, pl.keep)
                 return None
         if x_ready is not None:
             stream.wait_event(x_ready)
         if edge_in:
             flags |= _lib.FWD_EDGE_DONE
         check(lib.fesr_nnconv_forward(*args, _ptr(x), *graph, flags, _ptr(y), _ptr(ws), ws.numel(), sp), "fesr_nnconv_forward")
-    _prepared[key] = state
+    _prepared[key] = (state, pl.keep)
     return y
 
 
 # ---------------------------------------------------------------------------------- node weight
-def node_weight(pred, target, csr: Csr, edge_attr, node_ptr=None, clamp_max=float('inf')):
-    """Per-subdomain scalar of GradientbasedLoss.compute_node_weight -> [S] fp32."""
+def node_weight(pred, target, csr: Csr, edge_attr, node_ptr=None, clamp_max=float('inf'), out=None):
+    """Per-subdomain scalar of GradientbasedLoss.compute_node_weight -> [S] fp32 (written into `out` when given)."""
     dev = _require_cuda(pred, target, edge_attr)
     pred, target = _f32c(pred), _f32c(target)
     edge_attr = _f32c(edge_attr.reshape(-1))
     n_sub = 1 if node_ptr is None else int(node_ptr.numel() - 1)
-    out = torch.empty(n_sub, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(n_sub, dtype=torch.float32, device=dev)
+    elif not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != n_sub:
+        raise FesrError(f"out must be a contiguous fp32 CUDA tensor with {n_sub} entries")
     scratch = torch.empty(max(csr.n, 1), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         check(_lib.load().fesr_node_weight(_ptr(pred), _ptr(target), pred.shape[1], _ptr(csr.rowptr), _ptr(csr.src),
@@ -278,19 +318,28 @@ def occurrence_build(global_ids: torch.Tensor, N: int) -> Occurrence:
 
 
 def stitch_mean(values: torch.Tensor, occ: Occurrence, global_ids: torch.Tensor | None = None,
-                want_merged: bool = False, want_count: bool = True):
-    """values [n_tot, c] -> (field [N, c], count [N] | None, merged [n_tot, c] | None)."""
+                want_merged: bool = False, want_count: bool = True, node_range=None):
+    """values [n_tot, c] -> (field [N, c], count [N] | None, merged [n_tot, c] | None).
+    node_range = (lo, hi): only the global nodes lo..hi-1 are stitched -> field [hi-lo, c], count [hi-lo] (the
+    occurrence table is indexed from its row `lo`; a rank of a sharded run stitches its own slice of the mesh)."""
     dev = _require_cuda(values, occ.occ_ptr)
     values = _f32c(values)
     c = int(values.shape[1])
-    field = torch.empty(occ.N, c, dtype=torch.float32, device=dev)
-    count = torch.empty(occ.N, dtype=torch.int32, device=dev) if want_count else None
+    lo, hi = (0, occ.N) if node_range is None else (int(node_range[0]), int(node_range[1]))
+    if not (0 <= lo <= hi <= occ.N):
+        raise FesrError(f"node_range {node_range} outside [0, {occ.N}]")
+    if want_merged and (global_ids is None or (lo, hi) != (0, occ.N)):
+        raise FesrError("merged output needs global_ids and the full node range")
+    m = hi - lo
+    field = torch.empty(m, c, dtype=torch.float32, device=dev)
+    count = torch.empty(m, dtype=torch.int32, device=dev) if want_count else None
     merged = torch.empty(occ.n_tot, c, dtype=torch.float32, device=dev) if want_merged else None
-    if want_merged and global_ids is None:
-        raise FesrError("merged output needs global_ids")
+    if m == 0:
+        return field, count, merged
+    occ_ptr = occ.occ_ptr if lo == 0 else occ.occ_ptr[lo:]
     with torch.cuda.device(dev):
-        check(_lib.load().fesr_stitch_mean(_ptr(values), c, _ptr(occ.occ_ptr), _ptr(occ.occ_idx), _ptr(global_ids),
-                                           occ.n_tot, occ.N, _ptr(field), _ptr(count), _ptr(merged), _stream(dev)),
+        check(_lib.load().fesr_stitch_mean(_ptr(values), c, _ptr(occ_ptr), _ptr(occ.occ_idx), _ptr(global_ids),
+                                           occ.n_tot, m, _ptr(field), _ptr(count), _ptr(merged), _stream(dev)),
               "fesr_stitch_mean")
     return field, count, merged
 
@@ -313,6 +362,7 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
     with torch.cuda.device(dev):
         check(_lib.load().fesr_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(),
                                          lr, beta1, beta2, eps, step, _stream(dev)), "fesr_adam_step")
+    invalidate_prepared_weights()        # written through a raw pointer: no tensor `_version` changed
 
 
 # ---------------------------------------------------------------------------------- assembly
@@ -471,8 +521,10 @@ def reverse_csr(csr: Csr) -> Csr:
 
 
 def nnconv_backward(dims: ModelDims, tensors: dict, x, csr: Csr, edge_attr, precision, grad_y, fwd_ws,
-                    need_grad_x: bool = False):
-    """Runs fesr_nnconv_backward. Returns (grads dict shaped like `tensors`, grad_x | None)."""
+                    need_grad_x: bool = False, grads: dict | None = None):
+    """Runs fesr_nnconv_backward. Returns (grads dict shaped like `tensors`, grad_x | None).
+    grads: accumulators shaped like `tensors` that the call ADDS into (e.g. views of a flat gradient buffer);
+    default: fresh zero tensors."""
     dev = _require_cuda(x, grad_y)
     x = _f32c(x)
     grad_y = _f32c(grad_y)
@@ -480,8 +532,9 @@ def nnconv_backward(dims: ModelDims, tensors: dict, x, csr: Csr, edge_attr, prec
     rev = reverse_csr(csr)
     lib = _lib.load()
     p, keep = make_params(Params, tensors)
-    gt = {k: (None if v is None else torch.zeros_like(v) if torch.is_tensor(v) else [torch.zeros_like(t) for t in v])
-          for k, v in tensors.items()}
+    gt = grads if grads is not None else \
+        {k: (None if v is None else torch.zeros_like(v) if torch.is_tensor(v) else [torch.zeros_like(t) for t in v])
+         for k, v in tensors.items()}
     g, keep_g = make_params(ParamGrads, gt)
     grad_x = torch.empty_like(x) if need_grad_x else None
     n, E = csr.n, csr.E

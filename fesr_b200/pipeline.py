@@ -82,6 +82,50 @@ def all_gather_packed(pred_local: torch.Tensor, w_local: torch.Tensor, rows, cnt
     return pred, w
 
 
+class SlotLayout:
+    """Padded layout of the one all-gather of a sharded predict pass (fesr_allgatherv_pred): a [world, slot] fp32
+    buffer whose slot r holds, back to back, rank r's predictions [rows[r], c], (optionally) its rows of the
+    reference field [rows[r], c] and its subdomain weights [cnt[r]].  `slot` is a multiple of 4 c floats, so the
+    buffer is also a [world * slot / c, c] row array and a row of any rank has a ROW position in it: the stitch
+    reads the gathered buffer in place through an occurrence index remapped once to those positions."""
+
+    def __init__(self, rows, cnt, c: int, with_ref: bool):
+        self.rows, self.cnt, self.c, self.with_ref = [int(r) for r in rows], [int(k) for k in cnt], int(c), bool(with_ref)
+        self.world = len(self.rows)
+        per = [r * self.c * (2 if with_ref else 1) + k for r, k in zip(self.rows, self.cnt)]
+        q = 4 * self.c
+        self.slot = max(q, (max(per) + q - 1) // q * q)
+        self.row_offs = np.concatenate([[0], np.cumsum(self.rows)]).astype(np.int64)      # concatenated row index
+        self.sub_offs = np.concatenate([[0], np.cumsum(self.cnt)]).astype(np.int64)
+
+    # float offsets inside slot r
+    def pred_off(self, r):
+        return 0
+
+    def ref_off(self, r):
+        return self.rows[r] * self.c
+
+    def weight_off(self, r):
+        return self.rows[r] * self.c * (2 if self.with_ref else 1)
+
+    def row_positions(self, idx: torch.Tensor, ref: bool = False) -> torch.Tensor:
+        """Row index into the rank-order concatenation of the shards -> row index into the [world*slot/c, c] view of
+        the gathered buffer (int32); ref=True: the position of the same row of the reference block."""
+        offs = torch.as_tensor(self.row_offs, device=idx.device)
+        i = idx.long()
+        r = torch.bucketize(i, offs[1:], right=True)
+        pos = i - offs[r] + r * (self.slot // self.c)
+        if ref:
+            pos = pos + torch.as_tensor(np.asarray(self.rows, dtype=np.int64), device=idx.device)[r]
+        return pos.to(torch.int32).contiguous()
+
+    def weight_positions(self, device) -> torch.Tensor:
+        """Float offset in the flattened gathered buffer of every subdomain's weight, in subdomain order (int64)."""
+        out = np.concatenate([r * self.slot + self.weight_off(r) + np.arange(self.cnt[r], dtype=np.int64)
+                              for r in range(self.world)]) if self.world else np.zeros(0, np.int64)
+        return torch.as_tensor(out, device=device)
+
+
 def padded_positions(idx: torch.Tensor, rows) -> torch.Tensor:
     """Row index into the rank-order concatenation of the shards -> row index into the padded [world, max(rows)]
     all-gather buffer (int32)."""
@@ -90,6 +134,11 @@ def padded_positions(idx: torch.Tensor, rows) -> torch.Tensor:
     i = idx.long()
     r = torch.bucketize(i, offs[1:], right=True)
     return (i + r * mx - offs[r]).to(torch.int32).contiguous()
+
+
+def node_slice(N: int, rank: int, world: int):
+    """The contiguous range of global mesh nodes whose stitched values rank `rank` produces and keeps."""
+    return (N * rank) // world, (N * (rank + 1)) // world
 
 
 def make_shard(batch: ops.SubdomainBatch, s0: int, s1: int) -> Shard:
@@ -123,6 +172,9 @@ class MeshPredictor:
         node_ptr_h = self.batch.node_ptr.cpu().numpy()
         self.shard_rows = [int(node_ptr_h[self.bounds[r + 1]] - node_ptr_h[self.bounds[r]]) for r in range(world)]
         self.home_cells = np.bincount(self.part.home_leaf.cpu().numpy(), minlength=self.batch.n_sub)
+        if world > 1:
+            from . import comm
+            comm.init_from_torch_distributed(group)          # libfesr's own NCCL communicator (idempotent)
 
     def gather_inputs(self, field: torch.Tensor) -> torch.Tensor:
         """[N, c] mesh field -> [n_shard, c] per-subdomain copies (what the HDF5 store holds)."""
@@ -142,34 +194,44 @@ class MeshPredictor:
     def stitch(self, pred_all: torch.Tensor, want_merged=False):
         return ops.stitch_mean(pred_all, self.occ, self.batch.global_ids, want_merged=want_merged, want_count=False)
 
-    def _padded_gather(self, pred_shard: torch.Tensor) -> torch.Tensor:
-        """The all-gather of step(): every rank's block lands at [r, :rows[r]] of one persistent [world, max rows, c]
-        buffer (one copy into the send block + one `all_gather_into_tensor`); the stitch then reads the padded
-        buffer directly through an occurrence index remapped once to padded positions, so there is no pad / split /
-        concatenate traffic around the collective."""
-        import torch.distributed as dist
-        c = int(pred_shard.shape[1])
-        if getattr(self, "_gbuf", None) is None or self._gbuf.shape[2] != c:
-            dev = pred_shard.device
-            mx = max(self.shard_rows)
-            self._gbuf = torch.zeros(self.world, mx, c, dtype=torch.float32, device=dev)
-            self._send = torch.zeros(mx, c, dtype=torch.float32, device=dev)
-            self._occ_padded = ops.Occurrence(self.occ.occ_ptr, padded_positions(self.occ.occ_idx, self.shard_rows),
-                                              self.occ.N, self.world * mx)
-        self._send[:pred_shard.shape[0]].copy_(pred_shard)
-        work = dist.all_gather_into_tensor(self._gbuf.view(-1), self._send.view(-1), group=self.group, async_op=True)
-        return self._gbuf.view(-1, c), work
+    def _layout(self, c: int):
+        """Slot layout + remapped occurrence table of the sharded step (built once per channel count)."""
+        if getattr(self, "_lay", None) is None or self._lay.c != c:
+            lay = SlotLayout(self.shard_rows, [self.bounds[r + 1] - self.bounds[r] for r in range(self.world)], c, False)
+            self._lay = lay
+            self._occ_padded = ops.Occurrence(self.occ.occ_ptr, lay.row_positions(self.occ.occ_idx), self.occ.N,
+                                              self.world * lay.slot // c)
+            self._side = torch.cuda.Stream(self.occ.occ_ptr.device)
+        return self._lay
 
-    def step(self, x_shard, y_shard=None):
-        """forward (+ node weight) + all-gather + stitch; returns (field [N,c], weights [S_shard] | None)."""
-        pred = self.forward_shard(x_shard)
-        if self.world > 1:
-            # the collective runs on NCCL's stream underneath the node-weight kernels (they only need this rank's rows)
-            gathered, work = self._padded_gather(pred)
+    def step(self, x_shard, y_shard=None, full_field: bool = False):
+        """forward (+ node weight) + all-gather + stitch -> (field, weights [S_shard] | None, pred [n_shard, c]).
+        One rank: field is the whole stitched mesh field [N, c].  Several ranks: the forward writes straight into
+        this rank's slot of the gather buffer, ONE in-place fesr_allgatherv_pred (libfesr's communicator, issued
+        on a side stream underneath the node-weight kernels, which only need this rank's rows) fills the other
+        slots, and the rank stitches ITS slice of the mesh nodes (`node_slice`; full_field=True: all of them --
+        every rank then holds the bit-identical whole field)."""
+        if self.world == 1:
+            pred = self.forward_shard(x_shard)
             w = self.node_weight(pred, y_shard) if y_shard is not None else None
-            work.wait()
-            field, _, _ = ops.stitch_mean(gathered, self._occ_padded, None, want_merged=False, want_count=False)
+            field, _, _ = self.stitch(pred)
             return field, w, pred
+        from . import comm
+        c = int(self.model.dims.out_ch)
+        lay = self._layout(c)
+        dev = x_shard.device
+        gbuf = torch.empty(self.world, lay.slot, dtype=torch.float32, device=dev)
+        rows = lay.rows[self.rank]
+        pred = gbuf[self.rank, :rows * c].view(rows, c)
+        with torch.no_grad():
+            self.model(x_shard, self.shard.csr, self.shard.edge_attr, out=pred)
+        main = torch.cuda.current_stream(dev)
+        self._side.wait_stream(main)
+        comm.allgatherv_pred(gbuf, stream=self._side)
+        gbuf.record_stream(self._side)
         w = self.node_weight(pred, y_shard) if y_shard is not None else None
-        field, _, _ = self.stitch(pred)
+        main.wait_stream(self._side)
+        rng = None if full_field else node_slice(self.N, self.rank, self.world)
+        field, _, _ = ops.stitch_mean(gbuf.view(-1, c), self._occ_padded, None, want_merged=False, want_count=False,
+                                      node_range=rng)
         return field, w, pred

@@ -157,6 +157,12 @@ int fesr_csr_build(const int64_t* edge_index, int64_t E, int64_t n,
  * the smaller size.  Without it the query returns the fp32-stash size, which is always enough. */
 #define FESR_FWD_KEEP_Z16 16
 size_t fesr_forward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E, int keep_for_backward);
+/* fp16 range guard of the reduced-precision arms: byte offset, inside ANY forward workspace of `dims`, of one int32
+ * that the pass zeroes when it starts and sets to 1 if a value it packs into fp16 (edge features g, node features h,
+ * the Z stash) exceeds 65504 or is not a number.  When the flag is set y is filled with NaN instead of a plausible
+ * field built from clipped intermediates; the caller reads the flag (after the stream has reached the end of the
+ * pass) to tell "overflow: use FESR_PREC_TF32 / FP32" from NaN inputs. */
+size_t fesr_forward_overflow_offset(const fesr_model_dims* dims);
 int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params,
                         const float* x, const int32_t* rowptr, const int32_t* src_sorted,
                         const int32_t* perm, const float* edge_attr,
@@ -319,6 +325,31 @@ int fesr_boundary_faces(const float* pos, const int32_t* cells, int64_t N, int64
                         float* face_normal, int64_t* host_count, void* workspace, size_t workspace_bytes, void* stream);
 int fesr_wall_shear_stress(const float* grad_pt, const float* normal_pt, const int32_t* surf_nodes, int64_t M, float mu,
                            float* tau, float* mag, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Collectives of the sharded path, on the caller's stream (NCCL over NVLink / NVSwitch; the
+ * library resolves libnccl.so.2 at run time -- the copy the host process already uses).
+ * Replace the reference's multi-GPU fan-out / fan-in through mp.Process + Manager().dict()
+ * (models/scheduler_gnn.py:254-291, results pickled back to the parent) and the bucket
+ * all-reduce of DistributedDataParallel (models/scheduler_gnn.py:386).  One communicator per
+ * process (= per GPU).
+ *   fesr_comm_unique_id   rank 0 fills host_id[128]; the caller ships it to the other ranks
+ *                         (any side channel: torch.distributed store, MPI, a file)
+ *   fesr_comm_init        collective over all ranks; binds to the current CUDA device
+ *   fesr_allgatherv_pred  all-gather of per-rank blocks of different lengths through a padded,
+ *                         persistent layout: slots is [world, slot_elems] fp32, rank r has written its
+ *                         block (predictions [rows_r, c] | reference rows | subdomain weights ...) at the
+ *                         start of slot r; after the call every rank holds every slot.  In place (no send
+ *                         copy); the stitch reads the padded buffer through a remapped occurrence index.
+ *   fesr_allreduce_grads  flat[i] = mean over ranks of flat[i]   (sum, then * 1/world)
+ * ---------------------------------------------------------------------------------- */
+int fesr_comm_unique_id(void* host_id /* 128 bytes */);
+int fesr_comm_init(const void* host_id /* 128 bytes */, int rank, int world);
+int fesr_comm_destroy(void);
+int fesr_comm_rank(void);   /* -1 without a communicator */
+int fesr_comm_world(void);  /* 0 without a communicator */
+int fesr_allgatherv_pred(float* slots, int64_t slot_elems, void* stream);
+int fesr_allreduce_grads(float* flat, int64_t count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fesr_b200.pipeline import all_gather_packed, all_gather_rows, padded_positions, shard_bounds
+from fesr_b200.pipeline import SlotLayout, all_gather_packed, all_gather_rows, node_slice, padded_positions, shard_bounds
 
 
 def _free_port():
@@ -91,6 +91,37 @@ def test_padded_positions_address_the_gather_buffer():
     pos = padded_positions(idx, rows)
     assert pos.dtype == torch.int32
     assert torch.equal(buf.view(-1, c)[pos.long()], full[idx.long()])
+
+
+def test_slot_layout_addresses_the_in_place_gather_buffer():
+    """Host logic of fesr_allgatherv_pred's padded layout: every rank's predictions / reference rows / subdomain
+    weights are found at the positions SlotLayout hands to the stitch and to the host copies."""
+    for c, with_ref in ((4, False), (4, True), (3, True)):
+        rows, cnt = [5, 0, 9, 3], [2, 0, 3, 1]
+        lay = SlotLayout(rows, cnt, c, with_ref)
+        assert lay.slot % (4 * c) == 0 and lay.slot >= max(r * c * (2 if with_ref else 1) + k for r, k in zip(rows, cnt))
+        full = torch.arange(sum(rows) * c, dtype=torch.float32).reshape(-1, c)
+        ref = -full - 1.0
+        w = torch.arange(sum(cnt), dtype=torch.float32) + 0.25
+        buf = torch.full((len(rows), lay.slot), float("nan"))
+        for r in range(len(rows)):
+            r0, r1 = int(lay.row_offs[r]), int(lay.row_offs[r + 1])
+            buf[r, :rows[r] * c] = full[r0:r1].reshape(-1)
+            if with_ref:
+                buf[r, lay.ref_off(r):lay.ref_off(r) + rows[r] * c] = ref[r0:r1].reshape(-1)
+            s0 = int(lay.sub_offs[r])
+            buf[r, lay.weight_off(r):lay.weight_off(r) + cnt[r]] = w[s0:s0 + cnt[r]]
+        idx = torch.randperm(sum(rows)).to(torch.int32)
+        pos = lay.row_positions(idx)
+        assert pos.dtype == torch.int32
+        assert torch.equal(buf.view(-1, c)[pos.long()], full[idx.long()])
+        if with_ref:
+            assert torch.equal(buf.view(-1, c)[lay.row_positions(idx, ref=True).long()], ref[idx.long()])
+        assert torch.equal(buf.view(-1)[lay.weight_positions("cpu")], w)
+    # the node slices of the ranks tile the mesh
+    for N, world in ((10, 4), (896761, 8), (3, 8)):
+        sl = [node_slice(N, r, world) for r in range(world)]
+        assert sl[0][0] == 0 and sl[-1][1] == N and all(sl[r][1] == sl[r + 1][0] for r in range(world - 1))
 
 
 def test_tensor_list_is_lazy_and_fetches_remote_rows_on_demand():

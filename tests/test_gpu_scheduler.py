@@ -135,33 +135,49 @@ def test_gradient_loss_forward(golden):
 
 
 def test_sharded_predict_matches_single_rank(tmp_path, shipped, monkeypatch):
-    """The multi-rank predict path (cached shard + packed all-gather), both ranks of a world of 2 played one after
-    the other on this GPU: the union of what the ranks contribute equals the single-rank result bit for bit."""
-    from fesr_b200 import pipeline
+    """The multi-rank predict path (cached shard + slot layout + in-place all-gather), both ranks of a world of 2
+    played one after the other on this GPU with the collective emulated: the union of what the ranks contribute
+    equals the single-rank result bit for bit, and the two field slices make up the single-rank field."""
+    from fesr_b200 import comm
     from fesr_b200.models import scheduler_gnn as sg
     ds, model, sds = _setup(tmp_path, 1, shipped, monkeypatch)
     sched = sg.GNNPartitionScheduler("t", 1, ds, model, train=False)
     base = ds.get_one_full_sample(0)
-    p1, _, _, w1 = sched.predict(base)
-    full_p, full_w = p1.dev.clone(), torch.stack([w[0] for w in w1])
+    p1, r1, mi1, w1 = sched.predict(base)
+    full_p, full_w = p1.dev.clone(), torch.stack([w[0] for w in w1]).cuda()
+    full_field = ds.reconstruct_from_partition(p1, r1, 0, mi1, w1).field.clone()
     # host-input variant of the same sample (the sharded path copies only its own rows of x)
     c = ds._mesh(0)
     xh, yh = c["x"].cpu().pin_memory(), c["y"].cpu().pin_memory()
-    contributed = {}
-
     y_full = c["y"]
+    contributed = {}
+    state = {"rank": 0}
 
-    def fake_gather(pi, wi, rows, cnt, group=None):
-        contributed[fake_gather.rank] = (pi.clone(), wi.clone(), list(rows), list(cnt))
-        if pi.shape[1] == 8:          # host inputs: the reference-field rows ride in the same collective
-            return torch.cat([full_p, y_full], dim=1), full_w.cuda()
-        return full_p, full_w.cuda()
+    def fake_allgather(slots, stream=None):
+        rank = state["rank"]
+        (entry,) = base.batch._shards.values()
+        lay = entry["lay"]
+        assert slots.shape == (2, lay.slot) and lay.slot % (4 * lay.c) == 0
+        nr, ns = lay.rows[rank], lay.cnt[rank]
+        wo = lay.weight_off(rank)
+        contributed[rank] = (slots[rank, :nr * 4].view(nr, 4).clone(), slots[rank, wo:wo + ns].clone(), lay)
+        for r in range(2):
+            if r == rank:
+                continue
+            r0, r1_ = int(lay.row_offs[r]), int(lay.row_offs[r + 1])
+            slots[r, :(r1_ - r0) * 4] = full_p[r0:r1_].reshape(-1)
+            if lay.with_ref:
+                slots[r, (r1_ - r0) * 4:2 * (r1_ - r0) * 4] = y_full[r0:r1_].reshape(-1)
+            s0 = int(lay.sub_offs[r])
+            slots[r, lay.weight_off(r):lay.weight_off(r) + lay.cnt[r]] = full_w[s0:s0 + lay.cnt[r]]
 
-    monkeypatch.setattr(pipeline, "all_gather_packed", fake_gather)
+    monkeypatch.setattr(comm, "allgatherv_pred", fake_allgather)
+    N = c["mesh"].num_nodes
     for sample in (base, base.with_host_inputs(xh, yh)):
         contributed.clear()
+        slices = {}
         for rank in range(2):
-            fake_gather.rank = rank
+            state["rank"] = rank
             monkeypatch.setattr(sg, "_dist", lambda r=rank: (None, r, 2))
             base.batch.__dict__.pop("_shards", None)          # the cache is per process; here one process plays both
             p, r, mi, w = sched.predict(sample)
@@ -173,14 +189,22 @@ def test_sharded_predict_matches_single_rank(tmp_path, shipped, monkeypatch):
             assert p.rest is not None
             off = int(base.batch.node_ptr[s0])
             assert torch.equal(own_first, full_p[off:off + own_first.shape[0]].cpu())
+            out = ds.reconstruct_from_partition(p, r, 0, mi, w)
+            lo, hi = out.node_range
+            assert (lo, hi) == ((N * rank) // 2, (N * (rank + 1)) // 2)
+            slices[rank] = out.field_local.clone()
+            assert torch.equal(slices[rank], full_field[lo:hi])                  # the rank's slice, stitched eagerly
+            assert rel_l2(out.ref_field_local.numpy(), c["mesh"].y[lo:hi]) < 1e-6
+            assert torch.equal(out.field, full_field)                             # the whole field on demand
+            assert rel_l2(out.ref_field.numpy(), c["mesh"].y) < 1e-6
             assert torch.equal(torch.cat(list(p)), full_p.cpu())          # iterating fetches everything
             assert p.rest is None
+            assert torch.equal(p.dev, full_p)
             assert torch.equal(torch.stack([t[0] for t in w]).cpu(), full_w.cpu())
-            out = ds.reconstruct_from_partition(p, r, 0, mi, w)
-            assert rel_l2(out.ref_field.numpy(), c["mesh"].y) < 1e-6
-        (pa, wa, rows, cnt), (pb, wb, _, _) = contributed[0], contributed[1]
-        assert pa.shape[0] == rows[0] and pb.shape[0] == rows[1] and sum(cnt) == 16 and min(cnt) > 0
-        assert torch.equal(torch.cat([pa, pb])[:, :4], full_p)
+        assert torch.equal(torch.cat([slices[0], slices[1]]), full_field)
+        (pa, wa, lay), (pb, wb, _) = contributed[0], contributed[1]
+        assert pa.shape[0] == lay.rows[0] and pb.shape[0] == lay.rows[1] and sum(lay.cnt) == 16 and min(lay.cnt) > 0
+        assert torch.equal(torch.cat([pa, pb]), full_p)
         assert torch.equal(torch.cat([wa, wb]).cpu(), full_w.cpu())
 
 
