@@ -20,6 +20,9 @@ def test_reference_arm_json_contract():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "cells/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["value"] > 0 and d["n_gpus"] == 1 and d["data"] == "synthetic" and "workload" in d["config"]
+    # nothing measured or arm-specific lives in `config`: the driver compares the two arms' configs for equality
+    assert sorted(d["config"]) == ["cells", "l2", "layers", "model", "parallelism", "subdomains", "width", "workload"]
+    assert d["config"]["cells"] == 24 * 6 ** 3 and d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
