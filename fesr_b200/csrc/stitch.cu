@@ -5,9 +5,33 @@
 namespace fesr {
 
 // ------------------------------------------------------------------------------ stitch
-// One thread per global node; copies are visited in ascending batch position, summed in
-// fp32 and divided by the count -- exactly numpy's mean over the coincident points
-// (reference dataset/GraphDataset.py:1396-1397).
+// One thread per global node; copies are visited in ascending batch position and summed in fp32, then divided by
+// the count -- the arithmetic of the reference's np.mean over the coincident points (dataset/GraphDataset.py:
+// 1396-1397), INCLUDING its summation order, which the golden fixture tests/golden/stitch_vectors.npz (made by
+// executing the reference's own loop) pins bit for bit: the reference averages `velocity` [m, 3] and `pressure` [m]
+// as separate arrays; numpy reduces the [m, 3] array row by row (sequential in the copies) and the 1-D array with
+// its pairwise summation -- sequential below 8 copies, from 8 on eight interleaved partial sums r[j] += a[8k + j]
+// combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) followed by the m % 8 tail.  C = 4 is (velocity, pressure):
+// channels 0..2 sequential, channel 3 in the scalar order; C = 1 is a scalar array; other widths are vector arrays.
+__device__ __forceinline__ float numpy_scalar_sum(const float* __restrict__ values, const int32_t* __restrict__ occ_idx,
+                                                  int b, int e, int stride, int ch) {
+  // 8 <= e - b (callers use the sequential sum below 8); more than 128 copies of one node do not occur (numpy would
+  // split recursively there; the blocks of 8 simply continue here)
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = __ldg(values + (int64_t)occ_idx[b + j] * stride + ch);
+  const int m = e - b;
+  int i = 8;
+  for (; i < m - (m % 8); i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], __ldg(values + (int64_t)occ_idx[b + i + j] * stride + ch));
+  }
+  float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+  for (; i < m; ++i) res = __fadd_rn(res, __ldg(values + (int64_t)occ_idx[b + i] * stride + ch));
+  return res;
+}
+
 template <int C>
 __global__ void stitch_mean_kernel(const float* __restrict__ values, const int32_t* __restrict__ occ_ptr,
                                    const int32_t* __restrict__ occ_idx, int64_t N, float* __restrict__ field,
@@ -32,6 +56,10 @@ __global__ void stitch_mean_kernel(const float* __restrict__ values, const int32
     }
   }
   const int cnt = e - b;
+  if (cnt >= 8) {                      // scalar point arrays: numpy's pairwise order (rare: nodes shared by >= 8 subdomains)
+    if constexpr (C == 4) acc[3] = numpy_scalar_sum(values, occ_idx, b, e, 4, 3);
+    if constexpr (C == 1) acc[0] = numpy_scalar_sum(values, occ_idx, b, e, 1, 0);
+  }
   if (cnt > 0) {
     const float fc = (float)cnt;
 #pragma unroll

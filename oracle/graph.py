@@ -219,25 +219,61 @@ def occurrence_csr(global_ids: np.ndarray, N: int):
     return occ_ptr, occ_idx
 
 
+def _numpy_pairwise_order_sum(cols):
+    """Sum of m fp32 values per row in the order numpy's pairwise summation uses for a contiguous 1-D reduce
+    (numpy/core/src/umath/loops_utils.h.src, pairwise_sum): m < 8 sequential; 8 <= m <= 128 eight running partial
+    sums r[j] += a[8 k + j], combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the m % 8 tail sequentially.
+    cols: list of m float32 arrays (one per copy, same length)."""
+    m = len(cols)
+    if m < 8:
+        acc = np.zeros_like(cols[0])
+        for c in cols:
+            acc = acc + c
+        return acc
+    assert m <= 128, "a mesh node shared by more than 128 subdomains"
+    r = [cols[j].copy() for j in range(8)]
+    i = 8
+    while i < m - (m % 8):
+        for j in range(8):
+            r[j] = r[j] + cols[i + j]
+        i += 8
+    res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+    while i < m:
+        res = res + cols[i]
+        i += 1
+    return res
+
+
 def stitch_mean(values: np.ndarray, global_ids: np.ndarray, N: int):
     """Mean over all subdomain copies of each global node (GraphDataset.py:1383-1400:
     ``np.mean(sub_vals, axis=0)`` over the coincident points, written back to every copy).
 
-    fp32, summed sequentially in ascending concatenation order, divided by the count
-    (numpy's mean on a float32 [m,4] array for m < 8 is exactly that).
-    Returns (field[N,C] f32, count[N] int32, merged[sum n, C] f32).
+    PINNED against the reference's own loop (tests/golden/make_golden.py `make_stitch_golden` executes lines
+    1371-1400 of the reference; tests/test_oracle_golden.py compares bit for bit).  The reference averages its point
+    arrays one by one -- `velocity` [m, 3] and `pressure` [m] -- with fp32 np.mean, whose summation ORDER depends on
+    the array's rank: the [m, 3] vector arrays are reduced row by row (sequential in the copies, ascending
+    concatenation order), the 1-D scalar arrays through numpy's pairwise summation (sequential below 8 copies, eight
+    interleaved partial sums from 8 on).  values [sum n, C]: C = 4 is (velocity, pressure) -> channels 0..2
+    sequential, channel 3 pairwise; C = 1 is a scalar array (pairwise); any other C a vector array (sequential).
+    Division by the count in fp32.  Returns (field[N,C] f32, count[N] int32, merged[sum n, C] f32).
     """
     values = np.asarray(values, dtype=np.float32)
+    C = values.shape[1]
     occ_ptr, occ_idx = occurrence_csr(global_ids, N)
     count = np.diff(occ_ptr).astype(np.int32)
-    field = np.zeros((N, values.shape[1]), dtype=np.float32)
-    maxc = int(count.max()) if N else 0
-    acc = np.zeros_like(field)
-    for j in range(maxc):
-        sel = np.nonzero(count > j)[0]
-        acc[sel] = acc[sel] + values[occ_idx[occ_ptr[sel] + j]]
-    nz = count > 0
-    field[nz] = acc[nz] / count[nz, None].astype(np.float32)
+    field = np.zeros((N, C), dtype=np.float32)
+    scalar_ch = [3] if C == 4 else ([0] if C == 1 else [])
+    for m in np.unique(count):
+        if m == 0:
+            continue
+        sel = np.nonzero(count == m)[0]
+        cols = [values[occ_idx[occ_ptr[sel] + j]] for j in range(int(m))]       # copy j of every node with m copies
+        acc = np.zeros((sel.size, C), dtype=np.float32)
+        for c in cols:
+            acc = acc + c
+        for ch in scalar_ch:
+            acc[:, ch] = _numpy_pairwise_order_sum([c[:, ch] for c in cols])
+        field[sel] = acc / np.float32(m)
     merged = field[np.asarray(global_ids, dtype=np.int64)]
     return field, count, merged
 

@@ -152,6 +152,116 @@ class _FakeGrid:
         return _FakeCell(self.cells[i])
 
 
+# ---------------------------------------------------------------- a10: the reference's averaging loop
+class _FakeIdList:
+    def __init__(self):
+        self.ids = []
+
+    def GetNumberOfIds(self):
+        return len(self.ids)
+
+    def GetId(self, j):
+        return int(self.ids[j])
+
+
+class _FakePointLocator:
+    """vtkStaticPointLocator stand-in: FindPointsWithinRadius through scipy's cKDTree; ids ascending (VTK returns
+    them in bucket order -- within one bucket ascending point id; the coincident copies of a node share a bucket)."""
+
+    def SetDataSet(self, grid):
+        from scipy.spatial import cKDTree
+        self.tree = cKDTree(grid.points.astype(np.float64))
+
+    def AutomaticOn(self):
+        pass
+
+    def BuildLocator(self):
+        pass
+
+    def FindPointsWithinRadius(self, r, x, id_list):
+        id_list.ids = sorted(self.tree.query_ball_point(np.asarray(x, dtype=np.float64), r))
+
+
+class _FakePointData:
+    def __init__(self, arrays):
+        self.arrays = arrays                     # name -> numpy (what vtk_to_numpy hands back: [n, 3] or [n])
+        self.names = list(arrays)
+
+    def GetNumberOfArrays(self):
+        return len(self.names)
+
+    def GetArrayName(self, i):
+        return self.names[i]
+
+    def GetArray(self, name):
+        return self.arrays[name]
+
+
+class _FakeMergedGrid:
+    """The vtkAppendDataSets output: all partitions' points appended, with their point arrays."""
+
+    def __init__(self, points, arrays):
+        self.points, self.pd = points, _FakePointData(arrays)
+
+    def GetNumberOfPoints(self):
+        return self.points.shape[0]
+
+    def GetPoint(self, i):
+        return tuple(float(v) for v in self.points[i])
+
+    def GetPointData(self):
+        return self.pd
+
+
+def _reference_averaging(points, arrays):
+    """Executes the statements of AnsysDataset.reconstruct_from_partition between `locator = ...` and the end of the
+    per-point loop (dataset/GraphDataset.py:1371-1400) -- pulled out of the file with `ast`, unmodified -- on a
+    duck-typed merged grid.  Returns the averaged arrays (`array_np` of the reference)."""
+    path = os.path.join(REF, "dataset/GraphDataset.py")
+    tree = ast.parse(open(path).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "AnsysDataset"][0]
+    fn = [f for f in cls.body if isinstance(f, ast.FunctionDef) and f.name == "reconstruct_from_partition"][0]
+    first = [i for i, st in enumerate(fn.body) if isinstance(st, ast.Assign) and getattr(st.targets[0], "id", "") == "locator"][0]
+    last = [i for i, st in enumerate(fn.body) if isinstance(st, ast.For) and getattr(st.target, "id", "") == "i"
+            and i > first][0]
+    body = fn.body[first:last + 1]
+    assert body[0].lineno == 1371 and body[-1].end_lineno == 1400, (body[0].lineno, body[-1].end_lineno)
+    vtk = types.SimpleNamespace(vtkStaticPointLocator=_FakePointLocator, vtkIdList=_FakeIdList)
+    ns = {"vtk": vtk, "np": np, "vtk_to_numpy": lambda a: a,
+          "merged_grid": _FakeMergedGrid(points, {k: v.copy() for k, v in arrays.items()})}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns["array_np"]
+
+
+def make_stitch_golden():
+    """a10 fixture: per-subdomain predictions / reference rows of two small ducts appended the way the reference
+    appends its partitions (subdomain order), averaged by the reference's own loop."""
+    from fesr_b200.dataset.synthetic import make_duct_mesh
+    from oracle import graph as og
+    out = {}
+    for tag, n, levels in (("a", 3, 2), ("b", 6, 5)):
+        mesh = make_duct_mesh(n)
+        part = og.kd_partition(mesh.pos, mesh.cells, levels)
+        sub = og.build_subdomains(mesh.pos, mesh.cells, part["leaf_ptr"], part["leaf_cells"])
+        gids = sub["global_ids"]
+        rng = np.random.default_rng(7 + n)
+        # per-copy predictions differ between the subdomains that share a node (as real predictions do)
+        pred = (mesh.y[gids] + rng.normal(0.0, 0.05, size=(gids.size, 4))).astype(np.float32)
+        ref = mesh.y[gids].astype(np.float32)
+        arrays = {"velocity": pred[:, :3].copy(), "pressure": pred[:, 3].copy(),
+                  "ref_velocity": ref[:, :3].copy(), "ref_pressure": ref[:, 3].copy()}
+        avg = _reference_averaging(mesh.pos[gids], arrays)
+        cnt = np.bincount(gids, minlength=mesh.num_nodes)
+        out.update({f"{tag}_mesh_n": np.int64(n), f"{tag}_levels": np.int64(levels), f"{tag}_global_ids": gids.astype(np.int64),
+                    f"{tag}_pred": pred, f"{tag}_ref": ref, f"{tag}_max_copies": np.int64(cnt.max()),
+                    f"{tag}_merged": np.concatenate([avg["velocity"], avg["pressure"][:, None]], axis=1).astype(np.float32),
+                    f"{tag}_merged_ref": np.concatenate([avg["ref_velocity"], avg["ref_pressure"][:, None]], axis=1).astype(np.float32)})
+        print("stitch golden", tag, "points", gids.size, "copies histogram", np.bincount(cnt).tolist())
+    path = os.path.join(HERE, "stitch_vectors.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
     from fesr_b200.dataset.synthetic import make_duct_mesh
     from oracle import graph as og
@@ -256,4 +366,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "stitch":
+        make_stitch_golden()
+    else:
+        main()
+        make_stitch_golden()

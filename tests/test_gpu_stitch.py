@@ -18,7 +18,7 @@ def _subdomains(n, levels):
     return mesh, sub
 
 
-@pytest.mark.parametrize("n,levels", [(3, 2), (6, 4), (13, 4)])
+@pytest.mark.parametrize("n,levels", [(3, 2), (6, 4), (6, 5), (13, 4)])
 def test_stitch_bit_exact(n, levels):
     from fesr_b200 import ops
     mesh, sub = _subdomains(n, levels)
@@ -35,6 +35,31 @@ def test_stitch_bit_exact(n, levels):
     assert np.array_equal(c.cpu().numpy(), count)
     assert np.array_equal(mg.cpu().numpy().view(np.uint32), merged.view(np.uint32))
     assert count.max() >= 2                                   # the halo really overlaps
+
+
+def test_stitch_matches_the_references_own_averaging_loop():
+    """a10 pinned on the GPU: fesr_stitch_mean's merged arrays == what the reference's own loop
+    (dataset/GraphDataset.py:1371-1400, executed by tests/golden/make_golden.py) produced, bit for bit -- including the
+    nodes shared by 8 subdomains, where numpy sums the scalar `pressure` array in its pairwise order."""
+    import os
+    from fesr_b200 import ops
+    z = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "stitch_vectors.npz")))
+    for t in "ab":
+        g = z[t + "_global_ids"]
+        N = int(g.max()) + 1
+        gids = torch.from_numpy(g).cuda()
+        occ = ops.occurrence_build(gids, N)
+        for src, want in ((t + "_pred", t + "_merged"), (t + "_ref", t + "_merged_ref")):
+            f, c, mg = ops.stitch_mean(torch.from_numpy(z[src]).cuda(), occ, gids, want_merged=True)
+            assert np.array_equal(mg.cpu().numpy().view(np.uint32), z[want].view(np.uint32)), (t, src)
+            # the scalar (1-channel) entry point follows the scalar order too
+            f1, _, _ = ops.stitch_mean(torch.from_numpy(z[src][:, 3:4].copy()).cuda(), occ)
+            assert np.array_equal(f1.cpu().numpy()[g, 0].view(np.uint32), z[want][:, 3].view(np.uint32))
+        assert int(c.max()) == int(z[t + "_max_copies"])
+    # a node range (what a rank of a sharded run stitches) gives the same rows
+    f_all, _, _ = ops.stitch_mean(torch.from_numpy(z["b_pred"]).cuda(), occ)
+    f_part, c_part, _ = ops.stitch_mean(torch.from_numpy(z["b_pred"]).cuda(), occ, node_range=(100, 900))
+    assert torch.equal(f_part, f_all[100:900]) and c_part.shape == (800,)
 
 
 def test_stitch_of_consistent_copies_is_identity():

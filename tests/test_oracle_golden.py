@@ -104,3 +104,20 @@ def test_oracle_wall_shear_stress_properties():
     tau = 2.0 * (r["normals"] @ (A + A.T).T)
     tw = tau - np.einsum("ij,ij->i", tau, r["normals"])[:, None] * r["normals"]
     assert np.abs(r["wss"] - tw).max() < 1e-3
+
+
+def test_stitch_matches_the_references_own_averaging_loop():
+    """a10 pinned: tests/golden/stitch_vectors.npz holds what dataset/GraphDataset.py:1371-1400 (executed from the
+    reference's source by make_golden.py on a duck-typed merged grid) makes of two small ducts' appended partitions --
+    up to 8 copies per node, where numpy's summation order of the scalar arrays differs from the vector arrays'."""
+    import os
+    z = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "stitch_vectors.npz")))
+    for t in "ab":
+        g = z[t + "_global_ids"]
+        N = int(g.max()) + 1
+        for src, want in ((t + "_pred", t + "_merged"), (t + "_ref", t + "_merged_ref")):
+            field, count, merged = og.stitch_mean(z[src], g, N)
+            assert np.array_equal(merged.view(np.uint32), z[want].view(np.uint32)), (t, src)     # bit for bit
+            assert np.array_equal(field[g].view(np.uint32), z[want].view(np.uint32))
+        assert int(count.max()) == int(z[t + "_max_copies"])
+    assert int(z["b_max_copies"]) >= 8
