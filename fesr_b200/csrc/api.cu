@@ -14,6 +14,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static thread_local const float* g_cur_gcenter = nullptr;
+const float* cur_gcenter() { return g_cur_gcenter; }
+void set_cur_gcenter(const float* gc) { g_cur_gcenter = gc; }
+
 static thread_local int* g_cur_ovf = nullptr;
 int* cur_ovf() { return g_cur_ovf; }
 void set_cur_ovf(int* flag) { g_cur_ovf = flag; }

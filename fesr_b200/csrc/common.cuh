@@ -42,6 +42,16 @@ struct OvfScope {
   explicit OvfScope(int* flag) { set_cur_ovf(flag); }
   ~OvfScope() { set_cur_ovf(nullptr); }
 };
+// Centring of the edge features in the fused f16 predict arm: the planar g rows the fused
+// layer kernel consumes hold g_e - g(0) (and the constant FESR_LO_SCALE in one padding slot); cur_gcenter() is the
+// per-slot vector the edge-MLP kernels subtract (NULL: plain g), set like cur_ovf by the pass being issued.
+const float* cur_gcenter();
+void set_cur_gcenter(const float* gc);
+struct GcenterScope {
+  explicit GcenterScope(const float* gc) { set_cur_gcenter(gc); }
+  ~GcenterScope() { set_cur_gcenter(nullptr); }
+};
+#define FESR_LO_SCALE 0.00390625f      /* 2^-8: scale of the low-order weight terms carried by a padding slot */
 #ifdef __CUDACC__
 struct F16Guard {
   unsigned m;
@@ -102,12 +112,17 @@ struct Prepared {
   float* ttilde;     // [zk, wp]  T~[(k,b), a] = T'[(k,a), b] (every wp x wp block transposed) -- backward
   float* ttilde_t;   // [wp, zk]  K-major tf32 copy of T~
   void* tprime_t_h;  // [wp, zk]  K-major fp16 copy of T'   (FESR_PREC_F16)
+  void* tprime_t_h_lo;  // [wp, zk]  fp16(T' - fp16(T')): low-order term for the two-term predict GEMM
   void* ttilde_t_h;  // [wp, zk]  K-major fp16 copy of T~
   void* tfused_h;    // [parts, 48, 832] fp16 T' in the fused layer kernel's K order (layer_fused.cu), or NULL
   float* bias_p;     // [wp]
   float* fc1_wp;     // [in_ch, wp] transposed + padded
   float* fc1_bp;     // [wp] (TEECNet: constant-1 column set here)
   int* ovf;          // [1] fp16 overflow flag of the pass (F16Guard)
+  float* gcenter;    // [kp] slot layout: g(0) of every channel slot (0 for the constant-1 slot), -FESR_LO_SCALE in the
+                     //      lo slot (first padding slot), 0 elsewhere -- subtracted from g by the fused arm's edge MLP
+  float* mfull;      // [wp, wp] fp32: T'[(K, a), b] + sum_k g(0)[k] T'[(k, a), b], the weights of the constant-1 slot
+                     //      once g is centred
 };
 
 }  // namespace fesr

@@ -34,11 +34,11 @@ __global__ void __launch_bounds__(128)
 edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
                         const float* __restrict__ b1g, int w, int leaky, int kt, int ktp, int k1,
                         const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int64_t E,
-                        void* __restrict__ gv, int* ovf) {
+                        void* __restrict__ gv, int* ovf, const float* __restrict__ gcenter) {
   F16Guard guard;
   constexpr int KS = WPAD / 8, KP = NTO * 8, SB = KP + 8;
   constexpr int SST = KP + 4;                                          // stage row stride (floats)
-  __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1p[KP];
+  __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1p[KP], gcs[KP];
   __shared__ __align__(16) uint32_t whi[WPAD][SB];                     // [in][slot], tf32 bit patterns
   __shared__ __align__(16) uint32_t wlo[TERMS == 3 ? WPAD : 1][SB];
   extern __shared__ __align__(16) float stage_dyn[];                   // [4 warps][32 edges][SST]
@@ -51,6 +51,7 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
   for (int slot = tid; slot < KP; slot += blockDim.x) {
     const int q = slot / ktp, r = slot % ktp, ch = q * kt + r;
     b1p[slot] = (r < kt && ch < k1 - 1 && ch < w) ? b1g[ch] : ((r < kt && ch == k1 - 1) ? 1.f : 0.f);
+    gcs[slot] = (OMODE == 3 && gcenter != nullptr) ? gcenter[slot] : 0.f;
   }
   for (int i = tid; i < WPAD * KP; i += blockDim.x) {
     const int in = i / KP, slot = i % KP;
@@ -128,6 +129,10 @@ edge_hidden2_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float v0 = em_act(acc[mt][nt][2 * hh] + bz0, leaky), v1 = em_act(acc[mt][nt][2 * hh + 1] + bz1, leaky);
+          if (OMODE == 3) {
+            v0 -= gcs[c];
+            v1 -= gcs[c + 1];
+          }
           if (OMODE == 1) {
             v0 = __uint_as_float(em_tf32(v0));
             v1 = __uint_as_float(em_tf32(v1));
@@ -199,11 +204,11 @@ __global__ void __launch_bounds__(128, 6)
 edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
                         const float* __restrict__ b1g, int w, int kt, int ktp, int k1,
                         const float* __restrict__ edge_attr, const int32_t* __restrict__ perm, int E,
-                        __half* __restrict__ gh, int* ovf) {
+                        __half* __restrict__ gh, int* ovf, const float* __restrict__ gcenter) {
   F16Guard guard;
   constexpr int KS = WPAD / 16, KP = NTO * 8;
   constexpr int WST = WPAD + 8, SST = KP + 8;                          // row strides in halfs (+16 B: conflict-free)
-  __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1p[KP];
+  __shared__ __align__(16) float w0[WPAD], b0[WPAD], b1p[KP], gcs[KP];  // gcs: per-slot centre (common.cuh), 0 without
   __shared__ __align__(16) __half wsm[KP][WST];                        // [slot][in]: K contiguous
   __shared__ __align__(16) __half stage[4][32][SST];                   // [warp][edge][slot]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -215,6 +220,7 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
   for (int slot = tid; slot < KP; slot += blockDim.x) {
     const int q = slot / ktp, r = slot % ktp, ch = q * kt + r;
     b1p[slot] = (r < kt && ch < k1 - 1 && ch < w) ? b1g[ch] : ((r < kt && ch == k1 - 1) ? 1.f : 0.f);
+    gcs[slot] = gcenter != nullptr ? gcenter[slot] : 0.f;
   }
   for (int i = tid; i < KP * WPAD; i += blockDim.x) {
     const int slot = i / WPAD, in = i % WPAD;
@@ -294,8 +300,9 @@ edge_hidden2_f16_kernel(const float* __restrict__ w0g, const float* __restrict__
         for (int q = 0; q < 2; ++q) {
           const int nt = 2 * np + q;
           const float2 bz = *reinterpret_cast<const float2*>(&b1p[nt * 8 + 2 * tq]);
-          h[q][0] = em_pack(fmaxf(acc[mt][nt][0] + bz.x, 0.f), fmaxf(acc[mt][nt][1] + bz.y, 0.f), guard);
-          h[q][1] = em_pack(fmaxf(acc[mt][nt][2] + bz.x, 0.f), fmaxf(acc[mt][nt][3] + bz.y, 0.f), guard);
+          const float2 gc = *reinterpret_cast<const float2*>(&gcs[nt * 8 + 2 * tq]);
+          h[q][0] = em_pack(fmaxf(acc[mt][nt][0] + bz.x, 0.f) - gc.x, fmaxf(acc[mt][nt][1] + bz.y, 0.f) - gc.y, guard);
+          h[q][1] = em_pack(fmaxf(acc[mt][nt][2] + bz.x, 0.f) - gc.x, fmaxf(acc[mt][nt][3] + bz.y, 0.f) - gc.y, guard);
         }
         asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(s_addr + (uint32_t)((mt * 16 * SST + np * 16) * 2)),
                      "r"(h[0][0]), "r"(h[0][1]), "r"(h[1][0]), "r"(h[1][1])
@@ -341,14 +348,15 @@ __global__ void __launch_bounds__(128)
 edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g, const float* __restrict__ w1g,
                         const float* __restrict__ b1g, const float* __restrict__ w2g, const float* __restrict__ b2g,
                         int kt, int ktp, int k1, const float* __restrict__ edge_attr,
-                        const int32_t* __restrict__ perm, int E, void* __restrict__ gv, int* ovf) {
+                        const int32_t* __restrict__ perm, int E, void* __restrict__ gv, int* ovf,
+                        const float* __restrict__ gcenter) {
   F16Guard guard;
   constexpr int H0 = 32, H1 = 64, KP = 144;
   constexpr int CW = 48, NCH = KP / CW, NTC = CW / 8;                  // slots per chunk, chunks, n-tiles per chunk
   constexpr int KS0 = H0 / 16, KS1 = H1 / 16, NT1 = H1 / 8;
   constexpr int W1S = H0 + 8, W2S = H1 + 8;                            // row strides in halfs (+16 B: conflict-free)
   constexpr int SST = OMODE >= 2 ? (CW + 8) * 2 : (CW + 4) * 4;        // staged row stride in BYTES
-  __shared__ __align__(16) float w0[H0], b0[H0], b1[H1], b2p[KP];
+  __shared__ __align__(16) float w0[H0], b0[H0], b1[H1], b2p[KP], gcs[KP];
   extern __shared__ __align__(16) uint8_t eh3_dyn[];
   __half (*w1h)[W1S] = reinterpret_cast<__half (*)[W1S]>(eh3_dyn);     // [out][in]: K contiguous
   __half (*w1l)[W1S] = w1h + H1;
@@ -371,6 +379,7 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
   for (int slot = tid; slot < KP; slot += blockDim.x) {
     const int q = slot / ktp, r = slot % ktp, ch = q * kt + r;
     b2p[slot] = (r < kt && ch < k1 - 1) ? b2g[ch] : ((r < kt && ch == k1 - 1) ? 1.f : 0.f);
+    gcs[slot] = (OMODE == 3 && gcenter != nullptr) ? gcenter[slot] : 0.f;
   }
   for (int i = tid; i < KP * H1; i += blockDim.x) {
     const int slot = i / H1, in = i % H1;
@@ -499,8 +508,9 @@ edge_hidden3_mma_kernel(const float* __restrict__ w0g, const float* __restrict__
             for (int q = 0; q < 2; ++q) {
               const int nt = 2 * np + q;
               const float2 bz = *reinterpret_cast<const float2*>(&b2p[ch * CW + nt * 8 + 2 * tq]);
-              h[q][0] = em_pack(lrelu(acc[mt][nt][0] + bz.x), lrelu(acc[mt][nt][1] + bz.y), guard);
-              h[q][1] = em_pack(lrelu(acc[mt][nt][2] + bz.x), lrelu(acc[mt][nt][3] + bz.y), guard);
+              const float2 gc = *reinterpret_cast<const float2*>(&gcs[ch * CW + nt * 8 + 2 * tq]);
+              h[q][0] = em_pack(lrelu(acc[mt][nt][0] + bz.x) - gc.x, lrelu(acc[mt][nt][1] + bz.y) - gc.y, guard);
+              h[q][1] = em_pack(lrelu(acc[mt][nt][2] + bz.x) - gc.x, lrelu(acc[mt][nt][3] + bz.y) - gc.y, guard);
             }
             asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(s_addr + (uint32_t)(mt * 16 * SST + np * 32)),
                          "r"(h[0][0]), "r"(h[0][1]), "r"(h[1][0]), "r"(h[1][1])
@@ -572,13 +582,13 @@ int launch_edge_hidden3_mma(const fesr_model_dims& d, const fesr_params& p, cons
   ProfScope prof(PROF_EDGE_HIDDEN, s);
   if (omode == 3)
     edge_hidden3_mma_kernel<3><<<grid, 128, smem16, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
-                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g, cur_ovf());
+                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g, cur_ovf(), cur_gcenter());
   else if (omode == 2)
     edge_hidden3_mma_kernel<2><<<grid, 128, smem16, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
-                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g, cur_ovf());
+                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g, cur_ovf(), cur_gcenter());
   else
     edge_hidden3_mma_kernel<1><<<grid, 128, smem32, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], p.mlp_w[2], p.mlp_b[2],
-                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g, cur_ovf());
+                                                        d.kt, d.ktp, d.k1, edge_attr, perm, (int)E, g, cur_ovf(), cur_gcenter());
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
@@ -592,7 +602,7 @@ static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const flo
   constexpr size_t stage_bytes = (size_t)4 * 32 * (NTO * 8 + 4) * sizeof(float);
 #define FESR_EH(TERMS, OMODE)                                                                                   \
   edge_hidden2_mma_kernel<WPAD, NTO, TERMS, OMODE><<<grid, 128, stage_bytes, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], \
-                                                                        d.w, d.leaky, d.kt, d.ktp, d.k1, edge_attr, perm, E, g, cur_ovf())
+                                                                        d.w, d.leaky, d.kt, d.ktp, d.k1, edge_attr, perm, E, g, cur_ovf(), cur_gcenter())
   static bool attr_set = false;
   if (!attr_set) {   // static + dynamic shared memory exceeds 48 KB for the widest rows
     FESR_CUDA(cudaFuncSetAttribute(edge_hidden2_mma_kernel<WPAD, NTO, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
@@ -614,10 +624,10 @@ static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const flo
   else if (omode == 1) FESR_EH(1, 1);
   else if (!tf32_only && !d.leaky && omode == 2)
     edge_hidden2_f16_kernel<WPAD, NTO, 2><<<grid16, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
-                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g), cur_ovf());
+                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g), cur_ovf(), cur_gcenter());
   else if (!tf32_only && !d.leaky)
     edge_hidden2_f16_kernel<WPAD, NTO, 3><<<grid16, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], d.w, d.kt, d.ktp, d.k1,
-                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g), cur_ovf());
+                                                              edge_attr, perm, (int)E, reinterpret_cast<__half*>(g), cur_ovf(), cur_gcenter());
   else if (omode == 2) FESR_EH(1, 2);
   else FESR_EH(1, 3);
 #undef FESR_EH

@@ -79,7 +79,11 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   const int fuse_mode = fuse_env ? atoi(fuse_env) : 3;
   const bool fused = precision == FESR_PREC_F16 && !keep_for_backward && fuse_mode > 0 && layer_fused_supported(d) &&
                      ws.prep.tfused_h != nullptr && E > 0;
-  if (!edge_done && (rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s, fused ? 3 : rnd_in))) return rc;
+  {
+    // fused arm: centred edge features (g - g(0), the lo slot constant) against two-term weights -- DESIGN.md 4.2
+    GcenterScope gc_scope(fused ? ws.prep.gcenter : nullptr);
+    if (!edge_done && (rc = launch_edge_hidden(d, *params, edge_attr, perm, E, ws.g, s, fused ? 3 : rnd_in))) return rc;
+  }
   if (edge_only) return FESR_OK;
   if ((rc = launch_fc_in(d, ws.prep, x, n, ws.h[0], s, rnd_in))) return rc;
   const float* h_last = ws.h[0];
@@ -89,7 +93,7 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
     float* Z = keep_for_backward ? ws.Z[l] : ws.Z[0];
     if (fused) {
       if ((rc = launch_layer_fused_f16(d, rowptr, src_sorted, ws.g, E, h_in, n, ws.prep.tfused_h, ws.prep.bias_p, Z, h_out,
-                                       d.w <= 43 ? fuse_mode : (fuse_mode > 2 ? 2 : fuse_mode), s)))
+                                       d.w <= 43 ? fuse_mode : (fuse_mode > 2 ? 2 : fuse_mode), s, l == d.layers - 1)))
         return rc;
       h_last = h_out;
       continue;
@@ -111,16 +115,23 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
       rc = launch_zbuild_mma(d, rowptr, src_sorted, ws.g, h_in, n, Z, zmode, s);
     if (rc) return rc;
     const int epi = d.kind == FESR_TEECNET ? EPI_BIAS_CONST1 : EPI_BIAS_RELU;
-    if (precision == FESR_PREC_FP32)
+    // predict (nothing kept for a backward): multi-term operands, see gemm_tc.cu.  A kept forward runs the plain
+    // one-term product the backward differentiates.  FESR_FP32_SIMT=1: the CUDA-core fp32 GEMM (test cross-check)
+    static const bool fp32_simt = getenv("FESR_FP32_SIMT") && atoi(getenv("FESR_FP32_SIMT")) != 0;
+    const bool multi = !keep_for_backward;
+    if (precision == FESR_PREC_FP32 && (fp32_simt || d.zk > 4096 || !(d.wp % 16 == 0 && d.wp <= 64)))
       rc = launch_node_gemm_fp32(d, ws.prep.tprime, ws.prep.bias_p, epi, Z, n, h_out, s);
+    else if (precision == FESR_PREC_FP32)
+      rc = launch_node_gemm_tf32(d, ws.prep.tprime_t, ws.prep.bias_p, epi, Z, n, h_out, s, 0, ws.prep.tprime_t_lo, 3);
     else if (precision == FESR_PREC_TF32)
-      rc = launch_node_gemm_tf32(d, ws.prep.tprime_t, ws.prep.bias_p, epi, Z, n, h_out, s, 1);
+      rc = launch_node_gemm_tf32(d, ws.prep.tprime_t, ws.prep.bias_p, epi, Z, n, h_out, s, 1, ws.prep.tprime_t_lo, multi ? 2 : 1);
     else
-      rc = launch_node_gemm_f16(d, ws.prep.tprime_t_h, ws.prep.bias_p, epi, Z, n, h_out, s, 2);
+      rc = launch_node_gemm_f16(d, ws.prep.tprime_t_h, ws.prep.bias_p, epi, Z, n, h_out, s, 2,
+                                multi ? ws.prep.tprime_t_h_lo : nullptr);
     if (rc) return rc;
     h_last = h_out;
   }
-  return launch_fc_out(d, *params, h_last, n, y, s, precision == FESR_PREC_F16);
+  return launch_fc_out(d, *params, h_last, n, y, s, precision == FESR_PREC_F16 && !fused);
 }
 
 }  // extern "C"

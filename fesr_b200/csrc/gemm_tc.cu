@@ -11,6 +11,21 @@
 // (one elected lane), warps 2..5 = epilogue (tcgen05.ld -> +bias -> activation -> global).
 // The kernel is HBM-bound on streaming Z (AI = 2*wp/4 = 24 flop/B), so the 8-deep TMA ring
 // (176 KB in flight per SM) is what matters, not MMA issue rate.
+//
+// TERMS (multi-term operands; the tensor pipe has the slack, the kernel streams Z once either way):
+//   1  Z x T'                                   training forward (the backward differentiates exactly this product)
+//   2  Z x T'hi + Z x T'lo                      predict, tf32 / f16 arms: the weights enter with ~21 bits -- rounding T'
+//                                               to one 11-bit term is a COHERENT error (same weights on every node, every
+//                                               layer) and was the largest term of these arms' error
+//   3  Zhi x T'hi + Zlo x T'hi + Zhi x T'lo     the fp32 arm (3xTF32): Z arrives as fp32; four converter warps split every
+//                                               landed A tile into tf32 hi (low mantissa bits cleared, in place) and lo
+//                                               (a second tile) before the MMA warp may touch the stage; fp32 accumulate
+//                                               in TMEM.  The tensor core's fp32 accumulation rounds toward zero, so a
+//                                               K = 2176 chain drifts by ~K 2^-24 (measured: 6e-6 on the KernelNN
+//                                               field against 2e-7 for RN FFMA): K is therefore cut into TC_CHUNKS
+//                                               accumulators of <= 17 k-blocks that the epilogue adds in RN fp32.
+//                                               Shapes with zk > 4096 (TEECNet, K = 6400) stay on the CUDA-core GEMM
+//                                               (gemm_simt.cu), which is also the test cross-check (FESR_FP32_SIMT=1).
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -20,9 +35,16 @@ namespace fesr {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;           // fp32 elements = 128 bytes = one SWIZZLE_128B row
-constexpr int TC_STAGES = 8;
-constexpr int TC_THREADS = 192;     // 6 warps
-constexpr int TC_ACC_COLS = 64;     // TMEM columns per accumulator stage (>= wp)
+constexpr int TC_THREADS = 192;     // 6 warps (+ 4 converter warps when TERMS == 3)
+// as many pipeline stages (<= 8) as fit the 227 KB of shared memory an SM offers one CTA
+__host__ __device__ constexpr int tc_stage_bytes(int terms, int wp) {
+  return (terms == 3 ? 2 : 1) * TC_BM * TC_BK * 4 + (terms >= 2 ? 2 : 1) * wp * TC_BK * 4;
+}
+__host__ __device__ constexpr int tc_stages(int terms, int wp) {
+  return (227 * 1024 - 1280) / tc_stage_bytes(terms, wp) < 8 ? (227 * 1024 - 1280) / tc_stage_bytes(terms, wp) : 8;
+}
+constexpr int TC_ACC_COLS = 64;     // TMEM columns per accumulator (>= wp)
+constexpr int TC_CHUNKS = 4;        // TERMS == 3: accumulators per tile, each over 1 / TC_CHUNKS of K
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -111,22 +133,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t (&r)[16]) {
       : "r"(addr));
 }
 
-template <int WP, bool HALF>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int WP, bool HALF, int TERMS>
+__global__ void __launch_bounds__(TC_THREADS + (TERMS == 3 ? 128 : 0), 1)
 node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const float* __restrict__ bias_p, int64_t n, int zk, int w, int epi, int round_out,
-                      float* __restrict__ h_out, int* ovf) {
+                      const __grid_constant__ CUtensorMap tmBlo, const float* __restrict__ bias_p, int64_t n, int zk,
+                      int w, int epi, int round_out, float* __restrict__ h_out, int* ovf) {
+  static_assert(!(HALF && TERMS == 3), "the three-term form is the fp32 arm");
   F16Guard guard;
+  constexpr int TC_STAGES = tc_stages(TERMS, WP);
+  constexpr int NCH = TERMS == 3 ? TC_CHUNKS : 1;                 // accumulators per tile
+  constexpr uint32_t STAGE_COLS = NCH * TC_ACC_COLS;              // TMEM columns of one accumulator stage
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
   constexpr uint32_t B_BYTES = WP * TC_BK * 4;      // wp * 128 B
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TX_BYTES = A_BYTES + (TERMS >= 2 ? 2 : 1) * B_BYTES;                   // what TMA lands per stage
+  constexpr uint32_t STAGE_BYTES = (TERMS == 3 ? 2 : 1) * A_BYTES + (TERMS >= 2 ? 2 : 1) * B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + TC_STAGES * A_BYTES;
+  uint8_t* smem_alo = smem_a + TC_STAGES * A_BYTES;                                          // TERMS == 3 only
+  uint8_t* smem_b = smem_alo + (TERMS == 3 ? TC_STAGES * A_BYTES : 0);
+  uint8_t* smem_blo = smem_b + TC_STAGES * B_BYTES;                                          // TERMS >= 2 only
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + TC_STAGES;
-  uint64_t* tmem_full = empty_bar + TC_STAGES;
+  uint64_t* split_bar = empty_bar + TC_STAGES;      // TERMS == 3: the converter warps are done with the stage
+  uint64_t* tmem_full = split_bar + TC_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -138,11 +168,13 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (TERMS >= 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 4);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -152,7 +184,7 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
   if (warp == 2) {   // TMEM allocation: 2 accumulator stages
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(2 * TC_ACC_COLS));
+                 "r"(2 * STAGE_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -169,9 +201,10 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int row0 = (int)(tile * TC_BM);
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          mbar_expect_tx(&full_bar[stage], TX_BYTES);
           tma_load_2d(smem_a + stage * A_BYTES, &tmA, &full_bar[stage], kb * ELEMS_PER_KB, row0);
           tma_load_2d(smem_b + stage * B_BYTES, &tmB, &full_bar[stage], kb * ELEMS_PER_KB, 0);
+          if (TERMS >= 2) tma_load_2d(smem_blo + stage * B_BYTES, &tmBlo, &full_bar[stage], kb * ELEMS_PER_KB, 0);
           if (++stage == TC_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -192,17 +225,29 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[as], aphase ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_d = tmem_base + as * TC_ACC_COLS;
+      const int kb_per_chunk = (n_kb + NCH - 1) / NCH;
       for (int kb = 0; kb < n_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(TERMS == 3 ? &split_bar[stage] : &full_bar[stage], phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int chunk = kb / kb_per_chunk;
+        const uint32_t tmem_d = tmem_base + as * STAGE_COLS + chunk * TC_ACC_COLS;
+        const int kb0 = kb - chunk * kb_per_chunk;          // first k-block of an accumulator starts it from zero
         if (elect_one()) {
           const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + stage * A_BYTES));
           const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + stage * B_BYTES));
+          const uint64_t alodesc = make_sw128_desc(smem_u32(smem_alo + stage * A_BYTES));
+          const uint64_t blodesc = make_sw128_desc(smem_u32(smem_blo + stage * B_BYTES));
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k) {  // 32 bytes (8 tf32 / 16 f16) per MMA: advance the start address by 2 (x16 B)
-            if constexpr (HALF) umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            else umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (HALF) {
+              umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb0 | k) != 0);
+              if (TERMS >= 2) umma_f16(tmem_d, adesc + 2 * k, blodesc + 2 * k, idesc, 1);
+            } else {
+              // small terms first, so that they are not absorbed one by one into a large running sum
+              if (TERMS == 3) umma_tf32(tmem_d, alodesc + 2 * k, bdesc + 2 * k, idesc, (kb0 | k) != 0);
+              if (TERMS >= 2) umma_tf32(tmem_d, adesc + 2 * k, blodesc + 2 * k, idesc, TERMS == 3 || (kb0 | k) != 0);
+              umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, TERMS >= 2 || (kb0 | k) != 0);
+            }
           }
           umma_commit(&empty_bar[stage]);              // frees the smem slot when these MMAs retire
           if (kb == n_kb - 1) umma_commit(&tmem_full[as]);
@@ -211,6 +256,45 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (++stage == TC_STAGES) {
           stage = 0;
           phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    // ===== converter warps (TERMS == 3): split every landed fp32 A tile into tf32 hi (in place) + lo (second tile).
+    // The swizzle only permutes 16-byte chunks inside a tile, and hi / lo are elementwise, so the tile is walked as
+    // flat float4's: the lo tile gets the same bytes-in-place layout as the A tile.
+    if constexpr (TERMS == 3) {
+      const int ct = threadIdx.x - TC_THREADS;          // 0..127
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          float4* a4 = reinterpret_cast<float4*>(smem_a + stage * A_BYTES);
+          float4* l4 = reinterpret_cast<float4*>(smem_alo + stage * A_BYTES);
+#pragma unroll
+          for (int q = 0; q < (int)(A_BYTES / 16 / 128); ++q) {
+            const int i = q * 128 + ct;
+            float4 v = a4[i];
+            float4 hi, lo;
+            hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+            hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+            hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+            hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+            lo.x = v.x - hi.x;          // exact: at most 13 significant bits; the tensor core keeps its top 11
+            lo.y = v.y - hi.y;
+            lo.z = v.z - hi.z;
+            lo.w = v.w - hi.w;
+            a4[i] = hi;
+            l4[i] = lo;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> tensor-core reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[stage]);
+          if (++stage == TC_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -224,12 +308,24 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_wait(&tmem_full[as], aphase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t row = tile * TC_BM + quad * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * TC_ACC_COLS;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * STAGE_COLS;
 #pragma unroll
       for (int c0 = 0; c0 < WP; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + c0, r);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if constexpr (NCH > 1) {          // add the K-chunk accumulators in round-to-nearest fp32
+          const int kbc = (n_kb + NCH - 1) / NCH, used = (n_kb + kbc - 1) / kbc;      // short K: fewer accumulators in use
+#pragma unroll
+          for (int ch = 1; ch < NCH; ++ch) {
+            if (ch >= used) break;
+            uint32_t q[16];
+            tmem_ld16(taddr + ch * TC_ACC_COLS + c0, q);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(q[j])));
+          }
+        }
         if (row < n && round_out == 2) {          // fp16 h (FESR_PREC_F16): 16 columns = 2 x 16-byte stores
           uint32_t pk[8];
 #pragma unroll
@@ -288,7 +384,7 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * TC_ACC_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * STAGE_COLS));
   }
 }
 
@@ -325,52 +421,60 @@ static int encode_map(CUtensorMap* map, const void* base, bool half, uint64_t in
   return FESR_OK;
 }
 
-template <int WP, bool HALF>
-static int launch_tc(const fesr_model_dims& d, const void* B_kmajor, const float* bias_p, int epi, const void* Z,
-                     int64_t n, float* h_out, cudaStream_t s, int round_out) {
-  constexpr size_t smem = (size_t)TC_STAGES * (TC_BM * TC_BK * 4 + WP * TC_BK * 4) + 1024 /*align*/ + 256 /*barriers*/;
+template <int WP, bool HALF, int TERMS>
+static int launch_tc(const fesr_model_dims& d, const void* B_kmajor, const void* B_lo, const float* bias_p, int epi,
+                     const void* Z, int64_t n, float* h_out, cudaStream_t s, int round_out) {
+  constexpr int STAGES = tc_stages(TERMS, WP);
+  constexpr size_t smem = (size_t)STAGES * tc_stage_bytes(TERMS, WP) + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(smem <= 227 * 1024, "stage ring exceeds the shared memory of an SM");
   constexpr uint32_t box_inner = HALF ? 2 * TC_BK : TC_BK;
   static bool attr_set = false;
   if (!attr_set) {
-    FESR_CUDA(cudaFuncSetAttribute(node_gemm_tf32_kernel<WP, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FESR_CUDA(cudaFuncSetAttribute(node_gemm_tf32_kernel<WP, HALF, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     attr_set = true;
   }
   FESR_CHECK_ARG(d.zk % (int)box_inner == 0, "zk must be a multiple of %u", box_inner);
-  CUtensorMap tmA, tmB;
+  FESR_CHECK_ARG(TERMS == 1 || B_lo != nullptr, "multi-term node GEMM without a low-order weight copy");
+  CUtensorMap tmA, tmB, tmBlo;
   int rc;
   if ((rc = encode_map(&tmA, Z, HALF, (uint64_t)d.zk, (uint64_t)n, box_inner, TC_BM))) return rc;
   if ((rc = encode_map(&tmB, B_kmajor, HALF, (uint64_t)d.zk, (uint64_t)d.wp, box_inner, WP))) return rc;
+  if ((rc = encode_map(&tmBlo, TERMS >= 2 ? B_lo : B_kmajor, HALF, (uint64_t)d.zk, (uint64_t)d.wp, box_inner, WP))) return rc;
   const int64_t n_tiles = ceil_div(n, TC_BM);
   const int grid = (int)(n_tiles < num_sms() ? n_tiles : num_sms());
   ProfScope prof(PROF_NODE_GEMM, s);
-  node_gemm_tf32_kernel<WP, HALF><<<grid, TC_THREADS, smem, s>>>(tmA, tmB, bias_p, n, d.zk, d.w, epi, round_out, h_out, cur_ovf());
+  node_gemm_tf32_kernel<WP, HALF, TERMS><<<grid, TC_THREADS + (TERMS == 3 ? 128 : 0), smem, s>>>(
+      tmA, tmB, tmBlo, bias_p, n, d.zk, d.w, epi, round_out, h_out, cur_ovf());
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
 
-template <bool HALF>
-static int dispatch_tc(const fesr_model_dims& d, const void* B, const float* bias_p, int epi, const void* Z, int64_t n,
-                       float* h_out, cudaStream_t s, int round_out) {
+template <bool HALF, int TERMS>
+static int dispatch_tc(const fesr_model_dims& d, const void* B, const void* B_lo, const float* bias_p, int epi, const void* Z,
+                       int64_t n, float* h_out, cudaStream_t s, int round_out) {
   if (n == 0) return FESR_OK;
   switch (d.wp) {
-    case 16: return launch_tc<16, HALF>(d, B, bias_p, epi, Z, n, h_out, s, round_out);
-    case 32: return launch_tc<32, HALF>(d, B, bias_p, epi, Z, n, h_out, s, round_out);
-    case 48: return launch_tc<48, HALF>(d, B, bias_p, epi, Z, n, h_out, s, round_out);
-    case 64: return launch_tc<64, HALF>(d, B, bias_p, epi, Z, n, h_out, s, round_out);
+    case 16: return launch_tc<16, HALF, TERMS>(d, B, B_lo, bias_p, epi, Z, n, h_out, s, round_out);
+    case 32: return launch_tc<32, HALF, TERMS>(d, B, B_lo, bias_p, epi, Z, n, h_out, s, round_out);
+    case 48: return launch_tc<48, HALF, TERMS>(d, B, B_lo, bias_p, epi, Z, n, h_out, s, round_out);
+    case 64: return launch_tc<64, HALF, TERMS>(d, B, B_lo, bias_p, epi, Z, n, h_out, s, round_out);
   }
   set_error("unsupported padded width %d", d.wp);
   return FESR_EINVAL;
 }
 
 int launch_node_gemm_tf32(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi, const float* Z,
-                          int64_t n, float* h_out, cudaStream_t s, int round_out) {
-  return dispatch_tc<false>(d, B_kmajor, bias_p, epi, Z, n, h_out, s, round_out);
+                          int64_t n, float* h_out, cudaStream_t s, int round_out, const float* B_lo, int terms) {
+  if (terms == 3) return dispatch_tc<false, 3>(d, B_kmajor, B_lo, bias_p, epi, Z, n, h_out, s, round_out);
+  if (terms == 2) return dispatch_tc<false, 2>(d, B_kmajor, B_lo, bias_p, epi, Z, n, h_out, s, round_out);
+  return dispatch_tc<false, 1>(d, B_kmajor, nullptr, bias_p, epi, Z, n, h_out, s, round_out);
 }
 
 int launch_node_gemm_f16(const fesr_model_dims& d, const void* B_kmajor_h, const float* bias_p, int epi, const void* Z_h,
-                         int64_t n, float* h_out, cudaStream_t s, int round_out) {
-  return dispatch_tc<true>(d, B_kmajor_h, bias_p, epi, Z_h, n, h_out, s, round_out);
+                         int64_t n, float* h_out, cudaStream_t s, int round_out, const void* B_lo_h) {
+  if (B_lo_h != nullptr) return dispatch_tc<true, 2>(d, B_kmajor_h, B_lo_h, bias_p, epi, Z_h, n, h_out, s, round_out);
+  return dispatch_tc<true, 1>(d, B_kmajor_h, nullptr, bias_p, epi, Z_h, n, h_out, s, round_out);
 }
 
 }  // namespace fesr

@@ -42,12 +42,12 @@ int launch_zbuild_f16(const fesr_model_dims& d, const int32_t* rowptr, const int
 // layer_fused.cu: zbuild + node contraction + epilogue of one layer in one kernel (FESR_PREC_F16)
 bool layer_fused_supported(const fesr_model_dims& d);
 size_t layer_fused_tf_elems(const fesr_model_dims& d);
-int launch_prepare_tfused(const fesr_model_dims& d, const float* tprime, void* tf, cudaStream_t s);
+int launch_prepare_tfused(const fesr_model_dims& d, const float* tprime, const float* mfull, void* tf, cudaStream_t s);
 // g3: fp16 planar [kp/16][E][16] (launch_edge_hidden with round mode 3); P: fp32 [n, 48] scratch;
 // mode: parts per launch (0 = as many as the TMEM lanes hold)
 int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* g3,
                            int64_t E, const void* h_in, int64_t n, const void* tf, const float* bias_p, float* P,
-                           void* h_out, int mode, cudaStream_t s);
+                           void* h_out, int mode, cudaStream_t s, int out_f32 = 0);
 
 // gemm_simt.cu ------------------------------------------------------------------------
 // h_out[n, wp] = epilogue(Z[n, zk] x tprime[zk, wp] + bias)
@@ -59,10 +59,13 @@ int launch_node_gemm_fp32(const fesr_model_dims& d, const float* B_rowmajor, con
 
 // gemm_tc.cu --------------------------------------------------------------------------
 // fp16 variant: Z [n, zk] fp16, B_kmajor [wp, zk] fp16 (tcgen05 kind::f16, fp32 accumulate)
+// B_lo_h: [wp, zk] fp16 low-order term of T' (predict: two-term weights) or NULL (one term)
 int launch_node_gemm_f16(const fesr_model_dims& d, const void* B_kmajor_h, const float* bias_p, int epi,
-                         const void* Z_h, int64_t n, float* h_out, cudaStream_t s, int round_out = 0);
-// B_kmajor: [wp, zk] tf32-rounded
+                         const void* Z_h, int64_t n, float* h_out, cudaStream_t s, int round_out = 0,
+                         const void* B_lo_h = nullptr);
+// B_kmajor: [wp, zk] tf32-rounded; terms 1 | 2 (+ Z x B_lo) | 3 (3xTF32 on fp32 Z: the fp32 arm); B_lo: tf32 low-order term
 int launch_node_gemm_tf32(const fesr_model_dims& d, const float* B_kmajor, const float* bias_p, int epi,
-                          const float* Z, int64_t n, float* h_out, cudaStream_t s, int round_out = 0);
+                          const float* Z, int64_t n, float* h_out, cudaStream_t s, int round_out = 0,
+                          const float* B_lo = nullptr, int terms = 1);
 
 }  // namespace fesr

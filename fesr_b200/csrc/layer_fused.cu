@@ -152,8 +152,18 @@ __device__ __forceinline__ void fl_tmem_st16(uint32_t addr, const uint32_t (&r)[
 //   kb < 12 : a = (kb/2)*8 + a_in,  slot = part*16 + (kb%2)*8 + s_in  -> T'[(chan(slot), a), b]
 //   kb = 12 : a = a_in*8 + s_in (root block, last part only; the tail 16 entries are zero)
 // so that the 64 values one builder store instruction produces (8 a's x 8 slots) are one k-block row.
+//
+// Two-term weights where the rounding of T' to fp16 would otherwise dominate the arm's error.  The
+// edge features are centred, g~ = g - g(0): sum_k g_k T'_k = sum_k g~_k T'_k + M with M = T'_K + sum_k g(0)_k T'_k
+// (prepare_center_kernel, fp32).  For these models g varies by < 1 % over the mesh's edge lengths, so M -- applied
+// to the neighbour mean of h through the constant-1 slot -- carries almost the whole layer, and so does `root`
+// (applied to h_i): both get a hi + lo pair of fp16 weights at no run-time cost,
+//   constant-1 slot : fp16(M)                  lo slot (a padding slot, g = 2^-8)      : fp16((M - fp16(M)) 2^8)
+//   root block      : fp16(root)               root block of the part before the last : fp16((root - fp16(root)) 2^8)
+//                                              (its B rows get h_i deg 2^-8 from the consumer)
+// The other slots hold fp16(T'_k) against g~_k: their rounding errors now multiply a < 1 % signal.
 __global__ void prepare_tfused_kernel(fesr_model_dims d, int n_parts, const float* __restrict__ tprime,
-                                      __half* __restrict__ tf) {
+                                      const float* __restrict__ mfull, __half* __restrict__ tf) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)n_parts * FL_WP * FL_KP;
   if (idx >= total) return;
@@ -161,15 +171,27 @@ __global__ void prepare_tfused_kernel(fesr_model_dims d, int n_parts, const floa
   const int b = (int)((idx / FL_KP) % FL_WP);
   const int part = (int)(idx / ((int64_t)FL_KP * FL_WP));
   const int kb = K >> 6, e = K & 63;
+  const float inv_lo = 1.0f / FESR_LO_SCALE;
   float v = 0.f;
   if (kb < 12) {
     const int a = (kb >> 1) * 8 + (e >> 3);
     const int slot = part * 16 + (kb & 1) * 8 + (e & 7);
     const int q = slot / d.ktp, r = slot % d.ktp;
     const int chan = q * d.kt + r;
-    if (r < d.kt && chan < d.k1 && a < d.wp && b < d.wp) v = tprime[((size_t)chan * d.wp + a) * d.wp + b];
-  } else if (part == n_parts - 1 && e < d.wp) {
-    v = tprime[((size_t)d.zk_main + e) * d.wp + b];
+    if (a < d.wp && b < d.wp) {
+      if (slot == d.kt) {                                        // lo slot: low-order term of M
+        const float m = mfull[a * d.wp + b];
+        v = (m - __half2float(__float2half_rn(m))) * inv_lo;
+      } else if (r < d.kt && chan == d.k1 - 1) {                 // constant-1 slot: M
+        v = mfull[a * d.wp + b];
+      } else if (r < d.kt && chan < d.k1) {
+        v = tprime[((size_t)chan * d.wp + a) * d.wp + b];
+      }
+    }
+  } else if (e < d.wp) {
+    const float rt = tprime[((size_t)d.zk_main + e) * d.wp + b];
+    if (part == n_parts - 1) v = rt;
+    else if (part == n_parts - 2) v = (rt - __half2float(__float2half_rn(rt))) * inv_lo;      // low-order term of root
   }
   tf[idx] = __float2half_rn(v);
 }
@@ -420,6 +442,14 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
         hs.z = fl_hmul2(hv.z, dg);
         hs.w = fl_hmul2(hv.w, dg);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(zroot), "r"(hs.x), "r"(hs.y), "r"(hs.z), "r"(hs.w) : "memory");
+        if (PPL >= 2) {
+          // the same row scaled by 2^-8 for the part before the last: its root block holds the low-order term of
+          // `root` (prepare_tfused_kernel), so h_i root is applied with two-term fp16 weights
+          const __half2 dl = __float2half2_rn((float)(deg > 0 ? deg : 1) * FESR_LO_SCALE);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(zroot - (uint32_t)(FL_NODES * 128)), "r"(fl_hmul2(hv.x, dl)),
+                       "r"(fl_hmul2(hv.y, dl)), "r"(fl_hmul2(hv.z, dl)), "r"(fl_hmul2(hv.w, dl))
+                       : "memory");
+        }
         if (do_fix) {
           uint4 wr;     // root weights of this lane's chunk (lanes 6, 7: zeros)
           asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(wr.x), "=r"(wr.y), "=r"(wr.z), "=r"(wr.w) : "r"(wfl + (uint32_t)(12 * 128 + lane * 12)));
@@ -534,7 +564,10 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
               guard.note(v0, v1);
               guard.flush(ovf);
             }
-            *reinterpret_cast<uint32_t*>(h_out + row * FL_WP + c0) = fl_h2_sat(v0, v1);
+            if (relu & 2)      // the model's last layer: fp32 rows for fc2 (one rounding less on the way out)
+              *reinterpret_cast<float2*>(reinterpret_cast<float*>(h_out) + row * FL_WP + c0) = make_float2(v0, v1);
+            else
+              *reinterpret_cast<uint32_t*>(h_out + row * FL_WP + c0) = fl_h2_sat(v0, v1);
           }
         }
       }
@@ -733,10 +766,11 @@ bool layer_fused_supported(const fesr_model_dims& d) {
 int layer_fused_parts(const fesr_model_dims& d) { return d.kp / 16; }
 size_t layer_fused_tf_elems(const fesr_model_dims& d) { return (size_t)layer_fused_parts(d) * FL_WP * FL_KP; }
 
-int launch_prepare_tfused(const fesr_model_dims& d, const float* tprime, void* tf, cudaStream_t s) {
+int launch_prepare_tfused(const fesr_model_dims& d, const float* tprime, const float* mfull, void* tf, cudaStream_t s) {
   const int64_t total = (int64_t)layer_fused_tf_elems(d);
   ProfScope prof(PROF_PREPARE, s);
-  prepare_tfused_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(d, layer_fused_parts(d), tprime, static_cast<__half*>(tf));
+  prepare_tfused_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(d, layer_fused_parts(d), tprime, mfull,
+                                                                      static_cast<__half*>(tf));
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
@@ -745,7 +779,7 @@ int launch_prepare_tfused(const fesr_model_dims& d, const float* tprime, void* t
 // (only touched when the parts need more than one launch).  mode: parts per launch (0 = best).
 int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* g3,
                            int64_t E, const void* h_in, int64_t n, const void* tf, const float* bias_p, float* P,
-                           void* h_out, int mode, cudaStream_t s) {
+                           void* h_out, int mode, cudaStream_t s, int out_f32) {
   if (n == 0) return FESR_OK;
   if (!layer_fused_supported(d)) {
     set_error("fused layer: unsupported model shape");
@@ -755,7 +789,8 @@ int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, cons
   const __half* hh = static_cast<const __half*>(h_in);
   const __half* tfh = static_cast<const __half*>(tf);
   __half* ho = static_cast<__half*>(h_out);
-  const int relu = d.kind == FESR_KERNELNN ? 1 : 0;      // TEECNet: no activation between the layers (models/model.py:280-282)
+  // bit 0: ReLU (TEECNet has no activation between the layers, models/model.py:280-282); bit 1: fp32 output rows
+  const int relu = (d.kind == FESR_KERNELNN ? 1 : 0) | (out_f32 ? 2 : 0);
   ProfScope prof(PROF_LAYER_FUSED, s);
   int rc;
   if (d.kind == FESR_TEECNET) {

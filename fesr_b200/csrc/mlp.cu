@@ -26,12 +26,15 @@ Prepared carve_prepared(Carver& c, const fesr_model_dims& d) {
   w.ttilde = c.take<float>((size_t)d.zk * d.wp);
   w.ttilde_t = c.take<float>((size_t)d.zk * d.wp);
   w.tprime_t_h = c.take<__half>((size_t)d.zk * d.wp);
+  w.tprime_t_h_lo = c.take<__half>((size_t)d.zk * d.wp);
   w.ttilde_t_h = c.take<__half>((size_t)d.zk * d.wp);
   w.tfused_h = layer_fused_supported(d) ? c.take<__half>(layer_fused_tf_elems(d)) : nullptr;
   w.bias_p = c.take<float>(d.wp);
   w.fc1_wp = c.take<float>((size_t)d.in_ch * d.wp);
   w.fc1_bp = c.take<float>(d.wp);
   w.ovf = c.take<int>(1);
+  w.gcenter = c.take<float>(d.kp);
+  w.mfull = c.take<float>((size_t)d.wp * d.wp);
   return w;
 }
 
@@ -48,7 +51,7 @@ __global__ void prepare_tprime_kernel(fesr_model_dims d, const float* __restrict
                                       float* __restrict__ tprime, float* __restrict__ tprime_t,
                                       float* __restrict__ tprime_t_lo, float* __restrict__ ttilde,
                                       float* __restrict__ ttilde_t, __half* __restrict__ tprime_t_h,
-                                      __half* __restrict__ ttilde_t_h) {
+                                      __half* __restrict__ tprime_t_h_lo, __half* __restrict__ ttilde_t_h) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)d.zk * d.wp;
   if (idx >= total) return;
@@ -81,7 +84,9 @@ __global__ void prepare_tprime_kernel(fesr_model_dims d, const float* __restrict
   const float hi = tf32_rna(v);
   tprime_t[(size_t)b * d.zk + r] = hi;
   tprime_t_lo[(size_t)b * d.zk + r] = tf32_rna(v - hi);
-  tprime_t_h[(size_t)b * d.zk + r] = __float2half_rn(v);
+  const __half vh = __float2half_rn(v);
+  tprime_t_h[(size_t)b * d.zk + r] = vh;
+  tprime_t_h_lo[(size_t)b * d.zk + r] = __float2half_rn(v - __half2float(vh));
   // transposed blocks for the backward: row (kk*wp + b), column a  <-  T'[kk*wp + a, b]
   const int kk = r / d.wp, a = r % d.wp;
   const int rt = kk * d.wp + b;
@@ -89,6 +94,55 @@ __global__ void prepare_tprime_kernel(fesr_model_dims d, const float* __restrict
     ttilde[(size_t)rt * d.wp + a] = v;
     ttilde_t[(size_t)a * d.zk + rt] = hi;
     ttilde_t_h[(size_t)a * d.zk + rt] = __float2half_rn(v);
+  }
+}
+
+// Centring constants of the fused f16 arm.  One block.
+//   g0[k]   = hidden activations of the edge MLP at edge length 0 (a function of the weights alone)
+//   gcenter = g0 in the g-row slot layout (constant-1 slot: 0; lo slot: -FESR_LO_SCALE, so that "g - gcenter" leaves
+//             the constant FESR_LO_SCALE there; other padding: 0)
+//   mfull[a, b] = T'[(K, a), b] + sum_{k < K} g0[k] T'[(k, a), b]   (fp32; sum_k g_k T'_k = sum_k (g_k - g0_k) T'_k + this)
+__device__ __forceinline__ float pc_act(float v, int leaky) { return leaky ? (v > 0.f ? v : 0.01f * v) : fmaxf(v, 0.f); }
+struct CenterArgs {
+  const float* w[4];
+  const float* b[4];
+  int dims[4];
+  int n_hidden, leaky;
+};
+__global__ void __launch_bounds__(256)
+prepare_center_kernel(fesr_model_dims d, CenterArgs a, const float* __restrict__ tprime, float* __restrict__ gcenter,
+                      float* __restrict__ mfull) {
+  __shared__ float buf[2][128];
+  const int t = threadIdx.x;
+  float* in = buf[0];
+  float* out = buf[1];
+  for (int i = t; i < a.dims[0]; i += blockDim.x) in[i] = pc_act(a.b[0][i], a.leaky);      // layer 0 at d = 0
+  __syncthreads();
+  for (int l = 1; l < a.n_hidden; ++l) {
+    const int din = a.dims[l - 1], dout = a.dims[l];
+    for (int o = t; o < dout; o += blockDim.x) {
+      float acc = a.b[l][o];
+      for (int i = 0; i < din; ++i) acc = fmaf(a.w[l][o * din + i], in[i], acc);
+      out[o] = pc_act(acc, a.leaky);
+    }
+    __syncthreads();
+    float* tmp = in;
+    in = out;
+    out = tmp;
+  }
+  const int K = d.k1 - 1;
+  for (int slot = t; slot < d.kp; slot += blockDim.x) {
+    const int q = slot / d.ktp, r = slot % d.ktp, ch = q * d.kt + r;
+    float v = 0.f;
+    if (r < d.kt && ch < K) v = in[ch];
+    if (slot == d.kt) v = -FESR_LO_SCALE;          // the first padding slot (r == kt of group 0) is the lo slot
+    gcenter[slot] = v;
+  }
+  for (int idx = t; idx < d.wp * d.wp; idx += blockDim.x) {
+    const int a_ = idx / d.wp, b = idx % d.wp;
+    float acc = tprime[((size_t)K * d.wp + a_) * d.wp + b];
+    for (int k = 0; k < K; ++k) acc = fmaf(in[k], tprime[((size_t)k * d.wp + a_) * d.wp + b], acc);
+    mfull[idx] = acc;
   }
 }
 
@@ -119,11 +173,27 @@ int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const
                                                                       p.lin_b, p.root, w.tprime, w.tprime_t,
                                                                       w.tprime_t_lo, w.ttilde, w.ttilde_t,
                                                                       static_cast<__half*>(w.tprime_t_h),
+                                                                      static_cast<__half*>(w.tprime_t_h_lo),
                                                                       static_cast<__half*>(w.ttilde_t_h));
   FESR_LAUNCH_CHECK();
   prepare_small_kernel<<<1, 64, 0, s>>>(d, p.fc1_w, p.fc1_b, p.bias, w.bias_p, w.fc1_wp, w.fc1_bp);
   FESR_LAUNCH_CHECK();
-  if (w.tfused_h) return launch_prepare_tfused(d, w.tprime, w.tfused_h, s);
+  if (w.tfused_h) {
+    FESR_CHECK_ARG(d.ktp > d.kt, "the fused arm needs a padding slot per channel group");
+    CenterArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    for (int l = 0; l < d.n_hidden; ++l) {
+      FESR_CHECK_ARG(p.mlp_w[l] && p.mlp_b[l] && d.hidden[l] <= 128, "edge-MLP parameter %d missing or wider than 128", l);
+      ca.w[l] = p.mlp_w[l];
+      ca.b[l] = p.mlp_b[l];
+      ca.dims[l] = d.hidden[l];
+    }
+    ca.n_hidden = d.n_hidden;
+    ca.leaky = d.leaky;
+    prepare_center_kernel<<<1, 256, 0, s>>>(d, ca, w.tprime, w.gcenter, w.mfull);
+    FESR_LAUNCH_CHECK();
+    return launch_prepare_tfused(d, w.tprime, w.mfull, w.tfused_h, s);
+  }
   return FESR_OK;
 }
 

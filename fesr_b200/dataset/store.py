@@ -2,13 +2,13 @@
 
     mesh_{m}/subdomain_{i}/{x, y, pos, edge_index, edge_attr, global_node_ids}
 
-The reference writes it as HDF5 groups through h5py.  h5py is not part of this environment, so the store has two
-containers behind one reader / writer:
+The reference writes it as HDF5 groups through h5py.  Two containers behind one reader / writer:
 
-  * ``.h5`` / ``.hdf5`` -- read and written through h5py WHEN IT IS IMPORTABLE (the reference's own files load
-    unchanged); a clear error otherwise;
-  * ``.npz``           -- the same hierarchy with the group path as the key (``mesh_0/subdomain_3/x``); the 10-line
-    converter a maintainer runs once on the reference side is in INTEGRATION.md.
+  * ``.h5`` / ``.hdf5`` -- the reference's own files.  Read and written through ``hdf5_min`` (this package's
+    dependency-free implementation of the HDF5 subset h5py's defaults produce: version-0 superblock, symbol-table
+    groups, contiguous / compact / unfiltered-chunked datasets of little-endian numbers); when h5py happens to be
+    importable it is used instead (``FESR_HDF5=min`` forces the built-in reader);
+  * ``.npz``           -- the same hierarchy with the group path as the key (``mesh_0/subdomain_3/x``).
 
 ``StoredSubdomainDataset`` serves ``get_one_full_sample`` / ``reconstruct_from_partition`` from such a store: the
 stored subdomains (any edge order, as the reference's Python ``set`` leaves it) become one block-diagonal device batch
@@ -35,12 +35,15 @@ def _is_h5(path):
 
 
 def _h5py():
+    """h5py if it is importable and not switched off, else None (the built-in hdf5_min is used)."""
+    import os
+    if os.environ.get("FESR_HDF5", "") == "min":
+        return None
     try:
         import h5py
         return h5py
-    except ImportError as e:
-        raise ImportError("reading / writing the HDF5 container needs h5py, which is not installed here; convert the "
-                          "file to .npz on a machine that has it (INTEGRATION.md, 'On-disk subdomain store')") from e
+    except ImportError:
+        return None
 
 
 def save_partitioned(path, meshes):
@@ -50,7 +53,13 @@ def save_partitioned(path, meshes):
         return v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
 
     if _is_h5(path):
-        with _h5py().File(path, "w") as f:
+        h5py = _h5py()
+        if h5py is None:
+            from .hdf5_min import write_hdf5
+            write_hdf5(path, {f"mesh_{m}": {f"subdomain_{i}": {k: arr(d, k) for k in FIELDS} for i, d in enumerate(subs)}
+                              for m, subs in enumerate(meshes)})
+            return
+        with h5py.File(path, "w") as f:
             for m, subs in enumerate(meshes):
                 gm = f.create_group(f"mesh_{m}")
                 for i, d in enumerate(subs):
@@ -70,7 +79,26 @@ def load_partitioned(path, mesh_indices=None):
     """-> {mesh index: [dict(FIELDS -> numpy array) per subdomain, in subdomain order]}"""
     meshes = {}
     if _is_h5(path):
-        with _h5py().File(path, "r") as f:
+        h5py = _h5py()
+        if h5py is None:
+            from .hdf5_min import Hdf5File
+            with Hdf5File(path) as f:
+                for name in f.keys():
+                    if not name.startswith("mesh_"):
+                        continue
+                    m = int(name.split("_")[1])
+                    if mesh_indices is not None and m not in mesh_indices:
+                        continue
+                    subs = sorted((s for s in f.keys(name) if s.startswith("subdomain_")), key=lambda s: int(s.split("_")[1]))
+                    meshes[m] = []
+                    for s_ in subs:
+                        have = f.keys(f"{name}/{s_}")
+                        missing = [k for k in FIELDS if k not in have]
+                        if missing:
+                            raise ValueError(f"{name}/{s_}: missing {missing}")
+                        meshes[m].append({k: f[f"{name}/{s_}/{k}"] for k in FIELDS})
+            return meshes
+        with h5py.File(path, "r") as f:
             for name, gm in f.items():
                 m = int(name.split("_")[1])
                 if mesh_indices is not None and m not in mesh_indices:

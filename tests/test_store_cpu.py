@@ -50,8 +50,20 @@ def test_store_validation(tmp_path):
     np.savez(str(path), **z)
     with pytest.raises(ValueError, match="indices"):
         load_partitioned(str(path))
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        with pytest.raises(ImportError, match="h5py"):
-            load_partitioned(str(tmp_path / "reference.h5"))
+
+
+def test_hdf5_store_round_trip_without_h5py(tmp_path, monkeypatch):
+    """The reference's container (.h5) through the built-in reader / writer: same arrays, dtypes and shapes."""
+    monkeypatch.setenv("FESR_HDF5", "min")
+    meshes = _meshes(np.random.default_rng(2), n_mesh=3, n_sub=5)
+    path = tmp_path / "data.h5"
+    save_partitioned(str(path), meshes)
+    assert open(path, "rb").read(8) == b"\x89HDF\r\n\x1a\n"
+    back = load_partitioned(str(path))
+    assert sorted(back) == [0, 1, 2] and all(len(back[m]) == 5 for m in back)
+    for m, subs in enumerate(meshes):
+        for i, d in enumerate(subs):
+            for k in FIELDS:
+                want = getattr(d, k).numpy()
+                assert back[m][i][k].dtype == want.dtype and np.array_equal(back[m][i][k], want), (m, i, k)
+    assert sorted(load_partitioned(str(path), mesh_indices=[2])) == [2]
