@@ -634,6 +634,41 @@ fc_out_h48c4_kernel(const __half* __restrict__ h, const float* __restrict__ w2, 
   reinterpret_cast<float4*>(y)[i] = acc;
 }
 
+// fp32 rows of 48 (the fused arm's last layer writes fp32): same thread-per-node scheme, twelve 16-byte loads per row
+__global__ void __launch_bounds__(256)
+fc_out_f48c4_kernel(const float* __restrict__ h, const float* __restrict__ w2, const float* __restrict__ b2, int w,
+                    int64_t n, float* __restrict__ y, const int* __restrict__ ovf) {
+  __shared__ __align__(16) float wt[48][4];
+  for (int t = threadIdx.x; t < 48 * 4; t += blockDim.x) {
+    const int b = t >> 2, c = t & 3;
+    wt[b][c] = b < w ? w2[c * w + b] : 0.f;
+  }
+  __syncthreads();
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 acc = make_float4(b2[0], b2[1], b2[2], b2[3]);
+  if (ovf != nullptr && *ovf != 0) {      // an fp16 intermediate of this pass left the fp16 range: no plausible output
+    const float qn = __int_as_float(0x7fc00000);
+    reinterpret_cast<float4*>(y)[i] = make_float4(qn, qn, qn, qn);
+    return;
+  }
+  const float4* row = reinterpret_cast<const float4*>(h + i * 48);
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const float4 v = __ldg(row + q);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(wt[q * 4 + k]);
+      acc.x = fmaf(f[k], w0.x, acc.x);
+      acc.y = fmaf(f[k], w0.y, acc.y);
+      acc.z = fmaf(f[k], w0.z, acc.z);
+      acc.w = fmaf(f[k], w0.w, acc.w);
+    }
+  }
+  reinterpret_cast<float4*>(y)[i] = acc;
+}
+
 int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const void* h, int64_t n, float* y, cudaStream_t s,
                   int h_half) {
   if (n == 0) return FESR_OK;
@@ -642,6 +677,11 @@ int launch_fc_out(const fesr_model_dims& d, const fesr_params& p, const void* h,
   ProfScope prof(PROF_FC_OUT, s);
   if (h_half && d.wp == 48 && d.out_ch == 4 && d.w <= 48 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
     fc_out_h48c4_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(static_cast<const __half*>(h), p.fc2_w, p.fc2_b, d.w, n, y, cur_ovf());
+    FESR_LAUNCH_CHECK();
+    return FESR_OK;
+  }
+  if (!h_half && d.wp == 48 && d.out_ch == 4 && d.w <= 48 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    fc_out_f48c4_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(static_cast<const float*>(h), p.fc2_w, p.fc2_b, d.w, n, y, cur_ovf());
     FESR_LAUNCH_CHECK();
     return FESR_OK;
   }

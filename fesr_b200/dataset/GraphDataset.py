@@ -51,8 +51,9 @@ class StitchedMesh:
     slice `node_range` of the mesh nodes; the whole-mesh arrays (`field`, `ref_field`, `merged`, ...) are computed
     from the gathered predictions when somebody asks for them (`lazy`: name -> callable returning the device array)."""
 
-    def __init__(self, pos, cells, dev_arrays, global_ids, lazy=None, node_range=None):
+    def __init__(self, pos, cells, dev_arrays, global_ids, lazy=None, node_range=None, appended_cells=None):
         self.pos, self.cells = pos, cells            # original mesh (numpy)
+        self._appended_cells = appended_cells        # callable -> [sum cells, 4] int64 in appended numbering, or None
         self._dev = dict(dev_arrays)                 # name -> device tensor; copied to the host on first access
         self._lazy = dict(lazy or {})
         self._host = {}
@@ -89,29 +90,46 @@ class StitchedMesh:
     def GetNumberOfPoints(self):
         return int(self.global_ids.shape[0])
 
-    def write_vtu(self, path):
-        """ASCII .vtu of the ORIGINAL mesh with the stitched point arrays (run_ALDS_3D.py:33-38)."""
-        pos, cells = np.asarray(self.pos), np.asarray(self.cells)
-        f, r = self.field.numpy(), self.ref_field.numpy()
+    def write_vtu(self, path, appended: bool | None = None):
+        """Writes the result as VTK XML UnstructuredGrid (run_ALDS_3D.py:33-38).
+        appended=True: the grid the reference writes -- every partition appended (sum n_s points at their copies'
+        positions, each partition's cells in its own point numbering), point arrays `velocity`, `pressure`,
+        `ref_velocity`, `ref_pressure` = the averages written back to every copy, plus `GlobalPointIds`.
+        appended=False: the ORIGINAL mesh (N points) with the stitched fields -- smaller, same information.
+        Default: the reference's appended grid when this dataset knows the partitions' cells, else the original mesh."""
+        from .vtu import write_vtu
+        if appended is None:
+            appended = self._appended_cells is not None
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        with open(path, "w") as fh:
-            fh.write('<?xml version="1.0"?>\n<VTKFile type="UnstructuredGrid" version="0.1" byte_order="LittleEndian">\n')
-            fh.write(f'<UnstructuredGrid><Piece NumberOfPoints="{pos.shape[0]}" NumberOfCells="{cells.shape[0]}">\n')
-            fh.write('<PointData Vectors="velocity" Scalars="pressure">\n')
-            for name, arr, nc in (("velocity", f[:, :3], 3), ("pressure", f[:, 3:4], 1),
-                                  ("ref_velocity", r[:, :3], 3), ("ref_pressure", r[:, 3:4], 1)):
-                fh.write(f'<DataArray type="Float32" Name="{name}" NumberOfComponents="{nc}" format="ascii">\n')
-                np.savetxt(fh, arr, fmt="%.7g")
-                fh.write('</DataArray>\n')
-            fh.write('</PointData>\n<Points><DataArray type="Float32" NumberOfComponents="3" format="ascii">\n')
-            np.savetxt(fh, pos, fmt="%.7g")
-            fh.write('</DataArray></Points>\n<Cells>\n<DataArray type="Int32" Name="connectivity" format="ascii">\n')
-            np.savetxt(fh, cells, fmt="%d")
-            fh.write('</DataArray>\n<DataArray type="Int32" Name="offsets" format="ascii">\n')
-            np.savetxt(fh, np.arange(1, cells.shape[0] + 1) * cells.shape[1], fmt="%d")
-            fh.write('</DataArray>\n<DataArray type="UInt8" Name="types" format="ascii">\n')
-            np.savetxt(fh, np.full(cells.shape[0], 10), fmt="%d")
-            fh.write('</DataArray>\n</Cells>\n</Piece></UnstructuredGrid>\n</VTKFile>\n')
+        if appended:
+            if self._appended_cells is None:
+                raise ValueError("this dataset does not keep the partitions' cells: write_vtu(path, appended=False)")
+            m, r = self.merged.numpy(), self.merged_ref.numpy()
+            gids = self.global_ids.numpy() if torch.is_tensor(self.global_ids) else np.asarray(self.global_ids)
+            write_vtu(path, np.asarray(self.pos)[gids], self._appended_cells(),
+                      {"velocity": m[:, :3], "pressure": m[:, 3], "ref_velocity": r[:, :3], "ref_pressure": r[:, 3],
+                       "GlobalPointIds": gids.astype(np.int64)})
+            return
+        f, r = self.field.numpy(), self.ref_field.numpy()
+        write_vtu(path, np.asarray(self.pos), np.asarray(self.cells),
+                  {"velocity": f[:, :3], "pressure": f[:, 3], "ref_velocity": r[:, :3], "ref_pressure": r[:, 3]})
+
+
+def appended_cells_of(part, batch, cells, N):
+    """Cells of every partition in the appended grid's point numbering (vtkAppendDataSets over the partitions,
+    dataset/GraphDataset.py:1324-1367): cell j of subdomain s keeps its four corners, renumbered to the rows of
+    subdomain s's copies in the batch.  One searchsorted over the (subdomain, global id) keys, on the device."""
+    S = batch.n_sub
+    leaf_ptr = part.leaf_ptr.long()
+    sub_of_cell = torch.repeat_interleave(torch.arange(S, device=leaf_ptr.device), leaf_ptr[1:] - leaf_ptr[:-1])
+    corners = cells.long()[part.leaf_cells.long()]                                     # [pairs, 4] global ids
+    node_ptr = batch.node_ptr.long()
+    sub_of_node = torch.repeat_interleave(torch.arange(S, device=leaf_ptr.device), node_ptr[1:] - node_ptr[:-1])
+    node_key = sub_of_node * N + batch.global_ids                                      # ascending
+    want = (sub_of_cell.unsqueeze(1) * N + corners).reshape(-1)
+    pos = torch.searchsorted(node_key, want)
+    assert bool((node_key[pos] == want).all())
+    return pos.reshape(-1, 4).cpu().numpy()
 
 
 class SyntheticDuctDataset:
@@ -225,11 +243,17 @@ class SyntheticDuctDataset:
         c = self._mesh(subdomain_idx)
         if "gids_cpu" not in c:
             c["gids_cpu"] = c["batch"].global_ids.cpu()
+        def appended(c=c):
+            if "appended_cells" not in c:
+                c["appended_cells"] = appended_cells_of(c["part"], c["batch"], torch.from_numpy(c["mesh"].cells).to(self.device),
+                                                        c["mesh"].num_nodes)
+            return c["appended_cells"]
+
         return stitch_lists(c["batch"], c["occ"], c["mesh"].pos, c["mesh"].cells, c["gids_cpu"], c,
-                            subdomain_data_list, subdomain_ref_list, self.device)
+                            subdomain_data_list, subdomain_ref_list, self.device, appended_cells=appended)
 
 
-def stitch_lists(b, occ, pos, cells, gids_cpu, cache, pred_list, ref_list, dev):
+def stitch_lists(b, occ, pos, cells, gids_cpu, cache, pred_list, ref_list, dev, appended_cells=None):
     """The averaging of reconstruct_from_partition over predict()'s return lists (shared by the dataset classes).
     Lists that came out of a sharded predict carry the padded all-gather buffer (`padded`): the stitch reads it in
     place through an occurrence index remapped once per layout, and only this rank's slice of the mesh nodes is
@@ -285,13 +309,13 @@ def stitch_lists(b, occ, pos, cells, gids_cpu, cache, pred_list, ref_list, dev):
         lazy = {"field": lambda: whole("pred")[0], "ref_field": lambda: whole("ref")[0], "count": lambda: whole("pred")[1],
                 "merged": lambda: merged_of("pred"), "merged_ref": lambda: merged_of("ref")}
         return StitchedMesh(pos, cells, {"field_local": f_loc, "ref_field_local": r_loc, "count_local": cnt_loc},
-                            gids_cpu, lazy=lazy, node_range=rng)
+                            gids_cpu, lazy=lazy, node_range=rng, appended_cells=appended_cells)
 
     pred, ref = to_dev(pred_list), to_dev(ref_list)
     field, count, merged = ops.stitch_mean(pred, occ, b.global_ids, want_merged=True)
     rfield, _, rmerged = ops.stitch_mean(ref, occ, b.global_ids, want_merged=True)
     return StitchedMesh(pos, cells, {"field": field, "ref_field": rfield, "merged": merged, "merged_ref": rmerged,
-                                     "count": count}, gids_cpu)
+                                     "count": count}, gids_cpu, appended_cells=appended_cells)
 
 
 class AnsysDataset(SyntheticDuctDataset):

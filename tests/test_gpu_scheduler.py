@@ -76,8 +76,32 @@ def test_predict_and_stitch_single_cluster(tmp_path, shipped, monkeypatch):
     # generic path: plain list of Data without the attached device batch gives the same numbers
     p2, _, _, _ = sched.predict(list(x))
     assert rel_l2(torch.cat(list(p2)).numpy(), torch.cat(list(pred_y_list)).numpy()) < 1e-6
+    # .vtu export (run_ALDS_3D.py:33-38), parsed back: the reference's grid = every partition appended, the averaged
+    # arrays written to every copy; each partition's cells in the appended numbering are the mesh cells it holds
+    from fesr_b200.dataset.vtu import read_vtu
     out.write_vtu("logs/vtk/t/pred_1.vtu")
-    assert os.path.getsize("logs/vtk/t/pred_1.vtu") > 1000
+    back = read_vtu("logs/vtk/t/pred_1.vtu")
+    mesh = ds._mesh(1)["mesh"]
+    gids = sub["global_ids"]
+    assert back["points"].shape == (gids.size, 3) and np.array_equal(back["points"], mesh.pos[gids])
+    pdt = back["point_data"]
+    assert set(pdt) == {"velocity", "pressure", "ref_velocity", "ref_pressure", "GlobalPointIds"}
+    assert np.array_equal(pdt["GlobalPointIds"], gids)
+    assert np.array_equal(pdt["velocity"], out.merged.numpy()[:, :3]) and np.array_equal(pdt["pressure"], out.merged.numpy()[:, 3])
+    assert rel_l2(pdt["velocity"], merged[:, :3]) < 1e-5 and rel_l2(pdt["pressure"], merged[:, 3]) < 1e-5
+    assert rel_l2(pdt["ref_velocity"], mesh.y[gids][:, :3]) < 1e-6 and rel_l2(pdt["ref_pressure"], mesh.y[gids][:, 3]) < 1e-6
+    part = og.kd_partition(mesh.pos, mesh.cells, ds.levels)
+    assert back["cells"].shape == (part["leaf_cells"].size, 4) and bool((back["types"] == 10).all())
+    assert np.array_equal(gids[back["cells"]], mesh.cells[part["leaf_cells"]])           # same cells, appended numbering
+    sub_of_cell = np.repeat(np.arange(16), np.diff(part["leaf_ptr"]))
+    lo, hi = sub["node_ptr"][sub_of_cell], sub["node_ptr"][sub_of_cell + 1]
+    assert bool(((back["cells"] >= lo[:, None]) & (back["cells"] < hi[:, None])).all())   # inside their own partition
+    # the original-mesh variant
+    out.write_vtu("logs/vtk/t/pred_1_mesh.vtu", appended=False)
+    b2 = read_vtu("logs/vtk/t/pred_1_mesh.vtu")
+    assert np.array_equal(b2["points"], mesh.pos) and np.array_equal(b2["cells"], mesh.cells)
+    assert np.array_equal(b2["point_data"]["velocity"], out.field.numpy()[:, :3])
+    assert np.array_equal(b2["point_data"]["pressure"], out.field.numpy()[:, 3])
 
 
 def test_alds_routing_and_per_cluster_models(tmp_path, shipped, monkeypatch):
