@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libfesr.so")
+LIB_PATH = os.environ.get("FESR_LIB_PATH") or os.path.join(HERE, "lib", "libfesr.so")      # (env: tools/dev A/B builds)
 
 KERNELNN, TEECNET = 0, 1
 PREC_FP32, PREC_TF32, PREC_TF32X3, PREC_F16 = 0, 1, 2, 3

@@ -56,7 +56,23 @@ __device__ __forceinline__ void fl_mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fl_mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef FL_WAIT_MODE
+#define FL_WAIT_MODE 0
+#endif
+// tools/dev only (-DFL_TRACE): per-role clock64 accounting of the mbarrier waits, written to a global buffer, and
+// what-if switches in bits 8..11 of `relu` (0x100 no h gathers, 0x200 no fix-up row, 0x400 no outer-product MMAs,
+// 0x800 one k-block of the contraction) -- results are wrong by construction, only the time matters.  Production
+// builds compile both out (FL_WHATIF(x) == false).
+#ifdef FL_TRACE
+#define FL_WHATIF(bit) ((relu & (bit)) != 0)
+__device__ long long fl_trace_buf[148 * 24 * 4];
+#define FL_TWAIT(slot, call) { const long long t0__ = clock64(); call; tw[slot] += clock64() - t0__; }
+#else
+#define FL_WHATIF(bit) false
+#define FL_TWAIT(slot, call) call;
+#endif
 __device__ __forceinline__ void fl_mbar_wait(uint32_t bar, uint32_t parity) {
+#if FL_WAIT_MODE == 0
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -67,6 +83,29 @@ __device__ __forceinline__ void fl_mbar_wait(uint32_t bar, uint32_t parity) {
       "FL_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity), "r"(0x989680)     // suspend-time hint: a waiting warp sleeps instead of spinning
       : "memory");
+#elif FL_WAIT_MODE == 1
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "FL_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra FL_DONE;\n\t"
+      "bra FL_WAIT;\n\t"
+      "FL_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "FL_WAIT:\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra FL_DONE;\n\t"
+      "bra FL_WAIT;\n\t"
+      "FL_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+#endif
 }
 __device__ __forceinline__ bool fl_elect_one() {
   uint32_t pred = 0;
@@ -254,6 +293,10 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
+#ifdef FL_TRACE
+  long long tw[3] = {0, 0, 0};
+  long long t_begin = 0;
+#endif
   // Programmatic dependent launch: the next launch in the stream (the next layer) may be scheduled onto an SM as
   // soon as this CTA has left it, and runs its prologue (zero fill, barriers, TMEM allocation, T' into TMEM --
   // nothing that depends on this layer) under the tail of this grid; it waits for this grid's completion below.
@@ -334,6 +377,9 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
   // everything above touched only this launch's constants; h_in / P / h_out belong to the previous launch until it
   // has completed (no-op when this kernel was not launched as a programmatic dependent)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef FL_TRACE
+  t_begin = clock64();
+#endif
 
   if (warp < FL_BW) {
     // =========================================================================== consumers
@@ -351,7 +397,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     const uint32_t zst = zgrp + (uint32_t)(((lm & 1) * 2 + (lm >> 1)) * SLAB + j * 128 + ((lr ^ j) << 4));
     const uint32_t zroot = zgrp + (uint32_t)(12 * SLAB + ((PPL - 1) * FL_NODES + j) * 128 + ((lane ^ j) << 4));
     const uint32_t md = mdone + 8 * grp;
-    const bool do_fix = PPL == 3 && fix_b >= 0;
+    const bool do_fix = PPL == 3 && fix_b >= 0 && !FL_WHATIF(0x200);
     const uint32_t wfl = fl_smem(wfs) + (uint32_t)(lane * 4);
 
     // the group's own ring: buffers grp*NBG .. grp*NBG + NBG - 1 hold the segments of its tiles
@@ -373,7 +419,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
       uint4 hv = make_uint4(0u, 0u, 0u, 0u);       // own h row chunk (root block)
       do {
         const uint32_t base = rg_stage + (uint32_t)(buf * STG);
-        fl_mbar_wait(rg_full + 8 * buf, par);
+        FL_TWAIT(0, fl_mbar_wait(rg_full + 8 * buf, par))
         int seg_lo, seg_hi, pad;
         asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(seg_lo), "=r"(seg_hi), "=r"(lastw), "=r"(pad) : "r"(base + (uint32_t)(HDR + 48)));
         {
@@ -382,7 +428,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
           asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ee) : "r"(base + (uint32_t)(HDR + 4 * j + 4)));
           deg = ee - eb;
           const int lo = max(eb, seg_lo), hi = min(ee, seg_hi);
-          for (int c = lo; c < hi; c += FL_DEGC) {
+          for (int c = lo; c < hi && !FL_WHATIF(0x400); c += FL_DEGC) {
             const int rem = hi - c;
             const int r0 = c - seg_lo;
             const int ra = min(r0 + ka, seg_hi - seg_lo - 1);            // rows past the node's range: any finite row
@@ -415,7 +461,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
       } while (lastw == 0);
       // ---- once the tensor core has finished this group's previous tile (a wait the gather work above has
       // covered) the Z buffer is free: this tile's Z rows, raw sums (the epilogue applies 1/deg)
-      if (n_mine > 0) fl_mbar_wait(md, (uint32_t)((n_mine - 1) & 1));
+      if (n_mine > 0) FL_TWAIT(1, fl_mbar_wait(md, (uint32_t)((n_mine - 1) & 1)))
 #pragma unroll
       for (int pp = 0; pp < PPL; ++pp)
 #pragma unroll
@@ -500,7 +546,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     }
     for (int it = 0; it < n_it; ++it) {
       const int grp = it & 1, k = it >> 1;
-      fl_mbar_wait(mdone + 8 * grp, (uint32_t)(k & 1));
+      FL_TWAIT(0, fl_mbar_wait(mdone + 8 * grp, (uint32_t)(k & 1)))
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t r[N / 16][16];
 #pragma unroll
@@ -579,13 +625,13 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     const int nkb = has_root ? FL_NKB : FL_NKB - 1;
     for (int it = 0; it < n_it; ++it) {
       const int grp = it & 1;
-      fl_mbar_wait(dfree + 8 * grp, (uint32_t)(((it >> 1) & 1) ^ 1));     // the epilogue has read the previous result
-      fl_mbar_wait(zready + 8 * grp, (uint32_t)((it >> 1) & 1));
+      FL_TWAIT(0, fl_mbar_wait(dfree + 8 * grp, (uint32_t)(((it >> 1) & 1) ^ 1)))     // the epilogue has read the previous result
+      FL_TWAIT(1, fl_mbar_wait(zready + 8 * grp, (uint32_t)((it >> 1) & 1)))
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (fl_elect_one()) {
         const uint32_t zgrp = fl_smem(zbuf) + (uint32_t)(grp * ZBYTES);
         const uint32_t tmem_d = tmem_base + FL_ACOLS + grp * N;
-        for (int kk = 0; kk < nkb; ++kk) {
+        for (int kk = 0; kk < (FL_WHATIF(0x800) ? 1 : nkb); ++kk) {
           const uint64_t bdesc = fl_sw128_desc(zgrp + (uint32_t)(kk * SLAB));
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -659,7 +705,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
           const int sl = (u & 1) * NBG + bufs[u & 1];
           const uint32_t base = st_u32 + (uint32_t)(sl * STG);
           const uint32_t fb = sfull + 8 * sl;
-          fl_mbar_wait(sempty + 8 * sl, pars[u & 1]);
+          FL_TWAIT(0, fl_mbar_wait(sempty + 8 * sl, pars[u & 1]))
           if (pw == 0 && lane < 16) {   // header: rp[0..8] | .. | seg_lo, seg_hi, last
             int hw = rp0;
             if (lane == 12) hw = seg_lo;
@@ -692,7 +738,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
           const uint32_t gb = base + g0;
 #pragma unroll
           for (int i = 0; i < GOPS; ++i)
-            if (r0 + 16 * i < nseg)
+            if (r0 + 16 * i < nseg && !FL_WHATIF(0x100))
               asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(gb + (uint32_t)(1536 * i)), "l"(h16 + ((uint32_t)sidx[i] * 6u + c0)) : "memory");
           // the nodes' own rows ride with the tile's last segment
           if (last && own_lane && node0 + orow < n32)
@@ -709,12 +755,27 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     asm volatile("cp.async.wait_all;" ::: "memory");
   }
 
+#ifdef FL_TRACE
+  if (lane == 0) {
+    long long* o = fl_trace_buf + ((size_t)blockIdx.x * 24 + warp) * 4;
+    o[0] = clock64() - t_begin;
+    o[1] = tw[0];
+    o[2] = tw[1];
+    o[3] = n_it;
+  }
+#endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
+
+#ifdef FL_TRACE
+extern "C" int fesr_dev_fl_trace(long long* host_out /* [148*24*4] */) {
+  return cudaMemcpyFromSymbol(host_out, fl_trace_buf, sizeof(fl_trace_buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 template <int PPL, int NBUF>
 static size_t fl_smem_bytes() {
@@ -790,7 +851,8 @@ int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, cons
   const __half* tfh = static_cast<const __half*>(tf);
   __half* ho = static_cast<__half*>(h_out);
   // bit 0: ReLU (TEECNet has no activation between the layers, models/model.py:280-282); bit 1: fp32 output rows
-  const int relu = (d.kind == FESR_KERNELNN ? 1 : 0) | (out_f32 ? 2 : 0);
+  static const int what_if = getenv("FESR_FL_EXP") ? (atoi(getenv("FESR_FL_EXP")) & 0xf) << 8 : 0;      // tools/dev only
+  const int relu = (d.kind == FESR_KERNELNN ? 1 : 0) | (out_f32 ? 2 : 0) | what_if;
   ProfScope prof(PROF_LAYER_FUSED, s);
   int rc;
   if (d.kind == FESR_TEECNET) {
