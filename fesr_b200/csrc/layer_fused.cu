@@ -65,9 +65,11 @@ __device__ __forceinline__ void fl_mbar_arrive(uint32_t bar) {
 // builds compile both out (FL_WHATIF(x) == false).
 #ifdef FL_TRACE
 #define FL_WHATIF(bit) ((relu & (bit)) != 0)
-__device__ long long fl_trace_buf[148 * 24 * 4];
+__device__ long long fl_trace_buf[148 * 24 * 12];
 #define FL_TWAIT(slot, call) { const long long t0__ = clock64(); call; tw[slot] += clock64() - t0__; }
+#define FL_TMARK(slot) { const long long t1__ = clock64(); tw[slot] += t1__ - tmark; tmark = t1__; }
 #else
+#define FL_TMARK(slot)
 #define FL_WHATIF(bit) false
 #define FL_TWAIT(slot, call) call;
 #endif
@@ -165,6 +167,28 @@ __device__ __forceinline__ void fl_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
       "}" ::"r"(tmem_d),
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
+}
+// same with the accumulate flag known at compile time (no predicate set-up on the issuing thread's critical path)
+template <bool ACC>
+__device__ __forceinline__ void fl_umma_ts_c(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+  if (ACC)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc)
+        : "memory");
 }
 __device__ __forceinline__ void fl_umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -264,6 +288,14 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
   constexpr int FL_BW = 2 * FL_NODES;                  // consumer warps: two groups of 8
   constexpr int FL_NPROD = 3;                          // producer warps
   constexpr int FL_THREADS = (FL_BW + FL_NPROD + 1 + 4) * 32;   // + the MMA issuer warp + 4 epilogue warps
+  // warp ids of the roles: consumers 0..15, epilogue 16..19 (TMEM lane quadrant = warp % 4), MMA issuer 20,
+  // producers 21..23 -- FL_ROLE_ORDER 0 is the older order (producers 16..18, issuer 19, epilogue 20..23)
+#ifndef FL_ROLE_ORDER
+#define FL_ROLE_ORDER 1
+#endif
+  constexpr int W_EPI0 = FL_ROLE_ORDER ? FL_BW : FL_BW + FL_NPROD + 1;
+  constexpr int W_MMA = FL_ROLE_ORDER ? FL_BW + 4 : FL_BW + FL_NPROD;
+  constexpr int W_PROD0 = FL_ROLE_ORDER ? FL_BW + 5 : FL_BW;
   constexpr int N = (PPL * FL_NODES + 15) / 16 * 16;   // MMA N
   constexpr int SLAB = N * 128;                        // bytes per k-block of the Z tile
   constexpr int ZBYTES = FL_NKB * SLAB;
@@ -294,15 +326,22 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned FULL = 0xffffffffu;
 #ifdef FL_TRACE
-  long long tw[3] = {0, 0, 0};
-  long long t_begin = 0;
+  long long tw[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long t_begin = 0, tmark = 0;
 #endif
   // Programmatic dependent launch: the next launch in the stream (the next layer) may be scheduled onto an SM as
   // soon as this CTA has left it, and runs its prologue (zero fill, barriers, TMEM allocation, T' into TMEM --
   // nothing that depends on this layer) under the tail of this grid; it waits for this grid's completion below.
   asm volatile("griddepcontrol.launch_dependents;");
+  // CTA b owns a CONTIGUOUS chunk of tiles [t_first, t_first + n_it): consecutive tiles share rowptr / source-id cache
+  // lines and the CTA's gathers stay inside a compact range of h rows.  (Tiles used to be dealt out round-robin with a
+  // stride of gridDim.x: every rowptr read was then a lone DRAM miss whose latency the producers -- who need rowptr(t)
+  // one tile period after requesting it, to address the source ids -- could not cover: the per-role trace of
+  // profiles/r02_layer_fused_role_trace.txt showed them busy 2 350 of 2 430 cycles per tile without ever waiting.)
   const int64_t n_tiles = (n + FL_NODES - 1) / FL_NODES;
-  const int n_it = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);   // grid <= n_tiles
+  const int64_t t_per = n_tiles / gridDim.x, t_extra = n_tiles % gridDim.x;
+  const int64_t t_first = blockIdx.x * t_per + ((int64_t)blockIdx.x < t_extra ? (int64_t)blockIdx.x : t_extra);
+  const int n_it = (int)(t_per + ((int64_t)blockIdx.x < t_extra ? 1 : 0));       // grid <= n_tiles
 
   // the Z tiles start as zeros: unused rows, root-block rows of the parts without a root and the zero
   // tail of the root block are never written afterwards
@@ -379,6 +418,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
   asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef FL_TRACE
   t_begin = clock64();
+  tmark = t_begin;
 #endif
 
   if (warp < FL_BW) {
@@ -525,9 +565,9 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
       if (lane == 0) fl_mbar_arrive(zready + 8 * grp);
       ++n_mine;
     }
-  } else if (warp >= FL_BW + FL_NPROD + 1) {
+  } else if (warp >= W_EPI0 && warp < W_EPI0 + 4) {
     // =========================================================================== epilogue (4 warps, every tile)
-    const int qd = warp - (FL_BW + FL_NPROD + 1);     // TMEM lane quadrant (== warp % 4)
+    const int qd = warp - W_EPI0;                     // TMEM lane quadrant (== warp % 4)
     const int L = qd * 32 + lane;                     // TMEM lane = row (p, b) = (L / rs, L % rs)
     const int ep = L / rs, eb_ = L % rs;
     const bool row_ok = ep < PPL && eb_ < FL_WP;
@@ -574,7 +614,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
         }
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * FL_NODES;
+      const int64_t row0 = (t_first + it) * FL_NODES;
 #pragma unroll
       for (int i = 0; i < OUTI; ++i) {
         const int64_t row = row0 + oj[i];
@@ -619,7 +659,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-  } else if (warp == FL_BW + FL_NPROD) {
+  } else if (warp == W_MMA) {
     // =========================================================================== MMA issuer
     constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // D = F32, A = B = F16 K-major, N, M = 128
     const int nkb = has_root ? FL_NKB : FL_NKB - 1;
@@ -631,11 +671,21 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
       if (fl_elect_one()) {
         const uint32_t zgrp = fl_smem(zbuf) + (uint32_t)(grp * ZBYTES);
         const uint32_t tmem_d = tmem_base + FL_ACOLS + grp * N;
-        for (int kk = 0; kk < (FL_WHATIF(0x800) ? 1 : nkb); ++kk) {
-          const uint64_t bdesc = fl_sw128_desc(zgrp + (uint32_t)(kk * SLAB));
+        // The 52 MMAs of a tile are issued by ONE thread: every instruction it spends per MMA on descriptor arithmetic
+        // or predicates stretches the chain (it was busy 2 180 cycles per tile, 28 per MMA: issue-bound, not tensor
+        // bound).  Fully unrolled, the k-block / k-step offsets are immediates added to one base descriptor (the
+        // start-address field holds addr >> 4 and cannot carry: shared memory ends below 256 KB).
+        const uint64_t bdesc0 = fl_sw128_desc(zgrp);
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            fl_umma_ts(tmem_d, tmem_base + (uint32_t)(kk * 32 + q * 8), bdesc + 2 * q, idesc, (kk | q) != 0);
+        for (int kk = 0; kk < FL_NKB; ++kk) {
+          if ((kk == FL_NKB - 1 && nkb < FL_NKB) || (FL_WHATIF(0x800) && kk >= 1)) break;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t ta = tmem_base + (uint32_t)(kk * 32 + q * 8);
+            const uint64_t bd = bdesc0 + (uint64_t)((kk * SLAB + q * 32) >> 4);
+            if (kk == 0 && q == 0) fl_umma_ts_c<false>(tmem_d, ta, bd, idesc);
+            else fl_umma_ts_c<true>(tmem_d, ta, bd, idesc);
+          }
         }
         fl_umma_commit(mdone + 8 * grp);
       }
@@ -643,7 +693,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     }
   } else {
     // =========================================================================== producers
-    const int pw = warp - FL_BW;
+    const int pw = warp - W_PROD0;
     const uint32_t st_u32 = fl_smem(stage);
     // This lane's gather chunk-ops of a segment: op i is 16-byte chunk tc of staged row tr[i]; the flat index
     // t = (i * FL_NPROD + pw) * 32 + lane runs over rows x 6 chunks.  Destination offsets are lane constants.
@@ -664,7 +714,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
     const uint4* h16 = reinterpret_cast<const uint4*>(h_in);         // h rows as 6 sixteen-byte chunks
     const __half* gplane = g3 + (size_t)(part0 + (pw < PPL ? pw : 0)) * E * 16;   // this producer's g slot group
     const int n32 = (int)n, lane9 = lane < 9 ? lane : 8;
-    const int tile0 = (int)blockIdx.x, tstep = (int)gridDim.x;
+    const int tile0 = (int)t_first, tstep = 1;
     // rowptr of the tile's 9 node boundaries in lanes 0..8 (node ids fit 31 bits)
     auto load_rp = [&](int itx) { return __ldg(rowptr + min((tile0 + itx * tstep) * FL_NODES + lane9, n32)); };
     // source ids of this lane's gather ops for the first segment of a tile (clamped addresses)
@@ -692,10 +742,14 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
         const int it = it0 + u;
         if (it >= n_it) break;
         rp[(u + 3) & 3] = load_rp(it + 3);
+        if (pw == 0 && lane == 0)      // rowptr lines of the tiles well ahead: into L2 now, so that load_rp finds them there
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rowptr + min((tile0 + it + 32) * FL_NODES, n32)));
         load_srcs(rp[(u + 2) & 3], sc[(u + 2) & 3]);
+        FL_TMARK(2)
         const int rp0 = rp[u];
         const int node0 = (tile0 + it * tstep) * FL_NODES;
         const int e_lo = __shfl_sync(FULL, rp0, 0), e_hi = __shfl_sync(FULL, rp0, 8);
+        FL_TMARK(3)
         int seg_lo = e_lo;
         bool last;
         do {
@@ -706,6 +760,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
           const uint32_t base = st_u32 + (uint32_t)(sl * STG);
           const uint32_t fb = sfull + 8 * sl;
           FL_TWAIT(0, fl_mbar_wait(sempty + 8 * sl, pars[u & 1]))
+          FL_TMARK(4)
           if (pw == 0 && lane < 16) {   // header: rp[0..8] | .. | seg_lo, seg_hi, last
             int hw = rp0;
             if (lane == 12) hw = seg_lo;
@@ -727,6 +782,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
             }
           }
           __syncwarp();
+          FL_TMARK(5)
           // gathered h rows (later segments of a big tile: source ids not prefetched)
           int sidx[GOPS];
 #pragma unroll
@@ -736,6 +792,13 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
             for (int i = 0; i < GOPS; ++i) sidx[i] = __ldg(src_sorted + min(seg_lo + r0 + 16 * i, seg_hi - 1));
           }
           const uint32_t gb = base + g0;
+#ifdef FL_TRACE
+          { int acc__ = 0;
+#pragma unroll
+            for (int i = 0; i < GOPS; ++i) acc__ += sidx[i];
+            if (acc__ == 0x7fffffff) tw[9] += 1; }      // forces the source ids to have arrived before the next mark
+#endif
+          FL_TMARK(6)
 #pragma unroll
           for (int i = 0; i < GOPS; ++i)
             if (r0 + 16 * i < nseg && !FL_WHATIF(0x100))
@@ -743,7 +806,9 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
           // the nodes' own rows ride with the tile's last segment
           if (last && own_lane && node0 + orow < n32)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(base + odst), "l"(h16 + (uint32_t)((node0 + orow) * 6 + ot % 6)) : "memory");
+          FL_TMARK(7)
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(fb) : "memory");
+          FL_TMARK(8)
           if (++bufs[u & 1] == NBG) {
             bufs[u & 1] = 0;
             pars[u & 1] ^= 1;
@@ -757,11 +822,10 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
 
 #ifdef FL_TRACE
   if (lane == 0) {
-    long long* o = fl_trace_buf + ((size_t)blockIdx.x * 24 + warp) * 4;
+    long long* o = fl_trace_buf + ((size_t)blockIdx.x * 24 + warp) * 12;
     o[0] = clock64() - t_begin;
-    o[1] = tw[0];
-    o[2] = tw[1];
-    o[3] = n_it;
+    o[1] = n_it;
+    for (int q = 0; q < 10; ++q) o[2 + q] = tw[q];
   }
 #endif
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -772,7 +836,7 @@ layer_fused_f16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __rest
 }
 
 #ifdef FL_TRACE
-extern "C" int fesr_dev_fl_trace(long long* host_out /* [148*24*4] */) {
+extern "C" int fesr_dev_fl_trace(long long* host_out /* [148*24*12] */) {
   return cudaMemcpyFromSymbol(host_out, fl_trace_buf, sizeof(fl_trace_buf)) == cudaSuccess ? 0 : -1;
 }
 #endif
