@@ -201,15 +201,13 @@ class MeshPredictor:
             self._lay = lay
             self._occ_padded = ops.Occurrence(self.occ.occ_ptr, lay.row_positions(self.occ.occ_idx), self.occ.N,
                                               self.world * lay.slot // c)
-            self._side = torch.cuda.Stream(self.occ.occ_ptr.device)
         return self._lay
 
     def step(self, x_shard, y_shard=None, full_field: bool = False):
         """forward (+ node weight) + all-gather + stitch -> (field, weights [S_shard] | None, pred [n_shard, c]).
         One rank: field is the whole stitched mesh field [N, c].  Several ranks: the forward writes straight into
-        this rank's slot of the gather buffer, ONE in-place fesr_allgatherv_pred (libfesr's communicator, issued
-        on a side stream underneath the node-weight kernels, which only need this rank's rows) fills the other
-        slots, and the rank stitches ITS slice of the mesh nodes (`node_slice`; full_field=True: all of them --
+        this rank's slot of the gather buffer, ONE in-place fesr_allgatherv_pred (libfesr's communicator, on the
+        compute stream) fills the other slots, and the rank stitches ITS slice of the mesh nodes (`node_slice`; full_field=True: all of them --
         every rank then holds the bit-identical whole field)."""
         if self.world == 1:
             pred = self.forward_shard(x_shard)
@@ -225,12 +223,8 @@ class MeshPredictor:
         pred = gbuf[self.rank, :rows * c].view(rows, c)
         with torch.no_grad():
             self.model(x_shard, self.shard.csr, self.shard.edge_attr, out=pred)
-        main = torch.cuda.current_stream(dev)
-        self._side.wait_stream(main)
-        comm.allgatherv_pred(gbuf, stream=self._side)
-        gbuf.record_stream(self._side)
         w = self.node_weight(pred, y_shard) if y_shard is not None else None
-        main.wait_stream(self._side)
+        comm.allgatherv_pred(gbuf)          # in place, on the compute stream
         rng = None if full_field else node_slice(self.N, self.rank, self.world)
         field, _, _ = ops.stitch_mean(gbuf.view(-1, c), self._occ_padded, None, want_merged=False, want_count=False,
                                       node_range=rng)

@@ -17,13 +17,12 @@ with torch.no_grad():
     for _ in range(5): m(x, b.csr, b.edge_attr)
     torch.cuda.synchronize()
 lib = _lib.load()
-buf = (C.c_longlong * (148 * 24 * 12))()
+buf = (C.c_longlong * (148 * 24 * 4))()
 assert lib.fesr_dev_fl_trace(buf) == 0
-a = np.frombuffer(buf, dtype=np.int64).reshape(148, 24, 12).astype(np.float64)
-tiles = a[:, :, 1].mean()
-roles = {"consumer g0": slice(0, 8), "consumer g1": slice(8, 16), "producer": slice(16, 19), "mma": slice(19, 20), "epilogue": slice(20, 24)}
+a = np.frombuffer(buf, dtype=np.int64).reshape(148, 24, 4).astype(np.float64)
+tiles = a[:, :, 3].mean()
+roles = {"consumer g0": slice(0, 8), "consumer g1": slice(8, 16), "epilogue": slice(16, 20), "mma": slice(20, 21), "producer": slice(21, 24)}
 print(f"exp={os.environ.get('FESR_FL_EXP','0')} tiles per CTA {tiles:.1f}; cycles per tile (mean over CTAs and the role's warps):")
 for name, sl in roles.items():
-    tot, w0, w1 = a[:, sl, 0].mean() / tiles, a[:, sl, 2].mean() / tiles, a[:, sl, 3].mean() / tiles
-    extra = " ".join(f"m{q}={a[:, sl, 2 + q].mean() / tiles:6.0f}" for q in range(2, 9)) if name == "producer" else ""
-    print(f"  {name:12s} total {tot:7.0f}  wait0 {w0:7.0f}  wait1 {w1:7.0f}  busy {tot - w0 - w1:7.0f}  {extra}")
+    tot, w0, w1 = a[:, sl, 0].mean() / tiles, a[:, sl, 1].mean() / tiles, a[:, sl, 2].mean() / tiles
+    print(f"  {name:12s} total {tot:7.0f}  wait0 {w0:7.0f}  wait1 {w1:7.0f}  busy {tot - w0 - w1:7.0f}")
