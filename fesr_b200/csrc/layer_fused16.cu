@@ -46,7 +46,10 @@ constexpr int F2_NODES = 16;                  // nodes per tile
 #define F2_CAP_EDGES 112
 #endif
 constexpr int F2_CAP = F2_CAP_EDGES;          // staged edges per ring slot (A/B: 56 | 112 | 224)
-constexpr int F2_NBUF = 3 * 224 / F2_CAP;     // ring slots
+#ifndef F2_RING_SLOTS
+#define F2_RING_SLOTS (3 * 224 / F2_CAP_EDGES)
+#endif
+constexpr int F2_NBUF = F2_RING_SLOTS;        // ring slots
 constexpr int F2_NPROD = 3;                   // producer warps (slot s belongs to producer s)
 constexpr int F2_BW = F2_NODES;               // consumer warps
 constexpr int F2_THREADS = (F2_BW + 4 + 1 + F2_NPROD) * 32;
