@@ -27,8 +27,9 @@ __global__ void inv_deg_kernel(const int32_t* __restrict__ rowptr, int64_t n, fl
 }
 
 // dpre = dh * act'(h_next) on the first w columns, 0 on the padding (and on TEECNet's constant column)
+// (tf32 arm: rounded to tf32 here -- every consumer rounds it anyway, and the tcgen05 dZ product truncates what it is given)
 __global__ void mask_kernel(const float* __restrict__ dh, const float* __restrict__ h_next, int64_t n, int wp, int w,
-                            int relu, float* __restrict__ dpre) {
+                            int relu, int round_tf32, float* __restrict__ dpre) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= n * wp) return;
   const int c = (int)(idx % wp);
@@ -37,7 +38,20 @@ __global__ void mask_kernel(const float* __restrict__ dh, const float* __restric
     v = dh[idx];
     if (relu && !(h_next[idx] > 0.f)) v = 0.f;
   }
+  if (round_tf32) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    v = __uint_as_float(u);
+  }
   dpre[idx] = v;
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ in, int64_t count, float* __restrict__ out) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(in[idx]));
+  out[idx] = __uint_as_float(u);
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ index, int64_t rows,
@@ -157,6 +171,7 @@ struct BackwardWs {
   float* g_rev;
   float* dg;
   float* dT;
+  float* tprime_r;      // tf32-rounded copy of T' [zk, wp] for the tcgen05 dZ product
   float* inv_deg;
   float* dbias;
   float* dattr;
@@ -179,6 +194,7 @@ static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n
   w.g_rev = c.take<float>(ee * d.kp);
   w.dg = c.take<float>(ee * d.kp);
   w.dT = c.take<float>((size_t)d.zk * d.wp);
+  w.tprime_r = c.take<float>((size_t)d.zk * d.wp);
   w.inv_deg = c.take<float>(nn);
   w.dbias = c.take<float>(d.wp);
   w.dattr = c.take<float>(ee);
@@ -270,9 +286,17 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   FESR_CUDA(cudaMemsetAsync(w.dh[0], 0, (size_t)n * d.wp * sizeof(float), s));
   GEMM(grad_y, d.out_ch, 1, p.fc2_w, d.w, 1, w.dh[0], d.wp, 1, n, d.w, d.out_ch, 0);
 
+  // tf32 arm: dZ = dpre T'^T on tcgen05 (FESR_DZ_TC=0: the mma.sync kernel, for A/B measurements)
+  static const bool dz_tc_env = !(getenv("FESR_DZ_TC") && atoi(getenv("FESR_DZ_TC")) == 0);
+  const bool dz_tc = rnd && dz_tc_env && dz_tc_supported(d) && E > 0;
+  if (dz_tc) {
+    const int64_t cnt = (int64_t)d.zk * d.wp;
+    round_tf32_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(fw.prep.tprime, cnt, w.tprime_r);
+    FESR_LAUNCH_CHECK();
+  }
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
-    mask_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dh[cur], fw.h[l + 1], n, d.wp, d.w, relu, w.dpre);
+    mask_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dh[cur], fw.h[l + 1], n, d.wp, d.w, relu, rnd, w.dpre);
     FESR_LAUNCH_CHECK();
     if ((rc = launch_colsum(w.dpre, n, d.wp, d.wp, 1, w.dbias, w.colsum_ws, s))) return rc;
     // dT' += Z_l^T dpre
@@ -283,7 +307,9 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     }
     if (E > 0) {
       // dZ = dpre T'^T ; dg += edge_grad(dZ, h_l)
-      if (rnd) {
+      if (rnd && dz_tc) {
+        if ((rc = launch_dz_tc(d, w.dpre, w.tprime_r, n, w.BZ, s))) return rc;
+      } else if (rnd) {
         if ((rc = launch_dz_mma(d, w.dpre, fw.prep.tprime, n, w.BZ, s))) return rc;
       } else {
         GEMM(w.dpre, d.wp, 1, fw.prep.tprime, 1, d.wp, w.BZ, d.zk, 1, n, d.zk, d.wp, 0);

@@ -33,6 +33,9 @@ size_t wgrad_mma_ws_bytes(const fesr_model_dims& d);
 int launch_wgrad_mma(const fesr_model_dims& d, const void* Z, int z_half, const float* dpre, int64_t n, float* dT, float* ws,
                      cudaStream_t s);
 int launch_dz_mma(const fesr_model_dims& d, const float* dpre, const float* tprime, int64_t n, float* dZ, cudaStream_t s);
+// gemm_tc.cu: the same product on tcgen05 (TMA-fed, TMEM accumulators); operands tf32-rounded by the caller
+bool dz_tc_supported(const fesr_model_dims& d);
+int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, float* dZ, cudaStream_t s);
 
 // edge_mlp_bwd.cu (tf32 arm, KernelNN shape): the whole backward of the edge-MLP hidden layers in one kernel
 bool edge_mlp_bwd_supported(const fesr_model_dims& d);

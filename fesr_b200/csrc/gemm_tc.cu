@@ -421,6 +421,183 @@ static int encode_map(CUtensorMap* map, const void* base, bool half, uint64_t in
   return FESR_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward, tf32 arm:  dZ[n, zk] = dpre[n, wp] . T'^T  (reference: autograd of the last edge-MLP Linear + NNConv message,
+// models/model.py:311-315, 527-529, in the node-level form of DESIGN.md section 5).  K = wp is thin (6 MMAs per 128 x 256
+// output tile); the kernel exists to WRITE dZ (1.35 GB per layer at 527 k cells) at HBM rate:
+//   B = a 256-row chunk of T' [zk, wp] (K-major, tf32-rounded copy) stays in shared memory for the whole CTA;
+//   A = dpre tiles [128, wp] stream through a 3-stage TMA ring (two 128 x 32 boxes per tile: columns 48..63 of the second
+//       box are out of bounds and arrive as zeros, which pads K to the 64-float swizzle atom pair);
+//   D = [128, 256] fp32 in TMEM, two stages (all 512 columns): the epilogue of tile t overlaps the MMAs of tile t + 1;
+//   epilogue: tcgen05.ld (thread = node row, 32 columns) -> a swizzled [128 x 32] staging tile in shared memory -> one
+//       TMA store per tile and 32-column box (two staging buffers; cp.async.bulk.wait_group.read frees them).  Storing
+//       the rows straight from the registers (32 lanes = 32 rows, 16 bytes each) ran at the mma.sync kernel's 2.1 TB/s:
+//       half-filled sectors at twice the request rate.
+// Grid: ceil(zk / 256) column chunks x as many node ranges as fill the SMs.
+constexpr int DZ_BN = 256;
+constexpr int DZ_STAGES = 3;
+constexpr int DZ_THREADS = 192;
+
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+      "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(addr));
+}
+
+template <int WP>
+__global__ void __launch_bounds__(DZ_THREADS, 1)
+dz_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmD, int64_t n, int zk, int n_chunks) {
+  static_assert(WP > 32 && WP <= 64 && WP % 8 == 0, "two 32-float k-blocks");
+  constexpr uint32_t A_SLAB = TC_BM * TC_BK * 4;       // 16 KB: 128 rows x 128 B
+  constexpr uint32_t B_SLAB = DZ_BN * TC_BK * 4;       // 32 KB: 256 rows x 128 B
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem;                              // [2 k-blocks][256][128 B]
+  uint8_t* smem_a = smem_b + 2 * B_SLAB;               // [DZ_STAGES][2 k-blocks][128][128 B]
+  uint8_t* smem_d = smem_a + DZ_STAGES * 2 * A_SLAB;   // [2][128][128 B] staging tiles of the epilogue
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_d + 2 * A_SLAB);
+  uint64_t* empty_bar = full_bar + DZ_STAGES;
+  uint64_t* b_bar = empty_bar + DZ_STAGES;
+  uint64_t* tmem_full = b_bar + 1;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x % n_chunks;             // column chunk of this CTA
+  const int range = blockIdx.x / n_chunks, n_ranges = gridDim.x / n_chunks;
+  const int64_t n_tiles = (n + TC_BM - 1) / TC_BM;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < DZ_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(b_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: the T' chunk once, then the dpre tiles of this CTA's node range =====
+    if (elect_one()) {
+      mbar_expect_tx(b_bar, 2 * B_SLAB);
+      tma_load_2d(smem_b, &tmB, b_bar, 0, chunk * DZ_BN);
+      tma_load_2d(smem_b + B_SLAB, &tmB, b_bar, TC_BK, chunk * DZ_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = range; tile < n_tiles; tile += n_ranges) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], 2 * A_SLAB);
+        tma_load_2d(smem_a + (stage * 2) * A_SLAB, &tmA, &full_bar[stage], 0, (int)(tile * TC_BM));
+        tma_load_2d(smem_a + (stage * 2 + 1) * A_SLAB, &tmA, &full_bar[stage], TC_BK, (int)(tile * TC_BM));
+        if (++stage == DZ_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: D = F32, A = B = TF32 K-major, N = 256, M = 128; WP / 8 k-steps of 8 per tile =====
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DZ_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    mbar_wait(b_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int64_t tile = range; tile < n_tiles; tile += n_ranges, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tmem_empty[as], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&full_bar[stage], phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t tmem_d = tmem_base + as * DZ_BN;
+#pragma unroll
+        for (int k = 0; k < WP / 8; ++k) {
+          const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + (stage * 2 + (k >> 2)) * A_SLAB)) + 2 * (k & 3);
+          const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + (k >> 2) * B_SLAB)) + 2 * (k & 3);
+          umma_tf32(tmem_d, adesc, bdesc, idesc, k != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full[as]);
+      }
+      __syncwarp();
+      if (++stage == DZ_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4; thread = node row =====
+    const int quad = warp & 3;
+    const int rloc = quad * 32 + lane;                   // row of the tile
+    const bool issuer = warp == 2 && lane == 0;          // the thread that issues (and waits for) the TMA stores
+    const int col0 = chunk * DZ_BN;
+    const int ncol = min(DZ_BN, zk - col0);              // the last chunk may be short (a multiple of 32: zk % 32 == 0)
+    const uint32_t stg = smem_u32(smem_d) + (uint32_t)(rloc * 128);
+    const uint32_t sw = (uint32_t)(rloc & 7);
+    int it = 0, box = 0;
+    for (int64_t tile = range; tile < n_tiles; tile += n_ranges, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tmem_full[as], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * DZ_BN;
+      for (int c0 = 0; c0 < ncol; c0 += 32, ++box) {
+        const uint32_t buf = (uint32_t)(box & 1) * A_SLAB;
+        // the store that last read this staging buffer (two boxes ago) has finished reading it
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + buf + ((((uint32_t)j) ^ sw) << 4)), "r"(r[4 * j]),
+                       "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                       : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmD),
+                       "r"(smem_u32(smem_d) + buf), "r"(col0 + c0), "r"((int)(tile * TC_BM))
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 template <int WP, bool HALF, int TERMS>
 static int launch_tc(const fesr_model_dims& d, const void* B_kmajor, const void* B_lo, const float* bias_p, int epi,
                      const void* Z, int64_t n, float* h_out, cudaStream_t s, int round_out) {
@@ -476,5 +653,34 @@ int launch_node_gemm_f16(const fesr_model_dims& d, const void* B_kmajor_h, const
   if (B_lo_h != nullptr) return dispatch_tc<true, 2>(d, B_kmajor_h, B_lo_h, bias_p, epi, Z_h, n, h_out, s, round_out);
   return dispatch_tc<true, 1>(d, B_kmajor_h, nullptr, bias_p, epi, Z_h, n, h_out, s, round_out);
 }
+
+// dZ = dpre . T'^T on tcgen05 (tf32 arm of the backward); tprime_r: tf32-rounded copy of T' [zk, wp] row-major;
+// dpre must be tf32-rounded too (the tensor core truncates instead of rounding).  false: shape not covered (caller
+// falls back to the mma.sync kernel).
+bool dz_tc_supported(const fesr_model_dims& d) { return d.wp == 48 && d.zk % 32 == 0; }
+
+int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, float* dZ, cudaStream_t s) {
+  if (n == 0) return FESR_OK;
+  constexpr size_t smem = 1024 + 2 * (size_t)DZ_BN * TC_BK * 4 + (size_t)(DZ_STAGES + 1) * 2 * TC_BM * TC_BK * 4 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FESR_CUDA(cudaFuncSetAttribute(dz_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB, tmD;
+  int rc;
+  if ((rc = encode_map(&tmA, dpre, false, (uint64_t)d.wp, (uint64_t)n, TC_BK, TC_BM))) return rc;
+  if ((rc = encode_map(&tmB, tprime_r, false, (uint64_t)d.wp, (uint64_t)d.zk, TC_BK, DZ_BN))) return rc;
+  if ((rc = encode_map(&tmD, dZ, false, (uint64_t)d.zk, (uint64_t)n, TC_BK, TC_BM))) return rc;
+  const int n_chunks = (int)ceil_div(d.zk, DZ_BN);
+  const int64_t n_tiles = ceil_div(n, TC_BM);
+  int ranges = num_sms() / n_chunks;
+  if (ranges < 1) ranges = 1;
+  if (ranges > n_tiles) ranges = (int)n_tiles;
+  dz_tc_kernel<48><<<n_chunks * ranges, DZ_THREADS, smem, s>>>(tmA, tmB, tmD, n, d.zk, n_chunks);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
 
 }  // namespace fesr

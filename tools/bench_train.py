@@ -5,7 +5,7 @@
     torchrun --nproc-per-node N tools/bench_train.py ...
 
 All local subdomains of the rank's shard are one block-diagonal batch (the MSE is a mean over
-nodes x channels, so the loss definition is unchanged); weak scaling like bench.py.
+nodes x channels, so the loss definition is unchanged); the mesh is fixed, the ranks share its subdomains (strong).
 Prints one JSON line (cells/s over all ranks, max-over-ranks CUDA-event time).
 """
 import argparse
@@ -44,8 +44,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    levels = a.levels + int(np.log2(world))
-    mesh = make_mesh(a.mesh_n, world)
+    levels = a.levels
+    mesh = make_mesh(a.mesh_n)
     part, batch = ops.assemble(torch.from_numpy(mesh.pos).to(dev), torch.from_numpy(mesh.cells).to(dev), levels)
     bounds = shard_bounds(batch.edge_ptr.cpu().numpy(), world)
     sh = make_shard(batch, bounds[rank], bounds[rank + 1])
