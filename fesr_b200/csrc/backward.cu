@@ -289,6 +289,9 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   // tf32 arm: dZ = dpre T'^T on tcgen05 (FESR_DZ_TC=0: the mma.sync kernel, for A/B measurements)
   static const bool dz_tc_env = !(getenv("FESR_DZ_TC") && atoi(getenv("FESR_DZ_TC")) == 0);
   const bool dz_tc = rnd && dz_tc_env && dz_tc_supported(d) && E > 0;
+  // ... written as bf16 (FESR_DZ_BF16=0: fp32), which the edge-gradient MMAs read as exact tf32 operands
+  static const bool dz_bf16_env = !(getenv("FESR_DZ_BF16") && atoi(getenv("FESR_DZ_BF16")) == 0);
+  const int dz_bf16 = dz_tc && dz_bf16_env && d.wp == 48 ? 1 : 0;
   if (dz_tc) {
     const int64_t cnt = (int64_t)d.zk * d.wp;
     round_tf32_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(fw.prep.tprime, cnt, w.tprime_r);
@@ -308,13 +311,13 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     if (E > 0) {
       // dZ = dpre T'^T ; dg += edge_grad(dZ, h_l)
       if (rnd && dz_tc) {
-        if ((rc = launch_dz_tc(d, w.dpre, w.tprime_r, n, w.BZ, s))) return rc;
+        if ((rc = launch_dz_tc(d, w.dpre, w.tprime_r, n, w.BZ, dz_bf16, s))) return rc;
       } else if (rnd) {
         if ((rc = launch_dz_mma(d, w.dpre, fw.prep.tprime, n, w.BZ, s))) return rc;
       } else {
         GEMM(w.dpre, d.wp, 1, fw.prep.tprime, 1, d.wp, w.BZ, d.zk, 1, n, d.zk, d.wp, 0);
       }
-      if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, rnd, w.dg, s))) return rc;
+      if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, rnd, w.dg, s, dz_bf16))) return rc;
     }
     // dh_l = [sum over out-edges of g (x) dpre[dst]/deg[dst]  ++  dpre] T~
     if (rnd)

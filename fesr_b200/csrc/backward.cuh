@@ -25,8 +25,8 @@ int launch_colsum(const float* X, int64_t rows, int cols, int64_t ld, int accumu
                   cudaStream_t s);
 
 // dg[e, :] (+)= inv_deg[dst_e] * sum_a h[src_e, a] * dZ[dst_e, k, a]      (forward CSR order)
-int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* dZ,
-                     const float* h, int64_t n, int accumulate, float* dg, cudaStream_t s);
+int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* dZ,
+                     const float* h, int64_t n, int use_mma, float* dg, cudaStream_t s, int dz_bf16 = 0);
 
 // bwd_gemm_mma.cu (tf32 arm): dT' += Z^T dpre (ws: wgrad_mma_ws_bytes) and dZ = dpre T'^T
 size_t wgrad_mma_ws_bytes(const fesr_model_dims& d);
@@ -35,7 +35,9 @@ int launch_wgrad_mma(const fesr_model_dims& d, const void* Z, int z_half, const 
 int launch_dz_mma(const fesr_model_dims& d, const float* dpre, const float* tprime, int64_t n, float* dZ, cudaStream_t s);
 // gemm_tc.cu: the same product on tcgen05 (TMA-fed, TMEM accumulators); operands tf32-rounded by the caller
 bool dz_tc_supported(const fesr_model_dims& d);
-int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, float* dZ, cudaStream_t s);
+// out_bf16: dZ rows as bf16 (half the bytes written here and read by the edge-gradient kernel)
+int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, void* dZ, int out_bf16,
+                 cudaStream_t s);
 
 // edge_mlp_bwd.cu (tf32 arm, KernelNN shape): the whole backward of the edge-MLP hidden layers in one kernel
 bool edge_mlp_bwd_supported(const fesr_model_dims& d);

@@ -4,6 +4,7 @@
 // writes Z with (lane = 8*q + ag), loops over the node's incoming edges in CSR order, reduces the
 // partial dot products over the 8 column groups with shuffles and the ag == 0 lanes accumulate
 // into dg (one writer per element => deterministic).
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "backward.cuh"
@@ -90,11 +91,16 @@ __device__ __forceinline__ uint32_t eg_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return u;
 }
+__device__ __forceinline__ uint32_t eg_ldz(const float* p) { return eg_tf32(__ldg(p)); }
+__device__ __forceinline__ uint32_t eg_ldz(const __nv_bfloat16* p) {
+  return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16;
+}
 
-template <int WP>
+// ZT = float, or __nv_bfloat16 for the bf16 dZ of the tcgen05 product (bf16 -> tf32 is exact: no second rounding)
+template <int WP, typename ZT>
 __global__ void __launch_bounds__(128)
 edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
-                     const float* __restrict__ dZ, const float* __restrict__ h, int64_t n, int k1p, int kt, int ktp, int kp,
+                     const ZT* __restrict__ dZ, const float* __restrict__ h, int64_t n, int k1p, int kt, int ktp, int kp,
                      int zk, float* __restrict__ dg) {
   constexpr int KS = WP / 8;                // k-steps over the node-feature index a
   constexpr int NTC = 6;                    // channel n-tiles per pass (24 accumulator registers)
@@ -111,7 +117,7 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
     const int eb = rowptr[i], ee = rowptr[i + 1];
     if (ee == eb) continue;
     const float inv = 1.0f / (float)(ee - eb);
-    const float* zrow = dZ + i * (int64_t)zk;
+    const ZT* zrow = dZ + i * (int64_t)zk;
     for (int c0 = eb; c0 < ee; c0 += 16) {
       const int e0 = c0 + gq, e1 = c0 + gq + 8;
       const float* h0 = h + (int64_t)__ldg(src_sorted + min(e0, ee - 1)) * WP + tq;
@@ -135,10 +141,10 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
           if (nt0 + t < n_nt) {
             // B[a][channel]: b0 = dZ[chan = (nt0 + t) * 8 + gq][a = ks * 8 + tq], b1 = ... [a + 4]
             // (channels past k1p in the last tile: clamped row, masked on store)
-            const float* zp = zrow + (int64_t)min((nt0 + t) * 8 + gq, k1p - 1) * WP + tq;
+            const ZT* zp = zrow + (int64_t)min((nt0 + t) * 8 + gq, k1p - 1) * WP + tq;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-              const uint32_t b0 = eg_tf32(__ldg(zp + ks * 8)), b1 = eg_tf32(__ldg(zp + ks * 8 + 4));
+              const uint32_t b0 = eg_ldz(zp + ks * 8), b1 = eg_ldz(zp + ks * 8 + 4);
               asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                   : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
                   : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1));
@@ -192,8 +198,9 @@ static int eg_dispatch(const fesr_model_dims& d, const int32_t* rowptr, const in
   return FESR_OK;
 }
 
-int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const float* dZ,
-                     const float* h, int64_t n, int use_mma, float* dg, cudaStream_t s) {
+int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* dZv,
+                     const float* h, int64_t n, int use_mma, float* dg, cudaStream_t s, int dz_bf16) {
+  const float* dZ = static_cast<const float*>(dZv);
   // dg is zero-initialised by the caller and always accumulated into
   if (n == 0) return FESR_OK;
   ProfScope prof(PROF_BACKWARD, s);
@@ -202,10 +209,15 @@ int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int3
     const int64_t blocks = ceil_div(n, 4);
     const int grid = (int)(blocks < 16ll * num_sms() ? blocks : 16ll * num_sms());
     const size_t smem = (size_t)4 * 16 * d.kp * sizeof(float);      // <= 36.9 KB (kp = 144)
-    edge_grad_mma_kernel<48><<<grid, 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+    if (dz_bf16)
+      edge_grad_mma_kernel<48, __nv_bfloat16><<<grid, 128, smem, s>>>(rowptr, src_sorted, static_cast<const __nv_bfloat16*>(dZv), h, n,
+                                                                     d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+    else
+      edge_grad_mma_kernel<48, float><<<grid, 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
     FESR_LAUNCH_CHECK();
     return FESR_OK;
   }
+  FESR_CHECK_ARG(!dz_bf16, "bf16 dZ is read by the tensor-core edge-gradient kernel only");
   switch (d.kt) {
     case 4: return eg_dispatch<4>(d, rowptr, src_sorted, dZ, h, n, dg, s);
     case 8: return eg_dispatch<8>(d, rowptr, src_sorted, dZ, h, n, dg, s);

@@ -389,9 +389,9 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 static int encode_map(CUtensorMap* map, const void* base, bool half, uint64_t inner, uint64_t outer,
-                      uint32_t box_inner, uint32_t box_outer) {
+                      uint32_t box_inner, uint32_t box_outer, bool bf16 = false) {
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {inner * (half ? 2 : 4)};
+  cuuint64_t strides[1] = {inner * ((half || bf16) ? 2 : 4)};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   // the driver entry point is resolved at run time so that libfesr.so has no link-time
@@ -410,7 +410,7 @@ static int encode_map(CUtensorMap* map, const void* base, bool half, uint64_t in
     }
     encode = reinterpret_cast<encode_fn_t>(fn);
   }
-  CUresult r = encode(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                       const_cast<void*>(base), dims, strides, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -449,7 +449,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
       : "r"(addr));
 }
 
-template <int WP>
+template <int WP, bool BF16OUT>
 __global__ void __launch_bounds__(DZ_THREADS, 1)
 dz_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmD, int64_t n, int zk, int n_chunks) {
@@ -562,14 +562,28 @@ dz_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(&tmem_full[as], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + as * DZ_BN;
-      for (int c0 = 0; c0 < ncol; c0 += 32, ++box) {
+      constexpr int BOXC = BF16OUT ? 64 : 32;            // columns of one 128-byte staging row
+      for (int c0 = 0; c0 < ncol; c0 += BOXC, ++box) {
         const uint32_t buf = (uint32_t)(box & 1) * A_SLAB;
         // the store that last read this staging buffer (two boxes ago) has finished reading it
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
         uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if constexpr (BF16OUT) {
+          // bf16 dZ (a subset of tf32: the edge-gradient MMAs consume it without a second rounding)
+          uint32_t q0[32], q1[32];
+          tmem_ld32(taddr + c0, q0);
+          tmem_ld32(taddr + c0 + 32, q1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r[j]) : "f"(__uint_as_float(q0[2 * j + 1])), "f"(__uint_as_float(q0[2 * j])));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r[16 + j]) : "f"(__uint_as_float(q1[2 * j + 1])), "f"(__uint_as_float(q1[2 * j])));
+          }
+        } else {
+          tmem_ld32(taddr + c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + buf + ((((uint32_t)j) ^ sw) << 4)), "r"(r[4 * j]),
@@ -657,27 +671,30 @@ int launch_node_gemm_f16(const fesr_model_dims& d, const void* B_kmajor_h, const
 // dZ = dpre . T'^T on tcgen05 (tf32 arm of the backward); tprime_r: tf32-rounded copy of T' [zk, wp] row-major;
 // dpre must be tf32-rounded too (the tensor core truncates instead of rounding).  false: shape not covered (caller
 // falls back to the mma.sync kernel).
-bool dz_tc_supported(const fesr_model_dims& d) { return d.wp == 48 && d.zk % 32 == 0; }
+bool dz_tc_supported(const fesr_model_dims& d) { return d.wp == 48 && d.zk % 64 == 0; }
 
-int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, float* dZ, cudaStream_t s) {
+int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, void* dZ, int out_bf16,
+                 cudaStream_t s) {
   if (n == 0) return FESR_OK;
   constexpr size_t smem = 1024 + 2 * (size_t)DZ_BN * TC_BK * 4 + (size_t)(DZ_STAGES + 1) * 2 * TC_BM * TC_BK * 4 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    FESR_CUDA(cudaFuncSetAttribute(dz_tc_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FESR_CUDA(cudaFuncSetAttribute(dz_tc_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FESR_CUDA(cudaFuncSetAttribute(dz_tc_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   CUtensorMap tmA, tmB, tmD;
   int rc;
   if ((rc = encode_map(&tmA, dpre, false, (uint64_t)d.wp, (uint64_t)n, TC_BK, TC_BM))) return rc;
   if ((rc = encode_map(&tmB, tprime_r, false, (uint64_t)d.wp, (uint64_t)d.zk, TC_BK, DZ_BN))) return rc;
-  if ((rc = encode_map(&tmD, dZ, false, (uint64_t)d.zk, (uint64_t)n, TC_BK, TC_BM))) return rc;
+  if ((rc = encode_map(&tmD, dZ, false, (uint64_t)d.zk, (uint64_t)n, out_bf16 ? 2 * TC_BK : TC_BK, TC_BM, out_bf16 != 0))) return rc;
   const int n_chunks = (int)ceil_div(d.zk, DZ_BN);
   const int64_t n_tiles = ceil_div(n, TC_BM);
   int ranges = num_sms() / n_chunks;
   if (ranges < 1) ranges = 1;
   if (ranges > n_tiles) ranges = (int)n_tiles;
-  dz_tc_kernel<48><<<n_chunks * ranges, DZ_THREADS, smem, s>>>(tmA, tmB, tmD, n, d.zk, n_chunks);
+  if (out_bf16) dz_tc_kernel<48, true><<<n_chunks * ranges, DZ_THREADS, smem, s>>>(tmA, tmB, tmD, n, d.zk, n_chunks);
+  else dz_tc_kernel<48, false><<<n_chunks * ranges, DZ_THREADS, smem, s>>>(tmA, tmB, tmD, n, d.zk, n_chunks);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
