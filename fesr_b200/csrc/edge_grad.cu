@@ -91,9 +91,16 @@ __device__ __forceinline__ uint32_t eg_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return u;
 }
-__device__ __forceinline__ uint32_t eg_ldz(const float* p) { return eg_tf32(__ldg(p)); }
-__device__ __forceinline__ uint32_t eg_ldz(const __nv_bfloat16* p) {
-  return (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16;
+// two consecutive dZ values (a = 2 tq, 2 tq + 1 of a k-step) as tf32 operand bits, one load
+__device__ __forceinline__ void eg_ldz2(const float* p, uint32_t& b0, uint32_t& b1) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  b0 = eg_tf32(v.x);
+  b1 = eg_tf32(v.y);
+}
+__device__ __forceinline__ void eg_ldz2(const __nv_bfloat16* p, uint32_t& b0, uint32_t& b1) {
+  const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+  b0 = v << 16;
+  b1 = v & 0xffff0000u;
 }
 
 // ZT = float, or __nv_bfloat16 for the bf16 dZ of the tcgen05 product (bf16 -> tf32 is exact: no second rounding)
@@ -120,15 +127,20 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
     const ZT* zrow = dZ + i * (int64_t)zk;
     for (int c0 = eb; c0 < ee; c0 += 16) {
       const int e0 = c0 + gq, e1 = c0 + gq + 8;
-      const float* h0 = h + (int64_t)__ldg(src_sorted + min(e0, ee - 1)) * WP + tq;
-      const float* h1 = h + (int64_t)__ldg(src_sorted + min(e1, ee - 1)) * WP + tq;
+      // The MMA's k-slots of a k-step are a permutation of the 8 node-feature indices: slot tq <-> a = 2 tq, slot tq + 4
+      // <-> a = 2 tq + 1 (in A and B alike), so that a lane's two k-values are adjacent in memory: one 8-byte load per
+      // h row and k-step, one 4- / 8-byte load per dZ row and k-step (half the load instructions of the natural order).
+      const float* h0 = h + (int64_t)__ldg(src_sorted + min(e0, ee - 1)) * WP + 2 * tq;
+      const float* h1 = h + (int64_t)__ldg(src_sorted + min(e1, ee - 1)) * WP + 2 * tq;
       uint32_t a[KS][4];
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        a[ks][0] = eg_tf32(__ldg(h0 + ks * 8));
-        a[ks][1] = eg_tf32(__ldg(h1 + ks * 8));
-        a[ks][2] = eg_tf32(__ldg(h0 + ks * 8 + 4));
-        a[ks][3] = eg_tf32(__ldg(h1 + ks * 8 + 4));
+        const float2 v0 = __ldg(reinterpret_cast<const float2*>(h0 + ks * 8));
+        const float2 v1 = __ldg(reinterpret_cast<const float2*>(h1 + ks * 8));
+        a[ks][0] = eg_tf32(v0.x);
+        a[ks][1] = eg_tf32(v1.x);
+        a[ks][2] = eg_tf32(v0.y);
+        a[ks][3] = eg_tf32(v1.y);
       }
       for (int t = lane; t < 16 * q4; t += 32) reinterpret_cast<float4*>(tile)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
       __syncwarp();
@@ -139,12 +151,13 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
 #pragma unroll
         for (int t = 0; t < NTC; ++t) {
           if (nt0 + t < n_nt) {
-            // B[a][channel]: b0 = dZ[chan = (nt0 + t) * 8 + gq][a = ks * 8 + tq], b1 = ... [a + 4]
+            // B[a][channel]: b0 = dZ[chan = (nt0 + t) * 8 + gq][a = ks * 8 + 2 tq], b1 = ... [a + 1]
             // (channels past k1p in the last tile: clamped row, masked on store)
-            const ZT* zp = zrow + (int64_t)min((nt0 + t) * 8 + gq, k1p - 1) * WP + tq;
+            const ZT* zp = zrow + (int64_t)min((nt0 + t) * 8 + gq, k1p - 1) * WP + 2 * tq;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-              const uint32_t b0 = eg_ldz(zp + ks * 8), b1 = eg_ldz(zp + ks * 8 + 4);
+              uint32_t b0, b1;
+              eg_ldz2(zp + ks * 8, b0, b1);
               asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                   : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
                   : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1));
