@@ -325,8 +325,12 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     else
       rc = launch_zbuild(d, rowptr_t, src_t, w.g_rev, w.dpre, n, w.BZ, 0, s, /*mean=*/0, w.inv_deg);
     if (rc) return rc;
-    if (precision == FESR_PREC_FP32)
+    // fp32 arm: 3xTF32 on tcgen05 where the forward uses it (gemm_tc.cu TERMS == 3), the CUDA-core GEMM otherwise
+    static const bool fp32_simt = getenv("FESR_FP32_SIMT") && atoi(getenv("FESR_FP32_SIMT")) != 0;
+    if (precision == FESR_PREC_FP32 && (fp32_simt || d.zk > 4096 || !(d.wp % 16 == 0 && d.wp <= 64)))
       rc = launch_node_gemm_fp32(d, fw.prep.ttilde, nullptr, EPI_NONE, w.BZ, n, w.dh[cur ^ 1], s);
+    else if (precision == FESR_PREC_FP32)
+      rc = launch_node_gemm_tf32(d, fw.prep.ttilde_t, nullptr, EPI_NONE, w.BZ, n, w.dh[cur ^ 1], s, 0, fw.prep.ttilde_t_lo, 3);
     else
       rc = launch_node_gemm_tf32(d, fw.prep.ttilde_t, nullptr, EPI_NONE, w.BZ, n, w.dh[cur ^ 1], s);
     if (rc) return rc;

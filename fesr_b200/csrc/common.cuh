@@ -111,6 +111,7 @@ struct Prepared {
   float* tprime_t_lo;// [wp, zk]  lo part for TF32X3
   float* ttilde;     // [zk, wp]  T~[(k,b), a] = T'[(k,a), b] (every wp x wp block transposed) -- backward
   float* ttilde_t;   // [wp, zk]  K-major tf32 copy of T~
+  float* ttilde_t_lo;// [wp, zk]  lo part of T~ for the 3xTF32 dh product of the fp32 backward
   void* tprime_t_h;  // [wp, zk]  K-major fp16 copy of T'   (FESR_PREC_F16)
   void* tprime_t_h_lo;  // [wp, zk]  fp16(T' - fp16(T')): low-order term for the two-term predict GEMM
   void* ttilde_t_h;  // [wp, zk]  K-major fp16 copy of T~

@@ -25,6 +25,7 @@ Prepared carve_prepared(Carver& c, const fesr_model_dims& d) {
   w.tprime_t_lo = c.take<float>((size_t)d.zk * d.wp);
   w.ttilde = c.take<float>((size_t)d.zk * d.wp);
   w.ttilde_t = c.take<float>((size_t)d.zk * d.wp);
+  w.ttilde_t_lo = c.take<float>((size_t)d.zk * d.wp);
   w.tprime_t_h = c.take<__half>((size_t)d.zk * d.wp);
   w.tprime_t_h_lo = c.take<__half>((size_t)d.zk * d.wp);
   w.ttilde_t_h = c.take<__half>((size_t)d.zk * d.wp);
@@ -50,7 +51,8 @@ __global__ void prepare_tprime_kernel(fesr_model_dims d, const float* __restrict
                                       const float* __restrict__ lin_b, const float* __restrict__ root,
                                       float* __restrict__ tprime, float* __restrict__ tprime_t,
                                       float* __restrict__ tprime_t_lo, float* __restrict__ ttilde,
-                                      float* __restrict__ ttilde_t, __half* __restrict__ tprime_t_h,
+                                      float* __restrict__ ttilde_t, float* __restrict__ ttilde_t_lo,
+                                      __half* __restrict__ tprime_t_h,
                                       __half* __restrict__ tprime_t_h_lo, __half* __restrict__ ttilde_t_h) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)d.zk * d.wp;
@@ -93,6 +95,7 @@ __global__ void prepare_tprime_kernel(fesr_model_dims d, const float* __restrict
   if (rt < d.zk) {
     ttilde[(size_t)rt * d.wp + a] = v;
     ttilde_t[(size_t)a * d.zk + rt] = hi;
+    ttilde_t_lo[(size_t)a * d.zk + rt] = tf32_rna(v - hi);
     ttilde_t_h[(size_t)a * d.zk + rt] = __float2half_rn(v);
   }
 }
@@ -168,10 +171,11 @@ int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const
   ProfScope prof(PROF_PREPARE, s);
   FESR_CUDA(cudaMemsetAsync(w.ttilde, 0, (size_t)total * sizeof(float), s));      // partial tail block stays zero
   FESR_CUDA(cudaMemsetAsync(w.ttilde_t, 0, (size_t)total * sizeof(float), s));
+  FESR_CUDA(cudaMemsetAsync(w.ttilde_t_lo, 0, (size_t)total * sizeof(float), s));
   FESR_CUDA(cudaMemsetAsync(w.ttilde_t_h, 0, (size_t)total * sizeof(__half), s));
   prepare_tprime_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, s>>>(d, p.mlp_w[last], p.mlp_b[last], p.lin_w,
                                                                       p.lin_b, p.root, w.tprime, w.tprime_t,
-                                                                      w.tprime_t_lo, w.ttilde, w.ttilde_t,
+                                                                      w.tprime_t_lo, w.ttilde, w.ttilde_t, w.ttilde_t_lo,
                                                                       static_cast<__half*>(w.tprime_t_h),
                                                                       static_cast<__half*>(w.tprime_t_h_lo),
                                                                       static_cast<__half*>(w.ttilde_t_h));
