@@ -29,7 +29,8 @@ __global__ void inv_deg_kernel(const int32_t* __restrict__ rowptr, int64_t n, fl
 // dpre = dh * act'(h_next) on the first w columns, 0 on the padding (and on TEECNet's constant column)
 // (tf32 arm: rounded to tf32 here -- every consumer rounds it anyway, and the tcgen05 dZ product truncates what it is given)
 __global__ void mask_kernel(const float* __restrict__ dh, const float* __restrict__ h_next, int64_t n, int wp, int w,
-                            int relu, int round_tf32, float* __restrict__ dpre) {
+                            int relu, int round_tf32, float* __restrict__ dpre, float* __restrict__ dpre_hi,
+                            float* __restrict__ dpre_lo) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= n * wp) return;
   const int c = (int)(idx % wp);
@@ -44,14 +45,30 @@ __global__ void mask_kernel(const float* __restrict__ dh, const float* __restric
     v = __uint_as_float(u);
   }
   dpre[idx] = v;
+  if (dpre_hi != nullptr) {      // fp32 arm: tf32 hi + lo pair for the three-term tcgen05 dZ product
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    const float hi = __uint_as_float(u);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - hi));
+    dpre_hi[idx] = hi;
+    dpre_lo[idx] = __uint_as_float(u);
+  }
 }
 
-__global__ void round_tf32_kernel(const float* __restrict__ in, int64_t count, float* __restrict__ out) {
+// out = tf32(in) (and out_lo = tf32(in - out) when asked for)
+__global__ void round_tf32_kernel(const float* __restrict__ in, int64_t count, float* __restrict__ out,
+                                  float* __restrict__ out_lo) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= count) return;
   uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(in[idx]));
-  out[idx] = __uint_as_float(u);
+  const float v = in[idx];
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  const float hi = __uint_as_float(u);
+  out[idx] = hi;
+  if (out_lo != nullptr) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - hi));
+    out_lo[idx] = __uint_as_float(u);
+  }
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ index, int64_t rows,
@@ -172,6 +189,9 @@ struct BackwardWs {
   float* dg;
   float* dT;
   float* tprime_r;      // tf32-rounded copy of T' [zk, wp] for the tcgen05 dZ product
+  float* tprime_r_lo;   // ... and its lo part, dpre_hi / dpre_lo [n, wp]: the fp32 arm's three-term product
+  float* dpre_hi;
+  float* dpre_lo;
   float* inv_deg;
   float* dbias;
   float* dattr;
@@ -195,6 +215,9 @@ static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n
   w.dg = c.take<float>(ee * d.kp);
   w.dT = c.take<float>((size_t)d.zk * d.wp);
   w.tprime_r = c.take<float>((size_t)d.zk * d.wp);
+  w.tprime_r_lo = c.take<float>((size_t)d.zk * d.wp);
+  w.dpre_hi = c.take<float>(nn * d.wp);
+  w.dpre_lo = c.take<float>(nn * d.wp);
   w.inv_deg = c.take<float>(nn);
   w.dbias = c.take<float>(d.wp);
   w.dattr = c.take<float>(ee);
@@ -289,17 +312,19 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   // tf32 arm: dZ = dpre T'^T on tcgen05 (FESR_DZ_TC=0: the mma.sync kernel, for A/B measurements)
   static const bool dz_tc_env = !(getenv("FESR_DZ_TC") && atoi(getenv("FESR_DZ_TC")) == 0);
   const bool dz_tc = rnd && dz_tc_env && dz_tc_supported(d) && E > 0;
+  const bool dz_tc3 = !rnd && dz_tc_env && dz_tc_supported(d) && E > 0;      // fp32 arm: three-term product
   // ... written as bf16 (FESR_DZ_BF16=0: fp32), which the edge-gradient MMAs read as exact tf32 operands
   static const bool dz_bf16_env = !(getenv("FESR_DZ_BF16") && atoi(getenv("FESR_DZ_BF16")) == 0);
   const int dz_bf16 = dz_tc && dz_bf16_env && d.wp == 48 ? 1 : 0;
-  if (dz_tc) {
+  if (dz_tc || dz_tc3) {
     const int64_t cnt = (int64_t)d.zk * d.wp;
-    round_tf32_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(fw.prep.tprime, cnt, w.tprime_r);
+    round_tf32_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(fw.prep.tprime, cnt, w.tprime_r, dz_tc3 ? w.tprime_r_lo : nullptr);
     FESR_LAUNCH_CHECK();
   }
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
-    mask_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dh[cur], fw.h[l + 1], n, d.wp, d.w, relu, rnd, w.dpre);
+    mask_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dh[cur], fw.h[l + 1], n, d.wp, d.w, relu, rnd, w.dpre,
+                                                              dz_tc3 ? w.dpre_hi : nullptr, dz_tc3 ? w.dpre_lo : nullptr);
     FESR_LAUNCH_CHECK();
     if ((rc = launch_colsum(w.dpre, n, d.wp, d.wp, 1, w.dbias, w.colsum_ws, s))) return rc;
     // dT' += Z_l^T dpre
@@ -314,6 +339,8 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
         if ((rc = launch_dz_tc(d, w.dpre, w.tprime_r, n, w.BZ, dz_bf16, s))) return rc;
       } else if (rnd) {
         if ((rc = launch_dz_mma(d, w.dpre, fw.prep.tprime, n, w.BZ, s))) return rc;
+      } else if (dz_tc3) {
+        if ((rc = launch_dz_tc(d, w.dpre_hi, w.tprime_r, n, w.BZ, 0, s, w.dpre_lo, w.tprime_r_lo))) return rc;
       } else {
         GEMM(w.dpre, d.wp, 1, fw.prep.tprime, 1, d.wp, w.BZ, d.zk, 1, n, d.zk, d.wp, 0);
       }

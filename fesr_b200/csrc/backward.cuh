@@ -36,8 +36,9 @@ int launch_dz_mma(const fesr_model_dims& d, const float* dpre, const float* tpri
 // gemm_tc.cu: the same product on tcgen05 (TMA-fed, TMEM accumulators); operands tf32-rounded by the caller
 bool dz_tc_supported(const fesr_model_dims& d);
 // out_bf16: dZ rows as bf16 (half the bytes written here and read by the edge-gradient kernel)
+// dpre_lo / tprime_r_lo != NULL: the fp32 arm's three-term product (operands split into tf32 hi + lo by the caller)
 int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, void* dZ, int out_bf16,
-                 cudaStream_t s);
+                 cudaStream_t s, const float* dpre_lo = nullptr, const float* tprime_r_lo = nullptr);
 
 // edge_mlp_bwd.cu (tf32 arm, KernelNN shape): the whole backward of the edge-MLP hidden layers in one kernel
 bool edge_mlp_bwd_supported(const fesr_model_dims& d);

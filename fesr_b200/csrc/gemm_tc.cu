@@ -434,8 +434,11 @@ static int encode_map(CUtensorMap* map, const void* base, bool half, uint64_t in
 //       the rows straight from the registers (32 lanes = 32 rows, 16 bytes each) ran at the mma.sync kernel's 2.1 TB/s:
 //       half-filled sectors at twice the request rate.
 // Grid: ceil(zk / 256) column chunks x as many node ranges as fill the SMs.
-constexpr int DZ_BN = 256;
-constexpr int DZ_STAGES = 3;
+// TERMS == 3 (the fp32 arm): both operands arrive as tf32 hi + lo pairs (dpre_hi / dpre_lo written by the mask kernel,
+// T'hi / T'lo by the rounding kernel) and the chain is lo.hi + hi.lo + hi.hi -- K is only 48, so the truncating fp32
+// accumulation of the tensor core has nothing to drift over; 128-column chunks and a 2-stage ring fit the four tiles.
+__host__ __device__ constexpr int dz_bn(int terms) { return terms == 3 ? 128 : 256; }
+__host__ __device__ constexpr int dz_stages(int terms) { return terms == 3 ? 2 : 3; }
 constexpr int DZ_THREADS = 192;
 
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
@@ -449,18 +452,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&r)[32]) {
       : "r"(addr));
 }
 
-template <int WP, bool BF16OUT>
+template <int WP, bool BF16OUT, int TERMS>
 __global__ void __launch_bounds__(DZ_THREADS, 1)
 dz_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo,
              const __grid_constant__ CUtensorMap tmD, int64_t n, int zk, int n_chunks) {
+  constexpr int DZ_BN = dz_bn(TERMS), DZ_STAGES = dz_stages(TERMS);
+  constexpr int NT = TERMS == 3 ? 2 : 1;               // operand copies (hi, lo)
   static_assert(WP > 32 && WP <= 64 && WP % 8 == 0, "two 32-float k-blocks");
   constexpr uint32_t A_SLAB = TC_BM * TC_BK * 4;       // 16 KB: 128 rows x 128 B
-  constexpr uint32_t B_SLAB = DZ_BN * TC_BK * 4;       // 32 KB: 256 rows x 128 B
+  constexpr uint32_t B_SLAB = DZ_BN * TC_BK * 4;       // 256 (128) rows x 128 B
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_b = smem;                              // [2 k-blocks][256][128 B]
-  uint8_t* smem_a = smem_b + 2 * B_SLAB;               // [DZ_STAGES][2 k-blocks][128][128 B]
-  uint8_t* smem_d = smem_a + DZ_STAGES * 2 * A_SLAB;   // [2][128][128 B] staging tiles of the epilogue
+  uint8_t* smem_b = smem;                              // [NT][2 k-blocks][BN][128 B]
+  uint8_t* smem_a = smem_b + NT * 2 * B_SLAB;          // [DZ_STAGES][NT][2 k-blocks][128][128 B]
+  uint8_t* smem_d = smem_a + DZ_STAGES * NT * 2 * A_SLAB;   // [2][128][128 B] staging tiles of the epilogue
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_d + 2 * A_SLAB);
   uint64_t* empty_bar = full_bar + DZ_STAGES;
   uint64_t* b_bar = empty_bar + DZ_STAGES;
@@ -477,6 +483,10 @@ dz_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+    if (TERMS == 3) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmAlo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < DZ_STAGES; ++s) {
@@ -502,16 +512,24 @@ dz_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0) {
     // ===== TMA producer: the T' chunk once, then the dpre tiles of this CTA's node range =====
     if (elect_one()) {
-      mbar_expect_tx(b_bar, 2 * B_SLAB);
+      mbar_expect_tx(b_bar, NT * 2 * B_SLAB);
       tma_load_2d(smem_b, &tmB, b_bar, 0, chunk * DZ_BN);
       tma_load_2d(smem_b + B_SLAB, &tmB, b_bar, TC_BK, chunk * DZ_BN);
+      if (TERMS == 3) {
+        tma_load_2d(smem_b + 2 * B_SLAB, &tmBlo, b_bar, 0, chunk * DZ_BN);
+        tma_load_2d(smem_b + 3 * B_SLAB, &tmBlo, b_bar, TC_BK, chunk * DZ_BN);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t tile = range; tile < n_tiles; tile += n_ranges) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], 2 * A_SLAB);
-        tma_load_2d(smem_a + (stage * 2) * A_SLAB, &tmA, &full_bar[stage], 0, (int)(tile * TC_BM));
-        tma_load_2d(smem_a + (stage * 2 + 1) * A_SLAB, &tmA, &full_bar[stage], TC_BK, (int)(tile * TC_BM));
+        mbar_expect_tx(&full_bar[stage], NT * 2 * A_SLAB);
+        tma_load_2d(smem_a + (stage * NT * 2) * A_SLAB, &tmA, &full_bar[stage], 0, (int)(tile * TC_BM));
+        tma_load_2d(smem_a + (stage * NT * 2 + 1) * A_SLAB, &tmA, &full_bar[stage], TC_BK, (int)(tile * TC_BM));
+        if (TERMS == 3) {
+          tma_load_2d(smem_a + (stage * NT * 2 + 2) * A_SLAB, &tmAlo, &full_bar[stage], 0, (int)(tile * TC_BM));
+          tma_load_2d(smem_a + (stage * NT * 2 + 3) * A_SLAB, &tmAlo, &full_bar[stage], TC_BK, (int)(tile * TC_BM));
+        }
         if (++stage == DZ_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -534,9 +552,17 @@ dz_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t tmem_d = tmem_base + as * DZ_BN;
 #pragma unroll
         for (int k = 0; k < WP / 8; ++k) {
-          const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + (stage * 2 + (k >> 2)) * A_SLAB)) + 2 * (k & 3);
+          const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + (stage * NT * 2 + (k >> 2)) * A_SLAB)) + 2 * (k & 3);
           const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + (k >> 2) * B_SLAB)) + 2 * (k & 3);
-          umma_tf32(tmem_d, adesc, bdesc, idesc, k != 0);
+          if (TERMS == 3) {      // small terms first
+            const uint64_t alodesc = make_sw128_desc(smem_u32(smem_a + (stage * NT * 2 + 2 + (k >> 2)) * A_SLAB)) + 2 * (k & 3);
+            const uint64_t blodesc = make_sw128_desc(smem_u32(smem_b + (2 + (k >> 2)) * B_SLAB)) + 2 * (k & 3);
+            umma_tf32(tmem_d, alodesc, bdesc, idesc, k != 0);
+            umma_tf32(tmem_d, adesc, blodesc, idesc, 1);
+            umma_tf32(tmem_d, adesc, bdesc, idesc, 1);
+          } else {
+            umma_tf32(tmem_d, adesc, bdesc, idesc, k != 0);
+          }
         }
         umma_commit(&empty_bar[stage]);
         umma_commit(&tmem_full[as]);
@@ -673,31 +699,43 @@ int launch_node_gemm_f16(const fesr_model_dims& d, const void* B_kmajor_h, const
 // falls back to the mma.sync kernel).
 bool dz_tc_supported(const fesr_model_dims& d) { return d.wp == 48 && d.zk % 64 == 0; }
 
-int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, void* dZ, int out_bf16,
-                 cudaStream_t s) {
-  if (n == 0) return FESR_OK;
-  constexpr size_t smem = 1024 + 2 * (size_t)DZ_BN * TC_BK * 4 + (size_t)(DZ_STAGES + 1) * 2 * TC_BM * TC_BK * 4 + 256;
+template <bool BF16OUT, int TERMS>
+static int launch_dz_tc_t(const fesr_model_dims& d, const float* dpre, const float* dpre_lo, const float* tprime_r,
+                          const float* tprime_r_lo, int64_t n, void* dZ, cudaStream_t s) {
+  constexpr int BN = dz_bn(TERMS), STAGES = dz_stages(TERMS), NT = TERMS == 3 ? 2 : 1;
+  constexpr size_t smem = 1024 + (size_t)NT * 2 * BN * TC_BK * 4 + (size_t)(STAGES * NT + 1) * 2 * TC_BM * TC_BK * 4 + 256;
+  static_assert(smem <= 227 * 1024, "dZ tiles exceed the shared memory of an SM");
   static bool attr_set = false;
   if (!attr_set) {
-    FESR_CUDA(cudaFuncSetAttribute(dz_tc_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FESR_CUDA(cudaFuncSetAttribute(dz_tc_kernel<48, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FESR_CUDA(cudaFuncSetAttribute(dz_tc_kernel<48, BF16OUT, TERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  CUtensorMap tmA, tmB, tmD;
+  CUtensorMap tmA, tmB, tmAlo, tmBlo, tmD;
   int rc;
   if ((rc = encode_map(&tmA, dpre, false, (uint64_t)d.wp, (uint64_t)n, TC_BK, TC_BM))) return rc;
-  if ((rc = encode_map(&tmB, tprime_r, false, (uint64_t)d.wp, (uint64_t)d.zk, TC_BK, DZ_BN))) return rc;
-  if ((rc = encode_map(&tmD, dZ, false, (uint64_t)d.zk, (uint64_t)n, out_bf16 ? 2 * TC_BK : TC_BK, TC_BM, out_bf16 != 0))) return rc;
-  const int n_chunks = (int)ceil_div(d.zk, DZ_BN);
+  if ((rc = encode_map(&tmB, tprime_r, false, (uint64_t)d.wp, (uint64_t)d.zk, TC_BK, BN))) return rc;
+  if ((rc = encode_map(&tmAlo, TERMS == 3 ? dpre_lo : dpre, false, (uint64_t)d.wp, (uint64_t)n, TC_BK, TC_BM))) return rc;
+  if ((rc = encode_map(&tmBlo, TERMS == 3 ? tprime_r_lo : tprime_r, false, (uint64_t)d.wp, (uint64_t)d.zk, TC_BK, BN))) return rc;
+  if ((rc = encode_map(&tmD, dZ, false, (uint64_t)d.zk, (uint64_t)n, BF16OUT ? 2 * TC_BK : TC_BK, TC_BM, BF16OUT))) return rc;
+  const int n_chunks = (int)ceil_div(d.zk, BN);
   const int64_t n_tiles = ceil_div(n, TC_BM);
   int ranges = num_sms() / n_chunks;
   if (ranges < 1) ranges = 1;
   if (ranges > n_tiles) ranges = (int)n_tiles;
-  if (out_bf16) dz_tc_kernel<48, true><<<n_chunks * ranges, DZ_THREADS, smem, s>>>(tmA, tmB, tmD, n, d.zk, n_chunks);
-  else dz_tc_kernel<48, false><<<n_chunks * ranges, DZ_THREADS, smem, s>>>(tmA, tmB, tmD, n, d.zk, n_chunks);
+  dz_tc_kernel<48, BF16OUT, TERMS><<<n_chunks * ranges, DZ_THREADS, smem, s>>>(tmA, tmB, tmAlo, tmBlo, tmD, n, d.zk, n_chunks);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
 
+int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, void* dZ, int out_bf16,
+                 cudaStream_t s, const float* dpre_lo, const float* tprime_r_lo) {
+  if (n == 0) return FESR_OK;
+  if (dpre_lo != nullptr) {
+    FESR_CHECK_ARG(tprime_r_lo != nullptr && !out_bf16, "the three-term dZ product takes both lo operands and writes fp32");
+    return launch_dz_tc_t<false, 3>(d, dpre, dpre_lo, tprime_r, tprime_r_lo, n, dZ, s);
+  }
+  if (out_bf16) return launch_dz_tc_t<true, 1>(d, dpre, nullptr, tprime_r, nullptr, n, dZ, s);
+  return launch_dz_tc_t<false, 1>(d, dpre, nullptr, tprime_r, nullptr, n, dZ, s);
+}
 
 }  // namespace fesr
