@@ -313,6 +313,9 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   static const bool dz_tc_env = !(getenv("FESR_DZ_TC") && atoi(getenv("FESR_DZ_TC")) == 0);
   const bool dz_tc = rnd && dz_tc_env && dz_tc_supported(d) && E > 0;
   const bool dz_tc3 = !rnd && dz_tc_env && dz_tc_supported(d) && E > 0;      // fp32 arm: three-term product
+  // fp32 arm: dT' += Z^T dpre as 3xTF32 on mma.sync (FESR_WGRAD_3X=0: the CUDA-core split-K GEMM)
+  static const bool wgrad3_env = !(getenv("FESR_WGRAD_3X") && atoi(getenv("FESR_WGRAD_3X")) == 0);
+  const bool wgrad3 = !rnd && wgrad3_env && (d.wp == 16 || d.wp == 32 || d.wp == 48 || d.wp == 64);
   // ... written as bf16 (FESR_DZ_BF16=0: fp32), which the edge-gradient MMAs read as exact tf32 operands
   static const bool dz_bf16_env = !(getenv("FESR_DZ_BF16") && atoi(getenv("FESR_DZ_BF16")) == 0);
   const int dz_bf16 = dz_tc && dz_bf16_env && d.wp == 48 ? 1 : 0;
@@ -330,6 +333,8 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     // dT' += Z_l^T dpre
     if (rnd) {
       if ((rc = launch_wgrad_mma(d, fw.Z[l], z_stash_half(precision), w.dpre, n, w.dT, w.gemm_ws, s))) return rc;
+    } else if (wgrad3) {
+      if ((rc = launch_wgrad_mma(d, fw.Z[l], 0, w.dpre, n, w.dT, w.gemm_ws, s, 3))) return rc;
     } else {
       GEMM(fw.Z[l], 1, d.zk, w.dpre, d.wp, 1, w.dT, d.wp, 1, d.zk, d.wp, n, 1);
     }

@@ -30,8 +30,9 @@ int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int3
 
 // bwd_gemm_mma.cu (tf32 arm): dT' += Z^T dpre (ws: wgrad_mma_ws_bytes) and dZ = dpre T'^T
 size_t wgrad_mma_ws_bytes(const fesr_model_dims& d);
+// terms 3: fp32 Z and dpre split into tf32 hi + lo in registers (the fp32 arm)
 int launch_wgrad_mma(const fesr_model_dims& d, const void* Z, int z_half, const float* dpre, int64_t n, float* dT, float* ws,
-                     cudaStream_t s);
+                     cudaStream_t s, int terms = 1);
 int launch_dz_mma(const fesr_model_dims& d, const float* dpre, const float* tprime, int64_t n, float* dZ, cudaStream_t s);
 // gemm_tc.cu: the same product on tcgen05 (TMA-fed, TMEM accumulators); operands tf32-rounded by the caller
 bool dz_tc_supported(const fesr_model_dims& d);

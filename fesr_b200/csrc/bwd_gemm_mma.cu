@@ -33,7 +33,8 @@ constexpr int WG_BK = 32;      // nodes per stage
 constexpr int WG_THREADS = 256;
 
 // ZT = float, or __half for the fp16 Z stash of the tf32 arm (fp16 -> fp32 is exact and already tf32-representable)
-template <int WP, typename ZT>
+// TERMS == 3: the fp32 arm -- fp32 Z and dpre are split into tf32 hi + lo in registers, lo.hi + hi.lo + hi.hi (3xTF32)
+template <int WP, typename ZT, int TERMS>
 __global__ void __launch_bounds__(WG_THREADS)
 wgrad_mma_kernel(const ZT* __restrict__ Z, const float* __restrict__ dpre, int64_t n, int zk, int64_t nchunk,
                  float* __restrict__ partial) {
@@ -83,13 +84,23 @@ wgrad_mma_kernel(const ZT* __restrict__ Z, const float* __restrict__ dpre, int64
 #pragma unroll
     for (int ks = 0; ks < WG_BK / 8; ++ks) {
       const int r0 = ks * 8 + tq, r1 = r0 + 4;
-      uint32_t a[4];
-      a[0] = bg_tf32((float)zs[r0 * SZ + gq]);
-      a[1] = bg_tf32((float)zs[r0 * SZ + gq + 8]);
-      a[2] = bg_tf32((float)zs[r1 * SZ + gq]);
-      a[3] = bg_tf32((float)zs[r1 * SZ + gq + 8]);
+      const float av[4] = {(float)zs[r0 * SZ + gq], (float)zs[r0 * SZ + gq + 8], (float)zs[r1 * SZ + gq], (float)zs[r1 * SZ + gq + 8]};
+      uint32_t a[4], alo[4];
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) bg_mma(acc[nt], a, bg_tf32(ds[r0 * SD + nt * 8 + gq]), bg_tf32(ds[r1 * SD + nt * 8 + gq]));
+      for (int q = 0; q < 4; ++q) {
+        a[q] = bg_tf32(av[q]);
+        if (TERMS == 3) alo[q] = bg_tf32(av[q] - __uint_as_float(a[q]));
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float b0f = ds[r0 * SD + nt * 8 + gq], b1f = ds[r1 * SD + nt * 8 + gq];
+        const uint32_t b0 = bg_tf32(b0f), b1 = bg_tf32(b1f);
+        if (TERMS == 3) {
+          bg_mma(acc[nt], alo, b0, b1);
+          bg_mma(acc[nt], a, bg_tf32(b0f - __uint_as_float(b0)), bg_tf32(b1f - __uint_as_float(b1)));
+        }
+        bg_mma(acc[nt], a, b0, b1);
+      }
     }
     __syncthreads();
     st ^= 1;
@@ -125,7 +136,8 @@ int wgrad_mma_splits(int zk) {
 size_t wgrad_mma_ws_bytes(const fesr_model_dims& d) { return (size_t)wgrad_mma_splits(d.zk) * d.zk * d.wp * sizeof(float); }
 
 int launch_wgrad_mma(const fesr_model_dims& d, const void* Z, int z_half, const float* dpre, int64_t n, float* dT, float* ws,
-                     cudaStream_t s) {
+                     cudaStream_t s, int terms) {
+  FESR_CHECK_ARG(terms == 1 || (terms == 3 && !z_half), "3xTF32 weight gradient takes the fp32 Z stash");
   if (n == 0) return FESR_OK;
   const int ks = wgrad_mma_splits(d.zk);
   const int64_t nchunk = ceil_div(ceil_div(n, ks), WG_BK) * WG_BK;
@@ -136,14 +148,17 @@ int launch_wgrad_mma(const fesr_model_dims& d, const void* Z, int z_half, const 
     constexpr size_t smem = (size_t)2 * WG_BK * (WG_BM + 8 + WPV + 8) * sizeof(float);                      \
     static bool attr = false;                                                                               \
     if (!attr) {                                                                                            \
-      FESR_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<WPV, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      FESR_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<WPV, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      FESR_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<WPV, float, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      FESR_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<WPV, float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      FESR_CUDA(cudaFuncSetAttribute(wgrad_mma_kernel<WPV, __half, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr = true;                                                                                          \
     }                                                                                                       \
     if (z_half)                                                                                             \
-      wgrad_mma_kernel<WPV, __half><<<grid, WG_THREADS, smem, s>>>(static_cast<const __half*>(Z), dpre, n, d.zk, nchunk, ws); \
+      wgrad_mma_kernel<WPV, __half, 1><<<grid, WG_THREADS, smem, s>>>(static_cast<const __half*>(Z), dpre, n, d.zk, nchunk, ws); \
+    else if (terms == 3)                                                                                    \
+      wgrad_mma_kernel<WPV, float, 3><<<grid, WG_THREADS, smem, s>>>(static_cast<const float*>(Z), dpre, n, d.zk, nchunk, ws); \
     else                                                                                                    \
-      wgrad_mma_kernel<WPV, float><<<grid, WG_THREADS, smem, s>>>(static_cast<const float*>(Z), dpre, n, d.zk, nchunk, ws);   \
+      wgrad_mma_kernel<WPV, float, 1><<<grid, WG_THREADS, smem, s>>>(static_cast<const float*>(Z), dpre, n, d.zk, nchunk, ws);   \
   } while (0)
   switch (d.wp) {
     case 16: FESR_WG(16); break;
