@@ -178,3 +178,73 @@ def test_teecnet_arms_agree_full_size(shipped, monkeypatch):
         err = rel_l2(v, ref)
         print("teecnet 500k", k, f"rel-L2 vs fp32 arm: {err:.3e}")
         assert err < 1.5e-3, k
+
+
+def _gpu_grads(m, x, csr, ea, y, precision):
+    m.precision = precision
+    for p in m.parameters():
+        p.grad = None
+    loss = torch.nn.functional.mse_loss(m(x, csr, ea), y)
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss.detach()), {k: p.grad.detach().double().cpu().numpy() for k, p in m.named_parameters()}
+
+
+@pytest.mark.parametrize("precision,tol,tol_add", [("tf32", 5e-3, 2e-3), ("fp32", 2e-4, 2e-4)])
+def test_train_gradients_2M(shipped, precision, tol, tol_add):
+    """BASELINE config 4 (2 044 416 cells): (1) on a sample of subdomains the gradients of the MSE loss equal fp64
+    autograd of the oracle (reference order, models/model.py + scheduler_gnn.py:402-406) within the arm's gate; (2) at
+    full size the loss gradient is additive over a split of the batch into two halves of its subdomains,
+    n g = n1 g1 + n2 g2 (MSELoss is a mean over nodes x channels) -- every tiling / split-K range of the backward
+    kernels is exercised at the size bench.py's `train` record runs."""
+    from fesr_b200.models.model import KernelNN
+    from fesr_b200.models.scheduler_gnn import select_subdomains
+    from oracle import models as om
+    mesh, pos, cells, part, b, levels = _assembled("2M")
+    x = torch.from_numpy(mesh.x).cuda()[b.global_ids]
+    y = torch.from_numpy(mesh.y).cuda()[b.global_ids]
+    sd = shipped_state_dict(shipped, "neuralop")
+    m = KernelNN(43, 43, 5, in_width=4, out_width=4)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    S = b.n_sub
+
+    # (1) three subdomains against fp64 autograd
+    keep = torch.zeros(S, dtype=torch.bool, device="cuda")
+    keep[[1, S // 2, S - 2]] = True
+    sub, ea, nptr, node_keep = select_subdomains(b.csr, b.edge_attr, b.node_ptr, keep)
+    loss_g, g = _gpu_grads(m, x[node_keep], sub, ea, y[node_keep], precision)
+    rowptr = sub.rowptr.cpu().numpy().astype(np.int64)
+    dst = np.repeat(np.arange(sub.n, dtype=np.int64), np.diff(rowptr))
+    ei = torch.from_numpy(np.stack([sub.src.cpu().numpy().astype(np.int64), dst]))
+    o = om.make_model("neuralop", 43, 5).double()
+    o.load_state_dict({k: v.double() for k, v in sd.items()})
+    torch.set_num_threads(16)
+    lo = torch.nn.functional.mse_loss(o(x[node_keep].double().cpu(), ei, ea.double().cpu()), y[node_keep].double().cpu())
+    lo.backward()
+    assert abs(loss_g - float(lo)) <= max(tol, 1e-5) * abs(float(lo))
+    worst = 0.0
+    for k, p in o.named_parameters():
+        err = rel_l2(g[k], p.grad.numpy())
+        worst = max(worst, err)
+        assert err < tol, (k, err)
+    print(f"2M sample ({int(node_keep.sum())} nodes) {precision}: max gradient rel-L2 vs fp64 autograd {worst:.2e}")
+
+    # (2) additivity at full size
+    _, g_all = _gpu_grads(m, x, b.csr, b.edge_attr, y, precision)
+    halves = []
+    for lo_s, hi_s in ((0, S // 2), (S // 2, S)):
+        keep = torch.zeros(S, dtype=torch.bool, device="cuda")
+        keep[lo_s:hi_s] = True
+        sub, ea, nptr, node_keep = select_subdomains(b.csr, b.edge_attr, b.node_ptr, keep)
+        _, gh = _gpu_grads(m, x[node_keep], sub, ea, y[node_keep], precision)
+        halves.append((int(node_keep.sum()), gh))
+    n_all = halves[0][0] + halves[1][0]
+    assert n_all == b.n_tot
+    worst = 0.0
+    for k in g_all:
+        comb = (halves[0][0] * halves[0][1][k] + halves[1][0] * halves[1][1][k]) / n_all
+        err = rel_l2(g_all[k], comb)
+        worst = max(worst, err)
+        assert err < tol_add, (k, err)
+    print(f"2M full batch ({b.n_tot} nodes) {precision}: additivity over two halves, max rel-L2 {worst:.2e}")
