@@ -127,8 +127,10 @@ class GradientbasedLoss(nn.Module):
         return s.expand(num_nodes).contiguous()
 
 
-def _as_batch(x, device):
-    """list[Data] -> (csr, edge_attr, node_ptr, x_dev, y_dev, sizes) as one block-diagonal graph."""
+def _as_batch(x, device, between=None):
+    """list[Data] -> (csr, edge_attr, node_ptr, x_dev, y_dev, sizes) as one block-diagonal graph.
+    between: called after the copy of x has been ISSUED and before the copy of y (host inputs only) -- the caller
+    launches the part of the pass that does not read x there, so that the copy engine and the SMs start together."""
     if isinstance(x, SubdomainSample):
         b = x.batch
         if getattr(b, "_sizes", None) is None:
@@ -140,6 +142,9 @@ def _as_batch(x, device):
             with torch.cuda.stream(side):
                 x_dev = x.x_host.to(device, non_blocking=True)
                 x_dev.ready = side.record_event()
+            if between is not None:
+                between()
+            with torch.cuda.stream(side):
                 y_dev = x.y_host.to(device, non_blocking=True)
                 y_dev.ready = side.record_event()
             x_dev.record_stream(main)
@@ -274,10 +279,13 @@ class GNNPartitionScheduler():
             comm.init_from_torch_distributed()          # idempotent: libfesr's own NCCL communicator
         if world > 1 and self.num_partitions == 1 and isinstance(x, SubdomainSample):
             return self._predict_sharded(x, rank, world)
+        between = None
         if self.num_partitions == 1 and isinstance(x, SubdomainSample) and x.x_host is not None:
-            # inputs still on the host: start the GPU on the part of the pass that does not need them first
-            self.models[0].edge_phase(x.batch.csr, x.batch.edge_attr)
-        csr, edge_attr, node_ptr, x_dev, y_dev, sizes = _as_batch(x, dev)
+            # inputs still on the host: the copy of x is issued first (side stream), then the part of the pass that does
+            # not read it (weight preparation + edge MLP) -- the copy engine and the SMs start together; issuing the edge
+            # MLP first left x arriving ~70 us after it had finished (tools/dev/e2e_timeline.py)
+            between = lambda: self.models[0].edge_phase(x.batch.csr, x.batch.edge_attr)
+        csr, edge_attr, node_ptr, x_dev, y_dev, sizes = _as_batch(x, dev, between)
         y_ready, x_ready = getattr(y_dev, "ready", None), getattr(x_dev, "ready", None)
         S = len(sizes)
         if self.num_partitions == 1 and world == 1:          # one model, every subdomain: nothing to select
@@ -402,11 +410,12 @@ class GNNPartitionScheduler():
         main, side = torch.cuda.current_stream(dev), _side_stream(dev)
         y_ready = x_ready = None
         if host_in:
-            if nr > 0:
-                model.edge_phase(sh.csr, sh.edge_attr)
             with torch.cuda.stream(side):
                 xi = x.x_host[lo:hi].to(dev, non_blocking=True)
                 x_ready = side.record_event()
+            if nr > 0:
+                model.edge_phase(sh.csr, sh.edge_attr)       # does not read x: runs while the copy engine brings it
+            with torch.cuda.stream(side):
                 yi = x.y_host[lo:hi].to(dev, non_blocking=True)
                 y_ready = side.record_event()
             xi.record_stream(main)
