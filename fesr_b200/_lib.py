@@ -76,6 +76,8 @@ SIGNATURES = {
     "fesr_subdomain_count": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _vp, _vp, C.POINTER(_i64), _vp, _sz, _vp]),
     "fesr_subdomain_fill": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "fesr_cluster": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "fesr_gather_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "fesr_scatter_rows": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "fesr_interp_workspace_bytes": (_sz, [_i64, _i32]),
     "fesr_interp_gaussian": (C.c_int, [_vp, _vp, _i32, _i64, _vp, _i64, _f, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "fesr_tet_gradient": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),

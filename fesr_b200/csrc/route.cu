@@ -101,6 +101,42 @@ extern "C" int fesr_route(const float* x, int32_t channels, const int32_t* node_
   return FESR_OK;
 }
 
+// dst[r] = src[index[r]] (SCATTER: dst[index[r]] = src[r]); rows of q4 float4's, one thread per float4
+template <bool SCATTER>
+__global__ void move_rows_kernel(const float4* __restrict__ src, const int64_t* __restrict__ index, int64_t rows, int q4,
+                                 float4* __restrict__ dst) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= rows * q4) return;
+  const int64_t r = t / q4;
+  const int c = (int)(t - r * q4);
+  const int64_t j = __ldg(index + r);
+  if (SCATTER) dst[j * q4 + c] = src[t];
+  else dst[t] = __ldg(src + j * q4 + c);
+}
+
+template <bool SCATTER>
+static int move_rows(const float* src, const int64_t* index, int64_t rows, int32_t row_floats, float* dst, void* stream_) {
+  FESR_CHECK_ARG(rows >= 0 && row_floats > 0 && row_floats % 4 == 0, "rows of a multiple of 4 floats");
+  if (rows == 0) return FESR_OK;
+  FESR_CHECK_ARG(src && index && dst, "NULL pointer");
+  FESR_CHECK_ARG(((uintptr_t)src | (uintptr_t)dst) % 16 == 0, "16-byte aligned rows");
+  const int q4 = row_floats / 4;
+  move_rows_kernel<SCATTER><<<(unsigned)ceil_div(rows * q4, 256), 256, 0, as_stream(stream_)>>>(
+      reinterpret_cast<const float4*>(src), index, rows, q4, reinterpret_cast<float4*>(dst));
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
+extern "C" int fesr_gather_rows(const float* src, const int64_t* index, int64_t rows, int32_t row_floats, float* dst,
+                                void* stream_) {
+  return move_rows<false>(src, index, rows, row_floats, dst, stream_);
+}
+
+extern "C" int fesr_scatter_rows(const float* src, const int64_t* index, int64_t rows, int32_t row_floats, float* dst,
+                                 void* stream_) {
+  return move_rows<true>(src, index, rows, row_floats, dst, stream_);
+}
+
 extern "C" int fesr_cluster(const double* latent, int32_t n_sub, int32_t n_comp, const double* scaler_mean,
                             const double* scaler_scale, const double* centroids, int32_t n_clusters, int32_t* labels,
                             void* stream_) {

@@ -315,10 +315,12 @@ class GNNPartitionScheduler():
         pred = torch.zeros(csr.n, out_ch, dtype=torch.float32, device=dev)
         weight_s = torch.zeros(S, dtype=torch.float32, device=dev)
         for i, c in plan["clusters"]:
-            xi, yi = x_dev.index_select(0, c["nodes"]), y_dev.index_select(0, c["nodes"])
+            # (torch's index_select / advanced indexing take 84 us per 2.5 MB of 16-byte rows on a B200, whatever the
+            # index type -- tools/dev/gather_bench.py; these are 16-byte-row copies at HBM rate)
+            xi, yi = ops.gather_rows(x_dev, c["nodes"]), ops.gather_rows(y_dev, c["nodes"])
             pi = self.models[i](xi, c["csr"], c["edge_attr"])
             wi = ops.node_weight(pi, yi, c["csr"], c["edge_attr"], c["node_ptr"])
-            pred.index_copy_(0, c["nodes"], pi)
+            ops.scatter_rows(pi, c["nodes"], pred)
             weight_s.index_copy_(0, c["subs"], wi)
         if world > 1:
             # predictions of the other ranks: one in-place all-gather (libfesr's communicator) in rank = subdomain order
@@ -341,7 +343,9 @@ class GNNPartitionScheduler():
         gbuf[rank, :nr * oc].copy_(pred[lo:lo + nr].reshape(-1))
         gbuf[rank, lay.weight_off(rank):lay.weight_off(rank) + ns].copy_(weight_s[b0:b0 + ns])
         comm.allgatherv_pred(gbuf)
-        return gbuf.view(-1, oc).index_select(0, plan["pos"]), gbuf.view(-1).index_select(0, plan["wpos"])
+        rows = gbuf.view(-1, oc)
+        pred_all = ops.gather_rows(rows, plan["pos"]) if oc % 4 == 0 else rows.index_select(0, plan["pos"])
+        return pred_all, gbuf.view(-1).index_select(0, plan["wpos"])
 
     def _routing_plan(self, csr, edge_attr, node_ptr, labels_h, rank, world):
         from ..pipeline import shard_bounds

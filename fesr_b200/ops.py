@@ -505,6 +505,38 @@ def cluster(latent, scaler_mean, scaler_scale, centroids):
     return labels
 
 
+def gather_rows(src, index, out=None):
+    """out[r] = src[index[r]] for fp32 rows of a multiple of 4 floats (fesr_gather_rows; models/scheduler_gnn.py:240-251)."""
+    dev = _require_cuda(src)
+    src = src.contiguous()
+    index = index.to(torch.int64).contiguous()
+    rf = 1
+    for dim in src.shape[1:]:
+        rf *= int(dim)
+    if out is None:
+        out = torch.empty((int(index.numel()),) + tuple(src.shape[1:]), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(_lib.load().fesr_gather_rows(_ptr(src), _ptr(index), int(index.numel()), rf, _ptr(out), _stream(dev)),
+              "fesr_gather_rows")
+    return out
+
+
+def scatter_rows(src, index, out):
+    """out[index[r]] = src[r] (distinct indices; fesr_scatter_rows; reorder_predictions, models/scheduler_gnn.py:302-309)."""
+    dev = _require_cuda(src)
+    src = src.contiguous()
+    index = index.to(torch.int64).contiguous()
+    rf = 1
+    for dim in src.shape[1:]:
+        rf *= int(dim)
+    if not out.is_contiguous():
+        raise FesrError("scatter_rows needs a contiguous destination")
+    with torch.cuda.device(dev):
+        check(_lib.load().fesr_scatter_rows(_ptr(src), _ptr(index), int(index.numel()), rf, _ptr(out), _stream(dev)),
+              "fesr_scatter_rows")
+    return out
+
+
 # ---------------------------------------------------------------------------------- backward
 def reverse_csr(csr: Csr) -> Csr:
     """CSR of the reversed graph over the forward CSR slots: rowptr groups edges by SOURCE,

@@ -287,6 +287,15 @@ int fesr_cluster(const double* latent, int32_t n_sub, int32_t n_comp, const doub
                  const double* scaler_scale, const double* centroids, int32_t n_clusters,
                  int32_t* labels, void* stream);
 
+/* Row selection of the routed predict.  Replaces `x_in = [x[j] for j in idx]` (models/scheduler_gnn.py:240-251:
+ * the rows of the subdomains of one cluster, gathered into that cluster's block-diagonal sub-batch) and
+ * reorder_predictions (:302-309: the per-cluster results written back in subdomain order).
+ *   gather : dst[r, :] = src[index[r], :]      scatter : dst[index[r], :] = src[r, :]      r < rows
+ * rows of row_floats fp32 (a multiple of 4: 16-byte rows and pointers), index int64 on the device; the indices of a
+ * scatter must be distinct. */
+int fesr_gather_rows(const float* src, const int64_t* index, int64_t rows, int32_t row_floats, float* dst, void* stream);
+int fesr_scatter_rows(const float* src, const int64_t* index, int64_t rows, int32_t row_floats, float* dst, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Low-resolution -> high-resolution field transfer (the step BEFORE the path).  Replaces
  * AnsysDataset._lagrangian_interpolation (dataset/GraphDataset.py:1041-1105), i.e.

@@ -264,3 +264,21 @@ def test_stored_subdomains_flow_through_the_gpu_path(tmp_path, shipped, monkeypa
         assert rel_l2(out2.ref_field.numpy(), out.ref_field.numpy()) < 1e-6
         assert np.allclose(out2.pos, ds._mesh(m)["mesh"].pos)
         assert torch.allclose(torch.stack([t[0] for t in w2]), torch.stack([t[0] for t in w]), rtol=1e-4, atol=1e-6)
+
+
+def test_gather_scatter_rows():
+    """fesr_gather_rows / fesr_scatter_rows (the sub-batch selection and reorder_predictions of the routed predict,
+    models/scheduler_gnn.py:240-251, 302-309): bit-exact row moves, empty index, 4- and 8-float rows."""
+    from fesr_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    for rf in (4, 8):
+        src = torch.randn(10007, rf, generator=g).cuda()
+        idx = torch.randperm(10007, generator=g)[:6001].cuda()
+        got = ops.gather_rows(src, idx)
+        assert torch.equal(got, src[idx])
+        dst = torch.full((10007, rf), -7.0, device="cuda")
+        ops.scatter_rows(got, idx, dst)
+        ref = torch.full((10007, rf), -7.0, device="cuda")
+        ref[idx] = got
+        assert torch.equal(dst, ref)
+        assert ops.gather_rows(src, idx[:0]).shape == (0, rf)
