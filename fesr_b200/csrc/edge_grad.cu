@@ -91,16 +91,26 @@ __device__ __forceinline__ uint32_t eg_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return u;
 }
-// two consecutive dZ values (a = 2 tq, 2 tq + 1 of a k-step) as tf32 operand bits, one load
-__device__ __forceinline__ void eg_ldz2(const float* p, uint32_t& b0, uint32_t& b1) {
-  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
-  b0 = eg_tf32(v.x);
-  b1 = eg_tf32(v.y);
+// a lane's 12 consecutive dZ values (a = 12 tq .. 12 tq + 11 of one channel) as tf32 operand bits: b[2 ks], b[2 ks + 1]
+__device__ __forceinline__ void eg_ldz12(const float* p, uint32_t (&b)[12]) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
+    b[4 * q] = eg_tf32(v.x);
+    b[4 * q + 1] = eg_tf32(v.y);
+    b[4 * q + 2] = eg_tf32(v.z);
+    b[4 * q + 3] = eg_tf32(v.w);
+  }
 }
-__device__ __forceinline__ void eg_ldz2(const __nv_bfloat16* p, uint32_t& b0, uint32_t& b1) {
-  const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
-  b0 = v << 16;
-  b1 = v & 0xffff0000u;
+__device__ __forceinline__ void eg_ldz12(const __nv_bfloat16* p, uint32_t (&b)[12]) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + q);      // bf16 -> tf32 bits: exact
+    b[4 * q] = v.x << 16;
+    b[4 * q + 1] = v.x & 0xffff0000u;
+    b[4 * q + 2] = v.y << 16;
+    b[4 * q + 3] = v.y & 0xffff0000u;
+  }
 }
 
 // ZT = float, or __nv_bfloat16 for the bf16 dZ of the tcgen05 product (bf16 -> tf32 is exact: no second rounding)
@@ -127,23 +137,41 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
     const ZT* zrow = dZ + i * (int64_t)zk;
     for (int c0 = eb; c0 < ee; c0 += 16) {
       const int e0 = c0 + gq, e1 = c0 + gq + 8;
-      // The MMA's k-slots of a k-step are a permutation of the 8 node-feature indices: slot tq <-> a = 2 tq, slot tq + 4
-      // <-> a = 2 tq + 1 (in A and B alike), so that a lane's two k-values are adjacent in memory: one 8-byte load per
-      // h row and k-step, one 4- / 8-byte load per dZ row and k-step (half the load instructions of the natural order).
-      const float* h0 = h + (int64_t)__ldg(src_sorted + min(e0, ee - 1)) * WP + 2 * tq;
-      const float* h1 = h + (int64_t)__ldg(src_sorted + min(e1, ee - 1)) * WP + 2 * tq;
+      // The contraction index of the MMAs is a permutation of the 48 node-feature indices, the same in A and B: k-step ks,
+      // slot tq <-> a = 12 tq + 2 ks, slot tq + 4 <-> a = 12 tq + 2 ks + 1.  A lane then owns 12 CONSECUTIVE features of its
+      // rows for all six k-steps: three 16-byte loads per h row, three 8- / 16-byte loads per dZ channel row (a quarter of
+      // the load instructions of the natural order, each with four times the bytes in flight -- the kernel is bound by the
+      // latency of these loads: 80 % of its stall samples are long-scoreboard).
+      static_assert(WP == 48, "12 features per lane");
+      const float* h0 = h + (int64_t)__ldg(src_sorted + min(e0, ee - 1)) * WP + 12 * tq;
+      const float* h1 = h + (int64_t)__ldg(src_sorted + min(e1, ee - 1)) * WP + 12 * tq;
       uint32_t a[KS][4];
+      {
+        uint32_t v0[12], v1[12];
+        eg_ldz12(h0, v0);
+        eg_ldz12(h1, v1);
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const float2 v0 = __ldg(reinterpret_cast<const float2*>(h0 + ks * 8));
-        const float2 v1 = __ldg(reinterpret_cast<const float2*>(h1 + ks * 8));
-        a[ks][0] = eg_tf32(v0.x);
-        a[ks][1] = eg_tf32(v1.x);
-        a[ks][2] = eg_tf32(v0.y);
-        a[ks][3] = eg_tf32(v1.y);
+        for (int ks = 0; ks < KS; ++ks) {
+          a[ks][0] = v0[2 * ks];
+          a[ks][1] = v1[2 * ks];
+          a[ks][2] = v0[2 * ks + 1];
+          a[ks][3] = v1[2 * ks + 1];
+        }
       }
-      for (int t = lane; t < 16 * q4; t += 32) reinterpret_cast<float4*>(tile)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-      __syncwarp();
+      // the chunk's rows of dg are brought into the warp's tile by cp.async while the MMAs run (the read-modify-write of
+      // dg used to be 36 % of the kernel's stall samples: a dependent global load in front of every row update)
+      const int nrow = min(16, ee - c0);
+      float4* drow = reinterpret_cast<float4*>(dg + (int64_t)c0 * kp);
+      for (int t = lane; t < 16 * q4; t += 32) {
+        if (t < nrow * q4) {
+          const uint32_t dsts = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<float4*>(tile) + t);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts), "l"(drow + t) : "memory");
+        } else {
+          reinterpret_cast<float4*>(tile)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      bool landed = false;
       for (int nt0 = 0; nt0 < n_nt; nt0 += NTC) {
         float acc[NTC][4];
 #pragma unroll
@@ -151,18 +179,23 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
 #pragma unroll
         for (int t = 0; t < NTC; ++t) {
           if (nt0 + t < n_nt) {
-            // B[a][channel]: b0 = dZ[chan = (nt0 + t) * 8 + gq][a = ks * 8 + 2 tq], b1 = ... [a + 1]
+            // B[a][channel]: dZ[chan = (nt0 + t) * 8 + gq][a = 12 tq + 2 ks (+ 1)]
             // (channels past k1p in the last tile: clamped row, masked on store)
-            const ZT* zp = zrow + (int64_t)min((nt0 + t) * 8 + gq, k1p - 1) * WP + 2 * tq;
+            const ZT* zp = zrow + (int64_t)min((nt0 + t) * 8 + gq, k1p - 1) * WP + 12 * tq;
+            uint32_t b[12];
+            eg_ldz12(zp, b);
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
-              uint32_t b0, b1;
-              eg_ldz2(zp + ks * 8, b0, b1);
               asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                   : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
-                  : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1));
+                  : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b[2 * ks]), "r"(b[2 * ks + 1]));
             }
           }
+        }
+        if (!landed) {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+          __syncwarp();
+          landed = true;
         }
         // accumulator (row gq / gq + 8, channels 2 tq, 2 tq + 1 of tile t) -> dg[edge][slot(channel)]
 #pragma unroll
@@ -172,24 +205,14 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
             const int chan = (nt0 + t) * 8 + 2 * tq + j;
             if (nt0 + t < n_nt && chan < k1p) {
               const int off = (chan / kt) * ktp + (chan % kt);
-              tile[gq * kp + off] = acc[t][j] * inv;
-              tile[(gq + 8) * kp + off] = acc[t][2 + j] * inv;
+              tile[gq * kp + off] += acc[t][j] * inv;
+              tile[(gq + 8) * kp + off] += acc[t][2 + j] * inv;
             }
           }
         }
       }
       __syncwarp();
-      const int nrow = min(16, ee - c0);
-      float4* drow = reinterpret_cast<float4*>(dg + (int64_t)c0 * kp);
-      for (int t = lane; t < nrow * q4; t += 32) {
-        float4 v = drow[t];
-        const float4 u = reinterpret_cast<const float4*>(tile)[t];
-        v.x += u.x;
-        v.y += u.y;
-        v.z += u.z;
-        v.w += u.w;
-        drow[t] = v;
-      }
+      for (int t = lane; t < nrow * q4; t += 32) drow[t] = reinterpret_cast<const float4*>(tile)[t];
       __syncwarp();
     }
   }
