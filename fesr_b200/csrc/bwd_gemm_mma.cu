@@ -6,6 +6,7 @@
 // Both are HBM-bound (24 flop/B): mma.sync.m16n8k8 tf32 leaves the tensor pipe far from
 // saturated, and unlike tcgen05 it reads MN-major operands without a transposing copy.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "backward.cuh"
 
@@ -117,6 +118,96 @@ wgrad_mma_kernel(const ZT* __restrict__ Z, const float* __restrict__ dpre, int64
     }
 }
 
+// The tf32 arm's hot shape (fp16 Z stash, tf32-rounded dpre): the kernel above is ISSUE-bound (ncu: issue slots 70 % active,
+// 38 instructions per 6 MMAs -- scalar 16-bit fragment loads, a cvt per operand).  Here a warp owns 32 zk rows (two m-tiles
+// that share every dpre fragment), the MMA's rows gq / gq + 8 are the ADJACENT zk columns 2 gq / 2 gq + 1 (one 32-bit load
+// per fragment pair), and dpre needs no conversion: 24 instructions per 12 MMAs.
+constexpr int WG2_BM = 256;    // zk columns per CTA (8 warps x 32)
+template <int WP>
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_mma2_kernel(const __half* __restrict__ Z, const float* __restrict__ dpre, int64_t n, int zk, int64_t nchunk,
+                  float* __restrict__ partial) {
+  constexpr int NT = WP / 8;
+  constexpr int SZ = WG2_BM + 16, SD = WP + 8;       // row strides (halfs / floats): conflict-free fragment loads
+  extern __shared__ __align__(16) float smem[];
+  float* Ds = smem;                                              // [2][BK][SD]
+  __half* Zs = reinterpret_cast<__half*>(smem + 2 * WG_BK * SD); // [2][BK][SZ]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int m0 = blockIdx.x * WG2_BM;
+  const int64_t k_begin = (int64_t)blockIdx.y * nchunk, k_end = min(n, k_begin + nchunk);
+  float acc[2][NT][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[j][nt][r] = 0.f;
+
+  auto load_stage = [&](int st, int64_t k0) {
+    __half* zs = Zs + st * WG_BK * SZ;
+    float* ds = Ds + st * WG_BK * SD;
+    for (int t = tid; t < WG_BK * (WG2_BM / 8); t += WG_THREADS) {
+      const int r = t / (WG2_BM / 8), c = (t % (WG2_BM / 8)) * 8;
+      __half* dst = zs + r * SZ + c;
+      if (k0 + r < k_end && m0 + c < zk) bg_cp16(dst, Z + (k0 + r) * (int64_t)zk + m0 + c);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int t = tid; t < WG_BK * (WP / 4); t += WG_THREADS) {
+      const int r = t / (WP / 4), c = (t % (WP / 4)) * 4;
+      float* dst = ds + r * SD + c;
+      if (k0 + r < k_end) bg_cp16(dst, dpre + (k0 + r) * (int64_t)WP + c);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  int st = 0;
+  if (k_begin < k_end) load_stage(0, k_begin);
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += WG_BK) {
+    const bool more = k0 + WG_BK < k_end;
+    if (more) load_stage(st ^ 1, k0 + WG_BK);
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const __half* zs = Zs + st * WG_BK * SZ + warp * 32 + 2 * gq;
+    const float* ds = Ds + st * WG_BK * SD + gq;
+#pragma unroll
+    for (int ks = 0; ks < WG_BK / 8; ++ks) {
+      const int r0 = ks * 8 + tq, r1 = r0 + 4;
+      uint32_t a[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(zs + r0 * SZ + j * 16));   // rows gq, gq + 8 at node r0
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(zs + r1 * SZ + j * 16));   // ... at node r1
+        a[j][0] = __float_as_uint(lo.x);
+        a[j][1] = __float_as_uint(lo.y);
+        a[j][2] = __float_as_uint(hi.x);
+        a[j][3] = __float_as_uint(hi.y);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t b0 = __float_as_uint(ds[r0 * SD + nt * 8]), b1 = __float_as_uint(ds[r1 * SD + nt * 8]);
+        bg_mma(acc[0][nt], a[0], b0, b1);
+        bg_mma(acc[1][nt], a[1], b0, b1);
+      }
+    }
+    __syncthreads();
+    st ^= 1;
+  }
+  // partial[blockIdx.y][zk][WP]; MMA row gq <-> zk column 2 gq, row gq + 8 <-> 2 gq + 1 of the m-tile
+  float* out = partial + (int64_t)blockIdx.y * zk * WP;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int m = m0 + warp * 32 + j * 16 + 2 * gq + hh;
+        if (m < zk)
+          *reinterpret_cast<float2*>(out + (int64_t)m * WP + nt * 8 + 2 * tq) = make_float2(acc[j][nt][2 * hh], acc[j][nt][2 * hh + 1]);
+      }
+}
+
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int ks, int64_t count, float* __restrict__ dT) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= count) return;
@@ -126,7 +217,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int ks, i
 }
 
 int wgrad_mma_splits(int zk) {
-  const int mtiles = (zk + WG_BM - 1) / WG_BM;
+  const int mtiles = (zk + WG_BM - 1) / WG_BM;      // (the 256-column kernel has half the m-tiles: twice the node ranges, same workspace bound)
   // 6 CTAs per SM's worth of node ranges (4 are resident at 49 KB of shared memory each): with 2 the two 16 KB stages
   // in flight per CTA do not cover the HBM latency (train step 18.7 -> 18.3 ms)
   int ks = (6 * num_sms() + mtiles - 1) / mtiles;
@@ -139,6 +230,29 @@ int launch_wgrad_mma(const fesr_model_dims& d, const void* Z, int z_half, const 
                      cudaStream_t s, int terms) {
   FESR_CHECK_ARG(terms == 1 || (terms == 3 && !z_half), "3xTF32 weight gradient takes the fp32 Z stash");
   if (n == 0) return FESR_OK;
+  static const bool wide_env = !(getenv("FESR_WGRAD_WIDE") && atoi(getenv("FESR_WGRAD_WIDE")) == 0);      // A/B switch
+  if (z_half && terms == 1 && d.wp == 48 && wide_env) {
+    // dpre is tf32-rounded by the mask kernel in this arm (backward.cu): its bits are the operand.
+    // One wave: 3 CTAs are resident per SM (69 registers x 256 threads), so at most 3 x SMs CTAs in all.
+    int ks = (3 * num_sms()) / (int)ceil_div(d.zk, WG2_BM);
+    if (ks > wgrad_mma_splits(d.zk)) ks = wgrad_mma_splits(d.zk);       // the workspace is sized for that many partials
+    if (ks < 1) ks = 1;
+    const int64_t nchunk = ceil_div(ceil_div(n, ks), WG_BK) * WG_BK;
+    const int ks_eff = (int)ceil_div(n, nchunk);
+    constexpr size_t smem = (size_t)2 * WG_BK * (48 + 8) * sizeof(float) + (size_t)2 * WG_BK * (WG2_BM + 16) * sizeof(__half);
+    static bool attr = false;
+    if (!attr) {
+      FESR_CUDA(cudaFuncSetAttribute(wgrad_mma2_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    dim3 grid((unsigned)ceil_div(d.zk, WG2_BM), (unsigned)ks_eff);
+    wgrad_mma2_kernel<48><<<grid, WG_THREADS, smem, s>>>(static_cast<const __half*>(Z), dpre, n, d.zk, nchunk, ws);
+    FESR_LAUNCH_CHECK();
+    const int64_t count = (int64_t)d.zk * d.wp;
+    wgrad_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, s>>>(ws, ks_eff, count, dT);
+    FESR_LAUNCH_CHECK();
+    return FESR_OK;
+  }
   const int ks = wgrad_mma_splits(d.zk);
   const int64_t nchunk = ceil_div(ceil_div(n, ks), WG_BK) * WG_BK;
   const int ks_eff = (int)ceil_div(n, nchunk);
