@@ -30,13 +30,14 @@ __global__ void inv_deg_kernel(const int32_t* __restrict__ rowptr, int64_t n, fl
 // (tf32 arm: rounded to tf32 here -- every consumer rounds it anyway, and the tcgen05 dZ product truncates what it is given)
 __global__ void mask_kernel(const float* __restrict__ dh, const float* __restrict__ h_next, int64_t n, int wp, int w,
                             int relu, int round_tf32, float* __restrict__ dpre, float* __restrict__ dpre_hi,
-                            float* __restrict__ dpre_lo) {
+                            float* __restrict__ dpre_lo, const float* __restrict__ in_scale) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= n * wp) return;
   const int c = (int)(idx % wp);
   float v = 0.f;
   if (c < w) {
     v = dh[idx];
+    if (in_scale != nullptr) v *= __ldg(in_scale);      // dh of the scaled fp16 Z~ path: exact power-of-two unscaling
     if (relu && !(h_next[idx] > 0.f)) v = 0.f;
   }
   if (round_tf32) {
@@ -53,6 +54,39 @@ __global__ void mask_kernel(const float* __restrict__ dh, const float* __restric
     dpre_hi[idx] = hi;
     dpre_lo[idx] = __uint_as_float(u);
   }
+}
+
+// Scaled fp16 Z~ (tf32 arm).  The reversed-graph outer products Z~ = sum g (x) dpre[dst]/deg[dst] ++ dpre and the dh = Z~ T~
+// product move 2.7 GB per layer as fp32; the forward of this arm already keeps its Z in fp16 (same 11-bit mantissa as
+// tf32).  Gradients live far below fp16's range, so dpre is multiplied by a per-layer power of two S that brings its
+// largest magnitude to 2^6 (found on the device: absmax -> S, no host round trip), Z~ and T~ go through the fp16 kernels of
+// the forward, and the next layer's mask kernel multiplies dh by 1/S -- both scalings are exact.
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t count, unsigned* __restrict__ out) {
+  unsigned m = 0u;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    m = max(m, __float_as_uint(x[i]) & 0x7fffffffu);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(out, m);      // non-negative floats order like their bit patterns
+}
+
+// out = x * S with S = 2^floor(log2(target / absmax)); scale[0] = S, scale[1] = 1 / S
+__global__ void scale_copy_kernel(const float* __restrict__ x, int64_t count, const unsigned* __restrict__ amax_bits,
+                                  float target, float* __restrict__ out, float* __restrict__ scale) {
+  const float amax = __uint_as_float(*amax_bits);
+  float S = 1.f;
+  if (amax > 0.f && amax < 3.0e38f) S = exp2f(fminf(fmaxf(floorf(log2f(target / amax)), -100.f), 100.f));
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx == 0) {
+    scale[0] = S;
+    scale[1] = 1.0f / S;
+  }
+  if (idx < count) out[idx] = x[idx] * S;
+}
+
+__global__ void scale_inplace_kernel(float* __restrict__ x, int64_t count, const float* __restrict__ factor) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx < count) x[idx] *= __ldg(factor);
 }
 
 // out = tf32(in) (and out_lo = tf32(in - out) when asked for)
@@ -192,6 +226,9 @@ struct BackwardWs {
   float* tprime_r_lo;   // ... and its lo part, dpre_hi / dpre_lo [n, wp]: the fp32 arm's three-term product
   float* dpre_hi;
   float* dpre_lo;
+  float* dpre_s;        // dpre * S_l (scaled fp16 Z~ path), amax bit patterns and (S_l, 1 / S_l) per layer
+  unsigned* amax;
+  float* scales;
   float* inv_deg;
   float* dbias;
   float* dattr;
@@ -218,6 +255,9 @@ static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n
   w.tprime_r_lo = c.take<float>((size_t)d.zk * d.wp);
   w.dpre_hi = c.take<float>(nn * d.wp);
   w.dpre_lo = c.take<float>(nn * d.wp);
+  w.dpre_s = c.take<float>(nn * d.wp);
+  w.amax = c.take<unsigned>(64);
+  w.scales = c.take<float>(128);
   w.inv_deg = c.take<float>(nn);
   w.dbias = c.take<float>(d.wp);
   w.dattr = c.take<float>(ee);
@@ -324,10 +364,15 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     round_tf32_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(fw.prep.tprime, cnt, w.tprime_r, dz_tc3 ? w.tprime_r_lo : nullptr);
     FESR_LAUNCH_CHECK();
   }
+  // tf32 arm with the fp16 Z stash: Z~ and dh through the fp16 kernels, dpre scaled per layer (FESR_ZT_HALF=0: fp32 Z~)
+  static const bool zt_half_env = !(getenv("FESR_ZT_HALF") && atoi(getenv("FESR_ZT_HALF")) == 0);
+  const bool zt_half = rnd && zt_half_env && z_stash_half(precision) && L <= 60 && d.wp % 16 == 0 && d.wp <= 64;
+  if (zt_half) FESR_CUDA(cudaMemsetAsync(w.amax, 0, 64 * sizeof(unsigned), s));
+  const float* in_scale = nullptr;      // 1 / S of the layer processed before (dh arrives scaled by S)
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
     mask_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dh[cur], fw.h[l + 1], n, d.wp, d.w, relu, rnd, w.dpre,
-                                                              dz_tc3 ? w.dpre_hi : nullptr, dz_tc3 ? w.dpre_lo : nullptr);
+                                                              dz_tc3 ? w.dpre_hi : nullptr, dz_tc3 ? w.dpre_lo : nullptr, in_scale);
     FESR_LAUNCH_CHECK();
     if ((rc = launch_colsum(w.dpre, n, d.wp, d.wp, 1, w.dbias, w.colsum_ws, s))) return rc;
     // dT' += Z_l^T dpre
@@ -352,6 +397,21 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
       if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, rnd, w.dg, s, dz_bf16))) return rc;
     }
     // dh_l = [sum over out-edges of g (x) dpre[dst]/deg[dst]  ++  dpre] T~
+    if (zt_half) {
+      const int64_t cnt = n * d.wp;
+      absmax_kernel<<<(unsigned)(ceil_div(cnt, 256 * 8) < 4096 ? ceil_div(cnt, 256 * 8) : 4096), 256, 0, s>>>(w.dpre, cnt, w.amax + l);
+      FESR_LAUNCH_CHECK();
+      scale_copy_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(w.dpre, cnt, w.amax + l, 64.f, w.dpre_s, w.scales + 2 * l);
+      FESR_LAUNCH_CHECK();
+      rc = launch_zbuild_mma(d, rowptr_t, src_t, w.g_rev, w.dpre_s, n, w.BZ, 2, s, /*mean=*/0, w.inv_deg);
+      if (rc) return rc;
+      rc = launch_node_gemm_f16(d, fw.prep.ttilde_t_h, nullptr, EPI_NONE, w.BZ, n, w.dh[cur ^ 1], s);
+      if (rc) return rc;
+      in_scale = w.scales + 2 * l + 1;
+      cur ^= 1;
+      continue;
+    }
+    in_scale = nullptr;
     if (rnd)
       rc = launch_zbuild_mma(d, rowptr_t, src_t, w.g_rev, w.dpre, n, w.BZ, 1, s, /*mean=*/0, w.inv_deg);
     else
@@ -391,6 +451,10 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   }
 
   // ---- fc1:  h_0 = x W1^T + b1
+  if (in_scale != nullptr) {      // dh of layer 0 is still scaled
+    scale_inplace_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dh[cur], n * d.wp, in_scale);
+    FESR_LAUNCH_CHECK();
+  }
   const float* dh0 = w.dh[cur];
   GEMM(dh0, 1, d.wp, x, d.in_ch, 1, grads->fc1_w, d.in_ch, 1, d.w, d.in_ch, n, 1);
   if ((rc = launch_colsum(dh0, n, d.w, d.wp, 1, grads->fc1_b, w.colsum_ws, s))) return rc;

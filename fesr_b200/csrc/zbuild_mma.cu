@@ -358,10 +358,12 @@ static int zm_dispatch_mode(const fesr_model_dims& d, const int32_t* rowptr, con
                             const float* h, int64_t n, void* Z, int zmode, cudaStream_t s, int mean, const float* gsc) {
   const bool bwd = (mean == 0);
   if (bwd) {
-    if (!gsc || zmode != 1) {
-      set_error("backward zbuild needs a gather scale and the tf32 mode");
+    if (!gsc) {
+      set_error("backward zbuild needs a gather scale");
       return FESR_EINVAL;
     }
+    // zmode 2: the scaled fp16 Z~ of the tf32 arm's backward (backward.cu)
+    if (zmode == 2) return launch_zm<MT, WP, 2, true>(d, rowptr, src_sorted, g, h, n, Z, s, gsc);
     return launch_zm<MT, WP, 1, true>(d, rowptr, src_sorted, g, h, n, Z, s, gsc);
   }
   if (zmode == 2) return launch_zm<MT, WP, 2, false>(d, rowptr, src_sorted, g, h, n, Z, s, nullptr);
