@@ -32,3 +32,9 @@ print("per consumer warp (mean over CTAs): warp: total wait0 wait1 m2 m3 m9")
 for w in range(24):
     v = a[:, w, :].mean(axis=0) / tiles
     print(f"  w{w:2d} smsp{w%4} total {v[0]:6.0f} w0 {v[2]:6.0f} w1 {v[3]:6.0f} m2 {v[4]:6.0f} m3 {v[5]:6.0f} m9 {v[11]:6.0f}")
+tot = a[:, 0, 0]          # consumer warp 0: cycles from the start of the main loop to its end, per CTA
+nt = a[:, 0, 1]
+print(f"per-CTA span (consumer warp 0): mean {tot.mean():.0f} max {tot.max():.0f} min {tot.min():.0f} cycles; max/mean {tot.max()/tot.mean():.3f}; tiles per CTA min {nt.min():.0f} max {nt.max():.0f}")
+import numpy as np
+order = np.argsort(tot)
+print("slowest CTAs:", [(int(i), int(tot[i])) for i in order[-5:]], "fastest:", [(int(i), int(tot[i])) for i in order[:5]])
