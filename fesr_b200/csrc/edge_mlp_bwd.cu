@@ -38,6 +38,10 @@ edge_mlp_bwd_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g
   __shared__ __align__(16) float w0s[EB_W], b0s[EB_W];
   __shared__ __align__(16) float w1s[EB_W][EB_SW];          // [o][i], tf32 bit patterns
   __shared__ __align__(16) float da1s[4][32][EB_S1];        // [warp][edge][channel o] (un-permuted), tf32 bit patterns
+  // per-warp staging of the NEXT group's dg and g rows (cp.async, issued once this group's rows have been turned into
+  // the da1 tile): the loads used to sit in front of every group -- 12 dependent 16-byte load pairs per lane with 8 warps
+  // per SM (231 registers): 1.15 TB/s, 80 % of the stall samples long-scoreboard -- and now fly under the MMAs
+  extern __shared__ __align__(16) float eb_stage[];          // [4 warps][2 arrays][32 edges][kp]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
   for (int i = tid; i < EB_W; i += blockDim.x) {
     w0s[i] = i < w ? w0g[i] : 0.f;
@@ -68,17 +72,35 @@ edge_mlp_bwd_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g
   float (*tile)[EB_S1] = da1s[warp];
   const int n_groups = (E + 31) / 32;
   const int q4 = kp >> 2;
+  float4* sdg = reinterpret_cast<float4*>(eb_stage) + (size_t)warp * 2 * 32 * q4;
+  float4* sg = sdg + 32 * q4;
+  auto stage_group = [&](int grp_) {        // the group's rows are contiguous: [32][kp] floats of dg and of g
+    if (grp_ < n_groups) {
+      const int eb_ = grp_ * 32;
+      const int nrow = min(32, E - eb_);
+      const float4* pd = reinterpret_cast<const float4*>(dg + (int64_t)eb_ * kp);
+      const float4* pg = reinterpret_cast<const float4*>(g + (int64_t)eb_ * kp);
+      for (int t = lane; t < nrow * q4; t += 32) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sdg + t)), "l"(pd + t) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(sg + t)), "l"(pg + t) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_group(blockIdx.x * 4 + warp);
   for (int grp = blockIdx.x * 4 + warp; grp < n_groups; grp += gridDim.x * 4) {
     const int e_base = grp * 32;
     const int e_l = e_base + lane;
     const float d_lane = e_l < E ? __ldg(edge_attr + (perm ? __ldg(perm + e_l) : e_l)) : 0.f;
-    // ---- da1 = dg (.) relu'(g), un-permuted into the tile (coalesced 16-byte row loads, slot layout -> channel layout)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- da1 = dg (.) relu'(g), un-permuted into the tile (slot layout -> channel layout)
     for (int t = lane; t < 32 * q4; t += 32) {
       const int r = t / q4, c4 = t - r * q4;
       float4 dv = make_float4(0.f, 0.f, 0.f, 0.f), gv = dv;
       if (e_base + r < E) {
-        dv = __ldg(reinterpret_cast<const float4*>(dg + (int64_t)(e_base + r) * kp) + c4);
-        gv = __ldg(reinterpret_cast<const float4*>(g + (int64_t)(e_base + r) * kp) + c4);
+        dv = sdg[t];
+        gv = sg[t];
       }
       const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
@@ -91,6 +113,7 @@ edge_mlp_bwd_kernel(const float* __restrict__ w0g, const float* __restrict__ b0g
     if (w < EB_W)
       for (int t = lane; t < 32 * (EB_W - w); t += 32) tile[t / (EB_W - w)][w + t % (EB_W - w)] = 0.f;
     __syncwarp();
+    stage_group(grp + (int)gridDim.x * 4);        // the staging rows have been consumed: bring the next group's
     // ---- da0 = da1 W1 (edges on M), dpre0 = da0 (.) relu'(a0); its column sums feed dw0 / db0
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
@@ -213,7 +236,14 @@ int launch_edge_mlp_bwd(const fesr_model_dims& d, const fesr_params& p, const fl
   if (E == 0) return FESR_OK;
   const int grid = eb_grid(E);
   ProfScope prof(PROF_BACKWARD, s);
-  edge_mlp_bwd_kernel<<<grid, 128, 0, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], d.w, d.kt, d.ktp, d.kp, edge_attr, perm, dg, g, (int)E, ws);
+  const size_t smem = (size_t)4 * 2 * 32 * d.kp * sizeof(float);       // 48 KB at kp = 48 (+ 38 KB static): 2 CTAs per SM
+  static bool attr = false;
+  if (!attr) {
+    FESR_CUDA(cudaFuncSetAttribute(edge_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  FESR_CHECK_ARG(smem <= 64 * 1024, "edge-MLP backward: staging exceeds 64 KB");
+  edge_mlp_bwd_kernel<<<grid, 128, smem, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], d.w, d.kt, d.ktp, d.kp, edge_attr, perm, dg, g, (int)E, ws);
   FESR_LAUNCH_CHECK();
   edge_mlp_bwd_reduce_kernel<<<(unsigned)ceil_div(EB_PART, 256), 256, 0, s>>>(ws, grid * 4, d.w, grads->mlp_w[1], grads->mlp_b[1],
                                                                             grads->mlp_w[0], grads->mlp_b[0]);
