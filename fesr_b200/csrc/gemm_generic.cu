@@ -165,13 +165,30 @@ colsum_partial_kernel(const float* __restrict__ X, int64_t rows, int cols, int64
   __syncthreads();
   if (rg == 0 && j < cols) partial[(int64_t)blockIdx.x * cols + j] = (red[0][jl] + red[1][jl]) + (red[2][jl] + red[3][jl]);
 }
+// 64 columns x 4 groups per block: group q adds the partials b = q, q + 4, ... with four independent accumulators (the
+// single chain of nb = 512 dependent adds took 32 us), the groups are combined in a fixed order: deterministic
 __global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, int cols, int accumulate,
                                     float* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= cols) return;
-  float s = 0.f;
-  for (int b = 0; b < nb; ++b) s += partial[(int64_t)b * cols + j];
-  out[j] = accumulate ? out[j] + s : s;
+  __shared__ float red[4][64];
+  const int jl = threadIdx.x & 63, q = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + jl;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (j < cols) {
+    int b = q;
+    for (; b + 12 < nb; b += 16) {
+      s0 += partial[(int64_t)b * cols + j];
+      s1 += partial[(int64_t)(b + 4) * cols + j];
+      s2 += partial[(int64_t)(b + 8) * cols + j];
+      s3 += partial[(int64_t)(b + 12) * cols + j];
+    }
+    for (; b < nb; b += 4) s0 += partial[(int64_t)b * cols + j];
+  }
+  red[q][jl] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (q == 0 && j < cols) {
+    const float s = (red[0][jl] + red[1][jl]) + (red[2][jl] + red[3][jl]);
+    out[j] = accumulate ? out[j] + s : s;
+  }
 }
 
 size_t colsum_ws_bytes(int cols) { return (size_t)COLSUM_BLOCKS * cols * sizeof(float); }
@@ -185,7 +202,7 @@ int launch_colsum(const float* X, int64_t rows, int cols, int64_t ld, int accumu
   dim3 grid(nb, (unsigned)ceil_div(cols, 64));
   colsum_partial_kernel<<<grid, 256, 0, s>>>(X, rows, cols, ld, rchunk, ws);
   FESR_LAUNCH_CHECK();
-  colsum_final_kernel<<<(unsigned)ceil_div(cols, 64), 64, 0, s>>>(ws, nb, cols, accumulate, out);
+  colsum_final_kernel<<<(unsigned)ceil_div(cols, 64), 256, 0, s>>>(ws, nb, cols, accumulate, out);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }

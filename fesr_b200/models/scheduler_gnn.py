@@ -301,31 +301,55 @@ class GNNPartitionScheduler():
         labels = self._route(x_dev, node_ptr)
         # Routed and / or sharded: the plan -- this rank's contiguous edge-balanced share of the subdomain list and,
         # per cluster, the block-diagonal sub-batch of its subdomains -- depends only on the labels, so it is kept
-        # on the device batch and rebuilt only when the routing of this sample changes.
-        labels_h = labels.cpu().numpy()
+        # on the device batch and rebuilt only when the routing of this sample changes.  The labels come back from the
+        # device asynchronously: the pass is issued with the cached plan while they travel and is checked against them
+        # afterwards (a mid-pass `labels.cpu()` left the GPU idle behind the host on every call); only a changed routing
+        # -- or the first call -- pays the synchronous path.
         holder = x.batch.__dict__ if isinstance(x, SubdomainSample) else {}
         plan = holder.get("_alds_plan")
-        if (plan is None or plan["world"] != world or plan["rank"] != rank or plan["k"] != self.num_partitions
-                or not np.array_equal(plan["labels"], labels_h)):
-            plan = self._routing_plan(csr, edge_attr, node_ptr, labels_h, rank, world)
+        main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        labels_pin = torch.empty(S, dtype=torch.int32, pin_memory=True)
+        routed = main.record_event()
+        with torch.cuda.stream(side):
+            side.wait_event(routed)
+            labels_pin.copy_(labels, non_blocking=True)
+            labels_ready = side.record_event()
+        labels.record_stream(side)
+        usable = plan is not None and plan["world"] == world and plan["rank"] == rank and plan["k"] == self.num_partitions
+        if not usable:
+            labels_ready.synchronize()
+            plan = self._routing_plan(csr, edge_attr, node_ptr, labels_pin.numpy().copy(), rank, world)
             holder["_alds_plan"] = plan
         if y_ready is not None:
-            torch.cuda.current_stream(dev).wait_event(y_ready)
+            main.wait_event(y_ready)
         out_ch = self.models[0].dims.out_ch
-        pred = torch.zeros(csr.n, out_ch, dtype=torch.float32, device=dev)
-        weight_s = torch.zeros(S, dtype=torch.float32, device=dev)
-        for i, c in plan["clusters"]:
-            # (torch's index_select / advanced indexing take 84 us per 2.5 MB of 16-byte rows on a B200, whatever the
-            # index type -- tools/dev/gather_bench.py; these are 16-byte-row copies at HBM rate)
-            xi, yi = ops.gather_rows(x_dev, c["nodes"]), ops.gather_rows(y_dev, c["nodes"])
-            pi = self.models[i](xi, c["csr"], c["edge_attr"])
-            wi = ops.node_weight(pi, yi, c["csr"], c["edge_attr"], c["node_ptr"])
-            ops.scatter_rows(pi, c["nodes"], pred)
-            weight_s.index_copy_(0, c["subs"], wi)
-        if world > 1:
-            # predictions of the other ranks: one in-place all-gather (libfesr's communicator) in rank = subdomain order
-            pred, weight_s = self._gather_routed(pred, weight_s, plan, rank, world)
-        return self._to_host_lists(x, pred, weight_s, y_dev, sizes, labels)
+
+        def run(plan):
+            pred = torch.zeros(csr.n, out_ch, dtype=torch.float32, device=dev)
+            weight_s = torch.zeros(S, dtype=torch.float32, device=dev)
+            for i, c in plan["clusters"]:
+                # (torch's index_select / advanced indexing take 84 us per 2.5 MB of 16-byte rows on a B200, whatever the
+                # index type -- tools/dev/gather_bench.py; these are 16-byte-row copies at HBM rate)
+                xi, yi = ops.gather_rows(x_dev, c["nodes"]), ops.gather_rows(y_dev, c["nodes"])
+                pi = self.models[i](xi, c["csr"], c["edge_attr"])
+                wi = ops.node_weight(pi, yi, c["csr"], c["edge_attr"], c["node_ptr"])
+                ops.scatter_rows(pi, c["nodes"], pred)
+                weight_s.index_copy_(0, c["subs"], wi)
+            if world > 1:
+                # predictions of the other ranks: one in-place all-gather (libfesr's communicator) in rank = subdomain order
+                pred, weight_s = self._gather_routed(pred, weight_s, plan, rank, world)
+            return pred, weight_s
+
+        pred, weight_s = run(plan)
+        labels_ready.synchronize()                      # long since there: the copy was issued before the pass
+        labels_h = labels_pin.numpy()
+        if not np.array_equal(plan["labels"], labels_h):
+            # the routing of this sample differs from the cached plan's: what was just issued is discarded.  Every rank
+            # sees the same labels (same inputs), so all of them take this branch together (the all-gather inside pairs up)
+            plan = self._routing_plan(csr, edge_attr, node_ptr, labels_h.copy(), rank, world)
+            holder["_alds_plan"] = plan
+            pred, weight_s = run(plan)
+        return self._to_host_lists(x, pred, weight_s, y_dev, sizes, labels_h.copy())
 
     def _gather_routed(self, pred, weight_s, plan, rank, world):
         """ALDS on several ranks: this rank's rows of `pred` [n, c] / `weight_s` [S] -> the complete arrays."""
@@ -572,7 +596,10 @@ class GNNPartitionScheduler():
         if own is not None:
             weights_list.own = (own[2], own[3])
             weights_list.rest = rest_once
-        model_idx = np.zeros(S, dtype=int) if labels is None or self.num_partitions == 1 else labels.cpu().numpy().astype(int)
+        if labels is None or self.num_partitions == 1:
+            model_idx = np.zeros(S, dtype=int)
+        else:      # (the routed path hands over the host copy it already has)
+            model_idx = (labels if isinstance(labels, np.ndarray) else labels.cpu().numpy()).astype(int)
         return pred_y_list, ref_y_list, model_idx, weights_list
 
     # ----------------------------------------------------------------------------- train
