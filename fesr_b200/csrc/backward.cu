@@ -11,6 +11,7 @@
 // then the edge-MLP hidden layers, fc1 / fc2.  Replaces loss.backward() of the reference's train
 // step (models/scheduler_gnn.py:407) -- where autograd materialises the [E, w*w] edge matrices
 // and their gradients -- for the same parameters, named as in the state_dict.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "backward.cuh"
@@ -82,6 +83,43 @@ __global__ void scale_copy_kernel(const float* __restrict__ x, int64_t count, co
     scale[1] = 1.0f / S;
   }
   if (idx < count) out[idx] = x[idx] * S;
+}
+
+// Fused reversed-graph pass (KernelNN shape): the gathered rows q = dpre S / deg[node] and the own rows dpre S as fp16 rows
+// for layer_fused16_kernel in sum mode (Z~ stays on chip, as Z does in the predict arm)
+__global__ void scale_rows_f16_kernel(const float* __restrict__ x, int64_t n, int wp, const unsigned* __restrict__ amax_bits,
+                                      float target, const float* __restrict__ inv_deg, __half* __restrict__ own,
+                                      __half* __restrict__ q, float* __restrict__ scale) {
+  const float amax = __uint_as_float(*amax_bits);
+  float S = 1.f;
+  if (amax > 0.f && amax < 3.0e38f) S = exp2f(fminf(fmaxf(floorf(log2f(target / amax)), -100.f), 100.f));
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx == 0) {
+    scale[0] = S;
+    scale[1] = 1.0f / S;
+  }
+  if (idx >= n * wp) return;
+  const float v = x[idx] * S;
+  own[idx] = __float2half_rn(v);
+  q[idx] = __float2half_rn(v * inv_deg[idx / wp]);
+}
+
+// g rows [E, kp] fp32 (reversed-CSR order, slot layout) -> planar fp16 [kp / 16][E][16]; the lo slot (first padding slot)
+// holds the constant FESR_LO_SCALE that the fused kernel's two-term weights expect (layer_fused.cu)
+__global__ void g3_planar_kernel(const float* __restrict__ g, int64_t E, int kp, int lo_slot, __half* __restrict__ g3) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // one 8-slot chunk of one edge
+  const int c8 = kp / 8;
+  if (t >= E * c8) return;
+  const int64_t e = t / c8;
+  const int c = (int)(t - e * c8);
+  const float4 v0 = *reinterpret_cast<const float4*>(g + e * kp + c * 8), v1 = *reinterpret_cast<const float4*>(g + e * kp + c * 8 + 4);
+  float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  if (lo_slot >= c * 8 && lo_slot < c * 8 + 8) f[lo_slot - c * 8] = FESR_LO_SCALE;
+  __half2 h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+  const int part = (c * 8) / 16, off = (c * 8) % 16;
+  *reinterpret_cast<uint4*>(g3 + ((size_t)part * E + e) * 16 + off) = *reinterpret_cast<const uint4*>(h);
 }
 
 __global__ void scale_inplace_kernel(float* __restrict__ x, int64_t count, const float* __restrict__ factor) {
@@ -227,6 +265,11 @@ struct BackwardWs {
   float* dpre_hi;
   float* dpre_lo;
   float* dpre_s;        // dpre * S_l (scaled fp16 Z~ path), amax bit patterns and (S_l, 1 / S_l) per layer
+  __half* g3_rev;       // fused reversed pass: planar fp16 g (reversed order), T~ in the fused K order, own / gathered rows
+  __half* tfused_t;
+  __half* own16;
+  __half* q16;
+  float* zero_bias;
   unsigned* amax;
   float* scales;
   float* inv_deg;
@@ -256,6 +299,12 @@ static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n
   w.dpre_hi = c.take<float>(nn * d.wp);
   w.dpre_lo = c.take<float>(nn * d.wp);
   w.dpre_s = c.take<float>(nn * d.wp);
+  const bool fz = layer_fused_supported(d) && d.kind == FESR_KERNELNN && d.kp == 48 && d.w <= 43;
+  w.g3_rev = fz ? c.take<__half>(ee * d.kp) : nullptr;
+  w.tfused_t = fz ? c.take<__half>(layer_fused_tf_elems(d)) : nullptr;
+  w.own16 = fz ? c.take<__half>(nn * d.wp) : nullptr;
+  w.q16 = fz ? c.take<__half>(nn * d.wp) : nullptr;
+  w.zero_bias = c.take<float>(64);
   w.amax = c.take<unsigned>(64);
   w.scales = c.take<float>(128);
   w.inv_deg = c.take<float>(nn);
@@ -368,6 +417,17 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   static const bool zt_half_env = !(getenv("FESR_ZT_HALF") && atoi(getenv("FESR_ZT_HALF")) == 0);
   const bool zt_half = rnd && zt_half_env && z_stash_half(precision) && L <= 60 && d.wp % 16 == 0 && d.wp <= 64;
   if (zt_half) FESR_CUDA(cudaMemsetAsync(w.amax, 0, 64 * sizeof(unsigned), s));
+  // ... and, for the single-launch KernelNN shape, through the fused layer kernel in sum mode on the reversed CSR: Z~ never
+  // reaches HBM (FESR_ZT_FUSED=0: the two fp16 kernels)
+  static const bool zt_fused_env = !(getenv("FESR_ZT_FUSED") && atoi(getenv("FESR_ZT_FUSED")) == 0);
+  const bool zt_fused = zt_half && zt_fused_env && w.g3_rev != nullptr && E > 0;
+  if (zt_fused) {
+    FESR_CUDA(cudaMemsetAsync(w.zero_bias, 0, 64 * sizeof(float), s));
+    g3_planar_kernel<<<(unsigned)ceil_div(E * (d.kp / 8), T), T, 0, s>>>(w.g_rev, E, d.kp, d.kt, w.g3_rev);
+    FESR_LAUNCH_CHECK();
+    // T~ in the fused K order; the constant-1 slot carries T~'s own constant rows (no centring of g in this arm)
+    if ((rc = launch_prepare_tfused(d, fw.prep.ttilde, fw.prep.ttilde + (size_t)(d.k1 - 1) * d.wp * d.wp, w.tfused_t, s))) return rc;
+  }
   const float* in_scale = nullptr;      // 1 / S of the layer processed before (dh arrives scaled by S)
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
@@ -401,6 +461,17 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
       const int64_t cnt = n * d.wp;
       absmax_kernel<<<(unsigned)(ceil_div(cnt, 256 * 8) < 4096 ? ceil_div(cnt, 256 * 8) : 4096), 256, 0, s>>>(w.dpre, cnt, w.amax + l);
       FESR_LAUNCH_CHECK();
+      if (zt_fused) {
+        scale_rows_f16_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16, w.q16,
+                                                                       w.scales + 2 * l);
+        FESR_LAUNCH_CHECK();
+        rc = launch_layer_fused_f16(d, rowptr_t, src_t, w.g3_rev, E, w.q16, n, w.tfused_t, w.zero_bias, nullptr, w.dh[cur ^ 1], 3, s,
+                                    /*out_f32=*/1, /*sum_mode=*/1, w.own16);
+        if (rc) return rc;
+        in_scale = w.scales + 2 * l + 1;
+        cur ^= 1;
+        continue;
+      }
       scale_copy_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(w.dpre, cnt, w.amax + l, 64.f, w.dpre_s, w.scales + 2 * l);
       FESR_LAUNCH_CHECK();
       rc = launch_zbuild_mma(d, rowptr_t, src_t, w.g_rev, w.dpre_s, n, w.BZ, 2, s, /*mean=*/0, w.inv_deg);

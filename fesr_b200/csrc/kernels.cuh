@@ -47,7 +47,8 @@ int launch_prepare_tfused(const fesr_model_dims& d, const float* tprime, const f
 // mode: parts per launch (0 = as many as the TMEM lanes hold)
 int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* g3,
                            int64_t E, const void* h_in, int64_t n, const void* tf, const float* bias_p, float* P,
-                           void* h_out, int mode, cudaStream_t s, int out_f32 = 0);
+                           void* h_out, int mode, cudaStream_t s, int out_f32 = 0, int sum_mode = 0, const void* h_own = nullptr);
+// (sum_mode / h_own: the backward's reversed-graph pass, single-launch KernelNN shape only -- backward.cu)
 
 // gemm_simt.cu ------------------------------------------------------------------------
 // h_out[n, wp] = epilogue(Z[n, zk] x tprime[zk, wp] + bias)

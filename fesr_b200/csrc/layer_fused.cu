@@ -732,7 +732,7 @@ int launch_prepare_tfused(const fesr_model_dims& d, const float* tprime, const f
 // (only touched when the parts need more than one launch).  mode: parts per launch (0 = best).
 int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* g3,
                            int64_t E, const void* h_in, int64_t n, const void* tf, const float* bias_p, float* P,
-                           void* h_out, int mode, cudaStream_t s, int out_f32) {
+                           void* h_out, int mode, cudaStream_t s, int out_f32, int sum_mode, const void* h_own) {
   if (n == 0) return FESR_OK;
   if (!layer_fused_supported(d)) {
     set_error("fused layer: unsupported model shape");
@@ -744,11 +744,15 @@ int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, cons
   __half* ho = static_cast<__half*>(h_out);
   // bit 0: ReLU (TEECNet has no activation between the layers, models/model.py:280-282); bit 1: fp32 output rows
   static const int what_if = getenv("FESR_FL_EXP") ? (atoi(getenv("FESR_FL_EXP")) & 0xf) << 8 : 0;      // tools/dev only
-  const int relu = (d.kind == FESR_KERNELNN ? 1 : 0) | (out_f32 ? 2 : 0) | what_if;
+  const int relu = (d.kind == FESR_KERNELNN && !sum_mode ? 1 : 0) | (out_f32 ? 2 : 0) | (sum_mode ? 4 : 0) | what_if;
   ProfScope prof(PROF_LAYER_FUSED, s);
   int rc;
   // 16-node tiles (layer_fused16.cu) unless FESR_FL_TILE=8 asks for the 8-node kernel of this file (A/B measurements)
   static const bool tile16 = !(getenv("FESR_FL_TILE") && atoi(getenv("FESR_FL_TILE")) == 8);
+  if (sum_mode && !(tile16 && d.kind == FESR_KERNELNN && d.kp == 48 && d.w <= 43 && (mode == 0 || mode == 3))) {
+    set_error("fused layer: the sum mode covers the single-launch KernelNN shape of the 16-node kernel only");
+    return FESR_EINVAL;
+  }
   if (tile16) {
     if (d.kind == FESR_TEECNET) {
       const int fix_b = d.w == 43 ? 42 : -1;
@@ -762,7 +766,8 @@ int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, cons
     }
     if (mode == 0) mode = d.w <= 43 ? 3 : 2;
     if (mode == 3 && d.w <= 43)
-      return launch_fl16<3>(rowptr, src_sorted, gh, E, hh, n, 0, 1, tfh, bias_p, nullptr, nullptr, ho, 43, d.w == 43 ? 42 : -1, relu, s);
+      return launch_fl16<3>(rowptr, src_sorted, gh, E, hh, n, 0, 1, tfh, bias_p, nullptr, nullptr, ho, 43, d.w == 43 ? 42 : -1, relu, s,
+                            static_cast<const __half*>(h_own));
     if (mode == 2) {
       if ((rc = launch_fl16<2>(rowptr, src_sorted, gh, E, hh, n, 0, 0, tfh, bias_p, nullptr, P, nullptr, 64, -1, relu, s))) return rc;
       return launch_fl16<1>(rowptr, src_sorted, gh, E, hh, n, 2, 1, tfh, bias_p, P, nullptr, ho, 128, -1, relu, s);

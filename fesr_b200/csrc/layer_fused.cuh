@@ -186,6 +186,6 @@ __device__ __forceinline__ void fl_tmem_st16(uint32_t addr, const uint32_t (&r)[
 template <int PPL>
 int launch_fl16(const int32_t* rowptr, const int32_t* src_sorted, const __half* g3, int64_t E, const __half* h_in,
                 int64_t n, int part0, int has_root, const __half* tf, const float* bias_p, const float* p_in,
-                float* p_out, __half* h_out, int rs, int fix_b, int relu, cudaStream_t s);
+                float* p_out, __half* h_out, int rs, int fix_b, int relu, cudaStream_t s, const __half* h_own = nullptr);
 
 }  // namespace fesr

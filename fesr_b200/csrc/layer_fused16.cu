@@ -64,7 +64,10 @@ layer_fused16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
                      const __half* __restrict__ g3, int64_t E, const __half* __restrict__ h_in, int64_t n,
                      int part0, int has_root, const __half* __restrict__ tf, const float* __restrict__ bias_p,
                      const float* p_in, float* p_out, __half* __restrict__ h_out,
-                     int rs, int fix_b, int relu, int* ovf, int t_per, int t_extra) {
+                     int rs, int fix_b, int relu, int* ovf, int t_per, int t_extra, const __half* __restrict__ h_own) {
+  // relu: bit 0 ReLU, bit 1 fp32 output rows, bit 2 SUM mode (the backward's reversed-graph pass: no 1/deg, the root
+  // row enters unscaled); h_own: the nodes' own rows when they are not the gathered array's (backward: dpre against
+  // dpre / deg[dst]), NULL = h_in
   // warp ids of the roles: consumers 0..15, epilogue 16..19 (TMEM lane quadrant = warp % 4), MMA issuer 20, producers 21..23
   constexpr int W_EPI0 = F2_BW;
   constexpr int W_MMA = F2_BW + 4;
@@ -204,7 +207,8 @@ layer_fused16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
     const uint32_t wfl = fl_smem(wfs) + (uint32_t)(lane * 4);
     const uint32_t st_u32 = fl_smem(stage);
     const uint32_t fxp_u32 = fl_smem(fxp), deg_u32 = fl_smem(degs);
-    const uint4* h16 = reinterpret_cast<const uint4*>(h_in);
+    const uint4* h16 = reinterpret_cast<const uint4*>(h_own != nullptr ? h_own : h_in);      // own rows only (root block)
+    const bool sum_mode = (relu & 4) != 0;
     int buf = 0;
     uint32_t par = 0;             // parity of the ring's current pass
     const int n32 = (int)n;
@@ -294,7 +298,8 @@ layer_fused16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
       uint4 hs = make_uint4(0u, 0u, 0u, 0u);
       if (has_root && lane < 8) {
         // root block: h_i * max(deg, 1) so that the epilogue's 1/deg leaves h_i (lanes 6, 7: the zero tail)
-        const __half2 dg = __float2half2_rn((float)(deg > 0 ? deg : 1));
+        const float degf = sum_mode ? 1.f : (float)(deg > 0 ? deg : 1);
+        const __half2 dg = __float2half2_rn(degf);
         hs.x = fl_hmul2(hv.x, dg);
         hs.y = fl_hmul2(hv.y, dg);
         hs.z = fl_hmul2(hv.z, dg);
@@ -303,7 +308,7 @@ layer_fused16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         if (PPL >= 2) {
           // the same row scaled by 2^-8 for the part before the last: its root block holds the low-order term of
           // `root` (prepare_tfused_kernel), so h_i root is applied with two-term fp16 weights
-          const __half2 dl = __float2half2_rn((float)(deg > 0 ? deg : 1) * FESR_LO_SCALE);
+          const __half2 dl = __float2half2_rn(degf * FESR_LO_SCALE);
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(zroot - (uint32_t)(F2_NODES * 128)), "r"(fl_hmul2(hv.x, dl)),
                        "r"(fl_hmul2(hv.y, dl)), "r"(fl_hmul2(hv.z, dl)), "r"(fl_hmul2(hv.w, dl))
                        : "memory");
@@ -340,7 +345,7 @@ layer_fused16_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
         fsum += __shfl_xor_sync(FULL, fsum, 8);
         if (lane < 8) asm volatile("st.shared.f32 [%0], %1;" ::"r"(fxp_u32 + (uint32_t)((((it & 3) * F2_NODES + j) * 8 + lane) * 4)), "f"(fsum) : "memory");
       }
-      if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(deg_u32 + (uint32_t)(((it & 3) * F2_NODES + j) * 4)), "f"((float)(deg > 0 ? deg : 1)) : "memory");
+      if (lane == 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(deg_u32 + (uint32_t)(((it & 3) * F2_NODES + j) * 4)), "f"(sum_mode ? 1.f : (float)(deg > 0 ? deg : 1)) : "memory");
       __syncwarp();
       if (lane == 0) fl_mbar_arrive(fready + 8 * (it & 3));
       FL_TMARK(3)
@@ -630,7 +635,7 @@ static size_t f2_smem_bytes() {
 template <int PPL>
 int launch_fl16(const int32_t* rowptr, const int32_t* src_sorted, const __half* g3, int64_t E, const __half* h_in,
                 int64_t n, int part0, int has_root, const __half* tf, const float* bias_p, const float* p_in,
-                float* p_out, __half* h_out, int rs, int fix_b, int relu, cudaStream_t s) {
+                float* p_out, __half* h_out, int rs, int fix_b, int relu, cudaStream_t s, const __half* h_own) {
   int* ovf = cur_ovf();
   size_t smem = f2_smem_bytes<PPL>();
   if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: the kernel owns all 512 TMEM columns
@@ -654,16 +659,16 @@ int launch_fl16(const int32_t* rowptr, const int32_t* src_sorted, const __half* 
   cfg.numAttrs = pdl ? 1 : 0;
   const int t_per = (int)(n_tiles / grid), t_extra = (int)(n_tiles % grid);
   FESR_CUDA(cudaLaunchKernelEx(&cfg, layer_fused16_kernel<PPL>, rowptr, src_sorted, g3, E, h_in, n, part0, has_root, tf, bias_p,
-                               p_in, p_out, h_out, rs, fix_b, relu, ovf, t_per, t_extra));
+                               p_in, p_out, h_out, rs, fix_b, relu, ovf, t_per, t_extra, h_own));
   count_launch();
   return FESR_OK;
 }
 
 template int launch_fl16<1>(const int32_t*, const int32_t*, const __half*, int64_t, const __half*, int64_t, int, int, const __half*,
-                            const float*, const float*, float*, __half*, int, int, int, cudaStream_t);
+                            const float*, const float*, float*, __half*, int, int, int, cudaStream_t, const __half*);
 template int launch_fl16<2>(const int32_t*, const int32_t*, const __half*, int64_t, const __half*, int64_t, int, int, const __half*,
-                            const float*, const float*, float*, __half*, int, int, int, cudaStream_t);
+                            const float*, const float*, float*, __half*, int, int, int, cudaStream_t, const __half*);
 template int launch_fl16<3>(const int32_t*, const int32_t*, const __half*, int64_t, const __half*, int64_t, int, int, const __half*,
-                            const float*, const float*, float*, __half*, int, int, int, cudaStream_t);
+                            const float*, const float*, float*, __half*, int, int, int, cudaStream_t, const __half*);
 
 }  // namespace fesr
