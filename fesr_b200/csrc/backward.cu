@@ -270,6 +270,7 @@ struct BackwardWs {
   __half* own16;
   __half* q16;
   float* zero_bias;
+  float* fused_P;       // fp32 partial sums between the launches of a multi-launch shape (TEECNet)
   unsigned* amax;
   float* scales;
   float* inv_deg;
@@ -299,12 +300,13 @@ static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n
   w.dpre_hi = c.take<float>(nn * d.wp);
   w.dpre_lo = c.take<float>(nn * d.wp);
   w.dpre_s = c.take<float>(nn * d.wp);
-  const bool fz = layer_fused_supported(d) && d.kind == FESR_KERNELNN && d.kp == 48 && d.w <= 43;
+  const bool fz = layer_fused_supported(d) && d.w <= 43 && ((d.kind == FESR_KERNELNN && d.kp == 48) || d.kind == FESR_TEECNET);
   w.g3_rev = fz ? c.take<__half>(ee * d.kp) : nullptr;
   w.tfused_t = fz ? c.take<__half>(layer_fused_tf_elems(d)) : nullptr;
   w.own16 = fz ? c.take<__half>(nn * d.wp) : nullptr;
   w.q16 = fz ? c.take<__half>(nn * d.wp) : nullptr;
   w.zero_bias = c.take<float>(64);
+  w.fused_P = fz && d.kind == FESR_TEECNET ? c.take<float>(nn * d.wp) : nullptr;
   w.amax = c.take<unsigned>(64);
   w.scales = c.take<float>(128);
   w.inv_deg = c.take<float>(nn);
@@ -465,7 +467,8 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
         scale_rows_f16_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16, w.q16,
                                                                        w.scales + 2 * l);
         FESR_LAUNCH_CHECK();
-        rc = launch_layer_fused_f16(d, rowptr_t, src_t, w.g3_rev, E, w.q16, n, w.tfused_t, w.zero_bias, nullptr, w.dh[cur ^ 1], 3, s,
+        rc = launch_layer_fused_f16(d, rowptr_t, src_t, w.g3_rev, E, w.q16, n, w.tfused_t, w.zero_bias, w.fused_P, w.dh[cur ^ 1],
+                                    d.kind == FESR_KERNELNN ? 3 : 0, s,
                                     /*out_f32=*/1, /*sum_mode=*/1, w.own16);
         if (rc) return rc;
         in_scale = w.scales + 2 * l + 1;

@@ -749,8 +749,9 @@ int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, cons
   int rc;
   // 16-node tiles (layer_fused16.cu) unless FESR_FL_TILE=8 asks for the 8-node kernel of this file (A/B measurements)
   static const bool tile16 = !(getenv("FESR_FL_TILE") && atoi(getenv("FESR_FL_TILE")) == 8);
-  if (sum_mode && !(tile16 && d.kind == FESR_KERNELNN && d.kp == 48 && d.w <= 43 && (mode == 0 || mode == 3))) {
-    set_error("fused layer: the sum mode covers the single-launch KernelNN shape of the 16-node kernel only");
+  const bool sum_ok = tile16 && d.w <= 43 && ((d.kind == FESR_KERNELNN && d.kp == 48 && (mode == 0 || mode == 3)) || d.kind == FESR_TEECNET);
+  if (sum_mode && !sum_ok) {
+    set_error("fused layer: the sum mode covers the w <= 43 shapes of the 16-node kernel only");
     return FESR_EINVAL;
   }
   if (tile16) {
@@ -758,7 +759,8 @@ int launch_layer_fused_f16(const fesr_model_dims& d, const int32_t* rowptr, cons
       const int fix_b = d.w == 43 ? 42 : -1;
       if ((rc = launch_fl16<3>(rowptr, src_sorted, gh, E, hh, n, 0, 0, tfh, bias_p, nullptr, P, nullptr, 43, fix_b, relu, s))) return rc;
       if ((rc = launch_fl16<3>(rowptr, src_sorted, gh, E, hh, n, 3, 0, tfh, bias_p, P, P, nullptr, 43, fix_b, relu, s))) return rc;
-      return launch_fl16<3>(rowptr, src_sorted, gh, E, hh, n, 6, 1, tfh, bias_p, P, nullptr, ho, 43, fix_b, relu, s);
+      return launch_fl16<3>(rowptr, src_sorted, gh, E, hh, n, 6, 1, tfh, bias_p, P, nullptr, ho, 43, fix_b, relu, s,
+                            static_cast<const __half*>(h_own));
     }
     if (d.kp == 64) {
       if ((rc = launch_fl16<2>(rowptr, src_sorted, gh, E, hh, n, 0, 0, tfh, bias_p, nullptr, P, nullptr, 64, -1, relu, s))) return rc;
