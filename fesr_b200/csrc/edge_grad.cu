@@ -132,6 +132,16 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
   const int q4 = kp >> 2;
   for (int64_t i = warp_global; i < n; i += warp_stride) {
     const int eb = rowptr[i], ee = rowptr[i + 1];
+    {
+      // the next node's dZ block (zk values: 34 lines as bf16) into L1 while this node computes: its fragment loads are
+      // what the warp waits on (29 % of the kernel's stall samples)
+      const int64_t inext = i + warp_stride;
+      if (inext < n) {
+        const char* pz = reinterpret_cast<const char*>(dZ + inext * (int64_t)zk);
+        const int nline = (int)(((int64_t)zk * sizeof(ZT) + 127) / 128);
+        for (int l = lane; l < nline; l += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(pz + (size_t)l * 128));
+      }
+    }
     if (ee == eb) continue;
     const float inv = 1.0f / (float)(ee - eb);
     const ZT* zrow = dZ + i * (int64_t)zk;
