@@ -456,7 +456,8 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
       } else {
         GEMM(w.dpre, d.wp, 1, fw.prep.tprime, 1, d.wp, w.BZ, d.zk, 1, n, d.zk, d.wp, 0);
       }
-      if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, rnd, w.dg, s, dz_bf16))) return rc;
+      // (use_mma: 1 = tf32 arm, 3 = the fp32 arm's 3xTF32 form where the tensor-core kernel covers the shape)
+      if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, rnd ? 1 : 3, w.dg, s, dz_bf16))) return rc;
     }
     // dh_l = [sum over out-edges of g (x) dpre[dst]/deg[dst]  ++  dpre] T~
     if (zt_half) {

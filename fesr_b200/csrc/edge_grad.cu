@@ -102,6 +102,17 @@ __device__ __forceinline__ void eg_ldz12(const float* p, uint32_t (&b)[12]) {
     b[4 * q + 3] = eg_tf32(v.w);
   }
 }
+// the same 12 values unrounded (3xTF32: the caller splits them into hi + lo)
+__device__ __forceinline__ void eg_ldf12(const float* p, float (&b)[12]) {
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
+    b[4 * q] = v.x;
+    b[4 * q + 1] = v.y;
+    b[4 * q + 2] = v.z;
+    b[4 * q + 3] = v.w;
+  }
+}
 __device__ __forceinline__ void eg_ldz12(const __nv_bfloat16* p, uint32_t (&b)[12]) {
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -114,7 +125,8 @@ __device__ __forceinline__ void eg_ldz12(const __nv_bfloat16* p, uint32_t (&b)[1
 }
 
 // ZT = float, or __nv_bfloat16 for the bf16 dZ of the tcgen05 product (bf16 -> tf32 is exact: no second rounding)
-template <int WP, typename ZT>
+// TERMS == 3 (fp32 arm, ZT = float): h rows and dZ are split into tf32 hi + lo in registers, lo.hi + hi.lo + hi.hi
+template <int WP, typename ZT, int TERMS>
 __global__ void __launch_bounds__(128)
 edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted,
                      const ZT* __restrict__ dZ, const float* __restrict__ h, int64_t n, int k1p, int kt, int ktp, int kp,
@@ -156,7 +168,21 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
       const float* h0 = h + (int64_t)__ldg(src_sorted + min(e0, ee - 1)) * WP + 12 * tq;
       const float* h1 = h + (int64_t)__ldg(src_sorted + min(e1, ee - 1)) * WP + 12 * tq;
       uint32_t a[KS][4];
-      {
+      uint32_t alo[TERMS == 3 ? KS : 1][4];
+      if constexpr (TERMS == 3) {
+        float v0[12], v1[12];
+        eg_ldf12(h0, v0);
+        eg_ldf12(h1, v1);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const float f[4] = {v0[2 * ks], v1[2 * ks], v0[2 * ks + 1], v1[2 * ks + 1]};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            a[ks][q] = eg_tf32(f[q]);
+            alo[ks][q] = eg_tf32(f[q] - __uint_as_float(a[ks][q]));
+          }
+        }
+      } else {
         uint32_t v0[12], v1[12];
         eg_ldz12(h0, v0);
         eg_ldz12(h1, v1);
@@ -192,13 +218,32 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
             // B[a][channel]: dZ[chan = (nt0 + t) * 8 + gq][a = 12 tq + 2 ks (+ 1)]
             // (channels past k1p in the last tile: clamped row, masked on store)
             const ZT* zp = zrow + (int64_t)min((nt0 + t) * 8 + gq, k1p - 1) * WP + 12 * tq;
-            uint32_t b[12];
-            eg_ldz12(zp, b);
+            if constexpr (TERMS == 3) {
+              float bf[12];
+              eg_ldf12(reinterpret_cast<const float*>(zp), bf);
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                  : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
-                  : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b[2 * ks]), "r"(b[2 * ks + 1]));
+              for (int ks = 0; ks < KS; ++ks) {
+                const uint32_t b0 = eg_tf32(bf[2 * ks]), b1 = eg_tf32(bf[2 * ks + 1]);
+                const uint32_t l0 = eg_tf32(bf[2 * ks] - __uint_as_float(b0)), l1 = eg_tf32(bf[2 * ks + 1] - __uint_as_float(b1));
+                asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                    : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                    : "r"(alo[ks][0]), "r"(alo[ks][1]), "r"(alo[ks][2]), "r"(alo[ks][3]), "r"(b0), "r"(b1));
+                asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                    : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                    : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(l0), "r"(l1));
+                asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                    : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                    : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1));
+              }
+            } else {
+              uint32_t b[12];
+              eg_ldz12(zp, b);
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                    : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                    : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b[2 * ks]), "r"(b[2 * ks + 1]));
+              }
             }
           }
         }
@@ -251,15 +296,19 @@ int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int3
   if (n == 0) return FESR_OK;
   ProfScope prof(PROF_BACKWARD, s);
   static const bool no_mma = getenv("FESR_EDGE_GRAD_FFMA") != nullptr;      // A/B switch for profiling
+  static const bool no_3x = getenv("FESR_EDGE_GRAD_3X") && atoi(getenv("FESR_EDGE_GRAD_3X")) == 0;      // A/B switch
+  if (use_mma == 3 && (no_mma || no_3x || d.wp != 48)) use_mma = 0;
   if (use_mma && !no_mma && d.wp == 48) {
     const int64_t blocks = ceil_div(n, 4);
     const int grid = (int)(blocks < 16ll * num_sms() ? blocks : 16ll * num_sms());
     const size_t smem = (size_t)4 * 16 * d.kp * sizeof(float);      // <= 36.9 KB (kp = 144)
     if (dz_bf16)
-      edge_grad_mma_kernel<48, __nv_bfloat16><<<grid, 128, smem, s>>>(rowptr, src_sorted, static_cast<const __nv_bfloat16*>(dZv), h, n,
+      edge_grad_mma_kernel<48, __nv_bfloat16, 1><<<grid, 128, smem, s>>>(rowptr, src_sorted, static_cast<const __nv_bfloat16*>(dZv), h, n,
                                                                      d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+    else if (use_mma == 3)
+      edge_grad_mma_kernel<48, float, 3><<<grid, 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
     else
-      edge_grad_mma_kernel<48, float><<<grid, 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+      edge_grad_mma_kernel<48, float, 1><<<grid, 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
     FESR_LAUNCH_CHECK();
     return FESR_OK;
   }
