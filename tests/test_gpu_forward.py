@@ -214,6 +214,78 @@ def test_fused_layer_kernel_ragged_graph(shipped, monkeypatch):
         assert err < TOL["f16"], mode
 
 
+def test_fused_layer_kernel_hub_nodes(shipped, monkeypatch):
+    """in-degrees above one staged segment (112 edges): a node is then cut every 112 edges across ring slots (112, 113,
+    224, 225, 500 incoming edges), next to ordinary and isolated nodes, in every launch mode."""
+    rng = np.random.default_rng(11)
+    n = 16 * 9 + 3
+    deg = rng.integers(0, 20, size=n)
+    for node, dg in ((3, 112), (17, 113), (18, 224), (40, 225), (41, 0), (77, 500), (n - 1, 130)):
+        deg[node] = dg
+    dst = np.repeat(np.arange(n), deg)
+    src = rng.integers(0, n, size=dst.size)
+    order = rng.permutation(dst.size)
+    ei = np.stack([src[order], dst[order]]).astype(np.int64)
+    ea = rng.uniform(2e-3, 6e-3, size=dst.size).astype(np.float32)
+    x = rng.uniform(0.0, 1.0, size=(n, 4)).astype(np.float32)
+    m, o = _models("neuralop", 43, 5)
+    sd = shipped_state_dict(shipped, "neuralop")
+    m.load_state_dict(sd)
+    o.load_state_dict(sd)
+    with torch.no_grad():
+        yo = o(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ea)).numpy()
+    for mode in (0, 1, 2, 3):
+        y = _run_fuse_mode(monkeypatch, mode, m, x, ei, ea)
+        err = rel_l2(y, yo)
+        print(f"hub nodes, fused mode {mode}: rel-L2 {err:.3e}")
+        assert err < TOL["f16"], mode
+
+
+def test_eight_node_fused_kernel_in_its_own_process(shipped):
+    """FESR_FL_TILE=8 (the round-1 kernel, kept for A/B measurements) is read once per process: run the ragged graph
+    through it in a subprocess and compare with the 16-node kernel of this process -- both against the same oracle gate."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    from conftest import ROOT
+    rng = np.random.default_rng(5)
+    n = 16 * 21 + 7
+    deg = rng.integers(0, 30, size=n)
+    deg[5] = 150
+    dst = np.repeat(np.arange(n), deg)
+    src = rng.integers(0, n, size=dst.size)
+    ei = np.stack([src, dst]).astype(np.int64)
+    ea = rng.uniform(2e-3, 6e-3, size=dst.size).astype(np.float32)
+    x = rng.uniform(0.0, 1.0, size=(n, 4)).astype(np.float32)
+    m, o = _models("neuralop", 43, 5)
+    sd = shipped_state_dict(shipped, "neuralop")
+    m.load_state_dict(sd)
+    o.load_state_dict(sd)
+    with torch.no_grad():
+        yo = o(torch.from_numpy(x), torch.from_numpy(ei), torch.from_numpy(ea)).numpy()
+    with tempfile.TemporaryDirectory() as td:
+        np.savez(os.path.join(td, "in.npz"), x=x, ei=ei, ea=ea, **{"sd::" + k: v.numpy() for k, v in sd.items()})
+        code = (
+            "import sys, numpy as np, torch\n"
+            f"sys.path.insert(0, {ROOT!r})\n"
+            "from fesr_b200.models.model import KernelNN\n"
+            f"z = np.load({os.path.join(td, 'in.npz')!r})\n"
+            "m = KernelNN(43, 43, 5, in_width=4, out_width=4)\n"
+            "m.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd::')})\n"
+            "m = m.cuda().eval(); m.precision = 'f16'\n"
+            "with torch.no_grad():\n"
+            "    y = m(torch.from_numpy(z['x']).cuda(), torch.from_numpy(z['ei']).cuda(), torch.from_numpy(z['ea']).cuda())\n"
+            f"np.save({os.path.join(td, 'out.npy')!r}, y.cpu().numpy())\n")
+        env = dict(os.environ, FESR_FL_TILE="8", FESR_FUSE="3")
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        y8 = np.load(os.path.join(td, "out.npy"))
+    err8 = rel_l2(y8, yo)
+    print(f"8-node fused kernel (subprocess): rel-L2 {err8:.3e}")
+    assert err8 < TOL["f16"]
+
+
 @pytest.mark.parametrize("w", [40, 36])
 def test_fused_layer_kernel_narrower_widths(monkeypatch, w):
     """widths below 43 use the same kernel without the CUDA-core fix-up row."""
