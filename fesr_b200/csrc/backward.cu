@@ -127,6 +127,57 @@ __global__ void scale_inplace_kernel(float* __restrict__ x, int64_t count, const
   if (idx < count) x[idx] *= __ldg(factor);
 }
 
+// mask_kernel + the column sums of dpre (dbias) + its largest magnitude in ONE pass over dh (tf32 arm: the three used to be
+// three kernels reading the same 30 MB).  Blocks own row ranges like colsum_partial_kernel (64 columns x 4 row groups, a
+// thread walks its rows 4 apart with four independent accumulators, the groups are combined in a fixed order), so the partial
+// sums -- finished by colsum_final_kernel -- are deterministic; the absmax is order-independent.
+__global__ void __launch_bounds__(256)
+mask_colsum_kernel(const float* __restrict__ dh, const float* __restrict__ h_next, int64_t n, int wp, int w, int relu,
+                   const float* __restrict__ in_scale, int64_t rchunk, float* __restrict__ dpre, float* __restrict__ partial,
+                   unsigned* __restrict__ amax) {
+  __shared__ float red[4][64];
+  __shared__ unsigned mred[8];
+  const int j = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const float sc = in_scale != nullptr ? __ldg(in_scale) : 1.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  unsigned m = 0u;
+  if (j < wp) {
+    const int64_t r0 = (int64_t)blockIdx.x * rchunk, r1 = min(n, r0 + rchunk);
+    auto one = [&](int64_t i) {
+      float v = 0.f;
+      if (j < w) {
+        v = dh[i * wp + j] * sc;
+        if (relu && !(h_next[i * wp + j] > 0.f)) v = 0.f;
+      }
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+      v = __uint_as_float(u);
+      dpre[i * wp + j] = v;
+      m = max(m, u & 0x7fffffffu);
+      return v;
+    };
+    int64_t i = r0 + rg;
+    for (; i + 12 < r1; i += 16) {
+      s0 += one(i);
+      s1 += one(i + 4);
+      s2 += one(i + 8);
+      s3 += one(i + 12);
+    }
+    for (; i < r1; i += 4) s0 += one(i);
+  }
+  red[rg][j] = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) mred[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (rg == 0 && j < wp) partial[(int64_t)blockIdx.x * wp + j] = (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
+  if (threadIdx.x == 0 && amax != nullptr) {
+    unsigned mm = 0u;
+    for (int q = 0; q < 8; ++q) mm = max(mm, mred[q]);
+    if (mm != 0u) atomicMax(amax, mm);
+  }
+}
+
 // out = tf32(in) (and out_lo = tf32(in - out) when asked for)
 __global__ void round_tf32_kernel(const float* __restrict__ in, int64_t count, float* __restrict__ out,
                                   float* __restrict__ out_lo) {
@@ -433,10 +484,21 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   const float* in_scale = nullptr;      // 1 / S of the layer processed before (dh arrives scaled by S)
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
-    mask_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dh[cur], fw.h[l + 1], n, d.wp, d.w, relu, rnd, w.dpre,
-                                                              dz_tc3 ? w.dpre_hi : nullptr, dz_tc3 ? w.dpre_lo : nullptr, in_scale);
-    FESR_LAUNCH_CHECK();
-    if ((rc = launch_colsum(w.dpre, n, d.wp, d.wp, 1, w.dbias, w.colsum_ws, s))) return rc;
+    const bool mask_fused = rnd && d.wp <= 64 && n > 0;      // tf32 arm: mask + dbias partial sums + absmax in one pass
+    if (mask_fused) {
+      int nb = (int)(n < COLSUM_BLOCKS ? n : COLSUM_BLOCKS);
+      const int64_t rchunk = ceil_div(n, nb);
+      nb = (int)ceil_div(n, rchunk);
+      mask_colsum_kernel<<<nb, 256, 0, s>>>(w.dh[cur], fw.h[l + 1], n, d.wp, d.w, relu, in_scale, rchunk, w.dpre, w.colsum_ws,
+                                            zt_half ? w.amax + l : nullptr);
+      FESR_LAUNCH_CHECK();
+      if ((rc = launch_colsum_final(w.colsum_ws, nb, d.wp, 1, w.dbias, s))) return rc;
+    } else {
+      mask_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dh[cur], fw.h[l + 1], n, d.wp, d.w, relu, rnd, w.dpre,
+                                                                dz_tc3 ? w.dpre_hi : nullptr, dz_tc3 ? w.dpre_lo : nullptr, in_scale);
+      FESR_LAUNCH_CHECK();
+      if ((rc = launch_colsum(w.dpre, n, d.wp, d.wp, 1, w.dbias, w.colsum_ws, s))) return rc;
+    }
     // dT' += Z_l^T dpre
     if (rnd) {
       if ((rc = launch_wgrad_mma(d, fw.Z[l], z_stash_half(precision), w.dpre, n, w.dT, w.gemm_ws, s))) return rc;
@@ -462,8 +524,10 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     // dh_l = [sum over out-edges of g (x) dpre[dst]/deg[dst]  ++  dpre] T~
     if (zt_half) {
       const int64_t cnt = n * d.wp;
-      absmax_kernel<<<(unsigned)(ceil_div(cnt, 256 * 8) < 4096 ? ceil_div(cnt, 256 * 8) : 4096), 256, 0, s>>>(w.dpre, cnt, w.amax + l);
-      FESR_LAUNCH_CHECK();
+      if (!mask_fused) {
+        absmax_kernel<<<(unsigned)(ceil_div(cnt, 256 * 8) < 4096 ? ceil_div(cnt, 256 * 8) : 4096), 256, 0, s>>>(w.dpre, cnt, w.amax + l);
+        FESR_LAUNCH_CHECK();
+      }
       if (zt_fused) {
         scale_rows_f16_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16, w.q16,
                                                                        w.scales + 2 * l);

@@ -23,6 +23,7 @@ constexpr int COLSUM_BLOCKS = 512;
 size_t colsum_ws_bytes(int cols);
 int launch_colsum(const float* X, int64_t rows, int cols, int64_t ld, int accumulate, float* out, float* ws,
                   cudaStream_t s);
+int launch_colsum_final(const float* partial, int nb, int cols, int accumulate, float* out, cudaStream_t s);
 
 // dg[e, :] (+)= inv_deg[dst_e] * sum_a h[src_e, a] * dZ[dst_e, k, a]      (forward CSR order)
 int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* dZ,

@@ -191,6 +191,14 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, i
   }
 }
 
+// second stage alone (the caller produced `nb` rows of partial column sums itself)
+int launch_colsum_final(const float* partial, int nb, int cols, int accumulate, float* out, cudaStream_t s) {
+  if (cols == 0) return FESR_OK;
+  colsum_final_kernel<<<(unsigned)ceil_div(cols, 64), 256, 0, s>>>(partial, nb, cols, accumulate, out);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
 size_t colsum_ws_bytes(int cols) { return (size_t)COLSUM_BLOCKS * cols * sizeof(float); }
 
 int launch_colsum(const float* X, int64_t rows, int cols, int64_t ld, int accumulate, float* out, float* ws,
