@@ -106,13 +106,16 @@ __global__ void scale_rows_f16_kernel(const float* __restrict__ x, int64_t n, in
 
 // g rows [E, kp] fp32 (reversed-CSR order, slot layout) -> planar fp16 [kp / 16][E][16]; the lo slot (first padding slot)
 // holds the constant FESR_LO_SCALE that the fused kernel's two-term weights expect (layer_fused.cu)
-__global__ void g3_planar_kernel(const float* __restrict__ g, int64_t E, int kp, int lo_slot, __half* __restrict__ g3) {
+// (index != NULL: row e is g[index[e]] -- the forward-order g gathered into reversed order on the way)
+__global__ void g3_planar_kernel(const float* __restrict__ g, const int32_t* __restrict__ index, int64_t E, int kp, int lo_slot,
+                                 __half* __restrict__ g3) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // one 8-slot chunk of one edge
   const int c8 = kp / 8;
   if (t >= E * c8) return;
   const int64_t e = t / c8;
   const int c = (int)(t - e * c8);
-  const float4 v0 = *reinterpret_cast<const float4*>(g + e * kp + c * 8), v1 = *reinterpret_cast<const float4*>(g + e * kp + c * 8 + 4);
+  const float* row = g + (index != nullptr ? (int64_t)__ldg(index + e) : e) * kp + c * 8;
+  const float4 v0 = *reinterpret_cast<const float4*>(row), v1 = *reinterpret_cast<const float4*>(row + 4);
   float f[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
   if (lo_slot >= c * 8 && lo_slot < c * 8 + 8) f[lo_slot - c * 8] = FESR_LO_SCALE;
   __half2 h[4];
@@ -440,8 +443,6 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   FESR_CUDA(cudaMemsetAsync(w.dbias, 0, (size_t)d.wp * sizeof(float), s));
   if (E > 0) {
     FESR_CUDA(cudaMemsetAsync(w.dg, 0, (size_t)E * d.kp * sizeof(float), s));
-    gather_rows_kernel<<<(unsigned)ceil_div(E * (d.kp / 4), T), T, 0, s>>>(fw.g, rev_to_fwd, E, d.kp / 4, w.g_rev);
-    FESR_LAUNCH_CHECK();
   }
 
   // ---- fc2 / fc_out:  y = h_L W2^T + b2
@@ -476,8 +477,14 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   const bool zt_fused = zt_half && zt_fused_env && w.g3_rev != nullptr && E > 0;
   if (zt_fused) {
     FESR_CUDA(cudaMemsetAsync(w.zero_bias, 0, 64 * sizeof(float), s));
-    g3_planar_kernel<<<(unsigned)ceil_div(E * (d.kp / 8), T), T, 0, s>>>(w.g_rev, E, d.kp, d.kt, w.g3_rev);
+    // planar fp16 g in reversed order, gathered straight from the forward's g (the fp32 reversed copy is not needed here)
+    g3_planar_kernel<<<(unsigned)ceil_div(E * (d.kp / 8), T), T, 0, s>>>(fw.g, rev_to_fwd, E, d.kp, d.kt, w.g3_rev);
     FESR_LAUNCH_CHECK();
+  } else if (E > 0) {
+    gather_rows_kernel<<<(unsigned)ceil_div(E * (d.kp / 4), T), T, 0, s>>>(fw.g, rev_to_fwd, E, d.kp / 4, w.g_rev);
+    FESR_LAUNCH_CHECK();
+  }
+  if (zt_fused) {
     // T~ in the fused K order; the constant-1 slot carries T~'s own constant rows (no centring of g in this arm)
     if ((rc = launch_prepare_tfused(d, fw.prep.ttilde, fw.prep.ttilde + (size_t)(d.k1 - 1) * d.wp * d.wp, w.tfused_t, s))) return rc;
   }
