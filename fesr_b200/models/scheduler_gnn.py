@@ -325,6 +325,8 @@ class GNNPartitionScheduler():
         out_ch = self.models[0].dims.out_ch
 
         def run(plan):
+            if world > 1:
+                return self._run_routed_sharded(plan, x_dev, y_dev, out_ch, rank, world)
             pred = torch.zeros(csr.n, out_ch, dtype=torch.float32, device=dev)
             weight_s = torch.zeros(S, dtype=torch.float32, device=dev)
             for i, c in plan["clusters"]:
@@ -335,9 +337,6 @@ class GNNPartitionScheduler():
                 wi = ops.node_weight(pi, yi, c["csr"], c["edge_attr"], c["node_ptr"])
                 ops.scatter_rows(pi, c["nodes"], pred)
                 weight_s.index_copy_(0, c["subs"], wi)
-            if world > 1:
-                # predictions of the other ranks: one in-place all-gather (libfesr's communicator) in rank = subdomain order
-                pred, weight_s = self._gather_routed(pred, weight_s, plan, rank, world)
             return pred, weight_s
 
         pred, weight_s = run(plan)
@@ -349,23 +348,32 @@ class GNNPartitionScheduler():
             plan = self._routing_plan(csr, edge_attr, node_ptr, labels_h.copy(), rank, world)
             holder["_alds_plan"] = plan
             pred, weight_s = run(plan)
-        return self._to_host_lists(x, pred, weight_s, y_dev, sizes, labels_h.copy())
+        # several ranks: every rank holds the complete arrays on its device after the gather; the host lists are filled on
+        # first access (N full device -> host copies through one host were most of the step at 8 ranks)
+        own = (0, 0, 0, 0) if world > 1 else None
+        return self._to_host_lists(x, pred, weight_s, y_dev, sizes, labels_h.copy(), own=own)
 
-    def _gather_routed(self, pred, weight_s, plan, rank, world):
-        """ALDS on several ranks: this rank's rows of `pred` [n, c] / `weight_s` [S] -> the complete arrays."""
+    def _run_routed_sharded(self, plan, x_dev, y_dev, out_ch, rank, world):
+        """ALDS on several ranks.  The plan gives every rank a CLUSTER-MAJOR share of the subdomains (sorted by label, cut
+        into `world` edge-balanced chunks): a rank then runs one or two per-cluster models instead of all of them on
+        slivers of every cluster (20 fused-layer launches of a few tiles each per rank at 8 ranks were launch-bound: the
+        step was slower on 8 GPUs than on 4).  Each model writes its predictions and the node-weight kernel its weights
+        straight into the rank's slot of the [world, slot] buffer (`out=`), ONE in-place all-gather on libfesr's
+        communicator fills the other slots, and the complete arrays in subdomain order are one row gather away."""
         from .. import comm
-        from ..pipeline import SlotLayout
-        rows, cnt, lo, b0 = plan["rows"], plan["cnt"], plan["lo"], plan["b0"]
-        oc = int(pred.shape[1])
-        lay = plan.get("lay")
-        if lay is None:
-            lay = plan["lay"] = SlotLayout(rows, cnt, oc, with_ref=False)
-            plan["pos"] = lay.row_positions(torch.arange(pred.shape[0], device=pred.device)).long()
-            plan["wpos"] = lay.weight_positions(pred.device)
-        gbuf = torch.empty(world, lay.slot, dtype=torch.float32, device=pred.device)
-        nr, ns = rows[rank], cnt[rank]
-        gbuf[rank, :nr * oc].copy_(pred[lo:lo + nr].reshape(-1))
-        gbuf[rank, lay.weight_off(rank):lay.weight_off(rank) + ns].copy_(weight_s[b0:b0 + ns])
+        dev = self.device
+        slot, oc = plan["slot"], out_ch
+        gbuf = torch.empty(world, slot, dtype=torch.float32, device=dev)
+        mine = gbuf[rank]
+        nr, ns = plan["rows"][rank], plan["cnt"][rank]
+        pred_v = mine[:nr * oc].view(nr, oc)
+        w_v = mine[nr * oc:nr * oc + ns]
+        for i, c in plan["clusters"]:
+            xi, yi = ops.gather_rows(x_dev, c["nodes"]), ops.gather_rows(y_dev, c["nodes"])
+            r0, k0 = c["row0"], c["sub0"]
+            pi = pred_v[r0:r0 + int(c["nodes"].numel())]
+            self.models[i](xi, c["csr"], c["edge_attr"], out=pi)
+            ops.node_weight(pi, yi, c["csr"], c["edge_attr"], c["node_ptr"], out=w_v[k0:k0 + int(c["subs"].numel())])
         comm.allgatherv_pred(gbuf)
         rows = gbuf.view(-1, oc)
         pred_all = ops.gather_rows(rows, plan["pos"]) if oc % 4 == 0 else rows.index_select(0, plan["pos"])
@@ -376,13 +384,37 @@ class GNNPartitionScheduler():
         dev = self.device
         S = node_ptr.numel() - 1
         node_ptr_h = node_ptr.cpu().numpy().astype(np.int64)
+        sizes_h = np.diff(node_ptr_h)
+        plan = {"world": world, "rank": rank, "k": self.num_partitions, "labels": labels_h.copy()}
         if world > 1:
+            # cluster-major order of the subdomains, cut into `world` chunks balanced by edge count
             edge_cum = csr.rowptr[node_ptr.long()].cpu().numpy().astype(np.int64)
-            bounds = shard_bounds(edge_cum, world)
+            edges_h = np.diff(edge_cum)
+            order = np.argsort(labels_h, kind="stable")
+            bounds = shard_bounds(np.concatenate([[0], np.cumsum(edges_h[order])]), world)
+            sub_rank = np.zeros(S, dtype=np.int64)
+            sub_off = np.zeros(S, dtype=np.int64)          # row offset of the subdomain inside its rank's slot
+            sub_idx = np.zeros(S, dtype=np.int64)          # its index among the rank's subdomains
+            rows, cnt = [], []
+            for r in range(world):
+                subs_r = order[bounds[r]:bounds[r + 1]]
+                sub_rank[subs_r] = r
+                sub_off[subs_r] = np.concatenate([[0], np.cumsum(sizes_h[subs_r])[:-1]]) if subs_r.size else 0
+                sub_idx[subs_r] = np.arange(subs_r.size)
+                rows.append(int(sizes_h[subs_r].sum()))
+                cnt.append(int(subs_r.size))
+            oc = int(self.models[0].dims.out_ch)
+            q = 4 * oc
+            slot = max(q, (max(r_ * oc + k_ for r_, k_ in zip(rows, cnt)) + q - 1) // q * q)
+            slot_rows = slot // oc
+            row_pos = np.repeat(sub_rank * slot_rows + sub_off - node_ptr_h[:-1], sizes_h) + np.arange(int(node_ptr_h[-1]))
+            wpos = sub_rank * slot + np.asarray(rows, dtype=np.int64)[sub_rank] * oc + sub_idx
+            mine = sub_rank == rank
+            plan.update(rows=rows, cnt=cnt, slot=slot, pos=torch.from_numpy(row_pos).to(dev),
+                        wpos=torch.from_numpy(wpos).to(dev))
         else:
-            bounds = [0, S]
-        mine = np.zeros(S, dtype=bool)
-        mine[bounds[rank]:bounds[rank + 1]] = True
+            sub_off = sub_idx = None
+            mine = np.ones(S, dtype=bool)
         clusters = []
         for i in range(self.num_partitions):
             keep_h = (labels_h == i) & mine
@@ -390,12 +422,14 @@ class GNNPartitionScheduler():
                 continue
             keep = torch.from_numpy(keep_h).to(dev)
             sub, ea, nptr, node_keep = select_subdomains(csr, edge_attr, node_ptr, keep)
-            clusters.append((i, {"csr": sub, "edge_attr": ea, "node_ptr": nptr,
-                                 "nodes": node_keep.nonzero().squeeze(1), "subs": keep.nonzero().squeeze(1)}))
-        return {"world": world, "rank": rank, "k": self.num_partitions, "labels": labels_h.copy(), "clusters": clusters,
-                "rows": [int(node_ptr_h[bounds[r + 1]] - node_ptr_h[bounds[r]]) for r in range(world)],
-                "cnt": [bounds[r + 1] - bounds[r] for r in range(world)],
-                "lo": int(node_ptr_h[bounds[rank]]), "b0": bounds[rank]}
+            c = {"csr": sub, "edge_attr": ea, "node_ptr": nptr, "nodes": node_keep.nonzero().squeeze(1),
+                 "subs": keep.nonzero().squeeze(1)}
+            if world > 1:      # the cluster's rows / weights are one contiguous run of the rank's slot (cluster-major order)
+                first = int(np.flatnonzero(keep_h)[0])
+                c["row0"], c["sub0"] = int(sub_off[first]), int(sub_idx[first])
+            clusters.append((i, c))
+        plan["clusters"] = clusters
+        return plan
 
     def _predict_sharded(self, x, rank, world):
         """One model, several ranks, device-resident decomposition (reference fan-out / fan-in:
