@@ -380,38 +380,21 @@ class GNNPartitionScheduler():
         return pred_all, gbuf.view(-1).index_select(0, plan["wpos"])
 
     def _routing_plan(self, csr, edge_attr, node_ptr, labels_h, rank, world):
-        from ..pipeline import shard_bounds
         dev = self.device
         S = node_ptr.numel() - 1
         node_ptr_h = node_ptr.cpu().numpy().astype(np.int64)
         sizes_h = np.diff(node_ptr_h)
         plan = {"world": world, "rank": rank, "k": self.num_partitions, "labels": labels_h.copy()}
         if world > 1:
-            # cluster-major order of the subdomains, cut into `world` chunks balanced by edge count
+            # cluster-major order of the subdomains, cut into `world` chunks balanced by edge count (pipeline.py)
+            from ..pipeline import cluster_major_layout
             edge_cum = csr.rowptr[node_ptr.long()].cpu().numpy().astype(np.int64)
-            edges_h = np.diff(edge_cum)
-            order = np.argsort(labels_h, kind="stable")
-            bounds = shard_bounds(np.concatenate([[0], np.cumsum(edges_h[order])]), world)
-            sub_rank = np.zeros(S, dtype=np.int64)
-            sub_off = np.zeros(S, dtype=np.int64)          # row offset of the subdomain inside its rank's slot
-            sub_idx = np.zeros(S, dtype=np.int64)          # its index among the rank's subdomains
-            rows, cnt = [], []
-            for r in range(world):
-                subs_r = order[bounds[r]:bounds[r + 1]]
-                sub_rank[subs_r] = r
-                sub_off[subs_r] = np.concatenate([[0], np.cumsum(sizes_h[subs_r])[:-1]]) if subs_r.size else 0
-                sub_idx[subs_r] = np.arange(subs_r.size)
-                rows.append(int(sizes_h[subs_r].sum()))
-                cnt.append(int(subs_r.size))
             oc = int(self.models[0].dims.out_ch)
-            q = 4 * oc
-            slot = max(q, (max(r_ * oc + k_ for r_, k_ in zip(rows, cnt)) + q - 1) // q * q)
-            slot_rows = slot // oc
-            row_pos = np.repeat(sub_rank * slot_rows + sub_off - node_ptr_h[:-1], sizes_h) + np.arange(int(node_ptr_h[-1]))
-            wpos = sub_rank * slot + np.asarray(rows, dtype=np.int64)[sub_rank] * oc + sub_idx
-            mine = sub_rank == rank
-            plan.update(rows=rows, cnt=cnt, slot=slot, pos=torch.from_numpy(row_pos).to(dev),
-                        wpos=torch.from_numpy(wpos).to(dev))
+            lay = cluster_major_layout(labels_h, sizes_h, np.diff(edge_cum), world, oc)
+            sub_off, sub_idx = lay["sub_off"], lay["sub_idx"]
+            mine = lay["sub_rank"] == rank
+            plan.update(rows=lay["rows"], cnt=lay["cnt"], slot=lay["slot"], pos=torch.from_numpy(lay["row_pos"]).to(dev),
+                        wpos=torch.from_numpy(lay["wpos"]).to(dev))
         else:
             sub_off = sub_idx = None
             mine = np.ones(S, dtype=bool)

@@ -43,6 +43,43 @@ def shard_bounds(edge_ptr_host: np.ndarray, world: int):
     return bounds
 
 
+def cluster_major_layout(labels, sizes, edges, world: int, c: int):
+    """Host-side layout of the routed (ALDS) predict on several ranks.  The subdomains are sorted by cluster label (stable)
+    and that order is cut into `world` chunks balanced by edge count: a rank runs whole runs of one or two clusters instead
+    of slivers of all of them (reference fan-out: equal-count contiguous chunks, models/scheduler_gnn.py:269-271).
+    Slot r of the [world, slot] all-gather buffer holds rank r's prediction rows in that order ([rows[r], c]) followed by
+    its subdomain weights ([cnt[r]]).  Returns a dict:
+      sub_rank / sub_off / sub_idx [S]  owner rank, row offset inside the owner's slot, index among the owner's subdomains
+      rows / cnt [world], slot          rows and subdomains per rank, floats per slot (a multiple of 4 c)
+      row_pos [sum sizes]               row of the [world * slot / c, c] view of the buffer for every batch row
+      wpos [S]                          float offset of every subdomain's weight in the flattened buffer"""
+    labels = np.asarray(labels)
+    sizes = np.asarray(sizes, dtype=np.int64)
+    edges = np.asarray(edges, dtype=np.int64)
+    S = int(labels.size)
+    order = np.argsort(labels, kind="stable")
+    bounds = shard_bounds(np.concatenate([[0], np.cumsum(edges[order])]), world)
+    sub_rank = np.zeros(S, dtype=np.int64)
+    sub_off = np.zeros(S, dtype=np.int64)
+    sub_idx = np.zeros(S, dtype=np.int64)
+    rows, cnt = [], []
+    for r in range(world):
+        subs_r = order[bounds[r]:bounds[r + 1]]
+        sub_rank[subs_r] = r
+        if subs_r.size:
+            sub_off[subs_r] = np.concatenate([[0], np.cumsum(sizes[subs_r])[:-1]])
+            sub_idx[subs_r] = np.arange(subs_r.size)
+        rows.append(int(sizes[subs_r].sum()))
+        cnt.append(int(subs_r.size))
+    q = 4 * c
+    slot = max(q, (max(r_ * c + k_ for r_, k_ in zip(rows, cnt)) + q - 1) // q * q)
+    node_ptr = np.concatenate([[0], np.cumsum(sizes)])
+    row_pos = np.repeat(sub_rank * (slot // c) + sub_off - node_ptr[:-1], sizes) + np.arange(int(node_ptr[-1]))
+    wpos = sub_rank * slot + np.asarray(rows, dtype=np.int64)[sub_rank] * c + sub_idx
+    return {"sub_rank": sub_rank, "sub_off": sub_off, "sub_idx": sub_idx, "rows": rows, "cnt": cnt, "slot": int(slot),
+            "row_pos": row_pos, "wpos": wpos}
+
+
 def all_gather_rows(local: torch.Tensor, rows, group=None) -> torch.Tensor:
     """All-gather of row blocks of different lengths (rank r contributes rows[r] rows): every rank
     pads its block to max(rows), one equal-size all-gather, then the blocks are concatenated in

@@ -143,3 +143,81 @@ def test_tensor_list_is_lazy_and_fetches_remote_rows_on_demand():
     u.rest = lambda: fetched.append(2)
     assert torch.cat(list(u)).tolist() == [0.0, 1.0] and fetched == [1, 2]              # iteration needs everything
     assert TensorList([1, 2])[1] == 2 and len(TensorList()) == 0
+
+
+# ----------------------------------------------------------------------------- routed (ALDS) predict on several ranks
+def _routed_worker(rank, world, port, labels, sizes, edges, ret):
+    """What _run_routed_sharded does, with torch on CPU: every rank fills its slot cluster by cluster, one all-gather, one
+    row gather into subdomain order."""
+    from fesr_b200.pipeline import cluster_major_layout
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = 4
+        lay = cluster_major_layout(labels, sizes, edges, world, c)
+        node_ptr = np.concatenate([[0], np.cumsum(sizes)])
+        n = int(node_ptr[-1])
+        full = torch.arange(n * c, dtype=torch.float32).reshape(n, c)             # "predictions" of every batch row
+        w_full = torch.arange(len(sizes), dtype=torch.float32) + 0.25              # "weights" of every subdomain
+        gbuf = torch.full((world, lay["slot"]), -1.0)
+        nr, ns = lay["rows"][rank], lay["cnt"][rank]
+        pred_v = gbuf[rank, :nr * c].view(nr, c)
+        w_v = gbuf[rank, nr * c:nr * c + ns]
+        for s in np.flatnonzero(lay["sub_rank"] == rank):                          # (the GPU path does a whole cluster at once)
+            o = int(lay["sub_off"][s])
+            pred_v[o:o + sizes[s]] = full[node_ptr[s]:node_ptr[s + 1]]
+            w_v[int(lay["sub_idx"][s])] = w_full[s]
+        parts = [torch.empty(lay["slot"]) for _ in range(world)]
+        dist.all_gather(parts, gbuf[rank].clone())
+        g = torch.stack(parts)
+        pred_all = g.view(-1, c)[torch.from_numpy(lay["row_pos"])]
+        w_all = g.view(-1)[torch.from_numpy(lay["wpos"])]
+        ret[rank] = (bool(torch.equal(pred_all, full)), bool(torch.equal(w_all, w_full)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cluster_major_layout_properties():
+    from fesr_b200.pipeline import cluster_major_layout
+    rng = np.random.default_rng(3)
+    for S, k, world in ((128, 4, 8), (37, 3, 2), (5, 4, 8), (64, 1, 4)):
+        labels = rng.integers(0, k, size=S)
+        sizes = rng.integers(300, 2000, size=S)
+        edges = sizes * rng.integers(10, 15, size=S)
+        lay = cluster_major_layout(labels, sizes, edges, world, 4)
+        assert sum(lay["rows"]) == sizes.sum() and sum(lay["cnt"]) == S
+        assert lay["slot"] % 16 == 0 and all(r * 4 + q <= lay["slot"] for r, q in zip(lay["rows"], lay["cnt"]))
+        assert np.unique(lay["row_pos"]).size == sizes.sum()                        # every batch row has its own place
+        assert np.unique(lay["wpos"]).size == S
+        # weights never collide with prediction rows of the same slot
+        rows_as_floats = set((lay["row_pos"][:, None] * 4 + np.arange(4)).ravel().tolist())
+        assert not rows_as_floats & set(lay["wpos"].tolist())
+        for r in range(world):
+            mine = np.flatnonzero(lay["sub_rank"] == r)
+            if mine.size == 0:
+                continue
+            # cluster-major: inside a rank the subdomains of one cluster are one contiguous run of the slot, in index order
+            order = mine[np.argsort(lay["sub_idx"][mine])]
+            assert np.all(np.diff(labels[order]) >= 0)
+            assert len(set(labels[order].tolist())) <= max(1, -(-k // world) + 1)
+            off = 0
+            for s in order:
+                assert lay["sub_off"][s] == off
+                off += sizes[s]
+        if world > 1 and S >= 4 * world:
+            per = [edges[lay["sub_rank"] == r].sum() for r in range(world)]
+            assert max(per) - min(per) <= 2 * edges.max()
+
+
+def test_world2_gloo_routed_slot_gather():
+    rng = np.random.default_rng(9)
+    S = 48
+    labels = rng.integers(0, 4, size=S)
+    sizes = rng.integers(50, 400, size=S)
+    edges = sizes * 13
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_routed_worker, args=(2, port, labels, sizes, edges, ret), nprocs=2, join=True)
+    assert ret[0] == (True, True) and ret[1] == (True, True)
