@@ -68,7 +68,7 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params, 
   // two calls), every kernel that packs fp16 raises it on overflow, fc_out turns a raised flag into a NaN output
   if (!edge_done) FESR_CUDA(cudaMemsetAsync(ws.prep.ovf, 0, sizeof(int), s));
   OvfScope ovf_scope(ws.prep.ovf);
-  if (!(fwd_flags & FESR_FWD_WEIGHTS_PREPARED) && !edge_done && (rc = launch_prepare_weights(d, *params, ws.prep, s))) return rc;
+  if (!(fwd_flags & FESR_FWD_WEIGHTS_PREPARED) && !edge_done && (rc = launch_prepare_weights(d, *params, ws.prep, s, !keep_for_backward))) return rc;
   static const bool ffma_only = getenv("FESR_ZBUILD_FFMA") != nullptr;   // A/B switch for profiling
   // reduced-precision arms: g and h are rounded to tf32 by their producers, so the gather kernel
   // feeds them to the tensor cores without converting

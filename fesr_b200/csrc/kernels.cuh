@@ -7,7 +7,10 @@ namespace fesr {
 // mlp.cu ------------------------------------------------------------------------------
 size_t prepared_bytes(const fesr_model_dims& d);
 Prepared carve_prepared(Carver& c, const fesr_model_dims& d);
-int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const Prepared& w, cudaStream_t s);
+// with_fused: also the fused f16 predict arm's copies (g(0) centring, T' in the fused K order) -- not needed by a forward
+// that keeps its intermediates for a backward (one single-block kernel of 0.1 ms per train step)
+int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const Prepared& w, cudaStream_t s,
+                           bool with_fused = true);
 // g[E, kp]: hidden activations of the edge MLP in CSR edge order, channel-permuted layout
 int launch_edge_hidden(const fesr_model_dims& d, const fesr_params& p, const float* edge_attr,
                        const int32_t* perm, int64_t E, float* g, cudaStream_t s, int round_tf32 = 0);

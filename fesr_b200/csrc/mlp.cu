@@ -163,7 +163,7 @@ __global__ void prepare_small_kernel(fesr_model_dims d, const float* __restrict_
   }
 }
 
-int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const Prepared& w, cudaStream_t s) {
+int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const Prepared& w, cudaStream_t s, bool with_fused) {
   const int last = d.n_hidden;
   FESR_CHECK_ARG(p.mlp_w[last] && p.mlp_b[last] && p.root && p.bias && p.fc1_w && p.fc1_b, "NULL parameter");
   FESR_CHECK_ARG(d.kind != FESR_TEECNET || (p.lin_w && p.lin_b), "TEECNet needs kernel.linear");
@@ -182,7 +182,7 @@ int launch_prepare_weights(const fesr_model_dims& d, const fesr_params& p, const
   FESR_LAUNCH_CHECK();
   prepare_small_kernel<<<1, 64, 0, s>>>(d, p.fc1_w, p.fc1_b, p.bias, w.bias_p, w.fc1_wp, w.fc1_bp);
   FESR_LAUNCH_CHECK();
-  if (w.tfused_h) {
+  if (w.tfused_h && with_fused) {
     FESR_CHECK_ARG(d.ktp > d.kt, "the fused arm needs a padding slot per channel group");
     CenterArgs ca;
     memset(&ca, 0, sizeof(ca));
