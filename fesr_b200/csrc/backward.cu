@@ -457,6 +457,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   const bool dz_tc = rnd && dz_tc_env && dz_tc_supported(d) && E > 0;
   const bool dz_tc3 = !rnd && dz_tc_env && dz_tc_supported(d) && E > 0;      // fp32 arm: three-term product
   // fp32 arm: dT' += Z^T dpre as 3xTF32 on mma.sync (FESR_WGRAD_3X=0: the CUDA-core split-K GEMM)
+  static const bool wgrad_tc_env = !(getenv("FESR_WGRAD_TC") && atoi(getenv("FESR_WGRAD_TC")) == 0);      // A/B switch
   static const bool wgrad3_env = !(getenv("FESR_WGRAD_3X") && atoi(getenv("FESR_WGRAD_3X")) == 0);
   const bool wgrad3 = !rnd && wgrad3_env && (d.wp == 16 || d.wp == 32 || d.wp == 48 || d.wp == 64);
   // ... written as bf16 (FESR_DZ_BF16=0: fp32), which the edge-gradient MMAs read as exact tf32 operands
@@ -507,7 +508,14 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
       if ((rc = launch_colsum(w.dpre, n, d.wp, d.wp, 1, w.dbias, w.colsum_ws, s))) return rc;
     }
     // dT' += Z_l^T dpre
-    if (rnd) {
+    const bool wgrad_tc = wgrad_tc_env && zt_fused && mask_fused && z_stash_half(precision) && wgrad_tc_supported(d);
+    if (wgrad_tc) {
+      // the scaled fp16 rows of the fused reversed pass below are this product's operand too
+      scale_rows_f16_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16,
+                                                                          w.q16, w.scales + 2 * l);
+      FESR_LAUNCH_CHECK();
+      if ((rc = launch_wgrad_tc(d, fw.Z[l], w.own16, w.scales + 2 * l + 1, n, w.dT, w.gemm_ws, s))) return rc;
+    } else if (rnd) {
       if ((rc = launch_wgrad_mma(d, fw.Z[l], z_stash_half(precision), w.dpre, n, w.dT, w.gemm_ws, s))) return rc;
     } else if (wgrad3) {
       if ((rc = launch_wgrad_mma(d, fw.Z[l], 0, w.dpre, n, w.dT, w.gemm_ws, s, 3))) return rc;
@@ -536,9 +544,11 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
         FESR_LAUNCH_CHECK();
       }
       if (zt_fused) {
-        scale_rows_f16_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16, w.q16,
-                                                                       w.scales + 2 * l);
-        FESR_LAUNCH_CHECK();
+        if (!wgrad_tc) {
+          scale_rows_f16_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16,
+                                                                         w.q16, w.scales + 2 * l);
+          FESR_LAUNCH_CHECK();
+        }
         rc = launch_layer_fused_f16(d, rowptr_t, src_t, w.g3_rev, E, w.q16, n, w.tfused_t, w.zero_bias, w.fused_P, w.dh[cur ^ 1],
                                     d.kind == FESR_KERNELNN ? 3 : 0, s,
                                     /*out_f32=*/1, /*sum_mode=*/1, w.own16);

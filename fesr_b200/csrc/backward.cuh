@@ -42,6 +42,12 @@ bool dz_tc_supported(const fesr_model_dims& d);
 int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprime_r, int64_t n, void* dZ, int out_bf16,
                  cudaStream_t s, const float* dpre_lo = nullptr, const float* tprime_r_lo = nullptr);
 
+// gemm_tc.cu: dT' += Z^T dpre on tcgen05 (both operands MN-major); Z_half: the fp16 Z stash, dpre_half: fp16 rows of dpre S
+// (S the layer's power-of-two gradient scale), inv_scale -> 1 / S on the device; ws as for launch_wgrad_mma
+bool wgrad_tc_supported(const fesr_model_dims& d);
+int launch_wgrad_tc(const fesr_model_dims& d, const void* Z_half, const void* dpre_half, const float* inv_scale, int64_t n,
+                    float* dT, float* ws, cudaStream_t s);
+
 // edge_mlp_bwd.cu (tf32 arm, KernelNN shape): the whole backward of the edge-MLP hidden layers in one kernel
 bool edge_mlp_bwd_supported(const fesr_model_dims& d);
 size_t edge_mlp_bwd_ws_bytes(const fesr_model_dims& d, int64_t E);

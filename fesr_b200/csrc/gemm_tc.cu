@@ -29,7 +29,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
-#include "kernels.cuh"
+#include "backward.cuh"
 
 namespace fesr {
 
@@ -389,7 +389,7 @@ node_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 static int encode_map(CUtensorMap* map, const void* base, bool half, uint64_t inner, uint64_t outer,
-                      uint32_t box_inner, uint32_t box_outer, bool bf16 = false) {
+                      uint32_t box_inner, uint32_t box_outer, bool bf16 = false, bool swizzle32 = false) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {inner * ((half || bf16) ? 2 : 4)};
   cuuint32_t box[2] = {box_inner, box_outer};
@@ -412,7 +412,8 @@ static int encode_map(CUtensorMap* map, const void* base, bool half, uint64_t in
   }
   CUresult r = encode(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                       const_cast<void*>(base), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -736,6 +737,197 @@ int launch_dz_tc(const fesr_model_dims& d, const float* dpre, const float* tprim
   }
   if (out_bf16) return launch_dz_tc_t<true, 1>(d, dpre, nullptr, tprime_r, nullptr, n, dZ, s);
   return launch_dz_tc_t<false, 1>(d, dpre, nullptr, tprime_r, nullptr, n, dZ, s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Backward, tf32 arm:  dT'[zk, wp] += Z^T[zk, n] . dpre[n, wp]  (reference: autograd of the edge-MLP's last Linear through the
+// NNConv message, models/model.py:311-315, 527-529, in the node-level form of DESIGN.md section 5).  K = n is the long
+// dimension, so both operands are MN-major for the tensor core: the rows TMA brings in (one node = one K index) are
+// contiguous along M (Z: channels) and N (dpre: columns).
+//   A = Z^T: the fp16 Z stash [n, zk] row-major; a stage holds 64 nodes x (up to) 768 channels as twelve SWIZZLE_128B boxes of
+//       64 channels (128 B) x 64 nodes -- the canonical MN-major layout: 8 nodes per 1024-byte atom (SBO), the next 64
+//       channels one box further (LBO);
+//   B = the scaled fp16 dpre rows [n, 48] (scale_rows_f16_kernel's `own` rows: dpre S_l with the per-layer power of two S_l)
+//       as three SWIZZLE_32B boxes of 16 columns x 64 nodes (atoms of 8 nodes x 32 B);
+//   D = up to six [128 channels, 48] fp32 accumulators in TMEM, live for the CTA's whole node range (split-K over CTAs).
+// The 2176 channels of the shipped KernelNN take 17 m-tiles = three channel splits; grid = splits x node ranges, one CTA per
+// SM; every CTA writes its [channels, 48] partial and a second kernel adds them up in a fixed order, times 1 / S_l.
+// The operands carry the same 11 significant bits as the tf32 mma.sync kernel this replaces (bwd_gemm_mma.cu); that kernel
+// was bound by the mma.sync issue rate (tensor pipe 59 % busy at 3.2 TB/s), this one by the HBM stream of Z.
+constexpr int WT_KB = 64;                          // nodes per stage
+constexpr int WT_TILES = 6;                        // m-tiles per CTA: 6 x 64 TMEM columns
+constexpr int WT_STAGES = 2;
+constexpr int WT_THREADS = 192;
+constexpr uint32_t WT_ZBOX = WT_KB * 128;          // 8 KB
+constexpr uint32_t WT_DBOX = WT_KB * 32;           // 2 KB
+constexpr uint32_t WT_STAGE_BYTES = 2 * WT_TILES * WT_ZBOX + 3 * WT_DBOX;      // 102 KB (a multiple of 1024)
+
+// MN-major shared-memory matrix descriptor: lbo = bytes between swizzle-wide groups along M / N, sbo = bytes between
+// 8-row groups along K; layout 2 = SWIZZLE_128B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t make_mn_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmD, int64_t n, int zk, int msplit,
+                int64_t nchunk, float* __restrict__ partial) {
+  constexpr int WP = 48;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WT_STAGES * WT_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + WT_STAGES;
+  uint64_t* done_bar = empty_bar + WT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x % msplit, range = blockIdx.x / msplit;
+  const int box0 = split * 2 * WT_TILES;                       // first 64-channel box of this CTA
+  const int nbox = min(2 * WT_TILES, zk / 64 - box0);
+  const int tiles = (nbox + 1) / 2;                            // (an odd box count leaves the last tile's upper half unread)
+  const int64_t k_begin = (int64_t)range * nchunk, k_end = min(n, k_begin + nchunk);
+  const int iters = k_begin < k_end ? (int)((k_end - k_begin + WT_KB - 1) / WT_KB) : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmZ) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmD) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < WT_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      for (int it = 0; it < iters; ++it) {
+        const int stage = it % WT_STAGES;
+        mbar_wait(&empty_bar[stage], ((it / WT_STAGES) & 1) ^ 1);
+        uint8_t* zs = smem + stage * WT_STAGE_BYTES;
+        uint8_t* ds = zs + 2 * WT_TILES * WT_ZBOX;
+        const int node0 = (int)(k_begin + (int64_t)it * WT_KB);        // rows past n arrive as zeros
+        mbar_expect_tx(&full_bar[stage], nbox * WT_ZBOX + 3 * WT_DBOX);
+        for (int j = 0; j < 3; ++j) tma_load_2d(ds + j * WT_DBOX, &tmD, &full_bar[stage], j * 16, node0);
+        for (int b = 0; b < nbox; ++b) tma_load_2d(zs + b * WT_ZBOX, &tmZ, &full_bar[stage], (box0 + b) * 64, node0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: D = F32, A = B = F16, both MN-major, M = 128, N = 48, K = 16: four k-steps per stage and m-tile =====
+    constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(WP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    for (int it = 0; it < iters; ++it) {
+      const int stage = it % WT_STAGES;
+      mbar_wait(&full_bar[stage], (it / WT_STAGES) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+        const uint32_t zs = smem_u32(smem + stage * WT_STAGE_BYTES);
+        const uint32_t ds = zs + 2 * WT_TILES * WT_ZBOX;
+        for (int t = 0; t < tiles; ++t) {
+#pragma unroll
+          for (int j = 0; j < WT_KB / 16; ++j) {
+            const uint64_t adesc = make_mn_desc(zs + t * 2 * WT_ZBOX + j * 16 * 128, WT_ZBOX, 1024, 2);
+            const uint64_t bdesc = make_mn_desc(ds + j * 16 * 32, WT_DBOX, 256, 6);
+            umma_f16(tmem_base + t * 64, adesc, bdesc, idesc, (it | j) != 0);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (it == iters - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4; thread = one channel row of the partial =====
+    const int quad = warp & 3;
+    if (iters > 0) {
+      mbar_wait(done_bar, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    float* out = partial + (int64_t)range * zk * WP;
+    for (int t = 0; t < tiles; ++t) {
+      const int m0 = box0 * 64 + t * 128 + quad * 32;            // warp-uniform; zk is a multiple of 64
+      if (m0 >= zk) continue;
+      uint32_t r[3][16];
+      if (iters > 0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + t * 64;
+        tmem_ld16(taddr, r[0]);
+        tmem_ld16(taddr + 16, r[1]);
+        tmem_ld16(taddr + 32, r[2]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 48; ++j) r[j / 16][j % 16] = 0u;
+      }
+      float4* row = reinterpret_cast<float4*>(out + (int64_t)(m0 + lane) * WP);
+#pragma unroll
+      for (int j = 0; j < 12; ++j)
+        row[j] = make_float4(__uint_as_float(r[j / 4][(j % 4) * 4]), __uint_as_float(r[j / 4][(j % 4) * 4 + 1]),
+                             __uint_as_float(r[j / 4][(j % 4) * 4 + 2]), __uint_as_float(r[j / 4][(j % 4) * 4 + 3]));
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// dT[i] += inv_scale * sum over the node ranges, in range order
+__global__ void wgrad_tc_reduce_kernel(const float* __restrict__ partial, int ranges, int64_t count,
+                                       const float* __restrict__ inv_scale, float* __restrict__ dT) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float s = 0.f;
+  for (int z = 0; z < ranges; ++z) s += partial[(int64_t)z * count + i];
+  dT[i] += s * __ldg(inv_scale);
+}
+
+bool wgrad_tc_supported(const fesr_model_dims& d) { return d.wp == 48 && d.zk % 64 == 0; }
+
+int launch_wgrad_tc(const fesr_model_dims& d, const void* Z_half, const void* dpre_half, const float* inv_scale, int64_t n,
+                    float* dT, float* ws, cudaStream_t s) {
+  if (n == 0) return FESR_OK;
+  FESR_CHECK_ARG(wgrad_tc_supported(d), "weight gradient on tcgen05: wp == 48 and zk %% 64 == 0");
+  constexpr size_t smem = 1024 + (size_t)WT_STAGES * WT_STAGE_BYTES + 256;
+  static_assert(smem <= 227 * 1024, "weight-gradient stages exceed the shared memory of an SM");
+  static bool attr_set = false;
+  if (!attr_set) {
+    FESR_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  CUtensorMap tmZ, tmD;
+  int rc;
+  if ((rc = encode_map(&tmZ, Z_half, true, (uint64_t)d.zk, (uint64_t)n, 64, WT_KB))) return rc;
+  if ((rc = encode_map(&tmD, dpre_half, true, (uint64_t)d.wp, (uint64_t)n, 16, WT_KB, false, /*swizzle32=*/true))) return rc;
+  const int msplit = (int)ceil_div(d.zk / 64, 2 * WT_TILES);
+  int ranges = num_sms() / msplit;
+  const int cap = (int)(wgrad_mma_ws_bytes(d) / ((size_t)d.zk * d.wp * sizeof(float)));      // partials the workspace holds
+  if (ranges > cap) ranges = cap;
+  if (ranges < 1) ranges = 1;
+  const int64_t nchunk = ceil_div(ceil_div(n, ranges), WT_KB) * WT_KB;
+  ranges = (int)ceil_div(n, nchunk);
+  wgrad_tc_kernel<<<msplit * ranges, WT_THREADS, smem, s>>>(tmZ, tmD, n, d.zk, msplit, nchunk, ws);
+  FESR_LAUNCH_CHECK();
+  const int64_t count = (int64_t)d.zk * d.wp;
+  wgrad_tc_reduce_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, s>>>(ws, ranges, count, inv_scale, dT);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
 }
 
 }  // namespace fesr
