@@ -311,6 +311,7 @@ struct BackwardWs {
   float* dh[2];
   float* dpre;
   float* BZ;
+  uint16_t* BZx;        // bf16 dZ of layers 2.. when the edge gradient runs once over all layers (layers 0, 1 share BZ)
   float* g_rev;
   float* dg;
   float* dT;
@@ -346,6 +347,8 @@ static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n
   w.dh[1] = c.take<float>(nn * d.wp);
   w.dpre = c.take<float>(nn * d.wp);
   w.BZ = c.take<float>(nn * d.zk);
+  w.BZx = d.layers > 2 && dz_tc_supported(d) && edge_grad_layers_supported(d, d.layers)
+              ? c.take<uint16_t>((size_t)(d.layers - 2) * nn * d.zk) : nullptr;
   w.g_rev = c.take<float>(ee * d.kp);
   w.dg = c.take<float>(ee * d.kp);
   w.dT = c.take<float>((size_t)d.zk * d.wp);
@@ -441,9 +444,6 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   FESR_LAUNCH_CHECK();
   FESR_CUDA(cudaMemsetAsync(w.dT, 0, (size_t)d.zk * d.wp * sizeof(float), s));
   FESR_CUDA(cudaMemsetAsync(w.dbias, 0, (size_t)d.wp * sizeof(float), s));
-  if (E > 0) {
-    FESR_CUDA(cudaMemsetAsync(w.dg, 0, (size_t)E * d.kp * sizeof(float), s));
-  }
 
   // ---- fc2 / fc_out:  y = h_L W2^T + b2
   const float* hL = fw.h[L];
@@ -485,6 +485,21 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     gather_rows_kernel<<<(unsigned)ceil_div(E * (d.kp / 4), T), T, 0, s>>>(fw.g, rev_to_fwd, E, d.kp / 4, w.g_rev);
     FESR_LAUNCH_CHECK();
   }
+  // one edge-gradient pass over all layers at the end (dg written once) when every layer's bf16 dZ can be kept
+  static const bool eg_layers_env = !(getenv("FESR_EDGE_GRAD_LAYERS") && atoi(getenv("FESR_EDGE_GRAD_LAYERS")) == 0);      // A/B switch
+  const bool eg_layers = eg_layers_env && dz_bf16 && zt_fused && E > 0 && (L <= 2 || w.BZx != nullptr) &&
+                         edge_grad_layers_supported(d, L);
+  const void* dz_of[FESR_EG_MAX_LAYERS] = {nullptr};
+  const float* h_of[FESR_EG_MAX_LAYERS] = {nullptr};
+  if (eg_layers) {
+    for (int l = 0; l < L; ++l) {
+      dz_of[l] = l < 2 ? static_cast<const void*>(reinterpret_cast<uint16_t*>(w.BZ) + (size_t)l * n * d.zk)
+                       : static_cast<const void*>(w.BZx + (size_t)(l - 2) * n * d.zk);
+      h_of[l] = fw.h[l];
+    }
+  } else if (E > 0) {
+    FESR_CUDA(cudaMemsetAsync(w.dg, 0, (size_t)E * d.kp * sizeof(float), s));
+  }
   if (zt_fused) {
     // T~ in the fused K order; the constant-1 slot carries T~'s own constant rows (no centring of g in this arm)
     if ((rc = launch_prepare_tfused(d, fw.prep.ttilde, fw.prep.ttilde + (size_t)(d.k1 - 1) * d.wp * d.wp, w.tfused_t, s))) return rc;
@@ -525,7 +540,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     if (E > 0) {
       // dZ = dpre T'^T ; dg += edge_grad(dZ, h_l)
       if (rnd && dz_tc) {
-        if ((rc = launch_dz_tc(d, w.dpre, w.tprime_r, n, w.BZ, dz_bf16, s))) return rc;
+        if ((rc = launch_dz_tc(d, w.dpre, w.tprime_r, n, eg_layers ? const_cast<void*>(dz_of[l]) : w.BZ, dz_bf16, s))) return rc;
       } else if (rnd) {
         if ((rc = launch_dz_mma(d, w.dpre, fw.prep.tprime, n, w.BZ, s))) return rc;
       } else if (dz_tc3) {
@@ -534,7 +549,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
         GEMM(w.dpre, d.wp, 1, fw.prep.tprime, 1, d.wp, w.BZ, d.zk, 1, n, d.zk, d.wp, 0);
       }
       // (use_mma: 1 = tf32 arm, 3 = the fp32 arm's 3xTF32 form where the tensor-core kernel covers the shape)
-      if ((rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, rnd ? 1 : 3, w.dg, s, dz_bf16))) return rc;
+      if (!eg_layers && (rc = launch_edge_grad(d, rowptr, src_sorted, w.BZ, fw.h[l], n, rnd ? 1 : 3, w.dg, s, dz_bf16))) return rc;
     }
     // dh_l = [sum over out-edges of g (x) dpre[dst]/deg[dst]  ++  dpre] T~
     if (zt_half) {
@@ -584,6 +599,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     if (rc) return rc;
     cur ^= 1;
   }
+  if (eg_layers && (rc = launch_edge_grad_layers(d, rowptr, src_sorted, dz_of, h_of, L, n, w.dg, s))) return rc;
 
   // ---- conv bias / root / last edge-MLP layer / kernel.linear from dT'
   add_first_cols_kernel<<<1, 64, 0, s>>>(w.dbias, d.w, grads->bias);

@@ -29,6 +29,12 @@ int launch_colsum_final(const float* partial, int nb, int cols, int accumulate, 
 int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* dZ,
                      const float* h, int64_t n, int use_mma, float* dg, cudaStream_t s, int dz_bf16 = 0);
 
+// the same sum over all layers at once (tf32 arm): dZ_bf16[l] / h[l] per layer, dg written (not accumulated, no zero fill)
+#define FESR_EG_MAX_LAYERS 8
+bool edge_grad_layers_supported(const fesr_model_dims& d, int n_layers);
+int launch_edge_grad_layers(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* const* dZ_bf16,
+                            const float* const* h, int n_layers, int64_t n, float* dg, cudaStream_t s);
+
 // bwd_gemm_mma.cu (tf32 arm): dT' += Z^T dpre (ws: wgrad_mma_ws_bytes) and dZ = dpre T'^T
 size_t wgrad_mma_ws_bytes(const fesr_model_dims& d);
 // terms 3: fp32 Z and dpre split into tf32 hi + lo in registers (the fp32 arm)

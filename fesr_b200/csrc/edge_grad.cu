@@ -273,6 +273,116 @@ edge_grad_mma_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restri
   }
 }
 
+// All layers in one pass (tf32 arm, bf16 dZ kept per layer by the caller): dg[e, :] = inv_deg[dst_e] * sum over the layers l
+// of dZ_l[dst_e] . h_l[src_e].  dg is written once instead of read and re-written by every layer -- the [E, kp] fp32
+// read-modify-write was half of the per-layer kernel's traffic (0.70 of 1.40 GB per launch at 527 k cells,
+// profiles/r03f_train_kernels_summary.txt) -- and needs no zero fill: every edge row belongs to exactly one node.
+// One warp per node and 16-edge chunk as above; the accumulators stay in registers across the layers.
+struct EgLayers {
+  const __nv_bfloat16* dZ[FESR_EG_MAX_LAYERS];
+  const float* h[FESR_EG_MAX_LAYERS];
+  int nl;
+};
+
+__global__ void __launch_bounds__(128)
+edge_grad_layers_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted, const EgLayers lay, int64_t n,
+                        int k1p, int kt, int ktp, int kp, int zk, float* __restrict__ dg) {
+  constexpr int WP = 48, KS = WP / 8, NTC = 6;      // k1p <= 48: six channel n-tiles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int64_t warp_global = (int64_t)blockIdx.x * 4 + warp, warp_stride = (int64_t)gridDim.x * 4;
+  const int n_nt = (k1p + 7) / 8;
+  extern __shared__ __align__(16) float eg_tile[];
+  float* tile = eg_tile + (size_t)warp * 16 * kp;
+  const int q4 = kp >> 2;
+  const int nline = (int)(((int64_t)zk * sizeof(__nv_bfloat16) + 127) / 128);
+  for (int64_t i = warp_global; i < n; i += warp_stride) {
+    const int eb = rowptr[i], ee = rowptr[i + 1];
+    if (ee == eb) continue;
+    const float inv = 1.0f / (float)(ee - eb);
+    for (int c0 = eb; c0 < ee; c0 += 16) {
+      const int e0 = c0 + gq, e1 = c0 + gq + 8;
+      const int64_t s0 = (int64_t)__ldg(src_sorted + min(e0, ee - 1)) * WP + 12 * tq;
+      const int64_t s1 = (int64_t)__ldg(src_sorted + min(e1, ee - 1)) * WP + 12 * tq;
+      for (int t = lane; t < 16 * q4; t += 32) reinterpret_cast<float4*>(tile)[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float acc[NTC][4];
+#pragma unroll
+      for (int t = 0; t < NTC; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+      for (int l = 0; l < lay.nl; ++l) {
+        {
+          // the block read next (this node's next layer, or the first layer of the warp's next node) into L1 meanwhile
+          const __nv_bfloat16* nxt = nullptr;
+          if (l + 1 < lay.nl) nxt = lay.dZ[l + 1] + i * (int64_t)zk;
+          else if (c0 + 16 >= ee && i + warp_stride < n) nxt = lay.dZ[0] + (i + warp_stride) * (int64_t)zk;
+          if (nxt != nullptr) {
+            const char* pz = reinterpret_cast<const char*>(nxt);
+            for (int q = lane; q < nline; q += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(pz + (size_t)q * 128));
+          }
+        }
+        uint32_t v0[12], v1[12];
+        eg_ldz12(lay.h[l] + s0, v0);
+        eg_ldz12(lay.h[l] + s1, v1);
+        const __nv_bfloat16* zrow = lay.dZ[l] + i * (int64_t)zk + 12 * tq;
+#pragma unroll
+        for (int t = 0; t < NTC; ++t) {
+          if (t < n_nt) {
+            uint32_t b[12];
+            eg_ldz12(zrow + (int64_t)min(t * 8 + gq, k1p - 1) * WP, b);
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                  : "+f"(acc[t][0]), "+f"(acc[t][1]), "+f"(acc[t][2]), "+f"(acc[t][3])
+                  : "r"(v0[2 * ks]), "r"(v1[2 * ks]), "r"(v0[2 * ks + 1]), "r"(v1[2 * ks + 1]), "r"(b[2 * ks]), "r"(b[2 * ks + 1]));
+            }
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < NTC; ++t) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int chan = t * 8 + 2 * tq + j;
+          if (t < n_nt && chan < k1p) {
+            const int off = (chan / kt) * ktp + (chan % kt);
+            tile[gq * kp + off] = acc[t][j] * inv;
+            tile[(gq + 8) * kp + off] = acc[t][2 + j] * inv;
+          }
+        }
+      }
+      __syncwarp();
+      const int nrow = min(16, ee - c0);
+      float4* drow = reinterpret_cast<float4*>(dg + (int64_t)c0 * kp);
+      for (int t = lane; t < nrow * q4; t += 32) drow[t] = reinterpret_cast<const float4*>(tile)[t];
+      __syncwarp();
+    }
+  }
+}
+
+bool edge_grad_layers_supported(const fesr_model_dims& d, int n_layers) {
+  return d.wp == 48 && d.k1p <= 48 && n_layers >= 1 && n_layers <= FESR_EG_MAX_LAYERS;
+}
+
+int launch_edge_grad_layers(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src_sorted, const void* const* dZ_bf16,
+                            const float* const* h, int n_layers, int64_t n, float* dg, cudaStream_t s) {
+  FESR_CHECK_ARG(edge_grad_layers_supported(d, n_layers), "all-layer edge gradient: wp == 48, k1p <= 48, <= %d layers",
+                 FESR_EG_MAX_LAYERS);
+  if (n == 0) return FESR_OK;
+  ProfScope prof(PROF_BACKWARD, s);
+  EgLayers lay;
+  for (int l = 0; l < FESR_EG_MAX_LAYERS; ++l) {
+    lay.dZ[l] = static_cast<const __nv_bfloat16*>(dZ_bf16[l < n_layers ? l : 0]);
+    lay.h[l] = h[l < n_layers ? l : 0];
+  }
+  lay.nl = n_layers;
+  const int64_t blocks = ceil_div(n, 4);
+  const int grid = (int)(blocks < 16ll * num_sms() ? blocks : 16ll * num_sms());
+  const size_t smem = (size_t)4 * 16 * d.kp * sizeof(float);
+  edge_grad_layers_kernel<<<grid, 128, smem, s>>>(rowptr, src_sorted, lay, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+  FESR_LAUNCH_CHECK();
+  return FESR_OK;
+}
+
 template <int KT>
 static int eg_dispatch(const fesr_model_dims& d, const int32_t* rowptr, const int32_t* src, const float* dZ,
                        const float* h, int64_t n, float* dg, cudaStream_t s) {
