@@ -284,7 +284,10 @@ struct EgLayers {
   int nl;
 };
 
-__global__ void __launch_bounds__(128)
+#ifndef EGL_MINB
+#define EGL_MINB 6
+#endif
+__global__ void __launch_bounds__(128, EGL_MINB)
 edge_grad_layers_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted, const EgLayers lay, int64_t n,
                         int k1p, int kt, int ktp, int kp, int zk, float* __restrict__ dg) {
   constexpr int WP = 48, KS = WP / 8, NTC = 6;      // k1p <= 48: six channel n-tiles
@@ -311,6 +314,7 @@ edge_grad_layers_kernel(const int32_t* __restrict__ rowptr, const int32_t* __res
       for (int l = 0; l < lay.nl; ++l) {
         {
           // the block read next (this node's next layer, or the first layer of the warp's next node) into L1 meanwhile
+          // (a second prefetch, two blocks ahead into L2, measured no gain)
           const __nv_bfloat16* nxt = nullptr;
           if (l + 1 < lay.nl) nxt = lay.dZ[l + 1] + i * (int64_t)zk;
           else if (c0 + 16 >= ee && i + warp_stride < n) nxt = lay.dZ[0] + (i + warp_stride) * (int64_t)zk;

@@ -7,7 +7,8 @@ from fesr_b200 import build as B
 tag, flags = sys.argv[1], sys.argv[2:]
 OBJ = os.path.join(ROOT, "fesr_b200", "build_tr", tag)
 os.makedirs(OBJ, exist_ok=True)
-only = [f for f in B._sources() if f.startswith("layer_fused")]     # the variants differ in these files only
+PREFIX = tuple(os.environ.get("VARIANT_FILES", "layer_fused").split(","))      # the variants differ in these files only
+only = [f for f in B._sources() if f.startswith(PREFIX)]
 def comp(src):
     obj = os.path.join(OBJ, src[:-3] + ".o")
     r = subprocess.run([B.NVCC, *B.FLAGS, *flags, "-c", os.path.join(B.CSRC, src), "-o", obj], capture_output=True, text=True)
