@@ -93,15 +93,20 @@ __global__ void scale_rows_f16_kernel(const float* __restrict__ x, int64_t n, in
   const float amax = __uint_as_float(*amax_bits);
   float S = 1.f;
   if (amax > 0.f && amax < 3.0e38f) S = exp2f(fminf(fmaxf(floorf(log2f(target / amax)), -100.f), 100.f));
-  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (idx == 0) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // four consecutive elements of one row (wp % 4 == 0)
+  if (t == 0) {
     scale[0] = S;
     scale[1] = 1.0f / S;
   }
+  const int64_t idx = t * 4;
   if (idx >= n * wp) return;
-  const float v = x[idx] * S;
-  own[idx] = __float2half_rn(v);
-  q[idx] = __float2half_rn(v * inv_deg[idx / wp]);
+  const float4 v = *reinterpret_cast<const float4*>(x + idx);
+  const float d = __ldg(inv_deg + idx / wp);
+  const float a0 = v.x * S, a1 = v.y * S, a2 = v.z * S, a3 = v.w * S;
+  __half2 o[2] = {__floats2half2_rn(a0, a1), __floats2half2_rn(a2, a3)};
+  __half2 g[2] = {__floats2half2_rn(a0 * d, a1 * d), __floats2half2_rn(a2 * d, a3 * d)};
+  *reinterpret_cast<uint2*>(own + idx) = *reinterpret_cast<const uint2*>(o);
+  *reinterpret_cast<uint2*>(q + idx) = *reinterpret_cast<const uint2*>(g);
 }
 
 // g rows [E, kp] fp32 (reversed-CSR order, slot layout) -> planar fp16 [kp / 16][E][16]; the lo slot (first padding slot)
@@ -526,7 +531,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     const bool wgrad_tc = wgrad_tc_env && zt_fused && mask_fused && z_stash_half(precision) && wgrad_tc_supported(d);
     if (wgrad_tc) {
       // the scaled fp16 rows of the fused reversed pass below are this product's operand too
-      scale_rows_f16_kernel<<<(unsigned)ceil_div(n * d.wp, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16,
+      scale_rows_f16_kernel<<<(unsigned)ceil_div(n * d.wp / 4, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16,
                                                                           w.q16, w.scales + 2 * l);
       FESR_LAUNCH_CHECK();
       if ((rc = launch_wgrad_tc(d, fw.Z[l], w.own16, w.scales + 2 * l + 1, n, w.dT, w.gemm_ws, s))) return rc;
@@ -560,7 +565,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
       }
       if (zt_fused) {
         if (!wgrad_tc) {
-          scale_rows_f16_kernel<<<(unsigned)ceil_div(cnt, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16,
+          scale_rows_f16_kernel<<<(unsigned)ceil_div(cnt / 4, T), T, 0, s>>>(w.dpre, n, d.wp, w.amax + l, 64.f, w.inv_deg, w.own16,
                                                                          w.q16, w.scales + 2 * l);
           FESR_LAUNCH_CHECK();
         }

@@ -19,7 +19,7 @@ struct GemmArgs {
 size_t gemm_ws_bytes(int64_t M, int64_t N, int64_t K);
 int launch_gemm(const GemmArgs& a, float* ws, size_t ws_bytes, cudaStream_t s);
 
-constexpr int COLSUM_BLOCKS = 512;
+constexpr int COLSUM_BLOCKS = 1184;      // 8 blocks of 256 threads on each of the 148 SMs: one full wave
 size_t colsum_ws_bytes(int cols);
 int launch_colsum(const float* X, int64_t rows, int cols, int64_t ld, int accumulate, float* out, float* ws,
                   cudaStream_t s);

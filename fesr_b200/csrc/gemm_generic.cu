@@ -165,28 +165,31 @@ colsum_partial_kernel(const float* __restrict__ X, int64_t rows, int cols, int64
   __syncthreads();
   if (rg == 0 && j < cols) partial[(int64_t)blockIdx.x * cols + j] = (red[0][jl] + red[1][jl]) + (red[2][jl] + red[3][jl]);
 }
-// 64 columns x 4 groups per block: group q adds the partials b = q, q + 4, ... with four independent accumulators (the
-// single chain of nb = 512 dependent adds took 32 us), the groups are combined in a fixed order: deterministic
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, int cols, int accumulate,
-                                    float* __restrict__ out) {
-  __shared__ float red[4][64];
+// 64 columns x 16 groups per block: group q adds the partials b = q, q + 16, ... with four independent accumulators (a
+// single chain of nb dependent adds took 32 us at nb = 512), the groups are combined in a fixed order: deterministic
+constexpr int CF_GROUPS = 16;
+__global__ void __launch_bounds__(64 * CF_GROUPS)
+colsum_final_kernel(const float* __restrict__ partial, int nb, int cols, int accumulate, float* __restrict__ out) {
+  __shared__ float red[CF_GROUPS][64];
   const int jl = threadIdx.x & 63, q = threadIdx.x >> 6;
   const int j = blockIdx.x * 64 + jl;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (j < cols) {
     int b = q;
-    for (; b + 12 < nb; b += 16) {
+    for (; b + 3 * CF_GROUPS < nb; b += 4 * CF_GROUPS) {
       s0 += partial[(int64_t)b * cols + j];
-      s1 += partial[(int64_t)(b + 4) * cols + j];
-      s2 += partial[(int64_t)(b + 8) * cols + j];
-      s3 += partial[(int64_t)(b + 12) * cols + j];
+      s1 += partial[(int64_t)(b + CF_GROUPS) * cols + j];
+      s2 += partial[(int64_t)(b + 2 * CF_GROUPS) * cols + j];
+      s3 += partial[(int64_t)(b + 3 * CF_GROUPS) * cols + j];
     }
-    for (; b < nb; b += 4) s0 += partial[(int64_t)b * cols + j];
+    for (; b < nb; b += CF_GROUPS) s0 += partial[(int64_t)b * cols + j];
   }
   red[q][jl] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (q == 0 && j < cols) {
-    const float s = (red[0][jl] + red[1][jl]) + (red[2][jl] + red[3][jl]);
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < CF_GROUPS; g += 4) s += (red[g][jl] + red[g + 1][jl]) + (red[g + 2][jl] + red[g + 3][jl]);
     out[j] = accumulate ? out[j] + s : s;
   }
 }
@@ -194,7 +197,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int nb, i
 // second stage alone (the caller produced `nb` rows of partial column sums itself)
 int launch_colsum_final(const float* partial, int nb, int cols, int accumulate, float* out, cudaStream_t s) {
   if (cols == 0) return FESR_OK;
-  colsum_final_kernel<<<(unsigned)ceil_div(cols, 64), 256, 0, s>>>(partial, nb, cols, accumulate, out);
+  colsum_final_kernel<<<(unsigned)ceil_div(cols, 64), 64 * CF_GROUPS, 0, s>>>(partial, nb, cols, accumulate, out);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
@@ -210,7 +213,7 @@ int launch_colsum(const float* X, int64_t rows, int cols, int64_t ld, int accumu
   dim3 grid(nb, (unsigned)ceil_div(cols, 64));
   colsum_partial_kernel<<<grid, 256, 0, s>>>(X, rows, cols, ld, rchunk, ws);
   FESR_LAUNCH_CHECK();
-  colsum_final_kernel<<<(unsigned)ceil_div(cols, 64), 256, 0, s>>>(ws, nb, cols, accumulate, out);
+  colsum_final_kernel<<<(unsigned)ceil_div(cols, 64), 64 * CF_GROUPS, 0, s>>>(ws, nb, cols, accumulate, out);
   FESR_LAUNCH_CHECK();
   return FESR_OK;
 }
