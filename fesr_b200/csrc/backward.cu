@@ -136,49 +136,72 @@ __global__ void scale_inplace_kernel(float* __restrict__ x, int64_t count, const
 }
 
 // mask_kernel + the column sums of dpre (dbias) + its largest magnitude in ONE pass over dh (tf32 arm: the three used to be
-// three kernels reading the same 30 MB).  Blocks own row ranges like colsum_partial_kernel (64 columns x 4 row groups, a
-// thread walks its rows 4 apart with four independent accumulators, the groups are combined in a fixed order), so the partial
-// sums -- finished by colsum_final_kernel -- are deterministic; the absmax is order-independent.
+// three kernels reading the same 30 MB).  Blocks own row ranges like colsum_partial_kernel; a thread owns four consecutive
+// columns (16-byte loads and stores; wp / 4 threads per row, 256 / (wp / 4) row groups) and walks its rows with two
+// independent accumulator sets; the row groups are combined in a fixed order, so the partial sums -- finished by
+// colsum_final_kernel -- are deterministic; the absmax is order-independent.
 __global__ void __launch_bounds__(256)
 mask_colsum_kernel(const float* __restrict__ dh, const float* __restrict__ h_next, int64_t n, int wp, int w, int relu,
                    const float* __restrict__ in_scale, int64_t rchunk, float* __restrict__ dpre, float* __restrict__ partial,
                    unsigned* __restrict__ amax) {
-  __shared__ float red[4][64];
+  __shared__ float4 red[256];
   __shared__ unsigned mred[8];
-  const int j = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int cq = wp >> 2, ng = 256 / cq;                 // threads per row, row groups
+  const int jq = threadIdx.x % cq, rg = threadIdx.x / cq;
   const float sc = in_scale != nullptr ? __ldg(in_scale) : 1.f;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
   unsigned m = 0u;
-  if (j < wp) {
+  if (rg < ng) {
     const int64_t r0 = (int64_t)blockIdx.x * rchunk, r1 = min(n, r0 + rchunk);
-    auto one = [&](int64_t i) {
-      float v = 0.f;
-      if (j < w) {
-        v = dh[i * wp + j] * sc;
-        if (relu && !(h_next[i * wp + j] > 0.f)) v = 0.f;
+    const int c = 4 * jq;
+    auto one = [&](int64_t i, float4& acc) {
+      const float4 d = *reinterpret_cast<const float4*>(dh + i * wp + c);
+      float v[4] = {d.x * sc, d.y * sc, d.z * sc, d.w * sc};
+      if (relu) {
+        const float4 hn = *reinterpret_cast<const float4*>(h_next + i * wp + c);
+        if (!(hn.x > 0.f)) v[0] = 0.f;
+        if (!(hn.y > 0.f)) v[1] = 0.f;
+        if (!(hn.z > 0.f)) v[2] = 0.f;
+        if (!(hn.w > 0.f)) v[3] = 0.f;
       }
-      uint32_t u;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-      v = __uint_as_float(u);
-      dpre[i * wp + j] = v;
-      m = max(m, u & 0x7fffffffu);
-      return v;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (c + q >= w) v[q] = 0.f;
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v[q]));
+        v[q] = __uint_as_float(u);
+        m = max(m, u & 0x7fffffffu);
+      }
+      *reinterpret_cast<float4*>(dpre + i * wp + c) = make_float4(v[0], v[1], v[2], v[3]);
+      acc.x += v[0];
+      acc.y += v[1];
+      acc.z += v[2];
+      acc.w += v[3];
     };
     int64_t i = r0 + rg;
-    for (; i + 12 < r1; i += 16) {
-      s0 += one(i);
-      s1 += one(i + 4);
-      s2 += one(i + 8);
-      s3 += one(i + 12);
+    for (; i + ng < r1; i += 2 * ng) {
+      one(i, s0);
+      one(i + ng, s1);
     }
-    for (; i < r1; i += 4) s0 += one(i);
+    if (i < r1) one(i, s0);
   }
-  red[rg][j] = (s0 + s1) + (s2 + s3);
+  red[threadIdx.x] = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) mred[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (rg == 0 && j < wp) partial[(int64_t)blockIdx.x * wp + j] = (red[0][j] + red[1][j]) + (red[2][j] + red[3][j]);
+  if (threadIdx.x < wp) {
+    // column j = 4 jq' + q of every row group, groups in index order (two interleaved chains)
+    const int jq2 = threadIdx.x >> 2, q = threadIdx.x & 3;
+    float a0 = 0.f, a1 = 0.f;
+    int g = 0;
+    for (; g + 1 < ng; g += 2) {
+      a0 += reinterpret_cast<const float*>(&red[g * cq + jq2])[q];
+      a1 += reinterpret_cast<const float*>(&red[(g + 1) * cq + jq2])[q];
+    }
+    if (g < ng) a0 += reinterpret_cast<const float*>(&red[g * cq + jq2])[q];
+    partial[(int64_t)blockIdx.x * wp + threadIdx.x] = a0 + a1;
+  }
   if (threadIdx.x == 0 && amax != nullptr) {
     unsigned mm = 0u;
     for (int q = 0; q < 8; ++q) mm = max(mm, mred[q]);
@@ -512,7 +535,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
   const float* in_scale = nullptr;      // 1 / S of the layer processed before (dh arrives scaled by S)
   int cur = 0;
   for (int l = L - 1; l >= 0; --l) {
-    const bool mask_fused = rnd && d.wp <= 64 && n > 0;      // tf32 arm: mask + dbias partial sums + absmax in one pass
+    const bool mask_fused = rnd && d.wp <= 64 && d.wp % 4 == 0 && n > 0;      // tf32 arm: mask + dbias partial sums + absmax in one pass
     if (mask_fused) {
       int nb = (int)(n < COLSUM_BLOCKS ? n : COLSUM_BLOCKS);
       const int64_t rchunk = ceil_div(n, nb);
