@@ -151,3 +151,50 @@ def test_run_script_end_to_end(tmp_path, shipped):
     assert r.returncode == 0, r.stderr[-2000:]
     assert "Prediction time:" in r.stdout and "Reconstruction time:" in r.stdout and "Prediction done!" in r.stdout
     assert os.path.getsize(tmp_path / "logs/vtk/duct_neuralop/pred_1.vtu") > 10000
+
+
+def test_backward_kernel_switches_agree_in_their_own_process(shipped):
+    """The tcgen05 weight gradient and the all-layer edge gradient (default on) against the per-layer mma.sync kernels they
+    replaced (FESR_WGRAD_TC=0 FESR_EDGE_GRAD_LAYERS=0; the switches are read once per process, hence the subprocess), on a
+    ragged graph: isolated nodes, a hub of 150 in-edges (ten 16-edge chunks), a node count that is no multiple of 64."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    from conftest import ROOT
+    rng = np.random.default_rng(11)
+    n = 64 * 9 + 21
+    deg = rng.integers(0, 24, size=n)
+    deg[7] = 150
+    dst = np.repeat(np.arange(n), deg)
+    src = rng.integers(0, n, size=dst.size)
+    ei = np.stack([src, dst]).astype(np.int64)
+    ea = rng.uniform(2e-3, 6e-3, size=dst.size).astype(np.float32)
+    x = rng.uniform(0.0, 1.0, size=(n, 4)).astype(np.float32)
+    y = rng.uniform(0.0, 1.0, size=(n, 4)).astype(np.float32)
+    sd = shipped_state_dict(shipped, "neuralop")
+    m = _model("neuralop", 43, 5)
+    m.load_state_dict(sd)
+    loss, g = _grads(m, x, ei, ea, y, "tf32")
+    with tempfile.TemporaryDirectory() as td:
+        np.savez(os.path.join(td, "in.npz"), x=x, y=y, ei=ei, ea=ea, **{"sd::" + k: v.numpy() for k, v in sd.items()})
+        code = (
+            "import sys, numpy as np, torch\n"
+            f"sys.path.insert(0, {ROOT!r})\n"
+            "from fesr_b200.models.model import KernelNN\n"
+            f"z = np.load({os.path.join(td, 'in.npz')!r})\n"
+            "m = KernelNN(43, 43, 5, in_width=4, out_width=4)\n"
+            "m.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd::')})\n"
+            "m = m.cuda().train(); m.precision = 'tf32'\n"
+            "out = m(torch.from_numpy(z['x']).cuda(), torch.from_numpy(z['ei']).cuda(), torch.from_numpy(z['ea']).cuda())\n"
+            "torch.nn.functional.mse_loss(out, torch.from_numpy(z['y']).cuda()).backward()\n"
+            f"np.savez({os.path.join(td, 'out.npz')!r}, **{{k: p.grad.cpu().numpy() for k, p in m.named_parameters()}})\n")
+        env = dict(os.environ, FESR_WGRAD_TC="0", FESR_EDGE_GRAD_LAYERS="0")
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        old = dict(np.load(os.path.join(td, "out.npz")))
+    assert set(old) == set(g)
+    for k, v in g.items():
+        assert np.isfinite(v).all(), k
+        # both are tf32-class evaluations of the same gradient (5e-3 against fp64 autograd above)
+        assert rel_l2(v, old[k]) < 2e-3, (k, rel_l2(v, old[k]))
