@@ -285,7 +285,7 @@ struct EgLayers {
 };
 
 #ifndef EGL_MINB
-#define EGL_MINB 6
+#define EGL_MINB 5
 #endif
 __global__ void __launch_bounds__(128, EGL_MINB)
 edge_grad_layers_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ src_sorted, const EgLayers lay, int64_t n,
@@ -323,15 +323,37 @@ edge_grad_layers_kernel(const int32_t* __restrict__ rowptr, const int32_t* __res
             for (int q = lane; q < nline; q += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(pz + (size_t)q * 128));
           }
         }
+        if (l + 1 < lay.nl) {      // ... and the next layer's two gathered h rows (L2 hits at best: random rows)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(lay.h[l + 1] + s0));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(lay.h[l + 1] + s1));
+        }
         uint32_t v0[12], v1[12];
         eg_ldz12(lay.h[l] + s0, v0);
         eg_ldz12(lay.h[l] + s1, v1);
         const __nv_bfloat16* zrow = lay.dZ[l] + i * (int64_t)zk + 12 * tq;
+        // the channel tiles' dZ fragments are loaded one tile ahead of their MMAs (under the 80-register cap the compiler
+        // otherwise loads tile t + 1 after the MMAs of tile t: six exposed L1 / L2 latencies per layer, 43 % of the
+        // kernel's stall samples)
+        uint2 raw[2][3];
+        auto ldraw = [&](int t, uint2 (&r)[3]) {
+          const uint2* pz = reinterpret_cast<const uint2*>(zrow + (int64_t)min(t * 8 + gq, k1p - 1) * WP);
+          r[0] = __ldg(pz);
+          r[1] = __ldg(pz + 1);
+          r[2] = __ldg(pz + 2);
+        };
+        ldraw(0, raw[0]);
 #pragma unroll
         for (int t = 0; t < NTC; ++t) {
+          if (t + 1 < NTC && t + 1 < n_nt) ldraw(t + 1, raw[(t + 1) & 1]);
           if (t < n_nt) {
             uint32_t b[12];
-            eg_ldz12(zrow + (int64_t)min(t * 8 + gq, k1p - 1) * WP, b);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {      // bf16 -> tf32 bits: exact
+              b[4 * q] = raw[t & 1][q].x << 16;
+              b[4 * q + 1] = raw[t & 1][q].x & 0xffff0000u;
+              b[4 * q + 2] = raw[t & 1][q].y << 16;
+              b[4 * q + 3] = raw[t & 1][q].y & 0xffff0000u;
+            }
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
               asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
