@@ -367,6 +367,12 @@ struct BackwardWs {
   size_t bytes;
 };
 
+// A/B switch of the all-layer edge gradient; also decides whether the workspace holds the per-layer bf16 dZ buffers
+static bool eg_layers_enabled() {
+  static const bool on = !(getenv("FESR_EDGE_GRAD_LAYERS") && atoi(getenv("FESR_EDGE_GRAD_LAYERS")) == 0);
+  return on;
+}
+
 static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n, int64_t E) {
   Carver c(base);
   BackwardWs w;
@@ -375,7 +381,7 @@ static BackwardWs carve_backward(void* base, const fesr_model_dims& d, int64_t n
   w.dh[1] = c.take<float>(nn * d.wp);
   w.dpre = c.take<float>(nn * d.wp);
   w.BZ = c.take<float>(nn * d.zk);
-  w.BZx = d.layers > 2 && dz_tc_supported(d) && edge_grad_layers_supported(d, d.layers)
+  w.BZx = eg_layers_enabled() && d.layers > 2 && dz_tc_supported(d) && edge_grad_layers_supported(d, d.layers)
               ? c.take<uint16_t>((size_t)(d.layers - 2) * nn * d.zk) : nullptr;
   w.g_rev = c.take<float>(ee * d.kp);
   w.dg = c.take<float>(ee * d.kp);
@@ -514,8 +520,7 @@ int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
     FESR_LAUNCH_CHECK();
   }
   // one edge-gradient pass over all layers at the end (dg written once) when every layer's bf16 dZ can be kept
-  static const bool eg_layers_env = !(getenv("FESR_EDGE_GRAD_LAYERS") && atoi(getenv("FESR_EDGE_GRAD_LAYERS")) == 0);      // A/B switch
-  const bool eg_layers = eg_layers_env && dz_bf16 && zt_fused && E > 0 && (L <= 2 || w.BZx != nullptr) &&
+  const bool eg_layers = eg_layers_enabled() && dz_bf16 && zt_fused && E > 0 && (L <= 2 || w.BZx != nullptr) &&
                          edge_grad_layers_supported(d, L);
   const void* dz_of[FESR_EG_MAX_LAYERS] = {nullptr};
   const float* h_of[FESR_EG_MAX_LAYERS] = {nullptr};
