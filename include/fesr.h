@@ -174,7 +174,10 @@ int fesr_nnconv_forward(const fesr_model_dims* dims, const fesr_params* params,
  * of the REVERSED graph built from the forward CSR slots (fesr_csr_build on the [2,E] array
  * {dst of slot e ; src of slot e}): rowptr_t [n+1] groups the edges by SOURCE node, src_t [E] is
  * the original destination of each reversed slot and rev_to_fwd [E] its forward CSR slot.
- * grad_y [n, out_ch] in; parameter gradients are ADDED into *grads; grad_x [n, in_ch] may be NULL. */
+ * grad_y [n, out_ch] in; parameter gradients are ADDED into *grads; grad_x [n, in_ch] may be NULL.
+ * The workspace of the tf32 arm keeps one bf16 dZ [n, zk] per layer (2 * n * zk bytes each; layers <= 8) so that the
+ * edge gradient runs once over all layers; FESR_EDGE_GRAD_LAYERS=0 in the environment (read once per process, by the
+ * size query as well) drops those buffers and runs the edge gradient layer by layer. */
 size_t fesr_backward_workspace_bytes(const fesr_model_dims* dims, int64_t n, int64_t E);
 int fesr_nnconv_backward(const fesr_model_dims* dims, const fesr_params* params,
                          const float* x, const int32_t* rowptr, const int32_t* src_sorted,
