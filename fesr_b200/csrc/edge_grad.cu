@@ -402,7 +402,11 @@ int launch_edge_grad_layers(const fesr_model_dims& d, const int32_t* rowptr, con
   }
   lay.nl = n_layers;
   const int64_t blocks = ceil_div(n, 4);
-  const int grid = (int)(blocks < 16ll * num_sms() ? blocks : 16ll * num_sms());
+  // one persistent wave: EGL_MINB blocks are resident per SM (16 per SM = 3.2 waves left a tail: 6.08 vs 5.94 ms per train
+  // step at 527 k cells; 10 per SM 5.95, 32 per SM 5.99)
+  static const int per_sm = getenv("FESR_EGL_BLOCKS_PER_SM") && atoi(getenv("FESR_EGL_BLOCKS_PER_SM")) > 0
+                                ? atoi(getenv("FESR_EGL_BLOCKS_PER_SM")) : EGL_MINB;
+  const int grid = (int)(blocks < (int64_t)per_sm * num_sms() ? blocks : (int64_t)per_sm * num_sms());
   const size_t smem = (size_t)4 * 16 * d.kp * sizeof(float);
   edge_grad_layers_kernel<<<grid, 128, smem, s>>>(rowptr, src_sorted, lay, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
   FESR_LAUNCH_CHECK();
