@@ -439,16 +439,26 @@ int launch_edge_grad(const fesr_model_dims& d, const int32_t* rowptr, const int3
   static const bool no_3x = getenv("FESR_EDGE_GRAD_3X") && atoi(getenv("FESR_EDGE_GRAD_3X")) == 0;      // A/B switch
   if (use_mma == 3 && (no_mma || no_3x || d.wp != 48)) use_mma = 0;
   if (use_mma && !no_mma && d.wp == 48) {
+    // one persistent wave: as many blocks as are resident (16 per SM = 2.7-4 waves left a tail, see launch_edge_grad_layers)
     const int64_t blocks = ceil_div(n, 4);
-    const int grid = (int)(blocks < 16ll * num_sms() ? blocks : 16ll * num_sms());
     const size_t smem = (size_t)4 * 16 * d.kp * sizeof(float);      // <= 36.9 KB (kp = 144)
-    if (dz_bf16)
-      edge_grad_mma_kernel<48, __nv_bfloat16, 1><<<grid, 128, smem, s>>>(rowptr, src_sorted, static_cast<const __nv_bfloat16*>(dZv), h, n,
-                                                                     d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
-    else if (use_mma == 3)
-      edge_grad_mma_kernel<48, float, 3><<<grid, 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
-    else
-      edge_grad_mma_kernel<48, float, 1><<<grid, 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+    auto grid_of = [&](const void* fn) {
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, smem) != cudaSuccess || occ < 1) occ = 4;
+      const int64_t cap = (int64_t)occ * num_sms();
+      return (int)(blocks < cap ? blocks : cap);
+    };
+    if (dz_bf16) {
+      auto* fn = edge_grad_mma_kernel<48, __nv_bfloat16, 1>;
+      fn<<<grid_of(reinterpret_cast<const void*>(fn)), 128, smem, s>>>(rowptr, src_sorted, static_cast<const __nv_bfloat16*>(dZv), h, n,
+                                                                   d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+    } else if (use_mma == 3) {
+      auto* fn = edge_grad_mma_kernel<48, float, 3>;
+      fn<<<grid_of(reinterpret_cast<const void*>(fn)), 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+    } else {
+      auto* fn = edge_grad_mma_kernel<48, float, 1>;
+      fn<<<grid_of(reinterpret_cast<const void*>(fn)), 128, smem, s>>>(rowptr, src_sorted, dZ, h, n, d.k1p, d.kt, d.ktp, d.kp, d.zk, dg);
+    }
     FESR_LAUNCH_CHECK();
     return FESR_OK;
   }
