@@ -600,8 +600,16 @@ static int launch_eh2m(const fesr_model_dims& d, const fesr_params& p, const flo
   const int grid = (int)(blocks < 8ll * num_sms() ? blocks : 8ll * num_sms());
   ProfScope prof(PROF_EDGE_HIDDEN, s);
   constexpr size_t stage_bytes = (size_t)4 * 32 * (NTO * 8 + 4) * sizeof(float);
+  // persistent over edge groups: one wave of resident blocks (as for the fp16 kernels below; 8 blocks per SM with 5
+  // resident at 96 registers ran as a full wave plus a 60 % one)
+  auto wave = [&](const void* fn) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, 128, stage_bytes) != cudaSuccess || occ < 1) return grid;
+    const int64_t cap = (int64_t)occ * num_sms();
+    return (int)(blocks < cap ? blocks : cap);
+  };
 #define FESR_EH(TERMS, OMODE)                                                                                   \
-  edge_hidden2_mma_kernel<WPAD, NTO, TERMS, OMODE><<<grid, 128, stage_bytes, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], \
+  edge_hidden2_mma_kernel<WPAD, NTO, TERMS, OMODE><<<wave(reinterpret_cast<const void*>(&edge_hidden2_mma_kernel<WPAD, NTO, TERMS, OMODE>)), 128, stage_bytes, s>>>(p.mlp_w[0], p.mlp_b[0], p.mlp_w[1], p.mlp_b[1], \
                                                                         d.w, d.leaky, d.kt, d.ktp, d.k1, edge_attr, perm, E, g, cur_ovf(), cur_gcenter())
   static bool attr_set = false;
   if (!attr_set) {   // static + dynamic shared memory exceeds 48 KB for the widest rows
