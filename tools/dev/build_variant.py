@@ -1,5 +1,7 @@
 """Dev build: python tools/dev/build_variant.py <tag> [nvcc flags...] -> fesr_b200/lib/libfesr_<tag>.so (objects in
-fesr_b200/build_<tag>/); select it with FESR_LIB_PATH.  Used for same-box A/B timing of kernel variants."""
+fesr_b200/build_tr/<tag>/); select it with FESR_LIB_PATH.  Used for same-box A/B timing of kernel variants.
+VARIANT_FILES=<prefix>[,<prefix>...] names the source files that are recompiled with the flags (default: layer_fused*);
+e.g. VARIANT_FILES=edge_grad python tools/dev/build_variant.py minb6 -DEGL_MINB=6."""
 import os, subprocess, sys, concurrent.futures as cf
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
